@@ -1,0 +1,87 @@
+"""ctypes binding of ``libpano360_b200.so`` (the C ABI in include/pano360_b200.h).
+
+There is no CPU fallback: if the library is missing the import of any compute
+entry point raises, and every call checks the returned status and raises
+``RuntimeError`` with ``p360_last_error`` text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart first so the library shares torch's runtime)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpano360_b200.so")
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes; every function returns int.  Kept in one table so the
+# symbol-export test can walk it next to the header.
+SIGNATURES = {
+    "p360_version": [],
+    "p360_last_error": [C.c_char_p, _i],
+    "p360_device_info": [_i, C.POINTER(C.c_int32)],
+    "p360_warp_patch": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "p360_owner_to_alpha": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
+    "p360_band_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_collapse_finalize": [_vp, _i, _vp, _vp, _i64, _vp],
+    "p360_linear_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_linear_finalize": [_vp, _vp, _i64, _vp],
+    "p360_paste": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_pair_stats_blocks": [_i, _i],
+    "p360_pair_overlap_stats": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp],
+    "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
+}
+# entry points whose int return is a value, not a status
+_VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
+
+_lib = None
+launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
+_LAUNCHES = {"p360_warp_patch": 1, "p360_owner_update": 1, "p360_owner_to_alpha": 1,
+             "p360_gauss_blur": 2, "p360_band_accumulate": 1, "p360_collapse_finalize": 1,
+             "p360_linear_accumulate": 1, "p360_linear_finalize": 1, "p360_paste": 1,
+             "p360_pair_overlap_stats": 2, "p360_cover_update": 1}
+
+
+def load():
+    """dlopen the library (once) and declare prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m pano360_b200.build` "
+            "(pano360_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _i
+    _lib = lib
+    return lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    load().p360_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def call(name, *args):
+    """Invoke an entry point; raise on a non-zero status."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    if name in _VALUE_RETURN:
+        return rc
+    if rc != 0:
+        raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")
+    launch_count += _LAUNCHES.get(name, 0)
+    return 0
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,317 @@
+"""Device-side driver of the compositing path: owns HBM buffers (torch is used
+for allocation, streams and copies only) and sequences the sm_100a kernels of
+``libpano360_b200.so`` through the C ABI.
+
+Data layout in HBM
+------------------
+* source image      u8  [h][w][3]            as delivered by cv2.imread (BGR)
+* sample LUT        f32 [256] per image      u8 -> float value (gain folded in)
+* hat tables        f64 [h], [w]             shared by images of equal size
+* inverse-map tabs  f64 [pw][3], [ph][3]     per patch (column part, row part)
+* patch             f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid mask
+* accumulators      f32 [L][H][W][4]         {sum band*wgt (rgb), sum wgt}
+* owner / best      i32 [H][W], f32 [H][W]   running arg-max of alpha
+* covered           u8  [H][W]               union of valid pixels
+* mosaic            u8  [H][W][3]
+
+A *row window* ``(ya, yb)`` restricts all work to mosaic rows [ya, yb) plus a
+halo of the largest blur radius (strip sharding); patches are
+cropped in rows but keep their true columns, so reflections happen at true
+patch edges wherever they influence rows inside the window.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, geometry as geo
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("pano360_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"pano360_b200 runs on CUDA devices only, got {dev}")
+    return dev
+
+
+@dataclass
+class DevicePatch:
+    """One warped image resident in HBM.  Unpacks like the reference's patch
+    triple ``(warped, mask, irange)`` (stitcher.py:318-319)."""
+
+    rgba: torch.Tensor        # [ph, pw, 4] float32
+    invalid: torch.Tensor     # [ph, pw] uint8 (1 = masked)
+    box: tuple                # (x0, y0, x1, y1) in mosaic pixels
+    index: int = 0
+
+    @property
+    def irange(self):
+        x0, y0, x1, y1 = self.box
+        return (slice(y0, y1), slice(x0, x1))
+
+    def __iter__(self):
+        return iter((self.rgba, self.invalid, self.irange))
+
+    def to_numpy(self):
+        return (self.rgba.cpu().numpy(), self.invalid.cpu().numpy().astype(bool), self.irange)
+
+
+@dataclass
+class DeviceSources:
+    """Input images + per-image constants resident in HBM."""
+
+    pixels: list                       # u8 [h, w, c] tensors
+    luts: list                         # f32 [256] tensors
+    hats: dict = field(default_factory=dict)   # (h, w) -> (hat_y, hat_x) f64 tensors
+    shapes: list = field(default_factory=list)
+
+    @property
+    def nbytes(self):
+        return sum(p.numel() for p in self.pixels)
+
+
+class Compositor:
+    """Runs warp / gain / blend stages on one GPU."""
+
+    def __init__(self, device=None):
+        self.device = _require_cuda(device)
+        _lib.load()
+        self._pinned = {}
+
+    # -- plumbing -----------------------------------------------------------
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _to_device(self, array, pinned_key=None):
+        """Host ndarray -> device tensor through a (reused) pinned staging buffer."""
+        array = np.ascontiguousarray(array)
+        host = torch.from_numpy(array)
+        if pinned_key is not None:
+            stage, busy = self._pinned.get(pinned_key, (None, None))
+            if busy is not None:
+                busy.synchronize()            # previous async copy out of this buffer is done
+            if stage is None or stage.shape != host.shape or stage.dtype != host.dtype:
+                stage = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
+            stage.copy_(host)
+            dev = stage.to(self.device, non_blocking=True)
+            busy = torch.cuda.Event()
+            busy.record(torch.cuda.current_stream(self.device))
+            self._pinned[pinned_key] = (stage, busy)
+            return dev
+        return host.to(self.device)
+
+    def upload(self, regions, gains=None, pinned=None):
+        """H2D copy of the u8 images (+ LUT / hat tables).  ``pinned`` may be a
+        list of pinned uint8 tensors already holding the pixels."""
+        src = DeviceSources([], [])
+        for i, reg in enumerate(regions):
+            img = reg.img if pinned is None else None
+            if pinned is not None:
+                dev_img = pinned[i].to(self.device, non_blocking=True)
+            else:
+                if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+                    raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
+                dev_img = self._to_device(img)
+            h, w = dev_img.shape[:2]
+            src.pixels.append(dev_img)
+            src.shapes.append((h, w))
+            if (h, w) not in src.hats:
+                src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
+            gain = None if gains is None else gains[i]
+            src.luts.append(self._to_device(geo.sample_lut(gain)))
+        return src
+
+    def set_gains(self, src, gains):
+        src.luts = [self._to_device(geo.sample_lut(g)) for g in gains]
+
+    # -- K8 + host solve: exposure gains (stitcher.py:24-66) ------------------
+    def pair_statistics(self, regions, src, pairs=None):
+        """overlaps / sizes matrices of ``equalize_gains`` from device sums."""
+        n = len(regions)
+        h, w = src.shapes[0]
+        overlaps, sizes = np.zeros((n, n)), np.zeros((n, n))
+        todo = []
+        for i in range(n):
+            for j in range(i + 1, n):
+                hom, behind = geo.pair_homography(regions[i], regions[j], (h, w))
+                if not behind:
+                    todo.append((i, j, geo.invert3x3(hom)))
+        if pairs is not None:
+            todo = [t for k, t in enumerate(todo) if k in pairs]
+        if not todo:
+            return overlaps, sizes, todo
+        lut0 = self._to_device(geo.sample_lut(None))
+        hat_y, hat_x = src.hats[(h, w)]
+        nblocks = _lib.call("p360_pair_stats_blocks", h, w)
+        partial = torch.empty(3 * nblocks, dtype=torch.float64, device=self.device)
+        out = torch.zeros((len(todo), 3), dtype=torch.float64, device=self.device)
+        for k, (i, j, inv) in enumerate(todo):
+            if src.shapes[i] != (h, w) or src.shapes[j] != (h, w):
+                raise ValueError("exposure equalisation needs equally sized images (as the reference)")
+            inv_c = (C.c_double * 9)(*inv.ravel())
+            _lib.call("p360_pair_overlap_stats", _lib.ptr(src.pixels[i]), _lib.ptr(src.pixels[j]),
+                      h, w, src.pixels[i].shape[2], _lib.ptr(lut0), _lib.ptr(hat_y), _lib.ptr(hat_x),
+                      inv_c, _lib.ptr(partial), out[k].data_ptr(), self.stream)
+        sums = out.cpu().numpy()
+        for (i, j, _), (cnt, s_i, s_j) in zip(todo, sums):
+            sizes[i, j] = sizes[j, i] = cnt
+            if cnt > 0:
+                overlaps[i, j] = s_i / (3.0 * cnt)
+                overlaps[j, i] = s_j / (3.0 * cnt)
+        return overlaps, sizes, todo
+
+    # -- K1: warp -------------------------------------------------------------
+    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, keep=None):
+        """Warp every image into its (row-cropped) patch.  ``rows=(ya, yb)``
+        crops patches to those mosaic rows and shifts boxes so that row ya is
+        row 0.  Returns a list of DevicePatch (images with an empty crop are
+        skipped; ``index`` keeps the original image number)."""
+        crops, tabs, total = [], [], 0
+        for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
+            x0, y0, x1, y1 = box
+            ya, yb = (y0, y1) if rows is None else (max(y0, rows[0]), min(y1, rows[1]))
+            if ya >= yb or x0 >= x1 or (keep is not None and i not in keep):
+                continue
+            col_tab, row_tab = geo.inverse_map_tables(reg, (x0, ya, x1, yb), plan, proj)
+            crops.append((i, x0, ya, x1, yb, total, total + col_tab.size))
+            tabs += [col_tab.ravel(), row_tab.ravel()]
+            total += col_tab.size + row_tab.size
+        if not crops:
+            return []
+        dev_tabs = self._to_device(np.concatenate(tabs), pinned_key="tabs")
+        shift = 0 if rows is None else rows[0]
+        patches = []
+        for i, x0, ya, x1, yb, off_c, off_r in crops:
+            pw, ph = x1 - x0, yb - ya
+            rgba = torch.empty((ph, pw, 4), dtype=torch.float32, device=self.device)
+            invalid = torch.empty((ph, pw), dtype=torch.uint8, device=self.device)
+            h, w = src.shapes[i]
+            hat_y, hat_x = src.hats[(h, w)]
+            _lib.call("p360_warp_patch", _lib.ptr(src.pixels[i]), h, w, src.pixels[i].shape[2],
+                      _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
+                      dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
+                      pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), self.stream)
+            patches.append(DevicePatch(rgba, invalid, (x0, ya - shift, x1, yb - shift), i))
+        self._keepalive = dev_tabs
+        return patches
+
+    # -- blenders (device-resident patches in, device u8 mosaic out) ---------
+    def _args(self, p):
+        x0, y0, x1, y1 = p.box
+        return x1 - x0, y1 - y0, x0, y0
+
+    def blend_none(self, patches, shape):
+        """stitcher.py:160-168."""
+        h, w = shape
+        mosaic = torch.zeros((h, w, 3), dtype=torch.uint8, device=self.device)
+        for p in patches:
+            pw, ph, x0, y0 = self._args(p)
+            _lib.call("p360_paste", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0,
+                      _lib.ptr(mosaic), w, self.stream)
+        return mosaic
+
+    def blend_linear(self, patches, shape):
+        """stitcher.py:171-183."""
+        h, w = shape
+        acc = torch.zeros((h, w, 4), dtype=torch.float32, device=self.device)
+        for p in patches:
+            pw, ph, x0, y0 = self._args(p)
+            _lib.call("p360_linear_accumulate", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0,
+                      _lib.ptr(acc), w, self.stream)
+        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        _lib.call("p360_linear_finalize", _lib.ptr(acc), _lib.ptr(mosaic), h * w, self.stream)
+        return mosaic
+
+    def owner_map(self, patches, shape):
+        """stitcher.py:196-204 without the H x W x N tensor: (owner, covered)."""
+        h, w = shape
+        best = torch.zeros((h, w), dtype=torch.float32, device=self.device)
+        owner = torch.full((h, w), -1, dtype=torch.int32, device=self.device)
+        covered = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
+        for k, p in enumerate(patches):
+            pw, ph, x0, y0 = self._args(p)
+            _lib.call("p360_owner_update", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0, k,
+                      _lib.ptr(best), _lib.ptr(owner), _lib.ptr(covered), w, self.stream)
+        return owner, covered
+
+    def blur(self, rgba, sigma, out=None, tmp=None):
+        """cv2.GaussianBlur(rgba, (0, 0), sigma) on a device patch."""
+        taps = geo.gaussian_taps(sigma)
+        out = torch.empty_like(rgba) if out is None else out
+        tmp = torch.empty_like(rgba) if tmp is None else tmp
+        ph, pw = rgba.shape[:2]
+        _lib.call("p360_gauss_blur", _lib.ptr(rgba), _lib.ptr(out), _lib.ptr(tmp), pw, ph,
+                  taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps), self.stream)
+        return out
+
+    def blend_multiband(self, patches, shape, n_levels=5, stages=None):
+        """stitcher.py:186-241, patch-major: one accumulator plane per level so
+        the per-level sums still add patches in list order."""
+        h, w = shape
+        owner, covered = self.owner_map(patches, shape)
+        acc = torch.zeros((n_levels, h, w, 4), dtype=torch.float32, device=self.device)
+        plane = h * w * 16
+        biggest = max((p.rgba.numel() for p in patches), default=0)
+        scratch = [torch.empty(biggest, dtype=torch.float32, device=self.device) for _ in range(3)] \
+            if n_levels > 1 and biggest else []
+        for k, p in enumerate(patches):
+            pw, ph, x0, y0 = self._args(p)
+            _lib.call("p360_owner_to_alpha", _lib.ptr(p.rgba), pw, ph, x0, y0, k, _lib.ptr(owner), w,
+                      self.stream)
+            prev = p.rgba
+            for lvl in range(n_levels - 1):
+                views = [s[:p.rgba.numel()].view(p.rgba.shape) for s in scratch]
+                cur = views[lvl & 1]
+                self.blur(p.rgba, geo.band_sigma(lvl), out=cur, tmp=views[2])
+                _lib.call("p360_band_accumulate", _lib.ptr(prev), _lib.ptr(cur), pw, ph, x0, y0,
+                          acc.data_ptr() + lvl * plane, w, self.stream)
+                prev = cur
+            _lib.call("p360_band_accumulate", _lib.ptr(prev), None, pw, ph, x0, y0,
+                      acc.data_ptr() + (n_levels - 1) * plane, w, self.stream)
+        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        _lib.call("p360_collapse_finalize", _lib.ptr(acc), n_levels, _lib.ptr(covered), _lib.ptr(mosaic),
+                  h * w, self.stream)
+        if stages is not None:
+            stages.update(owner=owner, covered=covered, acc=acc)
+        return mosaic
+
+    def covered_mask(self, patches, shape):
+        """Area of validity for the crop stage (stitcher.py:266-271)."""
+        h, w = shape
+        covered = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
+        for p in patches:
+            pw, ph, x0, y0 = self._args(p)
+            _lib.call("p360_cover_update", _lib.ptr(p.invalid), pw, ph, x0, y0, _lib.ptr(covered), w,
+                      self.stream)
+        return covered
+
+    def blend(self, kind, patches, shape, n_levels=5):
+        if kind == "none":
+            return self.blend_none(patches, shape)
+        if kind == "linear":
+            return self.blend_linear(patches, shape)
+        if kind == "multiband":
+            return self.blend_multiband(patches, shape, n_levels)
+        raise ValueError(f"unknown blender {kind!r}")
+
+    # -- whole path, device resident ------------------------------------------
+    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None):
+        """warp + blend for the whole mosaic or for a row window [ya, yb)
+        (returned strip has exactly yb - ya rows)."""
+        if rows is None:
+            patches = self.warp(regions, src, plan, proj)
+            return self.blend(kind, patches, plan.shape, n_levels), patches
+        ya, yb = rows
+        halo = 0
+        if kind == "multiband" and n_levels > 1:
+            halo = (len(geo.gaussian_taps(geo.band_sigma(n_levels - 2))) - 1) // 2
+        wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
+        patches = self.warp(regions, src, plan, proj, rows=(wa, wb))
+        strip = self.blend(kind, patches, (wb - wa, plan.shape[1]), n_levels)
+        return strip[ya - wa:ya - wa + (yb - ya)], patches

@@ -1,0 +1,195 @@
+"""Host-side O(N) geometry of the compositing path, in float64 exactly as the
+reference does it: projections (stitcher.py:73-104), per-image angular range
+(:107-122), mosaic resolution and extent (:125-157), patch bounding boxes
+(:283-297) and the separable inverse-map tables the warp kernel consumes
+(:300-306).  Nothing here touches pixels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+PATCH_PAD = 10          # stitcher.py:296-297 (multiband only)
+BORDER_SAMPLES = 100    # stitcher.py:109
+
+
+class SphProj:
+    """Forward / backward spherical projection (stitcher.py:73-87)."""
+
+    KIND = "spherical"
+
+    @staticmethod
+    def hom2proj(pts):
+        horiz = np.sqrt(pts[:, 0] ** 2 + pts[:, 2] ** 2)
+        return np.stack([np.arctan2(pts[:, 0], pts[:, 2]), np.arctan2(pts[:, 1], horiz)], axis=-1)
+
+    @staticmethod
+    def proj2hom(pts):
+        return np.stack([np.sin(pts[:, 0]), np.tan(pts[:, 1]), np.cos(pts[:, 0])], axis=-1)
+
+
+class CylProj:
+    """Forward / backward cylindrical projection (stitcher.py:90-104)."""
+
+    KIND = "cylindrical"
+
+    @staticmethod
+    def hom2proj(pts):
+        horiz = np.sqrt(pts[:, 0] ** 2 + pts[:, 2] ** 2)
+        return np.stack([np.arctan2(pts[:, 0], pts[:, 2]), pts[:, 1] / horiz], axis=-1)
+
+    @staticmethod
+    def proj2hom(pts):
+        return np.stack([np.sin(pts[:, 0]), pts[:, 1], np.cos(pts[:, 0])], axis=-1)
+
+
+def hat(size):
+    """Triangular 0 - 0.5 - 0 profile (stitcher.py:251-254), float64."""
+    return 0.5 - np.abs((np.arange(size) - size / 2) / size)
+
+
+def image_range_border(shape, hom, proj=SphProj):
+    """(min, max) projected angles over 4 x 100 border samples; no wrap-around
+    handling, like the reference (stitcher.py:107-122)."""
+    h, w = shape
+    along_x = np.linspace(0, w, BORDER_SAMPLES)
+    along_y = np.linspace(0, h, BORDER_SAMPLES)
+    n = BORDER_SAMPLES
+    ring = np.empty((4 * n, 3))
+    ring[:, 2] = 1.0
+    ring[0 * n:1 * n, 0], ring[0 * n:1 * n, 1] = 0.0, along_y
+    ring[1 * n:2 * n, 0], ring[1 * n:2 * n, 1] = w, along_y
+    ring[2 * n:3 * n, 0], ring[2 * n:3 * n, 1] = along_x, 0.0
+    ring[3 * n:4 * n, 0], ring[3 * n:4 * n, 1] = along_x, h
+    ring -= np.array([w / 2, h / 2, 0])
+    ang = proj.hom2proj(hom.dot(ring.T).T)
+    return np.min(ang, axis=0), np.max(ang, axis=0)
+
+
+def image_range_corners(shape, hom, proj=SphProj):
+    """Extent from the four corners, pushed across the +-pi seam if needed
+    (stitcher.py:125-139)."""
+    h, w = shape
+    corners = np.array([[-w / 2, -h / 2, 1], [w / 2, -h / 2, 1],
+                        [-w / 2, h / 2, 1], [w / 2, h / 2, 1]])
+    ang = proj.hom2proj(hom.dot(corners.T).T)
+    x_lo, x_hi = min(ang[0, 0], ang[2, 0]), max(ang[1, 0], ang[3, 0])
+    y_lo, y_hi = min(ang[0, 1], ang[1, 1]), max(ang[2, 1], ang[3, 1])
+    if x_lo > x_hi:
+        x_hi += 2 * np.pi
+    if y_lo > y_hi:
+        y_hi += np.pi
+    return np.array([x_lo, y_lo]), np.array([x_hi, y_hi])
+
+
+@dataclass
+class MosaicPlan:
+    """Where every image lands (all integers are mosaic pixels)."""
+
+    shape: tuple              # (H, W)
+    resolution: np.ndarray    # rad/px for (theta, phi)
+    origin: np.ndarray        # (theta_min, phi_min)
+    boxes: list               # per image (x0, y0, x1, y1)
+    ranges: list              # per image (min, max) angles
+
+
+def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
+    """Mosaic shape and per-image boxes (stitcher.py:276-277, :283-297).
+    ``pad`` is True for the multiband blender (10-px pad, clamped)."""
+    ranges = [image_range_border(r.img.shape[:2], r.hom(), proj) for r in regions]
+    lo = np.min([r[0] for r in ranges], axis=0)
+    hi = np.max([r[1] for r in ranges], axis=0)
+    mid = regions[len(regions) // 2]
+    mid_lo, mid_hi = image_range_corners(mid.img.shape[:2], mid.hom(), proj)
+    resolution = (mid_hi - mid_lo) / np.array(mid.img.shape[:2][::-1])
+    longest = np.max((hi - lo) / resolution)
+    if longest > max_resolution:
+        resolution = resolution * (longest / max_resolution)
+    target = (hi - lo) / resolution
+    shape = tuple(int(t) for t in np.round(target))[::-1]
+    limit = target.astype(np.int32)               # truncating cast, stitcher.py:297
+    boxes = []
+    for r_lo, r_hi in ranges:
+        bottom = np.round((r_lo - lo) / resolution).astype(np.int32)
+        top = np.round((r_hi - lo) / resolution).astype(np.int32)
+        if pad:
+            bottom = np.maximum(bottom - PATCH_PAD, np.int32([0, 0]))
+            top = np.minimum(top + PATCH_PAD, limit)
+        boxes.append((int(bottom[0]), int(bottom[1]), int(top[0]), int(top[1])))
+    return MosaicPlan(shape, resolution, lo, boxes, ranges)
+
+
+def inverse_map_tables(region, box, plan, proj=SphProj):
+    """Separable float64 tables for one patch: ``p = K R proj2hom(theta, phi)``
+    splits into a per-column part (x and z components of the ray depend on
+    theta only) and a per-row part (the y component depends on phi only), for
+    both projections (stitcher.py:84-87, :101-104, :300-306).
+
+    Returns (col_tab [pw,3], row_tab [ph,3]) with p = col_tab[c] + row_tab[r].
+    """
+    x0, y0, x1, y1 = box
+    theta = (np.arange(x1 - x0) + x0) * plan.resolution[0] + plan.origin[0]
+    phi = (np.arange(y1 - y0) + y0) * plan.resolution[1] + plan.origin[1]
+    zeros_c, zeros_r = np.zeros_like(theta), np.zeros_like(phi)
+    ray_c = proj.proj2hom(np.stack([theta, zeros_c], axis=-1))   # (sin, f(0), cos)
+    ray_r = proj.proj2hom(np.stack([zeros_r, phi], axis=-1))     # (0, f(phi), 1)
+    k_r = region.proj()
+    col_tab = ray_c[:, [0]] * k_r[:, 0][None, :] + ray_c[:, [2]] * k_r[:, 2][None, :]
+    row_tab = ray_r[:, [1]] * k_r[:, 1][None, :]
+    return np.ascontiguousarray(col_tab), np.ascontiguousarray(row_tab)
+
+
+def gaussian_taps(sigma):
+    """float32 taps of ``cv2.GaussianBlur(img, (0, 0), sigma)`` on float data:
+    ksize = round(8 sigma + 1) | 1, exp(-x^2 / 2 sigma^2) / sum in float64
+    (the call at stitcher.py:226)."""
+    ksize = int(np.rint(sigma * 8 + 1)) | 1
+    x = np.arange(ksize, dtype=np.float64) - (ksize - 1) / 2.0
+    k = np.exp(-(x * x) / (2.0 * sigma * sigma))
+    return (k / k.sum()).astype(np.float32)
+
+
+def band_sigma(level):
+    """sigma of pyramid level ``level`` (stitcher.py:218)."""
+    return float(np.sqrt(2 * level + 1.0) * 4)
+
+
+def sample_lut(gain=None):
+    """float32 value of each u8 sample as the reference's float image holds it:
+    ``u8.astype(f32) / 255`` (stitcher.py:259), then — with ``-e`` —
+    ``clip(gain * v, 0, 1)`` evaluated in float64 and stored back into the
+    float32 image (stitcher.py:66)."""
+    lut = np.arange(256, dtype=np.uint8).astype(np.float32) / 255
+    if gain is not None:
+        lut = np.clip(np.float64(gain) * lut, 0, 1).astype(np.float32)
+    return lut
+
+
+def pair_homography(reg_i, reg_j, shape):
+    """Un-centred pixel homography taking image j into image i's frame, and
+    whether the reference skips the pair (a corner behind the camera)
+    (stitcher.py:42-55)."""
+    h, w = shape
+    shift = np.array([[1, 0, w / 2], [0, 1, h / 2], [0, 0, 1]])
+    unshift = np.array([[1, 0, -w / 2], [0, 1, -h / 2], [0, 0, 1]])
+    k_r_i = reg_i.intr.dot(reg_i.rot)
+    back_j = reg_j.rot.T.dot(np.linalg.inv(reg_j.intr))
+    hom = shift.dot(k_r_i.dot(back_j)).dot(unshift)
+    corners = np.array([[0, 0, 1], [w, 0, 1], [w, h, 1], [0, h, 1]])
+    behind = bool(np.any(hom.dot(corners.T).T[:, 2] < 0))
+    return hom, behind
+
+
+def invert3x3(m):
+    """Closed-form double-precision 3x3 inverse (what cv::invert does inside
+    cv2.warpPerspective)."""
+    m = np.asarray(m, dtype=np.float64)
+    c00 = m[1, 1] * m[2, 2] - m[1, 2] * m[2, 1]
+    c01 = m[1, 0] * m[2, 2] - m[1, 2] * m[2, 0]
+    c02 = m[1, 0] * m[2, 1] - m[1, 1] * m[2, 0]
+    d = 1.0 / (m[0, 0] * c00 - m[0, 1] * c01 + m[0, 2] * c02)
+    return np.array([
+        [c00 * d, (m[0, 2] * m[2, 1] - m[0, 1] * m[2, 2]) * d, (m[0, 1] * m[1, 2] - m[0, 2] * m[1, 1]) * d],
+        [-c01 * d, (m[0, 0] * m[2, 2] - m[0, 2] * m[2, 0]) * d, (m[0, 2] * m[1, 0] - m[0, 0] * m[1, 2]) * d],
+        [c02 * d, (m[0, 1] * m[2, 0] - m[0, 0] * m[2, 1]) * d, (m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]) * d]])

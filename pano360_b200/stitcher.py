@@ -1,0 +1,305 @@
+"""Drop-in replacement for the compositing half of the reference's
+``stitcher.py``: same names, signatures, module globals and CLI, with the
+projection + blending stages running as sm_100a kernels (no CPU fallback).
+
+Reference interface mirrored here (stitcher.py):
+  :17       MAX_RESOLUTION            :24-33    find_gains
+  :36-66    equalize_gains            :73-104   SphProj / CylProj
+  :160-241  no_blend / linear_blend / multiband_blend      :244-248 BLENDERS
+  :251-263  _hat / _add_weights       :266-271  _valid
+  :274-327  stitch                    :340-369  crop_mosaic     :390-451 main
+
+Registration (features.py, bundle_adj.py) is untouched host code: ``stitch``
+takes the ``bundle_adj.Image`` list that ``traverse()`` returns or that the
+reference caches in ``ba_<name>.pkl``.
+
+Differences a caller can observe (all friendlier):
+  * inputs are not mutated (the reference overwrites ``reg.img``/``reg.range``);
+  * blenders also accept device-resident patches (``DevicePatch``) besides the
+    reference's ``(warped, mask, irange)`` NumPy triples;
+  * ``-e`` never reads uninitialised memory: the overlap warp
+    starts from a zero destination, which is what the reference intends.
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import pickle
+import time
+
+import numpy as np
+
+from . import geometry as geo
+from .camera import hom_to_from as _hom_to_from, load_regions  # noqa: F401
+from .compositor import Compositor, DevicePatch
+from .geometry import CylProj, SphProj  # noqa: F401  (module globals, looked up at call time)
+
+MAX_RESOLUTION = 1400
+
+_compositors = {}
+
+
+def _compositor(device=None):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("pano360_b200.stitcher needs a CUDA device; there is no CPU fallback")
+    key = torch.cuda.current_device() if device is None else device
+    if key not in _compositors:
+        _compositors[key] = Compositor(device)
+    return _compositors[key]
+
+
+# ---------------------------------------------------------------------------
+# exposure gains (stitcher.py:24-66)
+# ---------------------------------------------------------------------------
+def find_gains(overlaps, sizes, stdn=0.1, stdg=2):
+    """Gains minimising intensity discrepancies on overlaps — Brown & Lowe
+    eq. (29) (stitcher.py:24-33).  N x N host solve."""
+    weight_n = (sizes + sizes.T) / (stdn * stdn)
+    weight_g = sizes / (stdg * stdg)
+    coupling = weight_n * overlaps
+    lhs = np.diag(np.sum(coupling * overlaps + weight_g, axis=1)) - coupling * overlaps.T
+    return np.linalg.solve(lhs, np.sum(weight_g, axis=1))
+
+
+def equalize_gains(regions, _src=None):
+    """Per-image exposure gains from pairwise overlap statistics computed on
+    the GPU (stitcher.py:36-66).  Returns the gain vector; ``stitch`` folds it
+    into each image's sample LUT (``clip(g * rgb, 0, 1)`` before sampling)."""
+    comp = _compositor()
+    src = comp.upload(regions) if _src is None else _src
+    logging.debug("Equalizing gain...")
+    overlaps, sizes, _ = comp.pair_statistics(regions, src)
+    return find_gains(overlaps, sizes)
+
+
+# ---------------------------------------------------------------------------
+# blenders (stitcher.py:160-248)
+# ---------------------------------------------------------------------------
+def _device_patches(comp, patches):
+    import torch
+    out = []
+    for k, patch in enumerate(patches):
+        if isinstance(patch, DevicePatch):
+            out.append(patch)
+            continue
+        warped, mask, (rows, cols) = patch
+        if warped.dtype != np.float32 or warped.ndim != 3 or warped.shape[2] != 4:
+            raise TypeError("patches must hold float32 HxWx4 images (stitcher.py:259)")
+        rgba = torch.from_numpy(np.ascontiguousarray(warped)).to(comp.device)
+        invalid = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.uint8)).to(comp.device)
+        out.append(DevicePatch(rgba, invalid, (cols.start, rows.start, cols.stop, rows.stop), k))
+    return out
+
+
+def no_blend(patches, shape):
+    """Paste the patches to the mosaic without blending (stitcher.py:160-168)."""
+    comp = _compositor()
+    return comp.blend_none(_device_patches(comp, patches), tuple(shape)).cpu().numpy()
+
+
+def linear_blend(patches, shape):
+    """Linearly blend patches (stitcher.py:171-183)."""
+    comp = _compositor()
+    return comp.blend_linear(_device_patches(comp, patches), tuple(shape)).cpu().numpy()
+
+
+def multiband_blend(patches, shape, n_levels=5):
+    """Multi-band blending, Brown & Lowe 2007 (stitcher.py:186-241).  Like the
+    reference, the alpha channel of the patches is overwritten with the
+    owner mask."""
+    comp = _compositor()
+    return comp.blend_multiband(_device_patches(comp, patches), tuple(shape), n_levels).cpu().numpy()
+
+
+BLENDERS = {
+    "none": no_blend,
+    "linear": linear_blend,
+    "multiband": multiband_blend,
+}
+
+
+def _blend_kind(blender):
+    """Map a blender callable (ours, or a same-named one such as the
+    reference's) to a kernel path; None for foreign callables."""
+    for kind, ours in BLENDERS.items():
+        if blender is ours:
+            return kind
+    name = getattr(blender, "__name__", "")
+    return {"no_blend": "none", "linear_blend": "linear", "multiband_blend": "multiband"}.get(name)
+
+
+def _hat(size):
+    """Triangular function 0-0.5-0 of a given size (stitcher.py:251-254)."""
+    return geo.hat(size)
+
+
+def _add_weights(img):
+    """float32 RGBA view of a u8 image with the hat-product weight in alpha
+    (stitcher.py:257-263).  Host helper for API parity; the kernels never
+    materialise this image."""
+    height, width = img.shape[:2]
+    out = np.empty((height, width, 4), np.float32)
+    out[..., :3] = img.astype(np.float32) / 255
+    out[..., 3] = _hat(height)[:, None] * _hat(width)[None, :]
+    return out
+
+
+def _valid(patches, shape):
+    """Area of validity, for crop (stitcher.py:266-271)."""
+    comp = _compositor()
+    return comp.covered_mask(_device_patches(comp, patches), tuple(shape)).cpu().numpy().astype(bool)
+
+
+# ---------------------------------------------------------------------------
+# stitch (stitcher.py:274-327)
+# ---------------------------------------------------------------------------
+def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None):
+    """Stitch the images together; returns the uint8 H x W x 3 mosaic.
+
+    ``n_levels`` (extra, optional) overrides the band count of the multiband
+    blender; by default the blender's own default applies, as in the reference
+    (stitcher.py:321)."""
+    comp = _compositor()
+    kind = _blend_kind(blender)
+    proj = globals()["SphProj"]            # honours `stitcher.SphProj = stitcher.CylProj`
+    src = comp.upload(regions)
+    if equalize:
+        comp.set_gains(src, equalize_gains(regions, src))
+    plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
+                           max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
+    patches = comp.warp(regions, src, plan, proj)
+    if kind is None:                       # foreign blender: hand it NumPy triples
+        mosaic = blender([p.to_numpy() for p in patches], plan.shape)
+    elif kind == "multiband":
+        levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
+        mosaic = comp.blend_multiband(patches, plan.shape, levels).cpu().numpy()
+    else:
+        mosaic = comp.blend(kind, patches, plan.shape).cpu().numpy()
+    if crop:
+        logging.debug("Cropping...")
+        mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))
+    return mosaic
+
+
+# ---------------------------------------------------------------------------
+# crop (stitcher.py:340-369) — host, after the blend
+# ---------------------------------------------------------------------------
+def _nearest_lower(heights):
+    """For every column the extent [left, right] over which it is the minimum
+    (ties extend), by monotonic stack."""
+    n = len(heights)
+    left, right = np.empty(n, np.int64), np.empty(n, np.int64)
+    stack = []
+    for j in range(n):
+        while stack and heights[stack[-1]] >= heights[j]:
+            stack.pop()
+        left[j] = stack[-1] + 1 if stack else 0
+        stack.append(j)
+    stack = []
+    for j in range(n - 1, -1, -1):
+        while stack and heights[stack[-1]] >= heights[j]:
+            stack.pop()
+        right[j] = stack[-1] - 1 if stack else n - 1
+        stack.append(j)
+    return left, right
+
+
+def crop_mosaic(mosaic, valid):
+    """Largest all-valid axis-aligned rectangle (histogram method,
+    stitcher.py:340-369).  Mirrors the reference's scan order and strict '>'
+    update so ties resolve identically, including its quirk that column 0
+    never extends to the right (its loop at :359 stops at j = 1)."""
+    height, width = valid.shape
+    heights = np.zeros(width, np.int64)
+    best = (0, 0, 0, 0, 0)         # area, left, right, height, last row
+    for i in range(height):
+        heights = np.where(valid[i], heights + 1, 0)
+        left, right = _nearest_lower(heights)
+        right[0] = 0
+        areas = (right - left + 1) * heights
+        j = int(np.argmax(areas))
+        if areas[j] > best[0]:
+            best = (int(areas[j]), int(left[j]), int(right[j]), int(heights[j]), i)
+    _, ll, rr, hh, last = best
+    return mosaic[last - hh + 1:last + 1, ll:rr + 1, :]
+
+
+# ---------------------------------------------------------------------------
+# CLI (stitcher.py:372-457)
+# ---------------------------------------------------------------------------
+def idx_to_keypoints(matches, kpts):
+    """Replace keypoint indices with homogeneous coordinates (stitcher.py:372-387)."""
+    kpts = [np.concatenate([kp, np.ones((kp.shape[0], 1))], axis=1) for kp in kpts]
+    matches = matches.item()
+    return {i: {j: (np.concatenate([kpts[i][m[:, 0]], kpts[j][m[:, 1]]], axis=1), h, len(m))
+                for j, (m, h) in col.items()} for i, col in matches.items()}
+
+
+def main(argv=None):
+    """Script entry point: same flags and cache files as the reference
+    (stitcher.py:390-451).  Registration is delegated to the reference's own
+    ``features`` / ``bundle_adj`` modules, which must be importable when the
+    caches are cold."""
+    import cv2
+    parser = argparse.ArgumentParser(description="Stitch images.")
+    parser.add_argument('path', type=str, help="directory with the images to process.")
+    parser.add_argument("-s", "--shrink", type=float, default=2,
+                        help="downsample the images by this amount.")
+    parser.add_argument("--ba", default="incr", choices=["none", "incr", "last"],
+                        help="bundle adjustment type.")
+    parser.add_argument("--equalize", "-e", action="store_true",
+                        help="equalize image gain before stitching.")
+    parser.add_argument("--crop", "-c", action="store_true", help="remove the black borders.")
+    parser.add_argument("--blend", "-b", default='multiband', choices=list(BLENDERS.keys()),
+                        help="blending algorithm.")
+    parser.add_argument("-o", "--out", type=str, help="save result to this file")
+    parser.add_argument("--no-show", action="store_true",
+                        help="(extra) do not open a window with the result.")
+    args = parser.parse_args(argv)
+
+    exts = [".jpg", ".png", ".bmp"]
+    exts += [ex.upper() for ex in exts]
+    name = f"{os.path.basename(os.path.normpath(args.path))}_s{args.shrink}"
+    files = [f for f in os.listdir(args.path) if any(f.endswith(ext) for ext in exts)]
+    imgs = [cv2.imread(os.path.join(args.path, f)) for f in files]
+    if args.shrink > 1:
+        imgs = [cv2.resize(im, None, fx=1 / args.shrink, fy=1 / args.shrink) for im in imgs]
+
+    try:
+        regions = load_regions(f"ba_{name}.pkl")
+    except IOError:
+        from bundle_adj import traverse          # the reference's, untouched
+        try:
+            arr = np.load(f"matches_{name}.npz", allow_pickle=True)
+            kpts, matches = arr['kpts'], arr['matches']
+        except IOError:
+            from features import matching        # the reference's, untouched
+            kpts, matches = matching(imgs)
+            np.savez(f"matches_{name}.npz", kpts=kpts, matches=matches)
+        start = time.time()
+        regions = traverse(imgs, idx_to_keypoints(matches, kpts), badjust=args.ba)
+        logging.info(f"Image registration, time: {time.time() - start}")
+        with open(f"ba_{name}.pkl", 'wb') as fid:
+            pickle.dump(regions, fid, protocol=pickle.HIGHEST_PROTOCOL)
+
+    start = time.time()
+    mosaic = stitch(regions, blender=BLENDERS[args.blend], equalize=args.equalize, crop=args.crop)
+    logging.info(f"Built mosaic, time: {time.time() - start}")
+
+    if args.out:
+        cv2.imwrite(args.out, mosaic)
+    if not args.no_show:
+        try:
+            cv2.imshow("Mosaic", mosaic)
+            if cv2.waitKey(0) & 0xff == 27:
+                cv2.destroyAllWindows()
+        except cv2.error:
+            logging.info("no display available; skipping imshow")
+    return mosaic
+
+
+if __name__ == '__main__':
+    logging.basicConfig(level=logging.DEBUG)
+    main()
