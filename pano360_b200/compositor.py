@@ -82,6 +82,7 @@ class Compositor:
         self.device = _require_cuda(device)
         _lib.load()
         self._pinned = {}
+        self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -106,6 +107,19 @@ class Compositor:
             return dev
         return host.to(self.device)
 
+    def _traced(self, name, nbytes, fn, *args):
+        """Run one C-ABI call; when tracing, bracket it with CUDA events on the
+        launching stream (bench.py reads per-kernel time from these)."""
+        if self.trace is None:
+            return _lib.call(fn, *args)
+        stream = torch.cuda.current_stream(self.device)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        rc = _lib.call(fn, *args)
+        end.record(stream)
+        self.trace.append((name, nbytes, start, end))
+        return rc
+
     def upload(self, regions, gains=None, pinned=None):
         """H2D copy of the u8 images (+ LUT / hat tables).  ``pinned`` may be a
         list of pinned uint8 tensors already holding the pixels."""
@@ -117,7 +131,8 @@ class Compositor:
             else:
                 if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
-                dev_img = self._to_device(img)
+                host = torch.from_numpy(np.ascontiguousarray(img))
+                dev_img = host.to(self.device, non_blocking=host.is_pinned())
             h, w = dev_img.shape[:2]
             src.pixels.append(dev_img)
             src.shapes.append((h, w))
@@ -193,10 +208,10 @@ class Compositor:
             invalid = torch.empty((ph, pw), dtype=torch.uint8, device=self.device)
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
-            _lib.call("p360_warp_patch", _lib.ptr(src.pixels[i]), h, w, src.pixels[i].shape[2],
-                      _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
-                      dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
-                      pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), self.stream)
+            self._traced("K1_warp", 17 * pw * ph, "p360_warp_patch", _lib.ptr(src.pixels[i]), h, w,
+                         src.pixels[i].shape[2], _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
+                         dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
+                         pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), self.stream)
             patches.append(DevicePatch(rgba, invalid, (x0, ya - shift, x1, yb - shift), i))
         self._keepalive = dev_tabs
         return patches
@@ -236,8 +251,9 @@ class Compositor:
         covered = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
-            _lib.call("p360_owner_update", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0, k,
-                      _lib.ptr(best), _lib.ptr(owner), _lib.ptr(covered), w, self.stream)
+            self._traced("K2_owner_update", 30 * pw * ph, "p360_owner_update", _lib.ptr(p.rgba),
+                         _lib.ptr(p.invalid), pw, ph, x0, y0, k, _lib.ptr(best), _lib.ptr(owner),
+                         _lib.ptr(covered), w, self.stream)
         return owner, covered
 
     def blur(self, rgba, sigma, out=None, tmp=None):
@@ -246,8 +262,9 @@ class Compositor:
         out = torch.empty_like(rgba) if out is None else out
         tmp = torch.empty_like(rgba) if tmp is None else tmp
         ph, pw = rgba.shape[:2]
-        _lib.call("p360_gauss_blur", _lib.ptr(rgba), _lib.ptr(out), _lib.ptr(tmp), pw, ph,
-                  taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps), self.stream)
+        self._traced("K3_gauss_blur", 32 * pw * ph, "p360_gauss_blur", _lib.ptr(rgba), _lib.ptr(out),
+                     _lib.ptr(tmp), pw, ph, taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps),
+                     self.stream)
         return out
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None):
@@ -262,21 +279,21 @@ class Compositor:
             if n_levels > 1 and biggest else []
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
-            _lib.call("p360_owner_to_alpha", _lib.ptr(p.rgba), pw, ph, x0, y0, k, _lib.ptr(owner), w,
-                      self.stream)
+            self._traced("K2_owner_to_alpha", 8 * pw * ph, "p360_owner_to_alpha", _lib.ptr(p.rgba), pw, ph,
+                         x0, y0, k, _lib.ptr(owner), w, self.stream)
             prev = p.rgba
             for lvl in range(n_levels - 1):
                 views = [s[:p.rgba.numel()].view(p.rgba.shape) for s in scratch]
                 cur = views[lvl & 1]
                 self.blur(p.rgba, geo.band_sigma(lvl), out=cur, tmp=views[2])
-                _lib.call("p360_band_accumulate", _lib.ptr(prev), _lib.ptr(cur), pw, ph, x0, y0,
-                          acc.data_ptr() + lvl * plane, w, self.stream)
+                self._traced("K4_band_accumulate", 64 * pw * ph, "p360_band_accumulate", _lib.ptr(prev),
+                             _lib.ptr(cur), pw, ph, x0, y0, acc.data_ptr() + lvl * plane, w, self.stream)
                 prev = cur
-            _lib.call("p360_band_accumulate", _lib.ptr(prev), None, pw, ph, x0, y0,
-                      acc.data_ptr() + (n_levels - 1) * plane, w, self.stream)
+            self._traced("K4_band_accumulate", 48 * pw * ph, "p360_band_accumulate", _lib.ptr(prev), None,
+                         pw, ph, x0, y0, acc.data_ptr() + (n_levels - 1) * plane, w, self.stream)
         mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        _lib.call("p360_collapse_finalize", _lib.ptr(acc), n_levels, _lib.ptr(covered), _lib.ptr(mosaic),
-                  h * w, self.stream)
+        self._traced("K5_collapse", (16 * n_levels + 4) * h * w, "p360_collapse_finalize", _lib.ptr(acc),
+                     n_levels, _lib.ptr(covered), _lib.ptr(mosaic), h * w, self.stream)
         if stages is not None:
             stages.update(owner=owner, covered=covered, acc=acc)
         return mosaic

@@ -155,12 +155,28 @@ def _valid(patches, shape):
 # ---------------------------------------------------------------------------
 # stitch (stitcher.py:274-327)
 # ---------------------------------------------------------------------------
-def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None):
+def _download(mosaic_dev, out=None):
+    """Device uint8 mosaic -> host ndarray (into ``out`` when given; a pinned
+    ``out`` makes the copy a plain DMA)."""
+    import torch
+    if out is None:
+        return mosaic_dev.cpu().numpy()
+    if out.shape != tuple(mosaic_dev.shape) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a C-contiguous uint8 array of shape {tuple(mosaic_dev.shape)}")
+    host = torch.from_numpy(out)
+    host.copy_(mosaic_dev, non_blocking=host.is_pinned())
+    torch.cuda.current_stream(mosaic_dev.device).synchronize()
+    return out
+
+
+def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None, out=None):
     """Stitch the images together; returns the uint8 H x W x 3 mosaic.
 
-    ``n_levels`` (extra, optional) overrides the band count of the multiband
-    blender; by default the blender's own default applies, as in the reference
-    (stitcher.py:321)."""
+    Extra optional arguments (defaults keep the reference behaviour):
+    ``n_levels`` overrides the band count of the multiband blender (by default
+    the blender's own default applies, stitcher.py:321); ``out`` is a
+    preallocated uint8 H x W x 3 array (e.g. pinned memory) to receive the
+    mosaic."""
     comp = _compositor()
     kind = _blend_kind(blender)
     proj = globals()["SphProj"]            # honours `stitcher.SphProj = stitcher.CylProj`
@@ -174,9 +190,9 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
     elif kind == "multiband":
         levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
-        mosaic = comp.blend_multiband(patches, plan.shape, levels).cpu().numpy()
+        mosaic = _download(comp.blend_multiband(patches, plan.shape, levels), out)
     else:
-        mosaic = comp.blend(kind, patches, plan.shape).cpu().numpy()
+        mosaic = _download(comp.blend(kind, patches, plan.shape), out)
     if crop:
         logging.debug("Cropping...")
         mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))

@@ -123,25 +123,34 @@ def render_view(env, width, height, focal, rot):
 
 
 def make_views(wl: Workload, noise=0.0, jitter=2e-3, photometric=True,
-               env=None):
+               env=None, only=None):
     """Render all views of a workload and return ``list[Image]``.
 
     Perturbations use ``default_rng(wl.view_seed)``: gain U[0.8,1.2],
     per-channel offset N(0,4), optional white noise +-``noise`` grey levels,
     and a registration error of ``jitter`` rad applied to the *reported*
-    rotation (the pixels are rendered with the true one).
+    rotation (the pixels are rendered with the true one).  ``only`` (a set of
+    view indices) skips rendering the other views — they get a zero stub of
+    the right shape — while keeping cameras and random draws identical.
     """
-    if env is None:
+    if env is None and (only is None or len(only)):
         env = make_env_map(wl.env_shape, wl.env_seed)
     rng = np.random.default_rng(wl.view_seed)
     k_mat = intrinsics(wl.focal)
     regions = []
-    for yaw, pitch in zip(wl.yaws, wl.pitches):
+    for idx, (yaw, pitch) in enumerate(zip(wl.yaws, wl.pitches)):
         rot = camera_rotation(pitch, yaw)
-        img = render_view(env, wl.width, wl.height, wl.focal, rot)
         gain = rng.uniform(0.8, 1.2)
         offs = rng.normal(0.0, 4.0, size=3)
         jit = rng.normal(0.0, jitter, size=3) if jitter else np.zeros(3)
+        rot_reported = rot @ rotation_to_mat(jit) if jitter else rot
+        if only is not None and idx not in only:
+            if noise:
+                rng.uniform(-noise, noise, size=(wl.height, wl.width, 3))
+            stub = np.broadcast_to(np.zeros((), np.uint8), (wl.height, wl.width, 3))
+            regions.append(Image(stub, rot_reported, k_mat.copy()))
+            continue
+        img = render_view(env, wl.width, wl.height, wl.focal, rot)
         if photometric or noise:
             pix = img.astype(np.float32)
             if photometric:
@@ -149,7 +158,6 @@ def make_views(wl: Workload, noise=0.0, jitter=2e-3, photometric=True,
             if noise:
                 pix += rng.uniform(-noise, noise, size=pix.shape).astype(np.float32)
             img = np.clip(pix, 0, 255).astype(np.uint8)
-        rot_reported = rot @ rotation_to_mat(jit) if jitter else rot
         regions.append(Image(np.ascontiguousarray(img), rot_reported, k_mat.copy()))
     return regions
 
