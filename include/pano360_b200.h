@@ -31,6 +31,7 @@ extern "C" {
 #define P360_VERSION 100          /* 0.1.0 */
 #define P360_EINVAL  (-22)
 #define P360_MAX_KSIZE 129        /* widest separable Gaussian supported */
+#define P360_MAX_LEVELS 8         /* most bands of the multiband blender */
 
 int  p360_version(void);
 /* Copies the calling thread's last error message into buf (NUL-terminated). */
@@ -118,6 +119,38 @@ int p360_pair_overlap_stats(const uint8_t *src_i, const uint8_t *src_j,
                             const double *hat_y, const double *hat_x,
                             const double *inv_hom_host, double *partial,
                             double *out3, void *stream);
+
+/* ---- reduced-resolution band pipeline (multiband hot path) ------------------
+ * The blurs of stitcher.py:226 are evaluated on coarse grids (f = 2 for level
+ * 0, f = 4 above) of the BORDER_REFLECT_101 extension of the patch by `pad`
+ * full-resolution pixels (pad % 4 == 0):
+ *   p360_pyramid_dims    -> {w2, h2, w4, h4}: sizes of the two coarse images
+ *   p360_pyramid_reduce  area-reduce rgba (alpha := owner == idx when owner is
+ *                        not NULL, stitcher.py:207-208) into d2 (f = 2) and d4
+ *                        (f = 4); blur them with p360_gauss_blur afterwards
+ *   p360_multiband_collapse  for every mosaic pixel, in patch order: expand
+ *                        the coarse levels bilinearly, form the bands and
+ *                        weights (stitcher.py:224-232), normalise per level,
+ *                        sum, clamp, truncate to uint8 (stitcher.py:236-241).
+ *                        Nothing is accumulated in HBM.
+ */
+typedef struct p360_band_patch {
+    const float *rgba;                        /* full-res patch (alpha ignored)        */
+    const float *low[P360_MAX_LEVELS - 1];    /* blurred coarse image of level l       */
+    int32_t lw[P360_MAX_LEVELS - 1];          /* its width in coarse pixels            */
+    int32_t shift[P360_MAX_LEVELS - 1];       /* log2 of its reduction factor (1 or 2) */
+    int32_t x0, y0, pw, ph;                   /* box in (window) mosaic pixels         */
+    int32_t pad;                              /* extension in full-res pixels          */
+    int32_t index;                            /* id of this patch in the owner map     */
+} p360_band_patch;
+
+int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]);
+int p360_pyramid_reduce(const float *rgba, int pw, int ph, int x0, int y0, int idx,
+                        const int32_t *owner, int W, int pad, float *d2, float *d4,
+                        void *stream);
+int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
+                            const int32_t *owner, const uint8_t *covered,
+                            uint8_t *out_u8, int H, int W, void *stream);
 
 /* ---- valid-area mask for the crop stage (stitcher.py:266-271) -------------*/
 int p360_cover_update(const uint8_t *invalid, int pw, int ph, int x0, int y0,

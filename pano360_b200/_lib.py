@@ -34,7 +34,22 @@ SIGNATURES = {
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
+    "p360_pyramid_reduce": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp],
+    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
 }
+MAX_LEVELS = 8
+
+
+class BandPatch(C.Structure):
+    """Mirror of ``p360_band_patch`` (include/pano360_b200.h)."""
+
+    _fields_ = [("rgba", C.c_void_p),
+                ("low", C.c_void_p * (MAX_LEVELS - 1)),
+                ("lw", C.c_int32 * (MAX_LEVELS - 1)),
+                ("shift", C.c_int32 * (MAX_LEVELS - 1)),
+                ("x0", C.c_int32), ("y0", C.c_int32), ("pw", C.c_int32), ("ph", C.c_int32),
+                ("pad", C.c_int32), ("index", C.c_int32)]
 # entry points whose int return is a value, not a status
 _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
 
@@ -43,7 +58,8 @@ launch_count = 0      # kernels launched through this binding (bench.py: gpu_lau
 _LAUNCHES = {"p360_warp_patch": 1, "p360_owner_update": 1, "p360_owner_to_alpha": 1,
              "p360_gauss_blur": 2, "p360_band_accumulate": 1, "p360_collapse_finalize": 1,
              "p360_linear_accumulate": 1, "p360_linear_finalize": 1, "p360_paste": 1,
-             "p360_pair_overlap_stats": 2, "p360_cover_update": 1}
+             "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_pyramid_reduce": 1,
+             "p360_multiband_collapse": 1}
 
 
 def load():

@@ -9,7 +9,7 @@ Data layout in HBM
 * hat tables        f64 [h], [w]             shared by images of equal size
 * inverse-map tabs  f64 [pw][3], [ph][3]     per patch (column part, row part)
 * patch             f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid mask
-* accumulators      f32 [L][H][W][4]         {sum band*wgt (rgb), sum wgt}
+* coarse levels     f32 [h/f][w/f][4]        blurred f=2 (level 0) / f=4 (levels >= 1) images per patch
 * owner / best      i32 [H][W], f32 [H][W]   running arg-max of alpha
 * covered           u8  [H][W]               union of valid pixels
 * mosaic            u8  [H][W][3]
@@ -182,17 +182,20 @@ class Compositor:
         return overlaps, sizes, todo
 
     # -- K1: warp -------------------------------------------------------------
-    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, keep=None):
-        """Warp every image into its (row-cropped) patch.  ``rows=(ya, yb)``
-        crops patches to those mosaic rows and shifts boxes so that row ya is
-        row 0.  Returns a list of DevicePatch (images with an empty crop are
-        skipped; ``index`` keeps the original image number)."""
+    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1):
+        """Warp every image into its patch.  ``rows=(ya, yb)`` crops patches
+        to those mosaic rows; a cropped top edge is moved up to a multiple of
+        ``row_align`` rows below the patch's true top so that coarse grids
+        anchored at the crop coincide with those anchored at the true patch.
+        Boxes stay in absolute mosaic coordinates.  Images with an empty crop
+        are skipped; ``index`` keeps the original image number."""
         crops, tabs, total = [], [], 0
         for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
             x0, y0, x1, y1 = box
             ya, yb = (y0, y1) if rows is None else (max(y0, rows[0]), min(y1, rows[1]))
-            if ya >= yb or x0 >= x1 or (keep is not None and i not in keep):
+            if ya >= yb or x0 >= x1:
                 continue
+            ya = y0 + (ya - y0) // row_align * row_align
             col_tab, row_tab = geo.inverse_map_tables(reg, (x0, ya, x1, yb), plan, proj)
             crops.append((i, x0, ya, x1, yb, total, total + col_tab.size))
             tabs += [col_tab.ravel(), row_tab.ravel()]
@@ -200,7 +203,6 @@ class Compositor:
         if not crops:
             return []
         dev_tabs = self._to_device(np.concatenate(tabs), pinned_key="tabs")
-        shift = 0 if rows is None else rows[0]
         patches = []
         for i, x0, ya, x1, yb, off_c, off_r in crops:
             pw, ph = x1 - x0, yb - ya
@@ -212,7 +214,7 @@ class Compositor:
                          src.pixels[i].shape[2], _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
                          dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
                          pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), self.stream)
-            patches.append(DevicePatch(rgba, invalid, (x0, ya - shift, x1, yb - shift), i))
+            patches.append(DevicePatch(rgba, invalid, (x0, ya, x1, yb), i))
         self._keepalive = dev_tabs
         return patches
 
@@ -267,35 +269,80 @@ class Compositor:
                      self.stream)
         return out
 
+    def blur_taps(self, rgba, taps, out=None, tmp=None):
+        """Separable convolution of a device RGBA image with explicit taps."""
+        out = torch.empty_like(rgba) if out is None else out
+        tmp = torch.empty_like(rgba) if tmp is None else tmp
+        ph, pw = rgba.shape[:2]
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self._traced("K3_gauss_blur", 32 * pw * ph, "p360_gauss_blur", _lib.ptr(rgba), _lib.ptr(out),
+                     _lib.ptr(tmp), pw, ph, taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps),
+                     self.stream)
+        return out
+
+    def coarse_levels(self, patch, k, owner, mosaic_w, n_levels, scratch):
+        """Blurred coarse images of levels 0 .. L-2 of one patch
+        (stitcher.py:218-229 evaluated at reduced resolution)."""
+        pad, plan = geo.coarse_band_plan(n_levels)
+        if not plan:
+            return pad, [], []
+        pw, ph, x0, y0 = self._args(patch)
+        dims = (C.c_int32 * 4)()
+        _lib.call("p360_pyramid_dims", pw, ph, pad, dims)
+        w2, h2, w4, h4 = dims
+        d2 = scratch["d2"][:h2 * w2 * 4].view(h2, w2, 4)
+        d4 = scratch["d4"][:h4 * w4 * 4].view(h4, w4, 4)
+        self._traced("K3a_pyramid_reduce", 25 * pw * ph, "p360_pyramid_reduce", _lib.ptr(patch.rgba), pw, ph,
+                     x0, y0, k, _lib.ptr(owner), mosaic_w, pad, _lib.ptr(d2), _lib.ptr(d4), self.stream)
+        lows, widths = [], []
+        for shift, taps in plan:
+            coarse = d2 if shift == 1 else d4
+            out = torch.empty_like(coarse)
+            tmp = scratch["tmp"][:coarse.numel()].view(coarse.shape)
+            self.blur_taps(coarse, taps, out=out, tmp=tmp)
+            lows.append(out)
+            widths.append(coarse.shape[1])
+        return pad, lows, widths
+
     def blend_multiband(self, patches, shape, n_levels=5, stages=None):
-        """stitcher.py:186-241, patch-major: one accumulator plane per level so
-        the per-level sums still add patches in list order."""
+        """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
+        and every mosaic pixel gathers its bands from the patches covering it,
+        in list order, so no mosaic-sized accumulator ever touches HBM."""
         h, w = shape
+        if not 1 <= n_levels <= _lib.MAX_LEVELS:
+            raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
         owner, covered = self.owner_map(patches, shape)
-        acc = torch.zeros((n_levels, h, w, 4), dtype=torch.float32, device=self.device)
-        plane = h * w * 16
-        biggest = max((p.rgba.numel() for p in patches), default=0)
-        scratch = [torch.empty(biggest, dtype=torch.float32, device=self.device) for _ in range(3)] \
-            if n_levels > 1 and biggest else []
+        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        if not patches:
+            return mosaic.zero_()
+        pad, plan = geo.coarse_band_plan(n_levels)
+        scratch = {}
+        if plan:
+            biggest = max(((p.box[2] - p.box[0] + 2 * pad + 7) * (p.box[3] - p.box[1] + 2 * pad + 7)
+                           for p in patches))
+            scratch = {"d2": torch.empty(biggest + 64, dtype=torch.float32, device=self.device),
+                       "d4": torch.empty(biggest // 4 + 64, dtype=torch.float32, device=self.device),
+                       "tmp": torch.empty(biggest + 64, dtype=torch.float32, device=self.device)}
+        descs = (_lib.BandPatch * len(patches))()
+        keep = []
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
-            self._traced("K2_owner_to_alpha", 8 * pw * ph, "p360_owner_to_alpha", _lib.ptr(p.rgba), pw, ph,
-                         x0, y0, k, _lib.ptr(owner), w, self.stream)
-            prev = p.rgba
-            for lvl in range(n_levels - 1):
-                views = [s[:p.rgba.numel()].view(p.rgba.shape) for s in scratch]
-                cur = views[lvl & 1]
-                self.blur(p.rgba, geo.band_sigma(lvl), out=cur, tmp=views[2])
-                self._traced("K4_band_accumulate", 64 * pw * ph, "p360_band_accumulate", _lib.ptr(prev),
-                             _lib.ptr(cur), pw, ph, x0, y0, acc.data_ptr() + lvl * plane, w, self.stream)
-                prev = cur
-            self._traced("K4_band_accumulate", 48 * pw * ph, "p360_band_accumulate", _lib.ptr(prev), None,
-                         pw, ph, x0, y0, acc.data_ptr() + (n_levels - 1) * plane, w, self.stream)
-        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        self._traced("K5_collapse", (16 * n_levels + 4) * h * w, "p360_collapse_finalize", _lib.ptr(acc),
-                     n_levels, _lib.ptr(covered), _lib.ptr(mosaic), h * w, self.stream)
+            _, lows, widths = self.coarse_levels(p, k, owner, w, n_levels, scratch)
+            keep.append(lows)
+            d = descs[k]
+            d.rgba = p.rgba.data_ptr()
+            for lvl, (low, lw) in enumerate(zip(lows, widths)):
+                d.low[lvl], d.lw[lvl], d.shift[lvl] = low.data_ptr(), lw, plan[lvl][0]
+            d.x0, d.y0, d.pw, d.ph, d.pad, d.index = x0, y0, pw, ph, pad, k
+        table = np.frombuffer(bytes(descs), dtype=np.uint8)
+        dev_table = self._to_device(table, pinned_key="bands")
+        gathered = sum((p.box[2] - p.box[0]) * (p.box[3] - p.box[1]) for p in patches)
+        self._traced("K4_multiband_collapse", 16 * gathered + 8 * h * w, "p360_multiband_collapse",
+                     _lib.ptr(dev_table), len(patches), n_levels, _lib.ptr(owner), _lib.ptr(covered),
+                     _lib.ptr(mosaic), h, w, self.stream)
         if stages is not None:
-            stages.update(owner=owner, covered=covered, acc=acc)
+            stages.update(owner=owner, covered=covered, lows=keep)
+        self._keepalive2 = (keep, dev_table, scratch)
         return mosaic
 
     def covered_mask(self, patches, shape):
@@ -318,17 +365,27 @@ class Compositor:
         raise ValueError(f"unknown blender {kind!r}")
 
     # -- whole path, device resident ------------------------------------------
+    def window_halo(self, kind, n_levels):
+        """Rows of context a row window needs on each side: the reach of the
+        widest coarse blur (reduce + blur + expand), 0 for pointwise blenders."""
+        if kind != "multiband" or n_levels < 2:
+            return 0
+        return geo.coarse_band_plan(n_levels)[0] + 4
+
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
-        (returned strip has exactly yb - ya rows)."""
+        (the returned strip has exactly yb - ya rows and is bit-identical to
+        those rows of the full composite)."""
         if rows is None:
             patches = self.warp(regions, src, plan, proj)
             return self.blend(kind, patches, plan.shape, n_levels), patches
         ya, yb = rows
-        halo = 0
-        if kind == "multiband" and n_levels > 1:
-            halo = (len(geo.gaussian_taps(geo.band_sigma(n_levels - 2))) - 1) // 2
+        halo = self.window_halo(kind, n_levels)
         wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
-        patches = self.warp(regions, src, plan, proj, rows=(wa, wb))
-        strip = self.blend(kind, patches, (wb - wa, plan.shape[1]), n_levels)
-        return strip[ya - wa:ya - wa + (yb - ya)], patches
+        patches = self.warp(regions, src, plan, proj, rows=(wa, wb), row_align=4 if halo else 1)
+        top = min([p.box[1] for p in patches] + [wa])          # aligned crops may start above wa
+        for p in patches:
+            x0, y0, x1, y1 = p.box
+            p.box = (x0, y0 - top, x1, y1 - top)
+        strip = self.blend(kind, patches, (wb - top, plan.shape[1]), n_levels)
+        return strip[ya - top:ya - top + (yb - ya)], patches

@@ -155,6 +155,26 @@ def band_sigma(level):
     return float(np.sqrt(2 * level + 1.0) * 4)
 
 
+def coarse_band_plan(n_levels):
+    """How the blurs of levels 0 .. L-2 are evaluated on coarse grids
+    (csrc/p360_pyramid.cu): level 0 on the f = 2 grid, higher levels on the
+    f = 4 grid, each with sigma' = sqrt(sigma^2 - (f^2-1)/12 - f^2/6) / f —
+    the area reduction (box of width f) and the bilinear expansion (triangle of
+    half-width f) already contribute that much variance.  Returns
+    ``(pad, [(shift, taps), ...])`` where ``pad`` (a multiple of 4) is how far
+    the reflected extension of a patch must reach so that no expanded value
+    depends on the coarse images' own borders."""
+    levels, pad = [], 0
+    for lvl in range(max(n_levels - 1, 0)):
+        shift = 1 if lvl == 0 else 2
+        f = 1 << shift
+        sigma = band_sigma(lvl)
+        taps = gaussian_taps(np.sqrt(sigma * sigma - (f * f - 1) / 12.0 - f * f / 6.0) / f)
+        levels.append((shift, taps))
+        pad = max(pad, f * ((len(taps) - 1) // 2 + 2))
+    return (pad + 3) // 4 * 4, levels
+
+
 def sample_lut(gain=None):
     """float32 value of each u8 sample as the reference's float image holds it:
     ``u8.astype(f32) / 255`` (stitcher.py:259), then — with ``-e`` —

@@ -25,7 +25,7 @@ def blur_halo(kind, n_levels):
     Gaussian the blender applies (stitcher.py:218, :226)."""
     if kind != "multiband" or n_levels < 2:
         return 0
-    return (len(geo.gaussian_taps(geo.band_sigma(n_levels - 2))) - 1) // 2
+    return geo.coarse_band_plan(n_levels)[0] + 4 + 3     # + alignment slack of cropped tops
 
 
 def row_costs(plan, kind="multiband", n_levels=5):

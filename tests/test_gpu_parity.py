@@ -130,23 +130,34 @@ def test_owner_map_matches_oracle(comp, tiny4):
     assert np.array_equal(covered.cpu().numpy().astype(bool), stages["covered"])
 
 
-def test_band_accumulators_match_oracle(comp, tiny4):
-    """K4: per-level layer / wsum sums (stitcher.py:231-232) to 1e-4 rel."""
+def test_coarse_levels_track_the_reference_blurs(comp, tiny4):
+    """K3a + K3 at reduced resolution, expanded on the host, against the
+    full-resolution cv2.GaussianBlur the reference applies (stitcher.py:226).
+    The approximation error budget (box + coarse Gaussian + bilinear vs the true
+    Gaussian) is ~1e-2 on white noise / hard mask edges; the uint8 parity tests
+    are the real gate."""
     _, regs = tiny4
-    patches_cpu, pl = rs.build_patches(regs, "multiband")
-    stages = {}
-    rs.multiband(patches_cpu, pl.shape, 5, stages=stages)
     plan = geo.plan_mosaic(regs, True, 1400)
     patches = comp.warp(regs, comp.upload(regs), plan)
-    dev_stages = {}
-    comp.blend_multiband(patches, plan.shape, 5, stages=dev_stages)
-    acc = dev_stages["acc"].cpu().numpy()
-    covered = stages["covered"]
-    for lvl, (layer, wsum) in enumerate(stages["levels"]):
-        got_w = np.where(acc[lvl, ..., 3] == 0, 1, acc[lvl, ..., 3])
-        np.testing.assert_allclose(got_w, wsum, rtol=1e-4, atol=1e-5)
-        got_l = np.where(covered[..., None], acc[lvl, ..., :3], 0)
-        np.testing.assert_allclose(got_l, layer, rtol=1e-4, atol=1e-5)
+    owner, _ = comp.owner_map(patches, plan.shape)
+    stages = {}
+    comp.blend_multiband(patches, plan.shape, 5, stages=stages)
+    pad, levels = geo.coarse_band_plan(5)
+    own = owner.cpu().numpy()
+    for k in (0, 2):
+        warped, _, (sy, sx) = patches[k].to_numpy()
+        warped[..., 3] = own[sy, sx] == k
+        ph, pw = warped.shape[:2]
+        for lvl, (shift, _) in enumerate(levels):
+            low = stages["lows"][k][lvl].cpu().numpy()
+            f = 1 << shift
+            u = ((np.arange(pw) + pad + 0.5) / f - 0.5).astype(np.float32)
+            v = ((np.arange(ph) + pad + 0.5) / f - 0.5).astype(np.float32)
+            mx, my = np.meshgrid(u, v)
+            got = cv2.remap(low, mx, my, cv2.INTER_LINEAR)
+            want = cv2.GaussianBlur(warped, (0, 0), geo.band_sigma(lvl))
+            assert np.abs(got - want).max() < 3e-2, (k, lvl, np.abs(got - want).max())
+            assert np.abs(got - want).mean() < 2e-3
 
 
 @pytest.mark.parametrize("blend", ["none", "linear", "multiband"])
