@@ -182,13 +182,16 @@ class Compositor:
         return overlaps, sizes, todo
 
     # -- K1: warp -------------------------------------------------------------
-    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1):
+    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
         """Warp every image into its patch.  ``rows=(ya, yb)`` crops patches
         to those mosaic rows; a cropped top edge is moved up to a multiple of
         ``row_align`` rows below the patch's true top so that coarse grids
         anchored at the crop coincide with those anchored at the true patch.
         Boxes stay in absolute mosaic coordinates.  Images with an empty crop
-        are skipped; ``index`` keeps the original image number."""
+        are skipped; ``index`` keeps the original image number.  With
+        ``split_dilate`` (columns) the all-invalid middle of seam-straddling
+        boxes is dropped (``geometry.active_column_runs``): such an image
+        yields two patches with the same ``index``."""
         crops, tabs, total = [], [], 0
         for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
             x0, y0, x1, y1 = box
@@ -196,10 +199,13 @@ class Compositor:
             if ya >= yb or x0 >= x1:
                 continue
             ya = y0 + (ya - y0) // row_align * row_align
-            col_tab, row_tab = geo.inverse_map_tables(reg, (x0, ya, x1, yb), plan, proj)
-            crops.append((i, x0, ya, x1, yb, total, total + col_tab.size))
-            tabs += [col_tab.ravel(), row_tab.ravel()]
-            total += col_tab.size + row_tab.size
+            runs = [(x0, x1)] if split_dilate is None else \
+                geo.active_column_runs(reg, box, plan, proj, dilate=split_dilate)
+            for cx0, cx1 in runs:
+                col_tab, row_tab = geo.inverse_map_tables(reg, (cx0, ya, cx1, yb), plan, proj)
+                crops.append((i, cx0, ya, cx1, yb, total, total + col_tab.size))
+                tabs += [col_tab.ravel(), row_tab.ravel()]
+                total += col_tab.size + row_tab.size
         if not crops:
             return []
         dev_tabs = self._to_device(np.concatenate(tabs), pinned_key="tabs")
@@ -376,13 +382,14 @@ class Compositor:
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
         those rows of the full composite)."""
+        halo = self.window_halo(kind, n_levels)
         if rows is None:
-            patches = self.warp(regions, src, plan, proj)
+            patches = self.warp(regions, src, plan, proj, split_dilate=2 * halo)
             return self.blend(kind, patches, plan.shape, n_levels), patches
         ya, yb = rows
-        halo = self.window_halo(kind, n_levels)
         wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
-        patches = self.warp(regions, src, plan, proj, rows=(wa, wb), row_align=4 if halo else 1)
+        patches = self.warp(regions, src, plan, proj, rows=(wa, wb), row_align=4 if halo else 1,
+                            split_dilate=2 * halo)
         top = min([p.box[1] for p in patches] + [wa])          # aligned crops may start above wa
         for p in patches:
             x0, y0, x1, y1 = p.box

@@ -1,64 +1,117 @@
-// K3: separable float32 Gaussian on RGBA patches, BORDER_REFLECT_101 at the
-// patch edges — cv2.GaussianBlur(warped, (0, 0), sigma) at stitcher.py:226.
-// Horizontal pass into tmp, vertical pass into out.  Taps arrive as a kernel
-// parameter (constant bank, uniform across the warp).
+// K3: separable float32 Gaussian on RGBA images, BORDER_REFLECT_101 at the
+// image edges — the arithmetic of cv2.GaussianBlur(img, (0, 0), sigma) at
+// stitcher.py:226.  Used on the coarse grids of the band pipeline and, as a
+// general primitive, on full-resolution patches.
+//
+// Both passes stage their input tile (with halo, reflection applied while
+// staging) in shared memory and give every thread R = 8 consecutive outputs
+// along the filter axis: an input sample is read from shared memory once and
+// scattered into the 8 accumulators it contributes to, so shared-memory
+// traffic is (R + ksize - 1) / R loads per output instead of ksize, and the
+// inner loop is pure packed FFMA2 (fma.rn.f32x2, two RGBA halves per tap).
 #include "p360_common.cuh"
 
 namespace p360 {
 
+constexpr int R = 8;                              // outputs per thread along the filter axis
+constexpr int TAP_SLOTS = P360_MAX_KSIZE + 3 * R; // taps, zero-padded by R-1 in front and 2R behind
+
 struct Taps {
-    float k[P360_MAX_KSIZE];
+    float k[TAP_SLOTS];     // k[t + R - 1] = tap t
     int ksize;
 };
 
-__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 &v) {
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+__device__ __forceinline__ void fma_rgba(float2 &lo, float2 &hi, float w, const float4 &v) {
+    const float2 ww = make_float2(w, w);
+    lo = __ffma2_rn(ww, make_float2(v.x, v.y), lo);
+    hi = __ffma2_rn(ww, make_float2(v.z, v.w), hi);
 }
 
-constexpr int HB = 256;      // output pixels per block (one row segment)
+// out[i] = sum_t k[t] * in[i + t], i = 0..R-1, with in[j] = load(j), j = 0 .. R + ksize - 2.
+template <class Load>
+__device__ __forceinline__ void convolve_r(float2 (&lo)[R], float2 (&hi)[R], const Taps &t, Load load) {
+    const int nj = R + t.ksize - 1;
+    for (int jc = 0; jc < nj; jc += R) {
+        float w[2 * R - 1];
+#pragma unroll
+        for (int c = 0; c < 2 * R - 1; ++c) w[c] = t.k[jc + c];
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+            const float4 v = load(jc + jj, jc + jj < nj);
+#pragma unroll
+            for (int i = 0; i < R; ++i) fma_rgba(lo[i], hi[i], w[jj - i + R - 1], v);
+        }
+    }
+}
 
-// Horizontal: the row segment plus a halo of r pixels each side is staged in
-// shared memory (reflect applied while staging), each thread then slides over
-// its ksize neighbours.
-__global__ void __launch_bounds__(HB)
-blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
-    extern __shared__ float4 tile[];
+// ---- horizontal ------------------------------------------------------------
+constexpr int H_WARPS = 4;             // rows per block (one warp per row)
+constexpr int H_SEG = 32 * R;          // outputs per warp
+__host__ __device__ __forceinline__ int h_phys(int q) { return q + (q >> 3); }   // 1 pad slot per 8: lane stride 9
+
+__global__ void __launch_bounds__(32 * H_WARPS)
+blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
+    extern __shared__ float4 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nxb = (pw + H_SEG - 1) / H_SEG;
+    const int row = (blockIdx.x / nxb) * H_WARPS + warp;
+    const int xb = (blockIdx.x % nxb) * H_SEG;
+    if (row >= ph) return;                              // warp-uniform, no block barrier below
+    float4 *tile = smem + (size_t)warp * pitch;
     const int r = t.ksize >> 1;
-    const int nxb = (pw + HB - 1) / HB;
-    const int row = blockIdx.x / nxb;
-    const int xb = (blockIdx.x % nxb) * HB;
     const float4 *src = in + (size_t)row * pw;
-    for (int i = threadIdx.x; i < HB + 2 * r; i += HB) {
-        tile[i] = src[reflect_101(xb - r + i, pw)];
+    const int nq = H_SEG + t.ksize - 1;
+    for (int q = lane; q < nq; q += 32) tile[h_phys(q)] = __ldg(src + reflect_101(xb - r + q, pw));
+    __syncwarp();
+    float2 lo[R], hi[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
+    const int base = R * lane;
+    convolve_r(lo, hi, t, [&](int j, bool ok) {
+        return ok ? tile[h_phys(base + j)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        tile[h_phys(base + i)] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
+    __syncwarp();
+    float4 *dst = out + (size_t)row * pw + xb;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+        const int x = c * 32 + lane;
+        if (xb + x < pw) dst[x] = tile[h_phys(x)];
     }
-    __syncthreads();
-    int x = xb + threadIdx.x;
-    if (x >= pw) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < t.ksize; ++k) fma4(acc, t.k[k], tile[threadIdx.x + k]);
-    out[(size_t)row * pw + x] = acc;
 }
 
-constexpr int VBX = 32, VBY = 8;
+// ---- vertical --------------------------------------------------------------
+constexpr int V_WARPS = 8;
+constexpr int V_ROWS = V_WARPS * R;    // output rows per block, 32 columns wide
 
-// Vertical: lanes along x (coalesced 512-byte row segments), every thread
-// walks the ksize rows above/below its pixel; reuse between neighbouring rows
-// is served by L1/L2.
-__global__ void __launch_bounds__(VBX *VBY)
+__global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
-    int x = blockIdx.x * VBX + threadIdx.x;
-    int y = blockIdx.y * VBY + threadIdx.y;
-    if (x >= pw || y >= ph) return;
+    extern __shared__ float4 smem[];   // [V_ROWS + ksize - 1][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int yb = blockIdx.y * V_ROWS;
     const int r = t.ksize >> 1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < t.ksize; ++k) {
-        int yy = reflect_101(y - r + k, ph);
-        fma4(acc, t.k[k], __ldg(in + (size_t)yy * pw + x));
+    const int nq = V_ROWS + t.ksize - 1;
+    const int xs = min(x, pw - 1);
+    for (int q = warp; q < nq; q += V_WARPS)
+        smem[q * 32 + lane] = __ldg(in + (size_t)reflect_101(yb - r + q, ph) * pw + xs);
+    __syncthreads();
+    float2 lo[R], hi[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
+    const int base = R * warp;
+    convolve_r(lo, hi, t, [&](int j, bool ok) {
+        return ok ? smem[(base + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    if (x >= pw) return;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int y = yb + base + i;
+        if (y < ph) out[(size_t)y * pw + x] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
     }
-    out[(size_t)y * pw + x] = acc;
 }
 
 }  // namespace p360
@@ -75,15 +128,27 @@ extern "C" int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp
     if (pw == 0 || ph == 0) return 0;
     Taps t;
     memset(&t, 0, sizeof(t));
-    memcpy(t.k, taps_host, sizeof(float) * ksize);
+    memcpy(t.k + R - 1, taps_host, sizeof(float) * ksize);
     t.ksize = ksize;
     auto in = reinterpret_cast<const float4 *>(in_rgba);
     auto tmp = reinterpret_cast<float4 *>(tmp_rgba);
     auto out = reinterpret_cast<float4 *>(out_rgba);
     cudaStream_t s = (cudaStream_t)stream;
-    size_t smem = sizeof(float4) * (HB + 2 * (ksize >> 1));
-    blur_h_kernel<<<cdiv(pw, HB) * (unsigned)ph, HB, smem, s>>>(in, tmp, pw, ph, t);
+
+    const int pitch = h_phys(H_SEG + ksize - 1) + 1;
+    const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
+    const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);
+    static thread_local size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
+    if (smem_h > h_limit) {
+        P360_CUDA(cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h), where);
+        h_limit = smem_h;
+    }
+    if (smem_v > v_limit) {
+        P360_CUDA(cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v), where);
+        v_limit = smem_v;
+    }
+    blur_h_kernel<<<cdiv(pw, H_SEG) * cdiv(ph, H_WARPS), 32 * H_WARPS, smem_h, s>>>(in, tmp, pw, ph, pitch, t);
     if (int e = check_launch(where)) return e;
-    blur_v_kernel<<<dim3(cdiv(pw, VBX), cdiv(ph, VBY)), dim3(VBX, VBY), 0, s>>>(tmp, out, pw, ph, t);
+    blur_v_kernel<<<dim3(cdiv(pw, 32), cdiv(ph, V_ROWS)), 32 * V_WARPS, smem_v, s>>>(tmp, out, pw, ph, t);
     return check_launch(where);
 }

@@ -120,6 +120,44 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
     return MosaicPlan(shape, resolution, lo, boxes, ranges)
 
 
+def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4):
+    """Column ranges of a patch box that can contain valid pixels.
+
+    The reference gives an image that straddles theta = +-pi a full-mosaic-
+    width box (no wrap handling in stitcher.py:107-122) of which
+    all but the two ends is invalid.  The image footprint is a convex spherical
+    quadrilateral, so the columns it touches are exactly the theta-extent of
+    its border: if the sorted border samples leave one wide interior gap, every
+    column inside the gap is invalid and the box is split in two.  Each part is
+    grown by ``dilate`` columns (callers pass twice the reach of the widest
+    blur, so that neither the dropped columns nor the reflection at the
+    artificial edge can influence a pixel with non-zero weight) plus a small
+    ``margin`` for the sampling of the border.  Returns [(x0, x1), ...] inside
+    the box, in ascending order; a single run equal to the box if no split."""
+    x0, y0, x1, y1 = box
+    h, w = region.img.shape[:2]
+    n = BORDER_SAMPLES
+    along_x, along_y = np.linspace(0, w, n), np.linspace(0, h, n)
+    ring = np.empty((4 * n, 3))
+    ring[:, 2] = 1.0
+    ring[0 * n:1 * n, 0], ring[0 * n:1 * n, 1] = 0.0, along_y
+    ring[1 * n:2 * n, 0], ring[1 * n:2 * n, 1] = w, along_y
+    ring[2 * n:3 * n, 0], ring[2 * n:3 * n, 1] = along_x, 0.0
+    ring[3 * n:4 * n, 0], ring[3 * n:4 * n, 1] = along_x, h
+    ring -= np.array([w / 2, h / 2, 0])
+    theta = np.sort(proj.hom2proj(region.hom().dot(ring.T).T)[:, 0])
+    gaps = np.diff(theta)
+    k = int(np.argmax(gaps))
+    left_end = int(np.ceil((theta[k] - plan.origin[0]) / plan.resolution[0])) + margin + dilate
+    right_start = int(np.floor((theta[k + 1] - plan.origin[0]) / plan.resolution[0])) - margin - dilate
+    left_end, right_start = min(left_end, x1), max(right_start, x0)
+    # only worth (and only safe) when the gap dwarfs both the sampling step and the dilation
+    if right_start - left_end < max(256, 4 * dilate) or gaps[k] < 20 * np.median(gaps):
+        return [(x0, x1)]
+    runs = [(x0, left_end), (right_start, x1)]
+    return [(a, b) for a, b in runs if b > a]
+
+
 def inverse_map_tables(region, box, plan, proj=SphProj):
     """Separable float64 tables for one patch: ``p = K R proj2hom(theta, phi)``
     splits into a per-column part (x and z components of the ray depend on

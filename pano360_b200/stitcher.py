@@ -185,11 +185,16 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         comp.set_gains(src, equalize_gains(regions, src))
     plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
                            max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
-    patches = comp.warp(regions, src, plan, proj)
+    levels = 5
+    if kind == "multiband":
+        levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
+    # foreign blenders get the reference's one-box-per-image patches; ours may
+    # drop the all-invalid middle of seam-straddling boxes
+    dilate = None if kind is None else 2 * comp.window_halo(kind, levels)
+    patches = comp.warp(regions, src, plan, proj, split_dilate=dilate)
     if kind is None:                       # foreign blender: hand it NumPy triples
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
     elif kind == "multiband":
-        levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
         mosaic = _download(comp.blend_multiband(patches, plan.shape, levels), out)
     else:
         mosaic = _download(comp.blend(kind, patches, plan.shape), out)

@@ -239,6 +239,40 @@ def test_row_window_equals_full_mosaic(st, comp, restore_globals):
             assert np.array_equal(strip.cpu().numpy(), full[rows[0]:rows[1]]), (kind, rows)
 
 
+def test_seam_split_is_exact(comp):
+    """Dropping the all-invalid middle of seam-straddling boxes (SURVEY.md F10,
+    H5) must not change a single output byte."""
+    data = load_golden("ring12")
+    regs = regions_from_golden(data)
+    for kind in ("multiband", "linear", "none"):
+        plan = geo.plan_mosaic(regs, kind == "multiband", 1e9)
+        src = comp.upload(regs)
+        whole = comp.warp(regs, src, plan)
+        halo = comp.window_halo(kind, 5)
+        parts = comp.warp(regs, src, plan, split_dilate=2 * halo)
+        assert len(parts) > len(whole)
+        a = comp.blend(kind, whole, plan.shape, 5).cpu().numpy()
+        b = comp.blend(kind, parts, plan.shape, 5).cpu().numpy()
+        assert np.array_equal(a, b), kind
+
+
+@pytest.mark.parametrize("ksize", [1, 3, 15, 33, 97, 129])
+def test_blur_kernel_generic_taps(comp, ksize):
+    """K3 with arbitrary odd tap counts against a float64 NumPy convolution."""
+    import torch
+    rng = np.random.default_rng(ksize)
+    img = rng.random((77, 301, 4), dtype=np.float32)
+    taps = rng.random(ksize).astype(np.float32)
+    taps /= taps.sum()
+    got = comp.blur_taps(torch.from_numpy(img).to(comp.device), taps).cpu().numpy()
+    r = ksize // 2
+    rows = np.pad(np.arange(77), r, mode="reflect") if r else np.arange(77)
+    cols = np.pad(np.arange(301), r, mode="reflect") if r else np.arange(301)
+    tmp = sum(taps[t].astype(np.float64) * img[:, cols[t:t + 301]].astype(np.float64) for t in range(ksize))
+    want = sum(taps[t].astype(np.float64) * tmp[rows[t:t + 77]] for t in range(ksize))
+    assert np.abs(got - want).max() < 5e-6
+
+
 def test_c_abi_reports_errors_without_aborting(comp):
     from pano360_b200 import _lib
     with pytest.raises(RuntimeError, match="p360_gauss_blur"):
