@@ -50,12 +50,19 @@ int  p360_device_info(int device, int32_t out_host[4]);
  *   row_tab     ph x 3 float64: K*R[:,1]*ry(r) per patch row
  *               (proj2hom is separable: stitcher.py:84-87, :101-104)
  *   out_rgba    ph x pw x 4 float32, out_invalid ph x pw u8 (1 = masked)
+ *   best/owner/covered  optional (all NULL to skip): the K2 owner-map update of
+ *               p360_owner_update fused into the same pass, for a patch placed
+ *               at (x0, y0) in a mosaic of width W and known as `idx`.
+ * p360_pack_rgbx widens u8 x 3 pixels to one aligned 32-bit word each so that
+ * every bilinear tap is a single load (src_c = 4).
  */
+int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t n_pixels, void *stream);
 int p360_warp_patch(const uint8_t *src, int src_h, int src_w, int src_c,
                     const float *lut, const double *hat_y, const double *hat_x,
                     const double *col_tab, const double *row_tab,
                     int pw, int ph, float *out_rgba, uint8_t *out_invalid,
-                    void *stream);
+                    int x0, int y0, int idx, float *best, int32_t *owner,
+                    uint8_t *covered, int W, void *stream);
 
 /* ---- K2: owner map (stitcher.py:196-208) -----------------------------------
  * p360_owner_update: running arg-max of alpha over patches visited in index

@@ -134,13 +134,23 @@ class Compositor:
                 host = torch.from_numpy(np.ascontiguousarray(img))
                 dev_img = host.to(self.device, non_blocking=host.is_pinned())
             h, w = dev_img.shape[:2]
-            src.pixels.append(dev_img)
+            src.pixels.append(self.pack_pixels(dev_img))
             src.shapes.append((h, w))
             if (h, w) not in src.hats:
                 src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
             gain = None if gains is None else gains[i]
             src.luts.append(self._to_device(geo.sample_lut(gain)))
         return src
+
+    def pack_pixels(self, dev_img):
+        """u8 x 3 -> u8 x 4 on the device: one aligned 32-bit word per pixel,
+        so each bilinear tap of the warp is a single load."""
+        if dev_img.shape[2] == 4:
+            return dev_img
+        h, w = dev_img.shape[:2]
+        packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
+        _lib.call("p360_pack_rgbx", _lib.ptr(dev_img), _lib.ptr(packed), h * w, self.stream)
+        return packed
 
     def set_gains(self, src, gains):
         src.luts = [self._to_device(geo.sample_lut(g)) for g in gains]
@@ -182,16 +192,16 @@ class Compositor:
         return overlaps, sizes, todo
 
     # -- K1: warp -------------------------------------------------------------
-    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
-        """Warp every image into its patch.  ``rows=(ya, yb)`` crops patches
-        to those mosaic rows; a cropped top edge is moved up to a multiple of
-        ``row_align`` rows below the patch's true top so that coarse grids
-        anchored at the crop coincide with those anchored at the true patch.
-        Boxes stay in absolute mosaic coordinates.  Images with an empty crop
-        are skipped; ``index`` keeps the original image number.  With
-        ``split_dilate`` (columns) the all-invalid middle of seam-straddling
-        boxes is dropped (``geometry.active_column_runs``): such an image
-        yields two patches with the same ``index``."""
+    def plan_crops(self, regions, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
+        """Host side of the warp: which (row-cropped, column-split) boxes get
+        warped, and their inverse-map tables.  ``rows=(ya, yb)`` crops boxes to
+        those mosaic rows; a cropped top edge is moved up to a multiple of
+        ``row_align`` rows below the box's true top so that coarse grids
+        anchored at the crop coincide with those anchored at the true box.
+        With ``split_dilate`` (columns) the all-invalid middle of seam-
+        straddling boxes is dropped (``geometry.active_column_runs``): such an
+        image yields two crops with the same image index.
+        Returns (crops, tables) with crops = [(image, x0, y0, x1, y1, col_off, row_off)]."""
         crops, tabs, total = [], [], 0
         for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
             x0, y0, x1, y1 = box
@@ -206,23 +216,50 @@ class Compositor:
                 crops.append((i, cx0, ya, cx1, yb, total, total + col_tab.size))
                 tabs += [col_tab.ravel(), row_tab.ravel()]
                 total += col_tab.size + row_tab.size
+        return crops, (np.concatenate(tabs) if tabs else np.zeros(0))
+
+    def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
+        """K1 over every crop.  Boxes of the returned patches are relative to
+        ``origin`` (x, y).  With ``owner_state = (best, owner, covered)``
+        (mosaic-sized, already initialised) the owner-map update of K2 is fused
+        into the warp; patch k of the returned list is known as k there."""
         if not crops:
             return []
-        dev_tabs = self._to_device(np.concatenate(tabs), pinned_key="tabs")
+        dev_tabs = self._to_device(tables, pinned_key="tabs")
+        ox, oy = origin
         patches = []
-        for i, x0, ya, x1, yb, off_c, off_r in crops:
+        for k, (i, x0, ya, x1, yb, off_c, off_r) in enumerate(crops):
             pw, ph = x1 - x0, yb - ya
             rgba = torch.empty((ph, pw, 4), dtype=torch.float32, device=self.device)
             invalid = torch.empty((ph, pw), dtype=torch.uint8, device=self.device)
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
-            self._traced("K1_warp", 17 * pw * ph, "p360_warp_patch", _lib.ptr(src.pixels[i]), h, w,
+            if owner_state is None:
+                fused = (0, 0, 0, None, None, None, 0)
+                nbytes = 17 * pw * ph
+            else:
+                best, owner, covered = owner_state
+                fused = (x0 - ox, ya - oy, k, _lib.ptr(best), _lib.ptr(owner), _lib.ptr(covered), owner.shape[1])
+                nbytes = 30 * pw * ph
+            self._traced("K1_warp", nbytes, "p360_warp_patch", _lib.ptr(src.pixels[i]), h, w,
                          src.pixels[i].shape[2], _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
                          dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
-                         pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), self.stream)
-            patches.append(DevicePatch(rgba, invalid, (x0, ya, x1, yb), i))
+                         pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), *fused, self.stream)
+            patches.append(DevicePatch(rgba, invalid, (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
         self._keepalive = dev_tabs
         return patches
+
+    def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
+        """plan_crops + warp_crops in absolute mosaic coordinates."""
+        crops, tables = self.plan_crops(regions, plan, proj, rows, row_align, split_dilate)
+        return self.warp_crops(src, crops, tables)
+
+    def new_owner_state(self, shape):
+        """(best, owner, covered) for a mosaic (or strip) of ``shape``."""
+        h, w = shape
+        return (torch.zeros((h, w), dtype=torch.float32, device=self.device),
+                torch.full((h, w), -1, dtype=torch.int32, device=self.device),
+                torch.zeros((h, w), dtype=torch.uint8, device=self.device))
 
     # -- blenders (device-resident patches in, device u8 mosaic out) ---------
     def _args(self, p):
@@ -254,9 +291,7 @@ class Compositor:
     def owner_map(self, patches, shape):
         """stitcher.py:196-204 without the H x W x N tensor: (owner, covered)."""
         h, w = shape
-        best = torch.zeros((h, w), dtype=torch.float32, device=self.device)
-        owner = torch.full((h, w), -1, dtype=torch.int32, device=self.device)
-        covered = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
+        best, owner, covered = self.new_owner_state(shape)
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
             self._traced("K2_owner_update", 30 * pw * ph, "p360_owner_update", _lib.ptr(p.rgba),
@@ -310,14 +345,17 @@ class Compositor:
             widths.append(coarse.shape[1])
         return pad, lows, widths
 
-    def blend_multiband(self, patches, shape, n_levels=5, stages=None):
+    def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM."""
         h, w = shape
         if not 1 <= n_levels <= _lib.MAX_LEVELS:
             raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
-        owner, covered = self.owner_map(patches, shape)
+        if owner_state is None:
+            owner, covered = self.owner_map(patches, shape)
+        else:
+            _, owner, covered = owner_state        # filled by the warp (fused K2)
         mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
             return mosaic.zero_()
@@ -384,15 +422,19 @@ class Compositor:
         those rows of the full composite)."""
         halo = self.window_halo(kind, n_levels)
         if rows is None:
-            patches = self.warp(regions, src, plan, proj, split_dilate=2 * halo)
-            return self.blend(kind, patches, plan.shape, n_levels), patches
-        ya, yb = rows
-        wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
-        patches = self.warp(regions, src, plan, proj, rows=(wa, wb), row_align=4 if halo else 1,
-                            split_dilate=2 * halo)
-        top = min([p.box[1] for p in patches] + [wa])          # aligned crops may start above wa
-        for p in patches:
-            x0, y0, x1, y1 = p.box
-            p.box = (x0, y0 - top, x1, y1 - top)
-        strip = self.blend(kind, patches, (wb - top, plan.shape[1]), n_levels)
+            ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
+            crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * halo)
+        else:
+            ya, yb = rows
+            wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
+            crops, tables = self.plan_crops(regions, plan, proj, rows=(wa, wb),
+                                            row_align=4 if halo else 1, split_dilate=2 * halo)
+        top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
+        shape = (wb - top, plan.shape[1])
+        state = self.new_owner_state(shape) if kind == "multiband" else None
+        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+        if kind == "multiband":
+            strip = self.blend_multiband(patches, shape, n_levels, owner_state=state)
+        else:
+            strip = self.blend(kind, patches, shape, n_levels)
         return strip[ya - top:ya - top + (yb - ya)], patches

@@ -83,22 +83,33 @@ struct BandPatch {
 };
 static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
 
-// bilinear sample of a coarse level at full-res pixel (px, py) of the patch
-__device__ __forceinline__ float4 expand_at(const float4 *__restrict__ low, int lw, int shift,
-                                            int pad, int px, int py) {
+// Position of full-res patch pixel (px, py) on a coarse grid of factor 2^shift
+// anchored `pad` pixels before the patch: u = (p + pad + 0.5) / f - 0.5.
+struct CoarseTap {
+    int ix, iy;
+    float fx, fy;
+};
+__device__ __forceinline__ CoarseTap coarse_tap(int shift, int pad, int px, int py) {
     const int f = 1 << shift;
     const int nx = 2 * (px + pad) + 1 - f, ny = 2 * (py + pad) + 1 - f;   // u = n / (2f)
-    const int ix = nx >> (shift + 1), iy = ny >> (shift + 1);
     const float inv = 0.5f / (float)f;
-    const float fx = (float)(nx & (2 * f - 1)) * inv, fy = (float)(ny & (2 * f - 1)) * inv;
-    const float4 *p = low + (size_t)iy * lw + ix;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lw), d = __ldg(p + lw + 1);
+    CoarseTap t;
+    t.ix = nx >> (shift + 1);
+    t.iy = ny >> (shift + 1);
+    t.fx = (float)(nx & (2 * f - 1)) * inv;
+    t.fy = (float)(ny & (2 * f - 1)) * inv;
+    return t;
+}
+// bilinear sample of a coarse level ("expand")
+__device__ __forceinline__ float4 expand_at(const float4 *__restrict__ low, int lw, const CoarseTap &t) {
+    const float4 *p = low + (size_t)t.iy * lw + t.ix;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lw), d = __ldg(p + lw + 1);
+    const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
     float4 o;
-    float gx = 1.0f - fx, gy = 1.0f - fy;
-    o.x = (a.x * gx + b.x * fx) * gy + (c.x * gx + d.x * fx) * fy;
-    o.y = (a.y * gx + b.y * fx) * gy + (c.y * gx + d.y * fx) * fy;
-    o.z = (a.z * gx + b.z * fx) * gy + (c.z * gx + d.z * fx) * fy;
-    o.w = (a.w * gx + b.w * fx) * gy + (c.w * gx + d.w * fx) * fy;
+    o.x = (a.x * gx + b.x * t.fx) * gy + (c.x * gx + d.x * t.fx) * t.fy;
+    o.y = (a.y * gx + b.y * t.fx) * gy + (c.y * gx + d.y * t.fx) * t.fy;
+    o.z = (a.z * gx + b.z * t.fx) * gy + (c.z * gx + d.z * t.fx) * t.fy;
+    o.w = (a.w * gx + b.w * t.fx) * gy + (c.w * gx + d.w * t.fx) * t.fy;
     return o;
 }
 
@@ -140,17 +151,53 @@ __device__ int build_tile_list(const BandPatch *__restrict__ patches, int n_patc
     return total;
 }
 
+// Drop from the tile list every patch whose blurred mask is identically zero
+// over the tile: its weights vanish at every level (the supports of the
+// truncated Gaussians nest and all taps are positive), so it contributes
+// exact zeros.  Tested on the coarse alpha of the widest level.
+template <int L>
+__device__ int cull_tile_list(const BandPatch *__restrict__ patches, int n_hit, int tx0, int ty0,
+                              int16_t *list) {
+    if (L < 2) return n_hit;
+    const int tid = threadIdx.y * CT_X + threadIdx.x;
+    int kept = 0;
+    for (int it = 0; it < n_hit; ++it) {
+        const int id = list[it];
+        const BandPatch &bp = patches[id];
+        const int shift = bp.shift[L - 2], lw = bp.lw[L - 2];
+        const int px0 = max(tx0, bp.x0) - bp.x0, px1 = min(tx0 + CT_X, bp.x0 + bp.pw) - 1 - bp.x0;
+        const int py0 = max(ty0, bp.y0) - bp.y0, py1 = min(ty0 + CT_Y, bp.y0 + bp.ph) - 1 - bp.y0;
+        const CoarseTap lo = coarse_tap(shift, bp.pad, px0, py0), hi = coarse_tap(shift, bp.pad, px1, py1);
+        const int nx = hi.ix + 2 - lo.ix, ny = hi.iy + 2 - lo.iy;
+        const float *alpha = reinterpret_cast<const float *>(bp.low[L - 2]) + 3;
+        bool any = false;
+        for (int i = tid; i < nx * ny; i += 256) {
+            const int cx = lo.ix + i % nx, cy = lo.iy + i / nx;
+            any |= __ldg(alpha + 4 * ((size_t)cy * lw + cx)) != 0.0f;
+        }
+        const bool keep = __syncthreads_or(any);
+        if (keep) {
+            if (tid == 0) list[kept] = (int16_t)id;     // kept <= it: never overtakes the read position
+            ++kept;
+        }
+    }
+    __syncthreads();
+    return kept;
+}
+
 template <int L>
 __global__ void __launch_bounds__(256)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const int32_t *__restrict__ owner, const uint8_t *__restrict__ covered,
                           uint8_t *__restrict__ out, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int n_hit = build_tile_list(patches, n_patches, blockIdx.x * CT_X, blockIdx.y * CT_Y, list);
-    const int X = blockIdx.x * CT_X + threadIdx.x;
+    const int tx0 = blockIdx.x * CT_X, ty0 = blockIdx.y * CT_Y;
+    int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
+    n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+    const int X = tx0 + threadIdx.x;
 #pragma unroll
     for (int sub = 0; sub < CT_Y / 4; ++sub) {
-        const int Y = blockIdx.y * CT_Y + threadIdx.y + 4 * sub;
+        const int Y = ty0 + threadIdx.y + 4 * sub;
         if (X >= W || Y >= H) continue;
         const size_t mi = (size_t)Y * W + X;
         float num[L][3], den[L];
@@ -165,9 +212,11 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                 if (px < 0 || py < 0 || px >= bp.pw || py >= bp.ph) continue;
                 float4 prev = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
                 prev.w = (own == bp.index) ? 1.0f : 0.0f;     // stitcher.py:207-208
+                const int pad = bp.pad;
+                const CoarseTap t2 = coarse_tap(1, pad, px, py), t4 = coarse_tap(2, pad, px, py);
 #pragma unroll
                 for (int l = 0; l < L - 1; ++l) {             // stitcher.py:224-232
-                    float4 cur = expand_at(bp.low[l], bp.lw[l], bp.shift[l], bp.pad, px, py);
+                    const float4 cur = expand_at(bp.low[l], bp.lw[l], bp.shift[l] == 1 ? t2 : t4);
                     num[l][0] += (prev.x - cur.x) * cur.w;
                     num[l][1] += (prev.y - cur.y) * cur.w;
                     num[l][2] += (prev.z - cur.z) * cur.w;

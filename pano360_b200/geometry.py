@@ -120,7 +120,7 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
     return MosaicPlan(shape, resolution, lo, boxes, ranges)
 
 
-def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4):
+def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4, align=4):
     """Column ranges of a patch box that can contain valid pixels.
 
     The reference gives an image that straddles theta = +-pi a full-mosaic-
@@ -132,7 +132,8 @@ def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4):
     grown by ``dilate`` columns (callers pass twice the reach of the widest
     blur, so that neither the dropped columns nor the reflection at the
     artificial edge can influence a pixel with non-zero weight) plus a small
-    ``margin`` for the sampling of the border.  Returns [(x0, x1), ...] inside
+    ``margin`` for the sampling of the border; the second part starts a
+    multiple of ``align`` columns from the box origin.  Returns [(x0, x1), ...] inside
     the box, in ascending order; a single run equal to the box if no split."""
     x0, y0, x1, y1 = box
     h, w = region.img.shape[:2]
@@ -151,6 +152,8 @@ def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4):
     left_end = int(np.ceil((theta[k] - plan.origin[0]) / plan.resolution[0])) + margin + dilate
     right_start = int(np.floor((theta[k + 1] - plan.origin[0]) / plan.resolution[0])) - margin - dilate
     left_end, right_start = min(left_end, x1), max(right_start, x0)
+    # keep coarse grids anchored at the second run in phase with those of the whole box
+    right_start = x0 + (right_start - x0) // align * align
     # only worth (and only safe) when the gap dwarfs both the sampling step and the dilation
     if right_start - left_end < max(256, 4 * dilate) or gaps[k] < 20 * np.median(gaps):
         return [(x0, x1)]

@@ -188,16 +188,12 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     levels = 5
     if kind == "multiband":
         levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
-    # foreign blenders get the reference's one-box-per-image patches; ours may
-    # drop the all-invalid middle of seam-straddling boxes
-    dilate = None if kind is None else 2 * comp.window_halo(kind, levels)
-    patches = comp.warp(regions, src, plan, proj, split_dilate=dilate)
-    if kind is None:                       # foreign blender: hand it NumPy triples
+    if kind is None:                       # foreign blender: the reference's one-box-per-image NumPy triples
+        patches = comp.warp(regions, src, plan, proj)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
-    elif kind == "multiband":
-        mosaic = _download(comp.blend_multiband(patches, plan.shape, levels), out)
     else:
-        mosaic = _download(comp.blend(kind, patches, plan.shape), out)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj)
+        mosaic = _download(mosaic_dev, out)
     if crop:
         logging.debug("Cropping...")
         mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))

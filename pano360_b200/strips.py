@@ -190,7 +190,7 @@ def upload_subset(comp, regions, need, pinned=None):
             else:
                 host = torch.from_numpy(np.ascontiguousarray(reg.img))
                 dev_img = host.to(comp.device, non_blocking=host.is_pinned())
-            src.pixels.append(dev_img)
+            src.pixels.append(comp.pack_pixels(dev_img))
             if (h, w) not in src.hats:
                 src.hats[(h, w)] = (comp._to_device(geo.hat(h)), comp._to_device(geo.hat(w)))
         else:
