@@ -244,7 +244,7 @@ def run_gpu_arm(args):
         t.numpy()[...] = reg.img
         reg.img = t.numpy()                      # numpy view of pinned memory
         pinned.append(t)
-    src = strips.upload_subset(comp, regions, need, pinned)
+    src = comp.upload(regions, need=need)
     src_bytes_all = sum(int(np.prod(r.img.shape)) for r in regions)
     h2d_bytes = sum(int(np.prod(regions[i].img.shape)) for i in need)
     out_pinned = torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True) if rank == 0 else None

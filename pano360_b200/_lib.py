@@ -9,6 +9,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+import numpy as np
+
 import torch  # noqa: F401  (loads libcudart first so the library shares torch's runtime)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -23,45 +25,44 @@ SIGNATURES = {
     "p360_last_error": [C.c_char_p, _i],
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
     "p360_pack_rgbx": [_vp, _vp, _i64, _vp],
-    "p360_warp_patch": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
-                        _i, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "p360_owner_to_alpha": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_warp_batch": [_vp, _i, _i, _i, _vp, _vp, _i, _vp],
+    "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "p360_owner_decode": [_vp, _vp, _i64, _vp],
     "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
-    "p360_band_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
-    "p360_collapse_finalize": [_vp, _i, _vp, _vp, _i64, _vp],
-    "p360_linear_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
-    "p360_linear_finalize": [_vp, _vp, _i64, _vp],
-    "p360_paste": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_blur_set_taps": [_i, C.POINTER(C.c_float), _i, _vp],
+    "p360_gauss_blur_batch": [_vp, _i, _i, _i, _vp],
+    "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
+    "p360_pyramid_reduce_batch": [_vp, _i, _i, _i, _vp, _i, _vp],
+    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _vp],
+    "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _vp],
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
-    "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
-    "p360_pyramid_reduce": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp],
-    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
 }
 MAX_LEVELS = 8
 
+# NumPy mirrors of the job records in include/pano360_b200.h (filled on the
+# host, shipped to the device as raw bytes)
+WARP_JOB = np.dtype([("src", "u8"), ("lut", "u8"), ("hat_y", "u8"), ("hat_x", "u8"), ("col_tab", "u8"),
+                     ("row_tab", "u8"), ("out", "u8"), ("invalid", "u8"), ("h", "i4"), ("w", "i4"),
+                     ("c", "i4"), ("pw", "i4"), ("ph", "i4"), ("x0", "i4"), ("y0", "i4"), ("patch", "i4")])
+BLUR_JOB = np.dtype([("in", "u8"), ("out", "u8"), ("tmp", "u8"), ("w", "i4"), ("h", "i4"), ("slot", "i4"),
+                     ("reserved", "i4")])
+BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "u8"),
+                       ("low", "u8", (MAX_LEVELS - 1,)), ("x0", "i4"), ("y0", "i4"), ("pw", "i4"),
+                       ("ph", "i4"), ("w4", "i4"), ("h4", "i4"), ("pad", "i4"), ("index", "i4")])
+assert WARP_JOB.itemsize == 96 and BLUR_JOB.itemsize == 40 and BAND_PATCH.itemsize == 120
 
-class BandPatch(C.Structure):
-    """Mirror of ``p360_band_patch`` (include/pano360_b200.h)."""
-
-    _fields_ = [("rgba", C.c_void_p),
-                ("low", C.c_void_p * (MAX_LEVELS - 1)),
-                ("lw", C.c_int32 * (MAX_LEVELS - 1)),
-                ("shift", C.c_int32 * (MAX_LEVELS - 1)),
-                ("x0", C.c_int32), ("y0", C.c_int32), ("pw", C.c_int32), ("ph", C.c_int32),
-                ("pad", C.c_int32), ("index", C.c_int32)]
 # entry points whose int return is a value, not a status
 _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
-_LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_patch": 1, "p360_owner_update": 1, "p360_owner_to_alpha": 1,
-             "p360_gauss_blur": 2, "p360_band_accumulate": 1, "p360_collapse_finalize": 1,
-             "p360_linear_accumulate": 1, "p360_linear_finalize": 1, "p360_paste": 1,
-             "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_pyramid_reduce": 1,
-             "p360_multiband_collapse": 1}
+_LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
+             "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,
+             "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
+             "p360_pair_overlap_stats": 2, "p360_cover_update": 1}
 
 
 def load():

@@ -2,22 +2,28 @@
 for allocation, streams and copies only) and sequences the sm_100a kernels of
 ``libpano360_b200.so`` through the C ABI.
 
+A whole composite is five launches, whatever the number of images: one warp
+over every patch (K1, grid.z = patch), one reduce, one horizontal and one
+vertical coarse blur over every (patch, level) job, one output-stationary
+collapse.  Per-patch parameters travel in small device tables.
+
 Data layout in HBM
 ------------------
-* source image      u8  [h][w][3]            as delivered by cv2.imread (BGR)
+* source image      u8  [h][w][4]            RGBX, packed on device from the u8x3 upload
 * sample LUT        f32 [256] per image      u8 -> float value (gain folded in)
 * hat tables        f64 [h], [w]             shared by images of equal size
 * inverse-map tabs  f64 [pw][3], [ph][3]     per patch (column part, row part)
-* patch             f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid mask
-* coarse levels     f32 [h/f][w/f][4]        blurred f=2 (level 0) / f=4 (levels >= 1) images per patch
-* owner / best      i32 [H][W], f32 [H][W]   running arg-max of alpha
+* patch pool        f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid, all patches back to back
+* owner keys        u64 [H][W]               float_bits(alpha) << 32 | ~patch (atomicMax)
 * covered           u8  [H][W]               union of valid pixels
-* mosaic            u8  [H][W][3]
+* coarse levels     f32 [h/f][w/f][4]        reduced (d2, d4), H-pass scratch and blurred
+                                             f=2 (level 0) / f=4 (levels >= 1) images per patch
+* mosaic            u8  [H][W][3]            the only mosaic-sized output
 
 A *row window* ``(ya, yb)`` restricts all work to mosaic rows [ya, yb) plus a
-halo of the largest blur radius (strip sharding); patches are
-cropped in rows but keep their true columns, so reflections happen at true
-patch edges wherever they influence rows inside the window.
+halo of the reach of the widest coarse blur (strip sharding, SURVEY.md §8e);
+patches are cropped in rows but keep their true columns, so reflections happen
+at true patch edges wherever they influence rows inside the window.
 """
 from __future__ import annotations
 
@@ -47,7 +53,7 @@ class DevicePatch:
     rgba: torch.Tensor        # [ph, pw, 4] float32
     invalid: torch.Tensor     # [ph, pw] uint8 (1 = masked)
     box: tuple                # (x0, y0, x1, y1) in mosaic pixels
-    index: int = 0
+    index: int = 0            # source image number
 
     @property
     def irange(self):
@@ -65,14 +71,10 @@ class DevicePatch:
 class DeviceSources:
     """Input images + per-image constants resident in HBM."""
 
-    pixels: list                       # u8 [h, w, c] tensors
+    pixels: list                       # u8 [h, w, 4] tensors (None for images a rank does not need)
     luts: list                         # f32 [256] tensors
     hats: dict = field(default_factory=dict)   # (h, w) -> (hat_y, hat_x) f64 tensors
     shapes: list = field(default_factory=list)
-
-    @property
-    def nbytes(self):
-        return sum(p.numel() for p in self.pixels)
 
 
 class Compositor:
@@ -82,6 +84,8 @@ class Compositor:
         self.device = _require_cuda(device)
         _lib.load()
         self._pinned = {}
+        self._taps_key = None
+        self._keep = {}
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
 
     # -- plumbing -----------------------------------------------------------
@@ -90,22 +94,28 @@ class Compositor:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _to_device(self, array, pinned_key=None):
-        """Host ndarray -> device tensor through a (reused) pinned staging buffer."""
+        """Host ndarray -> device tensor, optionally through a reused pinned
+        staging buffer (async copy)."""
         array = np.ascontiguousarray(array)
         host = torch.from_numpy(array)
         if pinned_key is not None:
             stage, busy = self._pinned.get(pinned_key, (None, None))
             if busy is not None:
                 busy.synchronize()            # previous async copy out of this buffer is done
-            if stage is None or stage.shape != host.shape or stage.dtype != host.dtype:
-                stage = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
-            stage.copy_(host)
-            dev = stage.to(self.device, non_blocking=True)
+            if stage is None or stage.numel() < host.numel() or stage.dtype != host.dtype:
+                stage = torch.empty(max(host.numel(), 1), dtype=host.dtype, pin_memory=True)
+            view = stage[:host.numel()].view(host.shape)
+            view.copy_(host)
+            dev = view.to(self.device, non_blocking=True)
             busy = torch.cuda.Event()
             busy.record(torch.cuda.current_stream(self.device))
             self._pinned[pinned_key] = (stage, busy)
             return dev
         return host.to(self.device)
+
+    def _table(self, records, key):
+        """Structured job table -> device bytes."""
+        return self._to_device(records.view(np.uint8).reshape(-1), pinned_key=key)
 
     def _traced(self, name, nbytes, fn, *args):
         """Run one C-ABI call; when tracing, bracket it with CUDA events on the
@@ -120,28 +130,7 @@ class Compositor:
         self.trace.append((name, nbytes, start, end))
         return rc
 
-    def upload(self, regions, gains=None, pinned=None):
-        """H2D copy of the u8 images (+ LUT / hat tables).  ``pinned`` may be a
-        list of pinned uint8 tensors already holding the pixels."""
-        src = DeviceSources([], [])
-        for i, reg in enumerate(regions):
-            img = reg.img if pinned is None else None
-            if pinned is not None:
-                dev_img = pinned[i].to(self.device, non_blocking=True)
-            else:
-                if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
-                    raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
-                host = torch.from_numpy(np.ascontiguousarray(img))
-                dev_img = host.to(self.device, non_blocking=host.is_pinned())
-            h, w = dev_img.shape[:2]
-            src.pixels.append(self.pack_pixels(dev_img))
-            src.shapes.append((h, w))
-            if (h, w) not in src.hats:
-                src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
-            gain = None if gains is None else gains[i]
-            src.luts.append(self._to_device(geo.sample_lut(gain)))
-        return src
-
+    # -- sources --------------------------------------------------------------
     def pack_pixels(self, dev_img):
         """u8 x 3 -> u8 x 4 on the device: one aligned 32-bit word per pixel,
         so each bilinear tap of the warp is a single load."""
@@ -151,6 +140,32 @@ class Compositor:
         packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
         _lib.call("p360_pack_rgbx", _lib.ptr(dev_img), _lib.ptr(packed), h * w, self.stream)
         return packed
+
+    def upload(self, regions, gains=None, need=None):
+        """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
+        pinned memory are copied asynchronously.  ``need`` (a set of indices)
+        restricts the copy to the images a rank's strip touches."""
+        src = DeviceSources([], [])
+        lut0 = None
+        for i, reg in enumerate(regions):
+            img = reg.img
+            h, w = img.shape[:2]
+            src.shapes.append((h, w))
+            if need is not None and i not in need:
+                src.pixels.append(None)
+            else:
+                if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+                    raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
+                host = torch.from_numpy(np.ascontiguousarray(img))
+                src.pixels.append(self.pack_pixels(host.to(self.device, non_blocking=host.is_pinned())))
+                if (h, w) not in src.hats:
+                    src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
+            if gains is None:
+                lut0 = self._to_device(geo.sample_lut(None)) if lut0 is None else lut0
+                src.luts.append(lut0)
+            else:
+                src.luts.append(self._to_device(geo.sample_lut(gains[i])))
+        return src
 
     def set_gains(self, src, gains):
         src.luts = [self._to_device(geo.sample_lut(g)) for g in gains]
@@ -180,9 +195,10 @@ class Compositor:
             if src.shapes[i] != (h, w) or src.shapes[j] != (h, w):
                 raise ValueError("exposure equalisation needs equally sized images (as the reference)")
             inv_c = (C.c_double * 9)(*inv.ravel())
-            _lib.call("p360_pair_overlap_stats", _lib.ptr(src.pixels[i]), _lib.ptr(src.pixels[j]),
-                      h, w, src.pixels[i].shape[2], _lib.ptr(lut0), _lib.ptr(hat_y), _lib.ptr(hat_x),
-                      inv_c, _lib.ptr(partial), out[k].data_ptr(), self.stream)
+            self._traced("K8_pair_overlap_stats", 6 * h * w, "p360_pair_overlap_stats",
+                         _lib.ptr(src.pixels[i]), _lib.ptr(src.pixels[j]), h, w, src.pixels[i].shape[2],
+                         _lib.ptr(lut0), _lib.ptr(hat_y), _lib.ptr(hat_x), inv_c, _lib.ptr(partial),
+                         out[k].data_ptr(), self.stream)
         sums = out.cpu().numpy()
         for (i, j, _), (cnt, s_i, s_j) in zip(todo, sums):
             sizes[i, j] = sizes[j, i] = cnt
@@ -218,35 +234,52 @@ class Compositor:
                 total += col_tab.size + row_tab.size
         return crops, (np.concatenate(tabs) if tabs else np.zeros(0))
 
+    def new_owner_state(self, shape):
+        """(owner keys u64, covered u8) for a mosaic (or strip) of ``shape``."""
+        h, w = shape
+        return (torch.zeros((h, w), dtype=torch.int64, device=self.device),
+                torch.zeros((h, w), dtype=torch.uint8, device=self.device))
+
     def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
-        """K1 over every crop.  Boxes of the returned patches are relative to
-        ``origin`` (x, y).  With ``owner_state = (best, owner, covered)``
-        (mosaic-sized, already initialised) the owner-map update of K2 is fused
+        """K1 over every crop in ONE launch.  Boxes of the returned patches
+        are relative to ``origin`` (x, y).  With ``owner_state = (keys,
+        covered)`` (mosaic-sized, zeroed) the owner-map competition is fused
         into the warp; patch k of the returned list is known as k there."""
         if not crops:
             return []
         dev_tabs = self._to_device(tables, pinned_key="tabs")
         ox, oy = origin
+        n = len(crops)
+        sizes = np.array([(c[3] - c[1]) * (c[4] - c[2]) for c in crops], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        rgba_pool = torch.empty(int(offs[-1]) * 4, dtype=torch.float32, device=self.device)
+        inv_pool = torch.empty(int(offs[-1]), dtype=torch.uint8, device=self.device)
+        jobs = np.zeros(n, dtype=_lib.WARP_JOB)
         patches = []
+        tab_base, rgba_base, inv_base = dev_tabs.data_ptr(), rgba_pool.data_ptr(), inv_pool.data_ptr()
         for k, (i, x0, ya, x1, yb, off_c, off_r) in enumerate(crops):
             pw, ph = x1 - x0, yb - ya
-            rgba = torch.empty((ph, pw, 4), dtype=torch.float32, device=self.device)
-            invalid = torch.empty((ph, pw), dtype=torch.uint8, device=self.device)
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
-            if owner_state is None:
-                fused = (0, 0, 0, None, None, None, 0)
-                nbytes = 17 * pw * ph
-            else:
-                best, owner, covered = owner_state
-                fused = (x0 - ox, ya - oy, k, _lib.ptr(best), _lib.ptr(owner), _lib.ptr(covered), owner.shape[1])
-                nbytes = 30 * pw * ph
-            self._traced("K1_warp", nbytes, "p360_warp_patch", _lib.ptr(src.pixels[i]), h, w,
-                         src.pixels[i].shape[2], _lib.ptr(src.luts[i]), _lib.ptr(hat_y), _lib.ptr(hat_x),
-                         dev_tabs.data_ptr() + 8 * off_c, dev_tabs.data_ptr() + 8 * off_r,
-                         pw, ph, _lib.ptr(rgba), _lib.ptr(invalid), *fused, self.stream)
-            patches.append(DevicePatch(rgba, invalid, (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
-        self._keepalive = dev_tabs
+            pix = src.pixels[i]
+            o = int(offs[k])
+            jobs[k] = (pix.data_ptr(), src.luts[i].data_ptr(), hat_y.data_ptr(), hat_x.data_ptr(),
+                       tab_base + 8 * off_c, tab_base + 8 * off_r, rgba_base + 16 * o, inv_base + o,
+                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, k)
+            patches.append(DevicePatch(rgba_pool[4 * o:4 * (o + pw * ph)].view(ph, pw, 4),
+                                       inv_pool[o:o + pw * ph].view(ph, pw),
+                                       (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
+        dev_jobs = self._table(jobs, "warp_jobs")
+        if owner_state is None:
+            keys = covered = None
+            width, per_px = 0, 17
+        else:
+            keys, covered = owner_state
+            width, per_px = keys.shape[1], 30
+        self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", _lib.ptr(dev_jobs), n,
+                     int(max(c[3] - c[1] for c in crops)), int(max(c[4] - c[2] for c in crops)),
+                     _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+        self._keep["warp"] = (dev_tabs, dev_jobs, rgba_pool, inv_pool)
         return patches
 
     def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
@@ -254,61 +287,28 @@ class Compositor:
         crops, tables = self.plan_crops(regions, plan, proj, rows, row_align, split_dilate)
         return self.warp_crops(src, crops, tables)
 
-    def new_owner_state(self, shape):
-        """(best, owner, covered) for a mosaic (or strip) of ``shape``."""
-        h, w = shape
-        return (torch.zeros((h, w), dtype=torch.float32, device=self.device),
-                torch.full((h, w), -1, dtype=torch.int32, device=self.device),
-                torch.zeros((h, w), dtype=torch.uint8, device=self.device))
-
     # -- blenders (device-resident patches in, device u8 mosaic out) ---------
-    def _args(self, p):
+    @staticmethod
+    def _args(p):
         x0, y0, x1, y1 = p.box
         return x1 - x0, y1 - y0, x0, y0
 
-    def blend_none(self, patches, shape):
-        """stitcher.py:160-168."""
-        h, w = shape
-        mosaic = torch.zeros((h, w, 3), dtype=torch.uint8, device=self.device)
-        for p in patches:
-            pw, ph, x0, y0 = self._args(p)
-            _lib.call("p360_paste", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0,
-                      _lib.ptr(mosaic), w, self.stream)
-        return mosaic
-
-    def blend_linear(self, patches, shape):
-        """stitcher.py:171-183."""
-        h, w = shape
-        acc = torch.zeros((h, w, 4), dtype=torch.float32, device=self.device)
-        for p in patches:
-            pw, ph, x0, y0 = self._args(p)
-            _lib.call("p360_linear_accumulate", _lib.ptr(p.rgba), _lib.ptr(p.invalid), pw, ph, x0, y0,
-                      _lib.ptr(acc), w, self.stream)
-        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        _lib.call("p360_linear_finalize", _lib.ptr(acc), _lib.ptr(mosaic), h * w, self.stream)
-        return mosaic
-
-    def owner_map(self, patches, shape):
-        """stitcher.py:196-204 without the H x W x N tensor: (owner, covered)."""
-        h, w = shape
-        best, owner, covered = self.new_owner_state(shape)
+    def owner_state_for(self, patches, shape):
+        """Owner keys + covered for patches that were not warped by us (K2)."""
+        keys, covered = self.new_owner_state(shape)
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
             self._traced("K2_owner_update", 30 * pw * ph, "p360_owner_update", _lib.ptr(p.rgba),
-                         _lib.ptr(p.invalid), pw, ph, x0, y0, k, _lib.ptr(best), _lib.ptr(owner),
-                         _lib.ptr(covered), w, self.stream)
-        return owner, covered
+                         _lib.ptr(p.invalid), pw, ph, x0, y0, k, _lib.ptr(keys), _lib.ptr(covered),
+                         shape[1], self.stream)
+        return keys, covered
 
-    def blur(self, rgba, sigma, out=None, tmp=None):
-        """cv2.GaussianBlur(rgba, (0, 0), sigma) on a device patch."""
-        taps = geo.gaussian_taps(sigma)
-        out = torch.empty_like(rgba) if out is None else out
-        tmp = torch.empty_like(rgba) if tmp is None else tmp
-        ph, pw = rgba.shape[:2]
-        self._traced("K3_gauss_blur", 32 * pw * ph, "p360_gauss_blur", _lib.ptr(rgba), _lib.ptr(out),
-                     _lib.ptr(tmp), pw, ph, taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps),
-                     self.stream)
-        return out
+    def owner_map(self, patches, shape, owner_state=None):
+        """stitcher.py:196-204 without the H x W x N tensor: (owner int32, covered)."""
+        keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
+        owner = torch.empty(shape, dtype=torch.int32, device=self.device)
+        _lib.call("p360_owner_decode", _lib.ptr(keys), _lib.ptr(owner), shape[0] * shape[1], self.stream)
+        return owner, covered
 
     def blur_taps(self, rgba, taps, out=None, tmp=None):
         """Separable convolution of a device RGBA image with explicit taps."""
@@ -321,29 +321,30 @@ class Compositor:
                      self.stream)
         return out
 
-    def coarse_levels(self, patch, k, owner, mosaic_w, n_levels, scratch):
-        """Blurred coarse images of levels 0 .. L-2 of one patch
-        (stitcher.py:218-229 evaluated at reduced resolution)."""
-        pad, plan = geo.coarse_band_plan(n_levels)
-        if not plan:
-            return pad, [], []
-        pw, ph, x0, y0 = self._args(patch)
-        dims = (C.c_int32 * 4)()
-        _lib.call("p360_pyramid_dims", pw, ph, pad, dims)
-        w2, h2, w4, h4 = dims
-        d2 = scratch["d2"][:h2 * w2 * 4].view(h2, w2, 4)
-        d4 = scratch["d4"][:h4 * w4 * 4].view(h4, w4, 4)
-        self._traced("K3a_pyramid_reduce", 25 * pw * ph, "p360_pyramid_reduce", _lib.ptr(patch.rgba), pw, ph,
-                     x0, y0, k, _lib.ptr(owner), mosaic_w, pad, _lib.ptr(d2), _lib.ptr(d4), self.stream)
-        lows, widths = [], []
-        for shift, taps in plan:
-            coarse = d2 if shift == 1 else d4
-            out = torch.empty_like(coarse)
-            tmp = scratch["tmp"][:coarse.numel()].view(coarse.shape)
-            self.blur_taps(coarse, taps, out=out, tmp=tmp)
-            lows.append(out)
-            widths.append(coarse.shape[1])
-        return pad, lows, widths
+    def blur(self, rgba, sigma, out=None, tmp=None):
+        """cv2.GaussianBlur(rgba, (0, 0), sigma) on a device image."""
+        return self.blur_taps(rgba, geo.gaussian_taps(sigma), out, tmp)
+
+    def _band_table(self, patches, pad=0, coarse=False):
+        """p360_band_patch records (+ coarse-grid sizes) for a patch list."""
+        table = np.zeros(len(patches), dtype=_lib.BAND_PATCH)
+        for k, p in enumerate(patches):
+            pw, ph, x0, y0 = self._args(p)
+            rec = table[k]
+            rec["rgba"], rec["invalid"] = p.rgba.data_ptr(), p.invalid.data_ptr()
+            rec["x0"], rec["y0"], rec["pw"], rec["ph"] = x0, y0, pw, ph
+            rec["pad"], rec["index"] = pad, k
+            if coarse:
+                rec["w4"], rec["h4"] = (pw + 2 * pad + 3) // 4, (ph + 2 * pad + 3) // 4
+        return table
+
+    def _set_taps(self, n_levels, plan):
+        if self._taps_key == n_levels:
+            return
+        for slot, (_, taps) in enumerate(plan):
+            _lib.call("p360_blur_set_taps", slot, taps.ctypes.data_as(C.POINTER(C.c_float)), len(taps),
+                      self.stream)
+        self._taps_key = n_levels
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
@@ -352,42 +353,85 @@ class Compositor:
         h, w = shape
         if not 1 <= n_levels <= _lib.MAX_LEVELS:
             raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
-        if owner_state is None:
-            owner, covered = self.owner_map(patches, shape)
-        else:
-            _, owner, covered = owner_state        # filled by the warp (fused K2)
         mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
             return mosaic.zero_()
+        keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
         pad, plan = geo.coarse_band_plan(n_levels)
-        scratch = {}
+        table = self._band_table(patches, pad, coarse=True)
+        n = len(patches)
+        lows = []
         if plan:
-            biggest = max(((p.box[2] - p.box[0] + 2 * pad + 7) * (p.box[3] - p.box[1] + 2 * pad + 7)
-                           for p in patches))
-            scratch = {"d2": torch.empty(biggest + 64, dtype=torch.float32, device=self.device),
-                       "d4": torch.empty(biggest // 4 + 64, dtype=torch.float32, device=self.device),
-                       "tmp": torch.empty(biggest + 64, dtype=torch.float32, device=self.device)}
-        descs = (_lib.BandPatch * len(patches))()
-        keep = []
-        for k, p in enumerate(patches):
-            pw, ph, x0, y0 = self._args(p)
-            _, lows, widths = self.coarse_levels(p, k, owner, w, n_levels, scratch)
-            keep.append(lows)
-            d = descs[k]
-            d.rgba = p.rgba.data_ptr()
-            for lvl, (low, lw) in enumerate(zip(lows, widths)):
-                d.low[lvl], d.lw[lvl], d.shift[lvl] = low.data_ptr(), lw, plan[lvl][0]
-            d.x0, d.y0, d.pw, d.ph, d.pad, d.index = x0, y0, pw, ph, pad, k
-        table = np.frombuffer(bytes(descs), dtype=np.uint8)
-        dev_table = self._to_device(table, pinned_key="bands")
-        gathered = sum((p.box[2] - p.box[0]) * (p.box[3] - p.box[1]) for p in patches)
-        self._traced("K4_multiband_collapse", 16 * gathered + 8 * h * w, "p360_multiband_collapse",
-                     _lib.ptr(dev_table), len(patches), n_levels, _lib.ptr(owner), _lib.ptr(covered),
-                     _lib.ptr(mosaic), h, w, self.stream)
+            c4 = table["w4"].astype(np.int64) * table["h4"]           # f=4 cells per patch
+            off4 = np.concatenate([[0], np.cumsum(c4)]).astype(np.uint64)
+            tot4 = int(off4[-1])
+            # pools: f=2 grid: d2, tmp, low0; f=4 grid: d4 + (tmp, low) per level >= 1
+            pool2 = torch.empty(3 * 4 * tot4 * 4, dtype=torch.float32, device=self.device)
+            pool4 = torch.empty((1 + 2 * (len(plan) - 1)) * tot4 * 4, dtype=torch.float32, device=self.device)
+            b2, b4 = np.uint64(pool2.data_ptr()), np.uint64(pool4.data_ptr())
+            s2, s4 = np.uint64(16 * 4 * tot4), np.uint64(16 * tot4)   # bytes per full plane
+            o2, o4 = np.uint64(64) * off4[:-1], np.uint64(16) * off4[:-1]
+            table["d2"] = b2 + o2
+            table["d4"] = b4 + o4
+            table["low"][:, 0] = b2 + np.uint64(2) * s2 + o2
+            for lvl in range(1, len(plan)):
+                table["low"][:, lvl] = b4 + np.uint64(2 * lvl) * s4 + o4
+            jobs = np.zeros(n * len(plan), dtype=_lib.BLUR_JOB)
+            for lvl in range(len(plan)):
+                sl = jobs[lvl * n:(lvl + 1) * n]
+                if lvl == 0:
+                    sl["in"], sl["tmp"] = table["d2"], b2 + s2 + o2
+                    sl["w"], sl["h"] = 2 * table["w4"], 2 * table["h4"]
+                else:
+                    sl["in"], sl["tmp"] = table["d4"], b4 + np.uint64(2 * lvl - 1) * s4 + o4
+                    sl["w"], sl["h"] = table["w4"], table["h4"]
+                sl["out"], sl["slot"] = table["low"][:, lvl], lvl
+            self._set_taps(n_levels, plan)
+        dev_table = self._table(table, "band_table")
+        pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
+        if plan:
+            dev_jobs = self._table(jobs, "blur_jobs")
+            self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
+                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, self.stream)
+            coarse_px = int(4 * tot4 + (len(plan) - 1) * tot4)
+            self._traced("K3_gauss_blur", 32 * coarse_px, "p360_gauss_blur_batch", _lib.ptr(dev_jobs),
+                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()), self.stream)
+            self._keep["bands"] = (pool2, pool4, dev_jobs)
+            if stages is not None:
+                for k in range(n):
+                    w4, h4, o = int(table["w4"][k]), int(table["h4"][k]), int(off4[k])
+                    per = [pool2[(2 * 4 * tot4 + 4 * o) * 4:][:4 * h4 * w4 * 4].view(2 * h4, 2 * w4, 4)]
+                    for lvl in range(1, len(plan)):
+                        per.append(pool4[(2 * lvl * tot4 + o) * 4:][:h4 * w4 * 4].view(h4, w4, 4))
+                    lows.append(per)
+        self._traced("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
+                     _lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic),
+                     h, w, self.stream)
+        self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
-            stages.update(owner=owner, covered=covered, lows=keep)
-        self._keepalive2 = (keep, dev_table, scratch)
+            stages.update(keys=keys, covered=covered, lows=lows)
         return mosaic
+
+    def _pointwise(self, fn, name, patches, shape):
+        h, w = shape
+        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        if not patches:
+            return mosaic.zero_()
+        table = self._band_table(patches)
+        dev_table = self._table(table, "band_table")
+        pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
+        self._traced(name, 17 * pix + 3 * h * w, fn, _lib.ptr(dev_table), len(patches), _lib.ptr(mosaic),
+                     h, w, self.stream)
+        self._keep["collapse"] = (dev_table,)
+        return mosaic
+
+    def blend_none(self, patches, shape):
+        """stitcher.py:160-168 (last valid writer wins), gather form."""
+        return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape)
+
+    def blend_linear(self, patches, shape):
+        """stitcher.py:171-183, gather form."""
+        return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""

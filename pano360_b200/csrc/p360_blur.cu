@@ -49,13 +49,13 @@ constexpr int H_WARPS = 4;             // rows per block (one warp per row)
 constexpr int H_SEG = 32 * R;          // outputs per warp
 __host__ __device__ __forceinline__ int h_phys(int q) { return q + (q >> 3); }   // 1 pad slot per 8: lane stride 9
 
-__global__ void __launch_bounds__(32 * H_WARPS)
-blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
+__device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                            int pw, int ph, int pitch, const Taps &t, int block) {
     extern __shared__ float4 smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nxb = (pw + H_SEG - 1) / H_SEG;
-    const int row = (blockIdx.x / nxb) * H_WARPS + warp;
-    const int xb = (blockIdx.x % nxb) * H_SEG;
+    const int row = (block / nxb) * H_WARPS + warp;
+    const int xb = (block % nxb) * H_SEG;
     if (row >= ph) return;                              // warp-uniform, no block barrier below
     float4 *tile = smem + (size_t)warp * pitch;
     const int r = t.ksize >> 1;
@@ -83,12 +83,35 @@ blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, i
     }
 }
 
+struct BlurJob {                       // == p360_blur_job
+    const float4 *in;
+    float4 *out;
+    float4 *tmp;
+    int w, h, slot, reserved;
+};
+static_assert(sizeof(BlurJob) == sizeof(p360_blur_job), "ABI struct mismatch");
+
+__constant__ Taps c_taps[P360_MAX_LEVELS];     // tap sets of the batched blurs (p360_blur_set_taps)
+
+__global__ void __launch_bounds__(32 * H_WARPS)
+blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
+    blur_h_body(in, out, pw, ph, pitch, t, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(32 * H_WARPS)
+blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch) {
+    const BlurJob &job = jobs[blockIdx.y];
+    const int blocks = ((job.w + H_SEG - 1) / H_SEG) * ((job.h + H_WARPS - 1) / H_WARPS);
+    if ((int)blockIdx.x >= blocks) return;
+    blur_h_body(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
+}
+
 // ---- vertical --------------------------------------------------------------
 constexpr int V_WARPS = 8;
 constexpr int V_ROWS = V_WARPS * R;    // output rows per block, 32 columns wide
 
-__global__ void __launch_bounds__(32 * V_WARPS)
-blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
+__device__ __forceinline__ void blur_v_body(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                            int pw, int ph, const Taps &t) {
     extern __shared__ float4 smem[];   // [V_ROWS + ksize - 1][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + lane;
@@ -114,6 +137,34 @@ blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, i
     }
 }
 
+__global__ void __launch_bounds__(32 * V_WARPS)
+blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
+    blur_v_body(in, out, pw, ph, t);
+}
+
+__global__ void __launch_bounds__(32 * V_WARPS)
+blur_v_batch_kernel(const BlurJob *__restrict__ jobs) {
+    const BlurJob &job = jobs[blockIdx.z];
+    if ((int)(blockIdx.x * 32) >= job.w || (int)(blockIdx.y * V_ROWS) >= job.h) return;   // block-uniform
+    blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot]);
+}
+
+inline void fill_taps(Taps &t, const float *taps_host, int ksize) {
+    memset(&t, 0, sizeof(t));
+    memcpy(t.k + R - 1, taps_host, sizeof(float) * ksize);
+    t.ksize = ksize;
+}
+
+// dynamic shared memory opt-in above 48 KB, remembered per kernel
+template <class K>
+int ensure_smem(K kernel, size_t bytes, size_t &limit, const char *where) {
+    if (bytes > limit) {
+        P360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), where);
+        limit = bytes;
+    }
+    return 0;
+}
+
 }  // namespace p360
 
 extern "C" int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp_rgba,
@@ -127,28 +178,58 @@ extern "C" int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp
     P360_REQUIRE(in_rgba != out_rgba && in_rgba != tmp_rgba && out_rgba != tmp_rgba, where);
     if (pw == 0 || ph == 0) return 0;
     Taps t;
-    memset(&t, 0, sizeof(t));
-    memcpy(t.k + R - 1, taps_host, sizeof(float) * ksize);
-    t.ksize = ksize;
+    fill_taps(t, taps_host, ksize);
     auto in = reinterpret_cast<const float4 *>(in_rgba);
     auto tmp = reinterpret_cast<float4 *>(tmp_rgba);
     auto out = reinterpret_cast<float4 *>(out_rgba);
     cudaStream_t s = (cudaStream_t)stream;
-
     const int pitch = h_phys(H_SEG + ksize - 1) + 1;
     const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
     const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);
-    static thread_local size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
-    if (smem_h > h_limit) {
-        P360_CUDA(cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h), where);
-        h_limit = smem_h;
-    }
-    if (smem_v > v_limit) {
-        P360_CUDA(cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v), where);
-        v_limit = smem_v;
-    }
+    static size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
+    if (int e = ensure_smem(blur_h_kernel, smem_h, h_limit, where)) return e;
+    if (int e = ensure_smem(blur_v_kernel, smem_v, v_limit, where)) return e;
     blur_h_kernel<<<cdiv(pw, H_SEG) * cdiv(ph, H_WARPS), 32 * H_WARPS, smem_h, s>>>(in, tmp, pw, ph, pitch, t);
     if (int e = check_launch(where)) return e;
     blur_v_kernel<<<dim3(cdiv(pw, 32), cdiv(ph, V_ROWS)), 32 * V_WARPS, smem_v, s>>>(tmp, out, pw, ph, t);
+    return check_launch(where);
+}
+
+static int g_slot_ksize[P360_MAX_LEVELS] = {0};
+
+extern "C" int p360_blur_set_taps(int slot, const float *taps_host, int ksize, void *stream) {
+    using namespace p360;
+    const char *where = "p360_blur_set_taps";
+    P360_REQUIRE(slot >= 0 && slot < P360_MAX_LEVELS && taps_host, where);
+    P360_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= P360_MAX_KSIZE, where);
+    Taps t;
+    fill_taps(t, taps_host, ksize);
+    P360_CUDA(cudaMemcpyToSymbolAsync(c_taps, &t, sizeof(Taps), (size_t)slot * sizeof(Taps),
+                                      cudaMemcpyHostToDevice, (cudaStream_t)stream), where);
+    g_slot_ksize[slot] = ksize;
+    return 0;
+}
+
+extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int max_h,
+                                     void *stream) {
+    using namespace p360;
+    const char *where = "p360_gauss_blur_batch";
+    P360_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= 65535 && max_w >= 0 && max_h >= 0, where);
+    if (n_jobs == 0 || max_w == 0 || max_h == 0) return 0;
+    int ksize = 1;
+    for (int i = 0; i < P360_MAX_LEVELS; ++i) ksize = g_slot_ksize[i] > ksize ? g_slot_ksize[i] : ksize;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int pitch = h_phys(H_SEG + ksize - 1) + 1;
+    const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
+    const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);
+    static size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
+    if (int e = ensure_smem(blur_h_batch_kernel, smem_h, h_limit, where)) return e;
+    if (int e = ensure_smem(blur_v_batch_kernel, smem_v, v_limit, where)) return e;
+    auto bj = reinterpret_cast<const BlurJob *>(jobs);
+    blur_h_batch_kernel<<<dim3(cdiv(max_w, H_SEG) * cdiv(max_h, H_WARPS), n_jobs), 32 * H_WARPS, smem_h, s>>>(bj, pitch);
+    if (int e = check_launch(where)) return e;
+    dim3 grid_v(cdiv(max_w, 32), cdiv(max_h, V_ROWS), n_jobs);
+    P360_REQUIRE(grid_v.y <= 65535, where);
+    blur_v_batch_kernel<<<grid_v, 32 * V_WARPS, smem_v, s>>>(bj);
     return check_launch(where);
 }

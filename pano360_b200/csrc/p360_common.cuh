@@ -61,6 +61,21 @@ __device__ __forceinline__ int to_fixed5(float v) {
 }
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 
+// ---- owner map (stitcher.py:196-204) as one 64-bit key per mosaic pixel ----
+// key = float_bits(alpha) << 32 | (0xFFFFFFFF - patch): atomicMax over the
+// patches gives the largest alpha and, among equal alphas, the smallest patch
+// number — np.argmax's "first maximum wins" — independent of execution order.
+// Only alpha > 0 ever competes, so key == 0 means "no owner" (-1).
+__device__ __forceinline__ unsigned long long owner_key(float alpha, int patch) {
+    return ((unsigned long long)__float_as_uint(alpha) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)patch);
+}
+__device__ __forceinline__ bool key_is_owner(unsigned long long key, int patch) {
+    return key != 0ull && (unsigned)(key & 0xFFFFFFFFull) == 0xFFFFFFFFu - (unsigned)patch;
+}
+__device__ __forceinline__ void owner_compete(unsigned long long *keys, size_t mi, float alpha, int patch) {
+    if (alpha > 0.0f) atomicMax(keys + mi, owner_key(alpha, patch));
+}
+
 // Streaming (read-once / write-once) 128-bit accesses: keep L1 for the gathers.
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
     float4 r;

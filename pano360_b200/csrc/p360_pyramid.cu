@@ -1,5 +1,5 @@
 // Reduced-resolution evaluation of the reference's wide Gaussians and the
-// output-stationary band blend that consumes them.
+// output-stationary blenders that consume them.
 //
 // The reference blurs every full-resolution RGBA patch with sigma = 4, 6.9,
 // 8.9, 10.6(, 12) (stitcher.py:218, :226).  Those filters are so smooth that
@@ -11,11 +11,13 @@
 // reducing the *reflected extension* of the patch: the coarse grids cover
 // [-R, n + R) in full-resolution pixels.
 //
-//   p360_pyramid_reduce      full-res RGBA (+ owner map) -> D2, D4    ("reduce")
-//   p360_gauss_blur          coarse blur (p360_blur.cu)
-//   p360_multiband_collapse  expand + band + weighted accumulate over the
-//                            patches covering each mosaic pixel + normalise +
-//                            clamp + uint8, nothing accumulated in HBM
+//   p360_pyramid_reduce_batch  full-res RGBA (+ owner keys) -> D2, D4  ("reduce")
+//   p360_gauss_blur_batch      coarse blurs (p360_blur.cu)
+//   p360_multiband_collapse    expand + band + weighted accumulate over the
+//                              patches covering each mosaic pixel + normalise +
+//                              clamp + uint8; nothing accumulated in HBM
+//   p360_linear_collapse / p360_paste_collapse   same gather form for the
+//                              linear blender and for pasting
 #include "p360_common.cuh"
 
 namespace p360 {
@@ -31,20 +33,35 @@ __device__ __forceinline__ float4 scale4(const float4 &v, float s) {
     return make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
 }
 
+// ---- the per-patch record shared by reduce and the collapse kernels --------
+struct BandPatch {                      // == p360_band_patch
+    const float4 *rgba;                 // full-res patch; alpha is replaced by (owner == index) for multiband
+    const uint8_t *invalid;             // ph x pw mask (linear / paste only)
+    float4 *d2, *d4;                    // reduce outputs (f = 2, f = 4)
+    const float4 *low[P360_MAX_LEVELS - 1];   // blurred coarse image of level l (level 0: f = 2, others f = 4)
+    int x0, y0, pw, ph;                 // box in (window) mosaic pixels
+    int w4, h4;                         // size of the f = 4 grid (f = 2 grid is twice that)
+    int pad;                            // extension R in full-res pixels (multiple of 4)
+    int index;                          // id of this patch in the owner keys
+};
+static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
+
 // ---- reduce ----------------------------------------------------------------
 // Block = 8 warps; warp w of block (bx, by) produces coarse row 8*by + w of D4
 // (two rows of D2) for 32 full-resolution columns: lanes run along x, so each
 // of the four row loads is one coalesced 512-byte request; 2x2 and 4x4 sums
-// are finished with xor-shuffles.
+// are finished with xor-shuffles.  grid.z = patch.
 __global__ void __launch_bounds__(256)
-pyramid_reduce_kernel(const float4 *__restrict__ rgba, int pw, int ph, int x0, int y0, int idx,
-                      const int32_t *__restrict__ owner, int W, int pad,
-                      float4 *__restrict__ d2, float4 *__restrict__ d4, int w4, int h4) {
+pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
+                      const unsigned long long *__restrict__ keys, int W) {
+    const BandPatch &bp = patches[blockIdx.z];
+    const int w4 = bp.w4, h4 = bp.h4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cy = blockIdx.y * 8 + warp;              // D4 row
     const int xe = blockIdx.x * 32 + lane;             // column in the extended frame
-    if (cy >= h4) return;                              // warp-uniform
-    const int w2 = 2 * w4;
+    if (cy >= h4 || (int)(blockIdx.x * 32) >= 4 * w4) return;   // warp-uniform
+    const int pw = bp.pw, ph = bp.ph, pad = bp.pad, w2 = 2 * w4;
+    const float4 *rgba = bp.rgba;
     const bool live = xe < 4 * w4;
     const int sx = reflect_101(xe - pad, pw);
     float4 s[2];
@@ -53,67 +70,26 @@ pyramid_reduce_kernel(const float4 *__restrict__ rgba, int pw, int ph, int x0, i
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            int sy = reflect_101(4 * cy + 2 * half + k - pad, ph);
+            const int sy = reflect_101(4 * cy + 2 * half + k - pad, ph);
             float4 v = live ? ld_stream(rgba + (size_t)sy * pw + sx) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (owner != nullptr && live)
-                v.w = (__ldg(owner + (size_t)(sy + y0) * W + (sx + x0)) == idx) ? 1.0f : 0.0f;
+            if (keys != nullptr && live)     // stitcher.py:207-208
+                v.w = key_is_owner(__ldg(keys + (size_t)(sy + bp.y0) * W + (sx + bp.x0)), bp.index) ? 1.0f : 0.0f;
             acc = add4(acc, v);
         }
         s[half] = add4(acc, shfl_xor4(acc, 1));        // 2x2 sums (both lanes of a pair hold it)
     }
     if (live && !(lane & 1)) {
-        size_t c2 = (size_t)(2 * cy) * w2 + (xe >> 1);
-        d2[c2] = scale4(s[0], 0.25f);
-        d2[c2 + w2] = scale4(s[1], 0.25f);
+        const size_t c2 = (size_t)(2 * cy) * w2 + (xe >> 1);
+        bp.d2[c2] = scale4(s[0], 0.25f);
+        bp.d2[c2 + w2] = scale4(s[1], 0.25f);
     }
     float4 q = add4(s[0], s[1]);                       // 2 columns x 4 rows
     q = add4(q, shfl_xor4(q, 2));                      // 4 x 4
-    if (live && !(lane & 3)) d4[(size_t)cy * w4 + (xe >> 2)] = scale4(q, 0.0625f);
+    if (live && !(lane & 3)) bp.d4[(size_t)cy * w4 + (xe >> 2)] = scale4(q, 0.0625f);
 }
 
-// ---- collapse (gather form) ------------------------------------------------
-struct BandPatch {
-    const float4 *rgba;                 // full-res patch, alpha ignored (owner map decides)
-    const float4 *low[P360_MAX_LEVELS - 1];   // blurred coarse image of level l
-    int lw[P360_MAX_LEVELS - 1];        // coarse width of level l
-    int shift[P360_MAX_LEVELS - 1];     // log2 of the reduction factor of level l
-    int x0, y0, pw, ph;                 // box in (window) mosaic pixels
-    int pad;                            // extension R in full-res pixels
-    int index;                          // value stored in the owner map for this patch
-};
-static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
-
-// Position of full-res patch pixel (px, py) on a coarse grid of factor 2^shift
-// anchored `pad` pixels before the patch: u = (p + pad + 0.5) / f - 0.5.
-struct CoarseTap {
-    int ix, iy;
-    float fx, fy;
-};
-__device__ __forceinline__ CoarseTap coarse_tap(int shift, int pad, int px, int py) {
-    const int f = 1 << shift;
-    const int nx = 2 * (px + pad) + 1 - f, ny = 2 * (py + pad) + 1 - f;   // u = n / (2f)
-    const float inv = 0.5f / (float)f;
-    CoarseTap t;
-    t.ix = nx >> (shift + 1);
-    t.iy = ny >> (shift + 1);
-    t.fx = (float)(nx & (2 * f - 1)) * inv;
-    t.fy = (float)(ny & (2 * f - 1)) * inv;
-    return t;
-}
-// bilinear sample of a coarse level ("expand")
-__device__ __forceinline__ float4 expand_at(const float4 *__restrict__ low, int lw, const CoarseTap &t) {
-    const float4 *p = low + (size_t)t.iy * lw + t.ix;
-    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lw), d = __ldg(p + lw + 1);
-    const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
-    float4 o;
-    o.x = (a.x * gx + b.x * t.fx) * gy + (c.x * gx + d.x * t.fx) * t.fy;
-    o.y = (a.y * gx + b.y * t.fx) * gy + (c.y * gx + d.y * t.fx) * t.fy;
-    o.z = (a.z * gx + b.z * t.fx) * gy + (c.z * gx + d.z * t.fx) * t.fy;
-    o.w = (a.w * gx + b.w * t.fx) * gy + (c.w * gx + d.w * t.fx) * t.fy;
-    return o;
-}
-
-constexpr int CT_X = 64, CT_Y = 8;      // mosaic tile per block; block = 64 x 4 threads, 2 rows each
+// ---- tile lists -------------------------------------------------------------
+constexpr int CT_X = 64, CT_Y = 32;     // mosaic tile per block; block = 64 x 4 threads, 8 rows each
 constexpr int MAX_TILE_PATCHES = 1024;  // patches that may overlap one tile
 
 // Ordered list (patch order = accumulation order, stitcher.py:223) of the
@@ -151,6 +127,16 @@ __device__ int build_tile_list(const BandPatch *__restrict__ patches, int n_patc
     return total;
 }
 
+// Position of full-res patch coordinate p on a coarse grid of factor 2^SHIFT
+// anchored `pad` pixels before the patch: u = (p + pad + 0.5) / f - 0.5.
+template <int SHIFT>
+__device__ __forceinline__ void coarse_coord(int pad, int p, int &i, float &frac) {
+    constexpr int F = 1 << SHIFT;
+    const int n = 2 * (p + pad) + 1 - F;               // u = n / (2f)
+    i = n >> (SHIFT + 1);
+    frac = (float)(n & (2 * F - 1)) * (0.5f / F);
+}
+
 // Drop from the tile list every patch whose blurred mask is identically zero
 // over the tile: its weights vanish at every level (the supports of the
 // truncated Gaussians nest and all taps are positive), so it contributes
@@ -159,20 +145,24 @@ template <int L>
 __device__ int cull_tile_list(const BandPatch *__restrict__ patches, int n_hit, int tx0, int ty0,
                               int16_t *list) {
     if (L < 2) return n_hit;
+    constexpr int SHIFT = (L == 2) ? 1 : 2;
     const int tid = threadIdx.y * CT_X + threadIdx.x;
     int kept = 0;
     for (int it = 0; it < n_hit; ++it) {
         const int id = list[it];
         const BandPatch &bp = patches[id];
-        const int shift = bp.shift[L - 2], lw = bp.lw[L - 2];
+        const int lw = bp.w4 * (SHIFT == 1 ? 2 : 1);
         const int px0 = max(tx0, bp.x0) - bp.x0, px1 = min(tx0 + CT_X, bp.x0 + bp.pw) - 1 - bp.x0;
         const int py0 = max(ty0, bp.y0) - bp.y0, py1 = min(ty0 + CT_Y, bp.y0 + bp.ph) - 1 - bp.y0;
-        const CoarseTap lo = coarse_tap(shift, bp.pad, px0, py0), hi = coarse_tap(shift, bp.pad, px1, py1);
-        const int nx = hi.ix + 2 - lo.ix, ny = hi.iy + 2 - lo.iy;
+        int ix0, ix1, iy0, iy1;
+        float unused;
+        coarse_coord<SHIFT>(bp.pad, px0, ix0, unused); coarse_coord<SHIFT>(bp.pad, px1, ix1, unused);
+        coarse_coord<SHIFT>(bp.pad, py0, iy0, unused); coarse_coord<SHIFT>(bp.pad, py1, iy1, unused);
+        const int nx = ix1 + 2 - ix0, ny = iy1 + 2 - iy0;
         const float *alpha = reinterpret_cast<const float *>(bp.low[L - 2]) + 3;
         bool any = false;
         for (int i = tid; i < nx * ny; i += 256) {
-            const int cx = lo.ix + i % nx, cy = lo.iy + i / nx;
+            const int cx = ix0 + i % nx, cy = iy0 + i / nx;
             any |= __ldg(alpha + 4 * ((size_t)cy * lw + cx)) != 0.0f;
         }
         const bool keep = __syncthreads_or(any);
@@ -185,57 +175,90 @@ __device__ int cull_tile_list(const BandPatch *__restrict__ patches, int n_hit, 
     return kept;
 }
 
+// ---- multiband collapse (gather form) ---------------------------------------
+struct Pair2 { float2 lo, hi; };       // RGBA as two packed halves for fma.rn.f32x2
+
+__device__ __forceinline__ Pair2 to_pair(const float4 &v) {
+    Pair2 p; p.lo = make_float2(v.x, v.y); p.hi = make_float2(v.z, v.w); return p;
+}
+// bilinear sample ("expand") of a coarse image: a*w00 + b*w01 + c*w10 + d*w11
+__device__ __forceinline__ Pair2 expand_at(const float4 *__restrict__ p, int lw, float w00, float w01,
+                                           float w10, float w11) {
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lw), d = __ldg(p + lw + 1);
+    const float2 k00 = make_float2(w00, w00), k01 = make_float2(w01, w01);
+    const float2 k10 = make_float2(w10, w10), k11 = make_float2(w11, w11);
+    Pair2 o;
+    o.lo = __fmul2_rn(make_float2(a.x, a.y), k00);
+    o.hi = __fmul2_rn(make_float2(a.z, a.w), k00);
+    o.lo = __ffma2_rn(make_float2(b.x, b.y), k01, o.lo);
+    o.hi = __ffma2_rn(make_float2(b.z, b.w), k01, o.hi);
+    o.lo = __ffma2_rn(make_float2(c.x, c.y), k10, o.lo);
+    o.hi = __ffma2_rn(make_float2(c.z, c.w), k10, o.hi);
+    o.lo = __ffma2_rn(make_float2(d.x, d.y), k11, o.lo);
+    o.hi = __ffma2_rn(make_float2(d.z, d.w), k11, o.hi);
+    return o;
+}
+
+constexpr int ROWS_PER_THREAD = CT_Y / 4;
+
 template <int L>
 __global__ void __launch_bounds__(256)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
-                          const int32_t *__restrict__ owner, const uint8_t *__restrict__ covered,
-                          uint8_t *__restrict__ out, int H, int W) {
+                          const unsigned long long *__restrict__ keys,
+                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = blockIdx.y * CT_Y;
     int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
     n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
     const int X = tx0 + threadIdx.x;
-#pragma unroll
-    for (int sub = 0; sub < CT_Y / 4; ++sub) {
+    if (X >= W) return;
+    for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
         const int Y = ty0 + threadIdx.y + 4 * sub;
-        if (X >= W || Y >= H) continue;
+        if (Y >= H) break;
         const size_t mi = (size_t)Y * W + X;
-        float num[L][3], den[L];
+        // per level: lo = (sum band.x*w, sum band.y*w), hi = (sum band.z*w, sum w)
+        float2 lo[L], hi[L];
 #pragma unroll
-        for (int l = 0; l < L; ++l) num[l][0] = num[l][1] = num[l][2] = den[l] = 0.f;
-        const bool cov = covered[mi] != 0;
-        if (cov) {
-            const int own = __ldg(owner + mi);
+        for (int l = 0; l < L; ++l) lo[l] = hi[l] = make_float2(0.f, 0.f);
+        if (covered[mi] != 0) {
+            const unsigned long long key = __ldg(keys + mi);
             for (int it = 0; it < n_hit; ++it) {              // patch order = list order
                 const BandPatch &bp = patches[list[it]];
                 const int px = X - bp.x0, py = Y - bp.y0;
-                if (px < 0 || py < 0 || px >= bp.pw || py >= bp.ph) continue;
-                float4 prev = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
-                prev.w = (own == bp.index) ? 1.0f : 0.0f;     // stitcher.py:207-208
-                const int pad = bp.pad;
-                const CoarseTap t2 = coarse_tap(1, pad, px, py), t4 = coarse_tap(2, pad, px, py);
+                if ((unsigned)px >= (unsigned)bp.pw || (unsigned)py >= (unsigned)bp.ph) continue;
+                const float4 pix = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
+                Pair2 prev = to_pair(pix);
+                prev.hi.y = key_is_owner(key, bp.index) ? 1.0f : 0.0f;     // stitcher.py:207-208
+                const int pad = bp.pad, w4 = bp.w4;
 #pragma unroll
                 for (int l = 0; l < L - 1; ++l) {             // stitcher.py:224-232
-                    const float4 cur = expand_at(bp.low[l], bp.lw[l], bp.shift[l] == 1 ? t2 : t4);
-                    num[l][0] += (prev.x - cur.x) * cur.w;
-                    num[l][1] += (prev.y - cur.y) * cur.w;
-                    num[l][2] += (prev.z - cur.z) * cur.w;
-                    den[l] += cur.w;
+                    int ix, iy;
+                    float fx, fy;
+                    if (l == 0) { coarse_coord<1>(pad, px, ix, fx); coarse_coord<1>(pad, py, iy, fy); }
+                    else        { coarse_coord<2>(pad, px, ix, fx); coarse_coord<2>(pad, py, iy, fy); }
+                    const int lw = (l == 0) ? 2 * w4 : w4;
+                    const float gx = 1.0f - fx, gy = 1.0f - fy;
+                    const Pair2 cur = expand_at(bp.low[l] + (size_t)iy * lw + ix, lw,
+                                                gy * gx, gy * fx, fy * gx, fy * fx);
+                    const float2 ww = make_float2(cur.hi.y, cur.hi.y);      // weight = blurred mask
+                    const float2 dlo = __fadd2_rn(prev.lo, make_float2(-cur.lo.x, -cur.lo.y));
+                    const float2 dhi = make_float2(prev.hi.x - cur.hi.x, 1.0f);
+                    lo[l] = __ffma2_rn(dlo, ww, lo[l]);
+                    hi[l] = __ffma2_rn(dhi, ww, hi[l]);
                     prev = cur;
                 }
-                num[L - 1][0] += prev.x * prev.w;
-                num[L - 1][1] += prev.y * prev.w;
-                num[L - 1][2] += prev.z * prev.w;
-                den[L - 1] += prev.w;
+                const float2 ww = make_float2(prev.hi.y, prev.hi.y);
+                lo[L - 1] = __ffma2_rn(prev.lo, ww, lo[L - 1]);
+                hi[L - 1] = __ffma2_rn(make_float2(prev.hi.x, 1.0f), ww, hi[L - 1]);
             }
         }
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;                   // stitcher.py:236-238
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            float w = den[l] == 0.0f ? 1.0f : den[l];
-            m0 = __fadd_rn(m0, __fdiv_rn(num[l][0], w));
-            m1 = __fadd_rn(m1, __fdiv_rn(num[l][1], w));
-            m2 = __fadd_rn(m2, __fdiv_rn(num[l][2], w));
+            const float w = hi[l].y == 0.0f ? 1.0f : hi[l].y;
+            m0 = __fadd_rn(m0, __fdiv_rn(lo[l].x, w));
+            m1 = __fadd_rn(m1, __fdiv_rn(lo[l].y, w));
+            m2 = __fadd_rn(m2, __fdiv_rn(hi[l].x, w));
         }
         uint8_t *o = out + mi * 3;                            // stitcher.py:240-241
         o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(m0, 0.f), 1.f)));
@@ -244,11 +267,58 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
     }
 }
 
+// ---- linear blend / paste (gather form) ------------------------------------
+// MODE 0: linear_blend (stitcher.py:171-183): sum alpha*rgb / sum alpha in patch order.
+// MODE 1: no_blend (stitcher.py:160-168): the last valid writer wins.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
+                          uint8_t *__restrict__ out, int H, int W) {
+    __shared__ int16_t list[MAX_TILE_PATCHES];
+    const int tx0 = blockIdx.x * CT_X, ty0 = blockIdx.y * CT_Y;
+    const int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
+    const int X = tx0 + threadIdx.x;
+    if (X >= W) return;
+    for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
+        const int Y = ty0 + threadIdx.y + 4 * sub;
+        if (Y >= H) break;
+        const size_t mi = (size_t)Y * W + X;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, wsum = 0.f;
+        for (int it = 0; it < n_hit; ++it) {
+            const BandPatch &bp = patches[list[it]];
+            const int px = X - bp.x0, py = Y - bp.y0;
+            if ((unsigned)px >= (unsigned)bp.pw || (unsigned)py >= (unsigned)bp.ph) continue;
+            const size_t pi = (size_t)py * bp.pw + px;
+            const bool bad = __ldg(bp.invalid + pi) != 0;
+            if (MODE == 1) {
+                if (bad) continue;
+                const float4 p = ld_stream(bp.rgba + pi);
+                a0 = p.x; a1 = p.y; a2 = p.z;
+            } else {
+                const float4 p = ld_stream(bp.rgba + pi);
+                a0 = __fadd_rn(a0, __fmul_rn(bad ? 0.f : p.x, p.w));
+                a1 = __fadd_rn(a1, __fmul_rn(bad ? 0.f : p.y, p.w));
+                a2 = __fadd_rn(a2, __fmul_rn(bad ? 0.f : p.z, p.w));
+                wsum = __fadd_rn(wsum, p.w);
+            }
+        }
+        if (MODE == 0) {
+            const float w = wsum == 0.0f ? 1.0f : wsum;
+            a0 = __fdiv_rn(a0, w); a1 = __fdiv_rn(a1, w); a2 = __fdiv_rn(a2, w);
+        }
+        // (255 * v).astype(uint8): truncation, no clip in either reference blender
+        uint8_t *o = out + mi * 3;
+        o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a0));
+        o[1] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a1));
+        o[2] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a2));
+    }
+}
+
 template <int L>
-int launch_collapse(const BandPatch *patches, int n_patches, const int32_t *owner,
+int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
                     const uint8_t *covered, uint8_t *out, int H, int W, cudaStream_t s) {
     dim3 grid(cdiv(W, CT_X), cdiv(H, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, owner, covered, out, H, W);
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, H, W);
     return check_launch("p360_multiband_collapse");
 }
 
@@ -264,38 +334,60 @@ extern "C" int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]) {
     return 0;
 }
 
-extern "C" int p360_pyramid_reduce(const float *rgba, int pw, int ph, int x0, int y0, int idx,
-                                   const int32_t *owner, int W, int pad, float *d2, float *d4,
-                                   void *stream) {
-    const char *where = "p360_pyramid_reduce";
-    P360_REQUIRE(rgba && d2 && d4 && aligned16(rgba) && aligned16(d2) && aligned16(d4), where);
-    P360_REQUIRE(pw > 0 && ph > 0 && pad >= 0 && pad % 4 == 0, where);
-    P360_REQUIRE(owner == nullptr || (W > 0 && x0 >= 0 && y0 >= 0 && x0 + pw <= W), where);
-    int w4 = (pw + 2 * pad + 3) / 4, h4 = (ph + 2 * pad + 3) / 4;
-    dim3 grid(cdiv(4 * w4, 32), cdiv(h4, 8));
+extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int max_w4,
+                                         int max_h4, const uint64_t *owner_keys, int W, void *stream) {
+    const char *where = "p360_pyramid_reduce_batch";
+    P360_REQUIRE(patches && n_patches >= 0 && n_patches <= 65535 && max_w4 >= 0 && max_h4 >= 0, where);
+    P360_REQUIRE(owner_keys == nullptr || W > 0, where);
+    if (n_patches == 0 || max_w4 == 0 || max_h4 == 0) return 0;
+    dim3 grid(cdiv(4 * max_w4, 32), cdiv(max_h4, 8), n_patches);
+    P360_REQUIRE(grid.y <= 65535, where);
     pyramid_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4 *>(rgba), pw, ph, x0, y0, idx, owner, W, pad,
-        reinterpret_cast<float4 *>(d2), reinterpret_cast<float4 *>(d4), w4, h4);
+        reinterpret_cast<const BandPatch *>(patches),
+        reinterpret_cast<const unsigned long long *>(owner_keys), W);
     return check_launch(where);
 }
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
-                                       const int32_t *owner, const uint8_t *covered,
+                                       const uint64_t *owner_keys, const uint8_t *covered,
                                        uint8_t *out_u8, int H, int W, void *stream) {
     const char *where = "p360_multiband_collapse";
-    P360_REQUIRE(patches && owner && covered && out_u8, where);
+    P360_REQUIRE(patches && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
     P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && H > 0 && W > 0, where);
     auto bp = reinterpret_cast<const BandPatch *>(patches);
+    auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 2: return launch_collapse<2>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 3: return launch_collapse<3>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 4: return launch_collapse<4>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 5: return launch_collapse<5>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 6: return launch_collapse<6>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        case 7: return launch_collapse<7>(bp, n_patches, owner, covered, out_u8, H, W, s);
-        default: return launch_collapse<8>(bp, n_patches, owner, covered, out_u8, H, W, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, H, W, s);
     }
+}
+
+static int pointwise_collapse(const char *where, int mode, const p360_band_patch *patches, int n_patches,
+                              uint8_t *out_u8, int H, int W, void *stream) {
+    P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && H > 0 && W > 0, where);
+    dim3 grid(cdiv(W, CT_X), cdiv(H, CT_Y)), block(CT_X, 4);
+    auto bp = reinterpret_cast<const BandPatch *>(patches);
+    if (mode == 0)
+        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, H, W);
+    else
+        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, H, W);
+    return check_launch(where);
+}
+
+extern "C" int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+                                    int H, int W, void *stream) {
+    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, H, W, stream);
+}
+
+extern "C" int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+                                   int H, int W, void *stream) {
+    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, H, W, stream);
 }

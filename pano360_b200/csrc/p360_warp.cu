@@ -1,28 +1,28 @@
-// K1: fused inverse projection + 1/32-px bilinear remap + validity mask.
-// Replaces stitcher.py:257-263 and :300-317 (NumPy coordinate maths, BLAS
-// 3x3 projection, cv2.remap, alpha masking) with one pass that reads the u8
-// source through L1 and writes each RGBA float4 exactly once, coalesced.
+// K1: fused inverse projection + 1/32-px bilinear remap + validity mask
+// (+ owner-map competition).  Replaces stitcher.py:257-263 and :300-317 (NumPy
+// coordinate maths, BLAS 3x3 projection, cv2.remap, alpha masking) and the
+// weights tensor / argmax of :196-204 with one pass that reads the u8 source
+// through L1 and writes each RGBA float4 exactly once, coalesced.
+// One launch serves every patch of a composite (grid.z = job).
 #include "p360_common.cuh"
 
 namespace p360 {
 
-struct SrcView {
-    const uint8_t *pix;
-    const float *lut;        // 256 entries
-    const double *hat_y;     // h entries
-    const double *hat_x;     // w entries
+struct WarpJob {                 // == p360_warp_job
+    const uint8_t *src;          // u8 [h][w][c]
+    const float *lut;            // 256 entries
+    const double *hat_y;         // h entries
+    const double *hat_x;         // w entries
+    const double *col_tab;       // pw x 3
+    const double *row_tab;       // ph x 3
+    float4 *out;                 // ph x pw RGBA
+    uint8_t *invalid;            // ph x pw
     int h, w, c;
-    float inv_2h, inv_2w;    // 1 / (2h), 1 / (2w): reflection period reciprocals
+    int pw, ph;
+    int x0, y0;                  // position in the (window) mosaic
+    int patch;                   // id in the owner map
 };
-
-// Optional fused K2 state (stitcher.py:196-204, :233-234): running arg-max of
-// alpha and the union of valid pixels, updated in patch order.
-struct OwnerState {
-    float *best;
-    int32_t *owner;
-    uint8_t *covered;
-    int x0, y0, W, idx;
-};
+static_assert(sizeof(WarpJob) == sizeof(p360_warp_job), "ABI struct mismatch");
 
 // BORDER_REFLECT for p in the int16 range without an integer division:
 // q = p mod 2n through a float reciprocal (|p| <= 2^15, so the quotient is off
@@ -35,9 +35,9 @@ __device__ __forceinline__ int reflect_fast(int p, int n, float inv_2n) {
     return q < n ? q : m - 1 - q;
 }
 
-__device__ __forceinline__ float4 sample(const SrcView &s, const float *lut, int y, int x, double hy,
+__device__ __forceinline__ float4 sample(const WarpJob &s, const float *lut, int y, int x, double hy,
                                          double hx) {
-    const uint8_t *p = s.pix + ((size_t)y * s.w + x) * s.c;
+    const uint8_t *p = s.src + ((size_t)y * s.w + x) * s.c;
     float4 v;
     if (s.c == 4) {
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(p));
@@ -62,33 +62,26 @@ __device__ __forceinline__ float blend4(float a, float b, float c, float d,
 
 constexpr int WARP_BX = 64, WARP_BY = 4;
 
-__global__ void __launch_bounds__(WARP_BX *WARP_BY)
-warp_patch_kernel(SrcView s, const double *__restrict__ col_tab, const double *__restrict__ row_tab,
-                  int pw, int ph, float half_w, float half_h, float max_x, float max_y,
-                  float4 *__restrict__ out, uint8_t *__restrict__ invalid, OwnerState own) {
-    __shared__ float lut[256];
-    lut[threadIdx.y * WARP_BX + threadIdx.x] = s.lut[threadIdx.y * WARP_BX + threadIdx.x];
-    __syncthreads();
-    int c = blockIdx.x * WARP_BX + threadIdx.x;
-    int r = blockIdx.y * WARP_BY + threadIdx.y;
-    if (c >= pw || r >= ph) return;
+__device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, int c, int r,
+                                           unsigned long long *keys, uint8_t *covered, int W) {
     // p = K R (rx, ry, rz): column part + row part, float64, then cast
     // (stitcher.py:303-306)
-    const double *ct = col_tab + (size_t)c * 3, *rt = row_tab + (size_t)r * 3;
-    float px = (float)(__ldg(ct) + __ldg(rt));
-    float py = (float)(__ldg(ct + 1) + __ldg(rt + 1));
-    float pz = (float)(__ldg(ct + 2) + __ldg(rt + 2));
-    bool bad = pz < 0.0f;                                  // stitcher.py:308
-    float x = __fadd_rn(__fdiv_rn(px, pz), half_w);        // stitcher.py:310
-    float y = __fadd_rn(__fdiv_rn(py, pz), half_h);
-    bad |= (x < 0.0f) | (x > max_x) | (y < 0.0f) | (y > max_y);   // :311-312
+    const double *ct = s.col_tab + (size_t)c * 3, *rt = s.row_tab + (size_t)r * 3;
+    const float px = (float)(__ldg(ct) + __ldg(rt));
+    const float py = (float)(__ldg(ct + 1) + __ldg(rt + 1));
+    const float pz = (float)(__ldg(ct + 2) + __ldg(rt + 2));
+    bool bad = pz < 0.0f;                                        // stitcher.py:308
+    const float x = __fadd_rn(__fdiv_rn(px, pz), (float)(s.w / 2.0));   // stitcher.py:310
+    const float y = __fadd_rn(__fdiv_rn(py, pz), (float)(s.h / 2.0));
+    bad |= (x < 0.0f) | (x > (float)(s.w - 1)) | (y < 0.0f) | (y > (float)(s.h - 1));   // :311-312
     const int sx = to_fixed5(x), sy = to_fixed5(y);
     const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);
     int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
     if ((unsigned)ix >= (unsigned)(s.w - 1) || (unsigned)iy >= (unsigned)(s.h - 1)) {
         // a tap falls outside the image: BORDER_REFLECT (cv2.remap at stitcher.py:315-316)
-        x0 = reflect_fast(ix, s.w, s.inv_2w); x1 = reflect_fast(ix + 1, s.w, s.inv_2w);
-        y0 = reflect_fast(iy, s.h, s.inv_2h); y1 = reflect_fast(iy + 1, s.h, s.inv_2h);
+        const float inv_2w = 1.0f / (2.0f * s.w), inv_2h = 1.0f / (2.0f * s.h);
+        x0 = reflect_fast(ix, s.w, inv_2w); x1 = reflect_fast(ix + 1, s.w, inv_2w);
+        y0 = reflect_fast(iy, s.h, inv_2h); y1 = reflect_fast(iy + 1, s.h, inv_2h);
     }
     const float ax = (float)(sx & 31) * 0.03125f, ay = (float)(sy & 31) * 0.03125f;
     const float w00 = __fmul_rn(1.0f - ay, 1.0f - ax), w01 = __fmul_rn(1.0f - ay, ax);
@@ -102,18 +95,32 @@ warp_patch_kernel(SrcView s, const double *__restrict__ col_tab, const double *_
     o.y = blend4(a.y, b.y, cc.y, d.y, w00, w01, w10, w11);
     o.z = blend4(a.z, b.z, cc.z, d.z, w00, w01, w10, w11);
     o.w = blend4(a.w, b.w, cc.w, d.w, w00, w01, w10, w11);
-    if (bad) o.w = 0.0f;                                   // stitcher.py:317
-    size_t idx = (size_t)r * pw + c;
-    st_stream(out + idx, o);
-    invalid[idx] = bad ? 1 : 0;
-    if (own.best != nullptr) {
-        const size_t mi = (size_t)(r + own.y0) * own.W + (c + own.x0);
-        if (o.w > own.best[mi]) {          // strict: the first maximum wins (np.argmax)
-            own.best[mi] = o.w;
-            own.owner[mi] = own.idx;
-        }
-        if (!bad) own.covered[mi] = 1;
+    if (bad) o.w = 0.0f;                                         // stitcher.py:317
+    const size_t idx = (size_t)r * s.pw + c;
+    st_stream(s.out + idx, o);
+    s.invalid[idx] = bad ? 1 : 0;
+    if (keys != nullptr) {
+        const size_t mi = (size_t)(r + s.y0) * W + (c + s.x0);
+        owner_compete(keys, mi, o.w, s.patch);                   // stitcher.py:196-204
+        if (!bad) covered[mi] = 1;                               // stitcher.py:233-234
     }
+}
+
+__global__ void __launch_bounds__(WARP_BX *WARP_BY)
+warp_batch_kernel(const WarpJob *__restrict__ jobs, unsigned long long *__restrict__ keys,
+                  uint8_t *__restrict__ covered, int W) {
+    __shared__ WarpJob job;
+    __shared__ float lut[256];
+    const int tid = threadIdx.y * WARP_BX + threadIdx.x;
+    if (tid < (int)(sizeof(WarpJob) / 4))
+        reinterpret_cast<uint32_t *>(&job)[tid] = reinterpret_cast<const uint32_t *>(jobs + blockIdx.z)[tid];
+    __syncthreads();
+    if ((int)(blockIdx.x * WARP_BX) >= job.pw || (int)(blockIdx.y * WARP_BY) >= job.ph) return;   // block-uniform
+    lut[tid] = __ldg(job.lut + tid);
+    __syncthreads();
+    const int c = blockIdx.x * WARP_BX + threadIdx.x, r = blockIdx.y * WARP_BY + threadIdx.y;
+    if (c >= job.pw || r >= job.ph) return;
+    warp_pixel(job, lut, c, r, keys, covered, W);
 }
 
 // u8 x 3 -> u8 x 4 (one aligned 32-bit word per source pixel for the gathers)
@@ -138,26 +145,16 @@ extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t
     return check_launch(where);
 }
 
-extern "C" int p360_warp_patch(const uint8_t *src, int src_h, int src_w, int src_c,
-                               const float *lut, const double *hat_y, const double *hat_x,
-                               const double *col_tab, const double *row_tab,
-                               int pw, int ph, float *out_rgba, uint8_t *out_invalid,
-                               int x0, int y0, int idx, float *best, int32_t *owner,
-                               uint8_t *covered, int W, void *stream) {
+extern "C" int p360_warp_batch(const p360_warp_job *jobs, int n_jobs, int max_pw, int max_ph,
+                               uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
     using namespace p360;
-    const char *where = "p360_warp_patch";
-    P360_REQUIRE(src && lut && hat_y && hat_x && col_tab && row_tab && out_rgba && out_invalid, where);
-    P360_REQUIRE(src_h > 0 && src_w > 0 && src_h <= 32767 && src_w <= 32767, where);
-    P360_REQUIRE(src_c == 3 || (src_c == 4 && (reinterpret_cast<uintptr_t>(src) & 3) == 0), where);
-    P360_REQUIRE(pw >= 0 && ph >= 0, where);
-    P360_REQUIRE(aligned16(out_rgba), where);
-    P360_REQUIRE(best == nullptr || (owner && covered && W > 0 && x0 >= 0 && y0 >= 0 && x0 + pw <= W), where);
-    if (pw == 0 || ph == 0) return 0;
-    SrcView s{src, lut, hat_y, hat_x, src_h, src_w, src_c, 1.0f / (2.0f * src_h), 1.0f / (2.0f * src_w)};
-    OwnerState own{best, owner, covered, x0, y0, W, idx};
-    dim3 block(WARP_BX, WARP_BY), grid(cdiv(pw, WARP_BX), cdiv(ph, WARP_BY));
-    warp_patch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-        s, col_tab, row_tab, pw, ph, (float)(src_w / 2.0), (float)(src_h / 2.0),
-        (float)(src_w - 1), (float)(src_h - 1), reinterpret_cast<float4 *>(out_rgba), out_invalid, own);
+    const char *where = "p360_warp_batch";
+    P360_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= 65535 && max_pw >= 0 && max_ph >= 0, where);
+    P360_REQUIRE(owner_keys == nullptr || (covered != nullptr && W > 0), where);
+    if (n_jobs == 0 || max_pw == 0 || max_ph == 0) return 0;
+    dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY), n_jobs);
+    P360_REQUIRE(grid.y <= 65535, where);
+    warp_batch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const WarpJob *>(jobs), reinterpret_cast<unsigned long long *>(owner_keys), covered, W);
     return check_launch(where);
 }

@@ -144,7 +144,7 @@ def all_pair_statistics(comp, regions, src, group=None):
 
 
 def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolution=1400,
-                  proj=geo.SphProj, group=None, pinned=None, to_host=True, out=None):
+                  proj=geo.SphProj, group=None, to_host=True, out=None):
     """Collective: every rank calls this with the same ``regions``; rank 0
     gets the full mosaic (NumPy uint8 if ``to_host`` else a device tensor),
     other ranks get None.  Each rank uploads only the images its strip needs.
@@ -159,7 +159,7 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     need = set(images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
     if equalize:
         need = set(range(len(regions)))          # pair statistics touch every image
-    src = upload_subset(comp, regions, need, pinned)
+    src = comp.upload(regions, need=need)
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
         comp.set_gains(src, find_gains(overlaps, sizes))
@@ -174,28 +174,3 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
         return mosaic
     from .stitcher import _download
     return _download(mosaic, out)
-
-
-def upload_subset(comp, regions, need, pinned=None):
-    """Like ``Compositor.upload`` but only images in ``need`` are copied; the
-    others get a placeholder so indices keep matching ``regions``."""
-    from .compositor import DeviceSources
-    src = DeviceSources([], [])
-    for i, reg in enumerate(regions):
-        h, w = reg.img.shape[:2]
-        src.shapes.append((h, w))
-        if i in need:
-            if pinned is not None:
-                dev_img = pinned[i].to(comp.device, non_blocking=True)
-            else:
-                host = torch.from_numpy(np.ascontiguousarray(reg.img))
-                dev_img = host.to(comp.device, non_blocking=host.is_pinned())
-            src.pixels.append(comp.pack_pixels(dev_img))
-            if (h, w) not in src.hats:
-                src.hats[(h, w)] = (comp._to_device(geo.hat(h)), comp._to_device(geo.hat(w)))
-        else:
-            src.pixels.append(None)
-        src.luts.append(None)
-    lut0 = comp._to_device(geo.sample_lut(None))
-    src.luts = [lut0] * len(regions)
-    return src
