@@ -286,6 +286,7 @@ def run_gpu_arm(args):
         for _ in range(n_steps):
             result = step_fn()
         end.record(torch.cuda.current_stream())
+        enqueue_s = time.perf_counter() - t_host          # host time to issue the steps (no sync)
         barrier()
         host_s = time.perf_counter() - t_host
         ms = start.elapsed_time(end)
@@ -299,6 +300,7 @@ def run_gpu_arm(args):
             n = torch.tensor([launched], dtype=torch.int64, device=comp.device)
             dist.all_reduce(n, op=dist.ReduceOp.SUM)
             launched = int(n.item())
+        timed.enqueue_ms = enqueue_s / n_steps * 1e3
         return ms, host_s, launched, trace_out, result
 
     for _ in range(args.warmup):
@@ -306,6 +308,7 @@ def run_gpu_arm(args):
     with ClockSampler(local) as clocks:
         ms, host_s, launches, trace, mosaic = timed(device_step, args.steps, trace=True)
     clock_summary = clocks.summary()
+    enqueue_ms = timed.enqueue_ms
     # e2e: host wall clock (includes the blocking D2H), max over ranks
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -371,6 +374,7 @@ def run_gpu_arm(args):
         "pipeline": pipeline,
         "kernels": shares,
         "host_ms_per_step": host_s / args.steps * 1e3,
+        "host_enqueue_ms_per_step": enqueue_ms,
     }
     if world == 1 and not args.no_cpu_baseline:
         base, _, _, _ = time_cpu(wl, 1, 1, args.cpu_budget_s / 4)

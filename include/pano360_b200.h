@@ -49,9 +49,12 @@ int  p360_device_info(int device, int32_t out_host[4]);
  *   lut         256 float32: value of a u8 sample (u8/255, optionally
  *               gain-scaled and clipped, stitcher.py:65-66)
  *   hat_y/hat_x float64 tables of `_hat(h)` / `_hat(w)` (stitcher.py:251-254)
- *   col_tab     pw x 3 float64: K*R[:,0]*rx(c) + K*R[:,2]*rz(c) per patch column
- *   row_tab     ph x 3 float64: K*R[:,1]*ry(r) per patch row
- *               (proj2hom is separable: stitcher.py:84-87, :101-104)
+ *   ray_x/ray_z float64 per MOSAIC column: x and z components of proj2hom
+ *   ray_y       float64 per MOSAIC row: y component of proj2hom (the projection
+ *               is separable: stitcher.py:84-87, :101-104); the patch origin
+ *               sits at (col0, row0) in these tables
+ *   kr          K*R row-major float64 (bundle_adj.py:31-33); p = kr . ray is
+ *               evaluated in float64 per pixel, then cast (stitcher.py:306)
  *   out         ph x pw x 4 float32; invalid: ph x pw u8 (1 = masked)
  *   x0, y0      position of the patch in the (window) mosaic of width W
  *   patch       id of the patch in the owner keys (its list position)
@@ -65,12 +68,14 @@ typedef struct p360_warp_job {
     const uint8_t *src;
     const float *lut;
     const double *hat_y, *hat_x;
-    const double *col_tab, *row_tab;
+    const double *ray_x, *ray_z, *ray_y;
     float *out;
     uint8_t *invalid;
+    double kr[9];
     int32_t h, w, c;
     int32_t pw, ph;
     int32_t x0, y0;
+    int32_t col0, row0;
     int32_t patch;
 } p360_warp_job;
 

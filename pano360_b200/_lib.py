@@ -44,15 +44,16 @@ MAX_LEVELS = 8
 
 # NumPy mirrors of the job records in include/pano360_b200.h (filled on the
 # host, shipped to the device as raw bytes)
-WARP_JOB = np.dtype([("src", "u8"), ("lut", "u8"), ("hat_y", "u8"), ("hat_x", "u8"), ("col_tab", "u8"),
-                     ("row_tab", "u8"), ("out", "u8"), ("invalid", "u8"), ("h", "i4"), ("w", "i4"),
-                     ("c", "i4"), ("pw", "i4"), ("ph", "i4"), ("x0", "i4"), ("y0", "i4"), ("patch", "i4")])
+WARP_JOB = np.dtype([("src", "u8"), ("lut", "u8"), ("hat_y", "u8"), ("hat_x", "u8"), ("ray_x", "u8"),
+                     ("ray_z", "u8"), ("ray_y", "u8"), ("out", "u8"), ("invalid", "u8"), ("kr", "f8", (9,)),
+                     ("h", "i4"), ("w", "i4"), ("c", "i4"), ("pw", "i4"), ("ph", "i4"), ("x0", "i4"),
+                     ("y0", "i4"), ("col0", "i4"), ("row0", "i4"), ("patch", "i4")])
 BLUR_JOB = np.dtype([("in", "u8"), ("out", "u8"), ("tmp", "u8"), ("w", "i4"), ("h", "i4"), ("slot", "i4"),
                      ("reserved", "i4")])
 BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "u8"),
                        ("low", "u8", (MAX_LEVELS - 1,)), ("x0", "i4"), ("y0", "i4"), ("pw", "i4"),
                        ("ph", "i4"), ("w4", "i4"), ("h4", "i4"), ("pad", "i4"), ("index", "i4")])
-assert WARP_JOB.itemsize == 96 and BLUR_JOB.itemsize == 40 and BAND_PATCH.itemsize == 120
+assert WARP_JOB.itemsize == 184 and BLUR_JOB.itemsize == 40 and BAND_PATCH.itemsize == 120
 
 # entry points whose int return is a value, not a status
 _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}

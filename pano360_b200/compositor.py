@@ -12,7 +12,7 @@ Data layout in HBM
 * source image      u8  [h][w][4]            RGBX, packed on device from the u8x3 upload
 * sample LUT        f32 [256] per image      u8 -> float value (gain folded in)
 * hat tables        f64 [h], [w]             shared by images of equal size
-* inverse-map tabs  f64 [pw][3], [ph][3]     per patch (column part, row part)
+* ray tables        f64 [W], [W], [H]        proj2hom per mosaic column (x, z) / row (y); K*R per patch
 * patch pool        f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid, all patches back to back
 * owner keys        u64 [H][W]               float_bits(alpha) << 32 | ~patch (atomicMax)
 * covered           u8  [H][W]               union of valid pixels
@@ -210,15 +210,16 @@ class Compositor:
     # -- K1: warp -------------------------------------------------------------
     def plan_crops(self, regions, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
         """Host side of the warp: which (row-cropped, column-split) boxes get
-        warped, and their inverse-map tables.  ``rows=(ya, yb)`` crops boxes to
-        those mosaic rows; a cropped top edge is moved up to a multiple of
-        ``row_align`` rows below the box's true top so that coarse grids
-        anchored at the crop coincide with those anchored at the true box.
-        With ``split_dilate`` (columns) the all-invalid middle of seam-
-        straddling boxes is dropped (``geometry.active_column_runs``): such an
-        image yields two crops with the same image index.
-        Returns (crops, tables) with crops = [(image, x0, y0, x1, y1, col_off, row_off)]."""
-        crops, tabs, total = [], [], 0
+        warped.  ``rows=(ya, yb)`` crops boxes to those mosaic rows; a cropped
+        top edge is moved up to a multiple of ``row_align`` rows below the
+        box's true top so that coarse grids anchored at the crop coincide with
+        those anchored at the true box.  With ``split_dilate`` (columns) the
+        all-invalid middle of seam-straddling boxes is dropped
+        (``geometry.active_column_runs``): such an image yields two crops with
+        the same image index.
+        Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R)], tables =
+        the per-mosaic-column / per-row ray tables of the projection."""
+        crops = []
         for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
             x0, y0, x1, y1 = box
             ya, yb = (y0, y1) if rows is None else (max(y0, rows[0]), min(y1, rows[1]))
@@ -226,13 +227,11 @@ class Compositor:
                 continue
             ya = y0 + (ya - y0) // row_align * row_align
             runs = [(x0, x1)] if split_dilate is None else \
-                geo.active_column_runs(reg, box, plan, proj, dilate=split_dilate)
+                geo.active_column_runs(i, box, plan, dilate=split_dilate)
+            k_r = np.ascontiguousarray(reg.proj(), dtype=np.float64).ravel()
             for cx0, cx1 in runs:
-                col_tab, row_tab = geo.inverse_map_tables(reg, (cx0, ya, cx1, yb), plan, proj)
-                crops.append((i, cx0, ya, cx1, yb, total, total + col_tab.size))
-                tabs += [col_tab.ravel(), row_tab.ravel()]
-                total += col_tab.size + row_tab.size
-        return crops, (np.concatenate(tabs) if tabs else np.zeros(0))
+                crops.append((i, cx0, ya, cx1, yb, k_r))
+        return crops, plan.rays(proj)
 
     def new_owner_state(self, shape):
         """(owner keys u64, covered u8) for a mosaic (or strip) of ``shape``."""
@@ -247,7 +246,10 @@ class Compositor:
         into the warp; patch k of the returned list is known as k there."""
         if not crops:
             return []
-        dev_tabs = self._to_device(tables, pinned_key="tabs")
+        ray_x, ray_z, ray_y = tables
+        dev_rays = self._to_device(np.concatenate([ray_x, ray_z, ray_y]), pinned_key="rays")
+        base_x = dev_rays.data_ptr()
+        base_z, base_y = base_x + 8 * len(ray_x), base_x + 8 * (len(ray_x) + len(ray_z))
         ox, oy = origin
         n = len(crops)
         sizes = np.array([(c[3] - c[1]) * (c[4] - c[2]) for c in crops], dtype=np.int64)
@@ -256,16 +258,16 @@ class Compositor:
         inv_pool = torch.empty(int(offs[-1]), dtype=torch.uint8, device=self.device)
         jobs = np.zeros(n, dtype=_lib.WARP_JOB)
         patches = []
-        tab_base, rgba_base, inv_base = dev_tabs.data_ptr(), rgba_pool.data_ptr(), inv_pool.data_ptr()
-        for k, (i, x0, ya, x1, yb, off_c, off_r) in enumerate(crops):
+        rgba_base, inv_base = rgba_pool.data_ptr(), inv_pool.data_ptr()
+        for k, (i, x0, ya, x1, yb, k_r) in enumerate(crops):
             pw, ph = x1 - x0, yb - ya
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
             pix = src.pixels[i]
             o = int(offs[k])
             jobs[k] = (pix.data_ptr(), src.luts[i].data_ptr(), hat_y.data_ptr(), hat_x.data_ptr(),
-                       tab_base + 8 * off_c, tab_base + 8 * off_r, rgba_base + 16 * o, inv_base + o,
-                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, k)
+                       base_x, base_z, base_y, rgba_base + 16 * o, inv_base + o, k_r,
+                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, x0, ya, k)
             patches.append(DevicePatch(rgba_pool[4 * o:4 * (o + pw * ph)].view(ph, pw, 4),
                                        inv_pool[o:o + pw * ph].view(ph, pw),
                                        (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
@@ -279,7 +281,7 @@ class Compositor:
         self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", _lib.ptr(dev_jobs), n,
                      int(max(c[3] - c[1] for c in crops)), int(max(c[4] - c[2] for c in crops)),
                      _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
-        self._keep["warp"] = (dev_tabs, dev_jobs, rgba_pool, inv_pool)
+        self._keep["warp"] = (dev_rays, dev_jobs, rgba_pool, inv_pool)
         return patches
 
     def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):

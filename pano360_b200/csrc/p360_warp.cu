@@ -13,13 +13,16 @@ struct WarpJob {                 // == p360_warp_job
     const float *lut;            // 256 entries
     const double *hat_y;         // h entries
     const double *hat_x;         // w entries
-    const double *col_tab;       // pw x 3
-    const double *row_tab;       // ph x 3
+    const double *ray_x;         // per mosaic column: x component of proj2hom (sin theta)
+    const double *ray_z;         // per mosaic column: z component (cos theta)
+    const double *ray_y;         // per mosaic row: y component (tan phi / phi)
     float4 *out;                 // ph x pw RGBA
     uint8_t *invalid;            // ph x pw
+    double kr[9];                // K * R, row-major (bundle_adj.py:31-33)
     int h, w, c;
     int pw, ph;
     int x0, y0;                  // position in the (window) mosaic
+    int col0, row0;              // absolute mosaic column / row of the patch origin (ray tables)
     int patch;                   // id in the owner map
 };
 static_assert(sizeof(WarpJob) == sizeof(p360_warp_job), "ABI struct mismatch");
@@ -64,12 +67,13 @@ constexpr int WARP_BX = 64, WARP_BY = 4;
 
 __device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, int c, int r,
                                            unsigned long long *keys, uint8_t *covered, int W) {
-    // p = K R (rx, ry, rz): column part + row part, float64, then cast
-    // (stitcher.py:303-306)
-    const double *ct = s.col_tab + (size_t)c * 3, *rt = s.row_tab + (size_t)r * 3;
-    const float px = (float)(__ldg(ct) + __ldg(rt));
-    const float py = (float)(__ldg(ct + 1) + __ldg(rt + 1));
-    const float pz = (float)(__ldg(ct + 2) + __ldg(rt + 2));
+    // p = K R (rx, ry, rz) in float64, k = 0, 1, 2 in order, then cast to
+    // float32 (stitcher.py:303-306)
+    const double rx = __ldg(s.ray_x + s.col0 + c), rz = __ldg(s.ray_z + s.col0 + c);
+    const double ry = __ldg(s.ray_y + s.row0 + r);
+    const float px = (float)fma(s.kr[2], rz, fma(s.kr[1], ry, s.kr[0] * rx));
+    const float py = (float)fma(s.kr[5], rz, fma(s.kr[4], ry, s.kr[3] * rx));
+    const float pz = (float)fma(s.kr[8], rz, fma(s.kr[7], ry, s.kr[6] * rx));
     bool bad = pz < 0.0f;                                        // stitcher.py:308
     const float x = __fadd_rn(__fdiv_rn(px, pz), (float)(s.w / 2.0));   // stitcher.py:310
     const float y = __fadd_rn(__fdiv_rn(py, pz), (float)(s.h / 2.0));

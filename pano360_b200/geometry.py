@@ -64,7 +64,7 @@ def image_range_border(shape, hom, proj=SphProj):
     ring[3 * n:4 * n, 0], ring[3 * n:4 * n, 1] = along_x, h
     ring -= np.array([w / 2, h / 2, 0])
     ang = proj.hom2proj(hom.dot(ring.T).T)
-    return np.min(ang, axis=0), np.max(ang, axis=0)
+    return np.min(ang, axis=0), np.max(ang, axis=0), np.sort(ang[:, 0])
 
 
 def image_range_corners(shape, hom, proj=SphProj):
@@ -92,12 +92,29 @@ class MosaicPlan:
     origin: np.ndarray        # (theta_min, phi_min)
     boxes: list               # per image (x0, y0, x1, y1)
     ranges: list              # per image (min, max) angles
+    border_theta: list = None # per image sorted longitudes of the border samples
+    _rays: tuple = None       # cached (ray_x[W], ray_z[W], ray_y[H]) of proj2hom
+
+    def rays(self, proj=SphProj):
+        """``proj2hom`` evaluated once per mosaic column / row (it is separable:
+        stitcher.py:84-87, :101-104): x and z components of the ray depend on
+        the column only, the y component on the row only."""
+        if self._rays is None or self._rays[0] is not proj:
+            height, width = self.shape
+            theta = np.arange(width + 1) * self.resolution[0] + self.origin[0]
+            phi = np.arange(height + 1) * self.resolution[1] + self.origin[1]
+            by_col = proj.proj2hom(np.stack([theta, np.zeros_like(theta)], axis=-1))
+            by_row = proj.proj2hom(np.stack([np.zeros_like(phi), phi], axis=-1))
+            self._rays = (proj, np.ascontiguousarray(by_col[:, 0]), np.ascontiguousarray(by_col[:, 2]),
+                          np.ascontiguousarray(by_row[:, 1]))
+        return self._rays[1:]
 
 
 def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
     """Mosaic shape and per-image boxes (stitcher.py:276-277, :283-297).
     ``pad`` is True for the multiband blender (10-px pad, clamped)."""
-    ranges = [image_range_border(r.img.shape[:2], r.hom(), proj) for r in regions]
+    samples = [image_range_border(r.img.shape[:2], r.hom(), proj) for r in regions]
+    ranges = [(s[0], s[1]) for s in samples]
     lo = np.min([r[0] for r in ranges], axis=0)
     hi = np.max([r[1] for r in ranges], axis=0)
     mid = regions[len(regions) // 2]
@@ -117,11 +134,11 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
             bottom = np.maximum(bottom - PATCH_PAD, np.int32([0, 0]))
             top = np.minimum(top + PATCH_PAD, limit)
         boxes.append((int(bottom[0]), int(bottom[1]), int(top[0]), int(top[1])))
-    return MosaicPlan(shape, resolution, lo, boxes, ranges)
+    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples])
 
 
-def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4, align=4):
-    """Column ranges of a patch box that can contain valid pixels.
+def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
+    """Column ranges of the box of image ``index`` that can contain valid pixels.
 
     The reference gives an image that straddles theta = +-pi a full-mosaic-
     width box (no wrap handling in stitcher.py:107-122) of which
@@ -133,20 +150,11 @@ def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4, alig
     blur, so that neither the dropped columns nor the reflection at the
     artificial edge can influence a pixel with non-zero weight) plus a small
     ``margin`` for the sampling of the border; the second part starts a
-    multiple of ``align`` columns from the box origin.  Returns [(x0, x1), ...] inside
-    the box, in ascending order; a single run equal to the box if no split."""
+    multiple of ``align`` columns from the box origin.  Returns
+    [(x0, x1), ...] inside the box, in ascending order; a single run equal to
+    the box if no split."""
     x0, y0, x1, y1 = box
-    h, w = region.img.shape[:2]
-    n = BORDER_SAMPLES
-    along_x, along_y = np.linspace(0, w, n), np.linspace(0, h, n)
-    ring = np.empty((4 * n, 3))
-    ring[:, 2] = 1.0
-    ring[0 * n:1 * n, 0], ring[0 * n:1 * n, 1] = 0.0, along_y
-    ring[1 * n:2 * n, 0], ring[1 * n:2 * n, 1] = w, along_y
-    ring[2 * n:3 * n, 0], ring[2 * n:3 * n, 1] = along_x, 0.0
-    ring[3 * n:4 * n, 0], ring[3 * n:4 * n, 1] = along_x, h
-    ring -= np.array([w / 2, h / 2, 0])
-    theta = np.sort(proj.hom2proj(region.hom().dot(ring.T).T)[:, 0])
+    theta = plan.border_theta[index]
     gaps = np.diff(theta)
     k = int(np.argmax(gaps))
     left_end = int(np.ceil((theta[k] - plan.origin[0]) / plan.resolution[0])) + margin + dilate
@@ -163,21 +171,17 @@ def active_column_runs(region, box, plan, proj=SphProj, dilate=0, margin=4, alig
 
 def inverse_map_tables(region, box, plan, proj=SphProj):
     """Separable float64 tables for one patch: ``p = K R proj2hom(theta, phi)``
-    splits into a per-column part (x and z components of the ray depend on
-    theta only) and a per-row part (the y component depends on phi only), for
-    both projections (stitcher.py:84-87, :101-104, :300-306).
+    splits into a per-column part and a per-row part (stitcher.py:300-306).
+    The kernels evaluate the same sum from the per-mosaic ray tables
+    (``MosaicPlan.rays``); this form is kept for inspection and tests.
 
     Returns (col_tab [pw,3], row_tab [ph,3]) with p = col_tab[c] + row_tab[r].
     """
     x0, y0, x1, y1 = box
-    theta = (np.arange(x1 - x0) + x0) * plan.resolution[0] + plan.origin[0]
-    phi = (np.arange(y1 - y0) + y0) * plan.resolution[1] + plan.origin[1]
-    zeros_c, zeros_r = np.zeros_like(theta), np.zeros_like(phi)
-    ray_c = proj.proj2hom(np.stack([theta, zeros_c], axis=-1))   # (sin, f(0), cos)
-    ray_r = proj.proj2hom(np.stack([zeros_r, phi], axis=-1))     # (0, f(phi), 1)
+    ray_x, ray_z, ray_y = plan.rays(proj)
     k_r = region.proj()
-    col_tab = ray_c[:, [0]] * k_r[:, 0][None, :] + ray_c[:, [2]] * k_r[:, 2][None, :]
-    row_tab = ray_r[:, [1]] * k_r[:, 1][None, :]
+    col_tab = ray_x[x0:x1, None] * k_r[:, 0][None, :] + ray_z[x0:x1, None] * k_r[:, 2][None, :]
+    row_tab = ray_y[y0:y1, None] * k_r[:, 1][None, :]
     return np.ascontiguousarray(col_tab), np.ascontiguousarray(row_tab)
 
 
