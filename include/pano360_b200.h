@@ -43,7 +43,9 @@ int  p360_device_info(int device, int32_t out_host[4]);
  * Replaces stitcher.py:257-263 (_add_weights) + :300-317 (coordinates, mask,
  * cv2.remap INTER_LINEAR/BORDER_REFLECT, alpha *= ~mask), fused; optionally
  * also the weights tensor / argmax of :196-204 and `allmask` of :233-234.
- * One launch warps every patch of a composite: `jobs` is a DEVICE array.
+ * One launch warps every patch of a composite (up to 128 per launch; the job
+ * records are staged in constant memory): `jobs_host` is a HOST array whose
+ * pointer members are device pointers.
  *   src         u8, h x w x c (c = 3, or 4 = one aligned word per pixel as
  *               produced by p360_pack_rgbx; 4th channel ignored)
  *   lut         256 float32: value of a u8 sample (u8/255, optionally
@@ -80,7 +82,7 @@ typedef struct p360_warp_job {
 } p360_warp_job;
 
 int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t n_pixels, void *stream);
-int p360_warp_batch(const p360_warp_job *jobs, int n_jobs, int max_pw, int max_ph,
+int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                     uint64_t *owner_keys, uint8_t *covered, int W, void *stream);
 
 /* ---- K2: owner map for externally supplied patches (stitcher.py:196-208) ---
@@ -130,6 +132,9 @@ int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int 
  *   p360_linear_collapse       stitcher.py:171-183 in the same gather form
  *   p360_paste_collapse        stitcher.py:160-168 in the same gather form
  * Nothing mosaic-sized is accumulated in HBM.  `patches` is a DEVICE array.
+ * The collapse kernels produce mosaic rows [y_begin, y_end) (y_begin % 32 == 0;
+ * y_end = H for the whole mosaic) so that callers can overlap the download of
+ * finished row bands with the computation of the next ones.
  */
 typedef struct p360_band_patch {
     const float *rgba;                        /* full-res patch                         */
@@ -147,11 +152,11 @@ int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int
                               int max_h4, const uint64_t *owner_keys, int W, void *stream);
 int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                             const uint64_t *owner_keys, const uint8_t *covered,
-                            uint8_t *out_u8, int H, int W, void *stream);
+                            uint8_t *out_u8, int y_begin, int y_end, int W, void *stream);
 int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                         int H, int W, void *stream);
+                         int y_begin, int y_end, int W, void *stream);
 int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                        int H, int W, void *stream);
+                        int y_begin, int y_end, int W, void *stream);
 
 /* ---- K8: pair overlap statistics for exposure gains (stitcher.py:48-63) ---
  * For every pixel of image i: fixed-point perspective map into image j

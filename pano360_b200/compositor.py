@@ -75,6 +75,7 @@ class DeviceSources:
     luts: list                         # f32 [256] tensors
     hats: dict = field(default_factory=dict)   # (h, w) -> (hat_y, hat_x) f64 tensors
     shapes: list = field(default_factory=list)
+    ready: list = None                 # per image CUDA event (uploads issued on the copy stream)
 
 
 class Compositor:
@@ -86,6 +87,8 @@ class Compositor:
         self._pinned = {}
         self._taps_key = None
         self._keep = {}
+        self._copy = None      # side stream for uploads / downloads that overlap the kernels
+        self._download = None
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
 
     # -- plumbing -----------------------------------------------------------
@@ -112,6 +115,11 @@ class Compositor:
             self._pinned[pinned_key] = (stage, busy)
             return dev
         return host.to(self.device)
+
+    def copy_stream(self):
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(self.device)
+        return self._copy
 
     def _table(self, records, key):
         """Structured job table -> device bytes."""
@@ -141,12 +149,20 @@ class Compositor:
         _lib.call("p360_pack_rgbx", _lib.ptr(dev_img), _lib.ptr(packed), h * w, self.stream)
         return packed
 
-    def upload(self, regions, gains=None, need=None):
+    def upload(self, regions, gains=None, need=None, overlap=False):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
-        restricts the copy to the images a rank's strip touches."""
+        restricts the copy to the images a rank's strip touches.  With
+        ``overlap`` the copies (and the RGBX packing) run on a side stream and
+        every image gets a ``ready`` event, so the warp of the first images
+        starts while the last ones are still crossing PCIe."""
         src = DeviceSources([], [])
         lut0 = None
+        main = torch.cuda.current_stream(self.device)
+        side = self.copy_stream() if overlap else main
+        if overlap:
+            src.ready = [None] * len(regions)
+            side.wait_stream(main)
         for i, reg in enumerate(regions):
             img = reg.img
             h, w = img.shape[:2]
@@ -157,7 +173,11 @@ class Compositor:
                 if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
                 host = torch.from_numpy(np.ascontiguousarray(img))
-                src.pixels.append(self.pack_pixels(host.to(self.device, non_blocking=host.is_pinned())))
+                with torch.cuda.stream(side):
+                    src.pixels.append(self.pack_pixels(host.to(self.device, non_blocking=host.is_pinned())))
+                    if overlap:
+                        src.ready[i] = torch.cuda.Event()
+                        src.ready[i].record(side)
                 if (h, w) not in src.hats:
                     src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
             if gains is None:
@@ -271,17 +291,29 @@ class Compositor:
             patches.append(DevicePatch(rgba_pool[4 * o:4 * (o + pw * ph)].view(ph, pw, 4),
                                        inv_pool[o:o + pw * ph].view(ph, pw),
                                        (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
-        dev_jobs = self._table(jobs, "warp_jobs")
         if owner_state is None:
             keys = covered = None
             width, per_px = 0, 17
         else:
             keys, covered = owner_state
             width, per_px = keys.shape[1], 30
-        self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", _lib.ptr(dev_jobs), n,
-                     int(max(c[3] - c[1] for c in crops)), int(max(c[4] - c[2] for c in crops)),
-                     _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
-        self._keep["warp"] = (dev_rays, dev_jobs, rgba_pool, inv_pool)
+        if src.ready is None:
+            self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", jobs.ctypes.data, n,
+                         _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+        else:                  # uploads in flight: warp image groups as they arrive
+            main = torch.cuda.current_stream(self.device)
+            group = max(1, -(-len(src.ready) // 8))
+            a = 0
+            while a < n:
+                last = (crops[a][0] // group + 1) * group - 1          # last image of this group
+                b = a
+                while b < n and crops[b][0] <= last:
+                    b += 1
+                main.wait_event(src.ready[max(c[0] for c in crops[a:b])])
+                _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
+                          _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+                a = b
+        self._keep["warp"] = (dev_rays, rgba_pool, inv_pool, jobs)
         return patches
 
     def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
@@ -348,7 +380,35 @@ class Compositor:
                       self.stream)
         self._taps_key = n_levels
 
-    def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None):
+    def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, bands=8):
+        """Launch a collapse kernel over the whole mosaic, or — when a pinned
+        host array is given — band by band with the download of each finished
+        band overlapping the computation of the next (side stream)."""
+        h, w = mosaic.shape[:2]
+        if out_host is None:
+            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), 0, h, w, self.stream)
+            return
+        host = torch.from_numpy(out_host)
+        main, side = torch.cuda.current_stream(self.device), self.copy_stream()
+        step = max(32, -(-h // bands + 31) // 32 * 32)
+        for y0 in range(0, h, step):
+            y1 = min(h, y0 + step)
+            _lib.call(fn, *head, _lib.ptr(mosaic), y0, y1, w, self.stream)
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                host[y0:y1].copy_(mosaic[y0:y1], non_blocking=True)
+        self._download = torch.cuda.Event()
+        self._download.record(side)
+
+    def finish_download(self):
+        """Block until a banded download started by ``_collapse`` has landed."""
+        if self._download is not None:
+            self._download.synchronize()
+            self._download = None
+
+    def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM."""
@@ -406,15 +466,14 @@ class Compositor:
                     for lvl in range(1, len(plan)):
                         per.append(pool4[(2 * lvl * tot4 + o) * 4:][:h4 * w4 * 4].view(h4, w4, 4))
                     lows.append(per)
-        self._traced("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
-                     _lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic),
-                     h, w, self.stream)
+        self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
+                       (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host)
         self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows)
         return mosaic
 
-    def _pointwise(self, fn, name, patches, shape):
+    def _pointwise(self, fn, name, patches, shape, out_host=None):
         h, w = shape
         mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
@@ -422,18 +481,17 @@ class Compositor:
         table = self._band_table(patches)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
-        self._traced(name, 17 * pix + 3 * h * w, fn, _lib.ptr(dev_table), len(patches), _lib.ptr(mosaic),
-                     h, w, self.stream)
+        self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host)
         self._keep["collapse"] = (dev_table,)
         return mosaic
 
-    def blend_none(self, patches, shape):
+    def blend_none(self, patches, shape, out_host=None):
         """stitcher.py:160-168 (last valid writer wins), gather form."""
-        return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape)
+        return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host)
 
-    def blend_linear(self, patches, shape):
+    def blend_linear(self, patches, shape, out_host=None):
         """stitcher.py:171-183, gather form."""
-        return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape)
+        return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""
@@ -445,13 +503,13 @@ class Compositor:
                       self.stream)
         return covered
 
-    def blend(self, kind, patches, shape, n_levels=5):
+    def blend(self, kind, patches, shape, n_levels=5, out_host=None):
         if kind == "none":
-            return self.blend_none(patches, shape)
+            return self.blend_none(patches, shape, out_host)
         if kind == "linear":
-            return self.blend_linear(patches, shape)
+            return self.blend_linear(patches, shape, out_host)
         if kind == "multiband":
-            return self.blend_multiband(patches, shape, n_levels)
+            return self.blend_multiband(patches, shape, n_levels, out_host=out_host)
         raise ValueError(f"unknown blender {kind!r}")
 
     # -- whole path, device resident ------------------------------------------
@@ -462,10 +520,12 @@ class Compositor:
             return 0
         return geo.coarse_band_plan(n_levels)[0] + 4
 
-    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None):
+    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
-        those rows of the full composite)."""
+        those rows of the full composite).  ``out_host`` (pinned uint8 H x W x 3,
+        whole-mosaic mode only) receives the mosaic through a banded download
+        that overlaps the collapse; call ``finish_download`` before reading it."""
         halo = self.window_halo(kind, n_levels)
         if rows is None:
             ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
@@ -479,8 +539,10 @@ class Compositor:
         shape = (wb - top, plan.shape[1])
         state = self.new_owner_state(shape) if kind == "multiband" else None
         patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+        if rows is not None:
+            out_host = None
         if kind == "multiband":
-            strip = self.blend_multiband(patches, shape, n_levels, owner_state=state)
+            strip = self.blend_multiband(patches, shape, n_levels, owner_state=state, out_host=out_host)
         else:
-            strip = self.blend(kind, patches, shape, n_levels)
+            strip = self.blend(kind, patches, shape, n_levels, out_host)
         return strip[ya - top:ya - top + (yb - ya)], patches

@@ -205,9 +205,10 @@ template <int L>
 __global__ void __launch_bounds__(256)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
-                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int H, int W) {
+                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int row0,
+                          int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int tx0 = blockIdx.x * CT_X, ty0 = blockIdx.y * CT_Y;
+    const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
     int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
     n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
     const int X = tx0 + threadIdx.x;
@@ -230,16 +231,20 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                 Pair2 prev = to_pair(pix);
                 prev.hi.y = key_is_owner(key, bp.index) ? 1.0f : 0.0f;     // stitcher.py:207-208
                 const int pad = bp.pad, w4 = bp.w4;
+                // bilinear weights on the f = 2 grid (level 0) and the f = 4 grid (levels >= 1)
+                int ix2, iy2, ix4, iy4;
+                float fx2, fy2, fx4, fy4;
+                coarse_coord<1>(pad, px, ix2, fx2); coarse_coord<1>(pad, py, iy2, fy2);
+                coarse_coord<2>(pad, px, ix4, fx4); coarse_coord<2>(pad, py, iy4, fy4);
+                const size_t off2 = (size_t)iy2 * (2 * w4) + ix2, off4 = (size_t)iy4 * w4 + ix4;
+                const float a2 = (1.0f - fy2) * (1.0f - fx2), b2 = (1.0f - fy2) * fx2;
+                const float c2 = fy2 * (1.0f - fx2), d2 = fy2 * fx2;
+                const float a4 = (1.0f - fy4) * (1.0f - fx4), b4 = (1.0f - fy4) * fx4;
+                const float c4 = fy4 * (1.0f - fx4), d4 = fy4 * fx4;
 #pragma unroll
                 for (int l = 0; l < L - 1; ++l) {             // stitcher.py:224-232
-                    int ix, iy;
-                    float fx, fy;
-                    if (l == 0) { coarse_coord<1>(pad, px, ix, fx); coarse_coord<1>(pad, py, iy, fy); }
-                    else        { coarse_coord<2>(pad, px, ix, fx); coarse_coord<2>(pad, py, iy, fy); }
-                    const int lw = (l == 0) ? 2 * w4 : w4;
-                    const float gx = 1.0f - fx, gy = 1.0f - fy;
-                    const Pair2 cur = expand_at(bp.low[l] + (size_t)iy * lw + ix, lw,
-                                                gy * gx, gy * fx, fy * gx, fy * fx);
+                    const Pair2 cur = (l == 0) ? expand_at(bp.low[0] + off2, 2 * w4, a2, b2, c2, d2)
+                                               : expand_at(bp.low[l] + off4, w4, a4, b4, c4, d4);
                     const float2 ww = make_float2(cur.hi.y, cur.hi.y);      // weight = blurred mask
                     const float2 dlo = __fadd2_rn(prev.lo, make_float2(-cur.lo.x, -cur.lo.y));
                     const float2 dhi = make_float2(prev.hi.x - cur.hi.x, 1.0f);
@@ -255,10 +260,12 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;                   // stitcher.py:236-238
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            const float w = hi[l].y == 0.0f ? 1.0f : hi[l].y;
-            m0 = __fadd_rn(m0, __fdiv_rn(lo[l].x, w));
-            m1 = __fadd_rn(m1, __fdiv_rn(lo[l].y, w));
-            m2 = __fadd_rn(m2, __fdiv_rn(hi[l].x, w));
+            // one reciprocal per level instead of three correctly rounded divisions:
+            // the coarse evaluation is ~1e-3 accurate, a 1-ulp quotient is noise
+            const float inv = hi[l].y == 0.0f ? 1.0f : __frcp_rn(hi[l].y);
+            m0 = fmaf(lo[l].x, inv, m0);
+            m1 = fmaf(lo[l].y, inv, m1);
+            m2 = fmaf(hi[l].x, inv, m2);
         }
         uint8_t *o = out + mi * 3;                            // stitcher.py:240-241
         o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(m0, 0.f), 1.f)));
@@ -273,9 +280,9 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
-                          uint8_t *__restrict__ out, int H, int W) {
+                          uint8_t *__restrict__ out, int row0, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int tx0 = blockIdx.x * CT_X, ty0 = blockIdx.y * CT_Y;
+    const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
     const int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
     const int X = tx0 + threadIdx.x;
     if (X >= W) return;
@@ -316,9 +323,9 @@ pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 
 template <int L>
 int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
-                    const uint8_t *covered, uint8_t *out, int H, int W, cudaStream_t s) {
-    dim3 grid(cdiv(W, CT_X), cdiv(H, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, H, W);
+                    const uint8_t *covered, uint8_t *out, int y0, int y1, int W, cudaStream_t s) {
+    dim3 grid(cdiv(W, CT_X), cdiv(y1 - y0, CT_Y)), block(CT_X, 4);
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, y0, y1, W);
     return check_launch("p360_multiband_collapse");
 }
 
@@ -350,44 +357,49 @@ extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_p
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                                        const uint64_t *owner_keys, const uint8_t *covered,
-                                       uint8_t *out_u8, int H, int W, void *stream) {
+                                       uint8_t *out_u8, int y_begin, int y_end, int W, void *stream) {
     const char *where = "p360_multiband_collapse";
     P360_REQUIRE(patches && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
-    P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && H > 0 && W > 0, where);
+    P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && W > 0, where);
+    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin && y_begin % 32 == 0, where);
+    if (y_end == y_begin) return 0;
+    const int H = y_end;
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, H, W, s);
-        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, H, W, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
     }
 }
 
 static int pointwise_collapse(const char *where, int mode, const p360_band_patch *patches, int n_patches,
-                              uint8_t *out_u8, int H, int W, void *stream) {
-    P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && H > 0 && W > 0, where);
-    dim3 grid(cdiv(W, CT_X), cdiv(H, CT_Y)), block(CT_X, 4);
+                              uint8_t *out_u8, int y_begin, int y_end, int W, void *stream) {
+    P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && W > 0, where);
+    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin && y_begin % 32 == 0, where);
+    if (y_end == y_begin) return 0;
+    dim3 grid(cdiv(W, CT_X), cdiv(y_end - y_begin, CT_Y)), block(CT_X, 4);
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     if (mode == 0)
-        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, H, W);
+        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, y_begin, y_end, W);
     else
-        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, H, W);
+        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, y_begin, y_end, W);
     return check_launch(where);
 }
 
 extern "C" int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                                    int H, int W, void *stream) {
-    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, H, W, stream);
+                                    int y_begin, int y_end, int W, void *stream) {
+    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, y_begin, y_end, W, stream);
 }
 
 extern "C" int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                                   int H, int W, void *stream) {
-    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, H, W, stream);
+                                   int y_begin, int y_end, int W, void *stream) {
+    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, y_begin, y_end, W, stream);
 }

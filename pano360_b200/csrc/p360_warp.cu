@@ -38,14 +38,20 @@ __device__ __forceinline__ int reflect_fast(int p, int n, float inv_2n) {
     return q < n ? q : m - 1 - q;
 }
 
+__device__ __forceinline__ float lut_at(const float *lut, uint32_t byte_offset) {
+    return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(lut) + byte_offset);
+}
+
 __device__ __forceinline__ float4 sample(const WarpJob &s, const float *lut, int y, int x, double hy,
                                          double hx) {
-    const uint8_t *p = s.src + ((size_t)y * s.w + x) * s.c;
     float4 v;
     if (s.c == 4) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(p));
-        v.x = lut[u & 0xff]; v.y = lut[(u >> 8) & 0xff]; v.z = lut[(u >> 16) & 0xff];
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(s.src) + (y * s.w + x));
+        v.x = lut_at(lut, (u << 2) & 0x3fc);          // byte k pre-scaled by sizeof(float)
+        v.y = lut_at(lut, (u >> 6) & 0x3fc);
+        v.z = lut_at(lut, (u >> 14) & 0x3fc);
     } else {
+        const uint8_t *p = s.src + ((size_t)y * s.w + x) * s.c;
         v.x = lut[__ldg(p)]; v.y = lut[__ldg(p + 1)]; v.z = lut[__ldg(p + 2)];
     }
     v.w = (float)(hy * hx);          // float32(hat_y * hat_x), stitcher.py:261
@@ -110,16 +116,15 @@ __device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, i
     }
 }
 
+constexpr int WARP_JOBS_PER_LAUNCH = 128;
+__constant__ WarpJob c_warp_jobs[WARP_JOBS_PER_LAUNCH];   // block-uniform reads: no LSU traffic per pixel
+
 __global__ void __launch_bounds__(WARP_BX *WARP_BY)
-warp_batch_kernel(const WarpJob *__restrict__ jobs, unsigned long long *__restrict__ keys,
-                  uint8_t *__restrict__ covered, int W) {
-    __shared__ WarpJob job;
+warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
     __shared__ float lut[256];
-    const int tid = threadIdx.y * WARP_BX + threadIdx.x;
-    if (tid < (int)(sizeof(WarpJob) / 4))
-        reinterpret_cast<uint32_t *>(&job)[tid] = reinterpret_cast<const uint32_t *>(jobs + blockIdx.z)[tid];
-    __syncthreads();
+    const WarpJob &job = c_warp_jobs[blockIdx.z];
     if ((int)(blockIdx.x * WARP_BX) >= job.pw || (int)(blockIdx.y * WARP_BY) >= job.ph) return;   // block-uniform
+    const int tid = threadIdx.y * WARP_BX + threadIdx.x;
     lut[tid] = __ldg(job.lut + tid);
     __syncthreads();
     const int c = blockIdx.x * WARP_BX + threadIdx.x, r = blockIdx.y * WARP_BY + threadIdx.y;
@@ -149,16 +154,34 @@ extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t
     return check_launch(where);
 }
 
-extern "C" int p360_warp_batch(const p360_warp_job *jobs, int n_jobs, int max_pw, int max_ph,
+extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                                uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_batch";
-    P360_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= 65535 && max_pw >= 0 && max_ph >= 0, where);
+    P360_REQUIRE(jobs_host && n_jobs >= 0, where);
     P360_REQUIRE(owner_keys == nullptr || (covered != nullptr && W > 0), where);
-    if (n_jobs == 0 || max_pw == 0 || max_ph == 0) return 0;
-    dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY), n_jobs);
-    P360_REQUIRE(grid.y <= 65535, where);
-    warp_batch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const WarpJob *>(jobs), reinterpret_cast<unsigned long long *>(owner_keys), covered, W);
-    return check_launch(where);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int first = 0; first < n_jobs; first += WARP_JOBS_PER_LAUNCH) {
+        const int count = n_jobs - first < WARP_JOBS_PER_LAUNCH ? n_jobs - first : WARP_JOBS_PER_LAUNCH;
+        int max_pw = 0, max_ph = 0;
+        for (int k = first; k < first + count; ++k) {
+            const p360_warp_job &j = jobs_host[k];
+            P360_REQUIRE(j.src && j.lut && j.hat_y && j.hat_x && j.ray_x && j.ray_z && j.ray_y && j.out && j.invalid, where);
+            P360_REQUIRE(j.h > 0 && j.w > 0 && j.h <= 32767 && j.w <= 32767 && j.pw >= 0 && j.ph >= 0, where);
+            P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0), where);
+            P360_REQUIRE(aligned16(j.out), where);
+            P360_REQUIRE(owner_keys == nullptr || (j.x0 >= 0 && j.y0 >= 0 && j.x0 + j.pw <= W), where);
+            max_pw = j.pw > max_pw ? j.pw : max_pw;
+            max_ph = j.ph > max_ph ? j.ph : max_ph;
+        }
+        if (max_pw == 0 || max_ph == 0) continue;
+        // stream-ordered: waits for the previous launch that still reads the table
+        P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host + first, sizeof(WarpJob) * count, 0,
+                                          cudaMemcpyHostToDevice, s), where);
+        dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY), count);
+        P360_REQUIRE(grid.y <= 65535, where);
+        warp_batch_kernel<<<grid, block, 0, s>>>(reinterpret_cast<unsigned long long *>(owner_keys), covered, W);
+        if (int e = check_launch(where)) return e;
+    }
+    return 0;
 }

@@ -169,6 +169,12 @@ def _download(mosaic_dev, out=None):
     return out
 
 
+def _is_pinned_out(out, shape):
+    import torch
+    return (out is not None and out.dtype == np.uint8 and out.flags.c_contiguous
+            and out.shape == tuple(shape) + (3,) and torch.from_numpy(out).is_pinned())
+
+
 def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None, out=None):
     """Stitch the images together; returns the uint8 H x W x 3 mosaic.
 
@@ -180,7 +186,7 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     comp = _compositor()
     kind = _blend_kind(blender)
     proj = globals()["SphProj"]            # honours `stitcher.SphProj = stitcher.CylProj`
-    src = comp.upload(regions)
+    src = comp.upload(regions, overlap=not equalize)       # warp starts while late images still upload
     if equalize:
         comp.set_gains(src, equalize_gains(regions, src))
     plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
@@ -192,8 +198,13 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         patches = comp.warp(regions, src, plan, proj)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
     else:
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj)
-        mosaic = _download(mosaic_dev, out)
+        banded = out if _is_pinned_out(out, plan.shape) else None
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded)
+        if banded is not None:
+            comp.finish_download()
+            mosaic = out
+        else:
+            mosaic = _download(mosaic_dev, out)
     if crop:
         logging.debug("Cropping...")
         mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))
