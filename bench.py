@@ -260,11 +260,7 @@ def run_gpu_arm(args):
             overlaps, sizes = strips.all_pair_statistics(comp, regions, src)
             from pano360_b200.stitcher import find_gains
             comp.set_gains(src, find_gains(overlaps, sizes))
-        if rows[1] > rows[0]:
-            strip, _ = comp.composite(regions, src, plan, kind, levels, rows=rows if world > 1 else None)
-        else:
-            strip = torch.empty((0, plan.shape[1], 3), dtype=torch.uint8, device=comp.device)
-        return strips.gather_strips(strip, parts, plan.shape, 0)
+        return strips.composite_gather(comp, regions, src, plan, kind, levels, parts)
 
     def e2e_step():
         """e2e leg: public API, host buffers in, host mosaic out."""
@@ -346,6 +342,14 @@ def run_gpu_arm(args):
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
                     "launch_ms": t_ms / count, "algorithmic_bytes_per_launch": nbytes / count,
                     "share_of_step": t_ms / ms}
+    # per-rank load (strip balance): traced kernel time of every rank, gathered on rank 0
+    my_kernel_ms = sum(v[0] for v in per_kernel.values()) / args.steps if per_kernel else 0.0
+    per_rank = [my_kernel_ms]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=comp.device)
+        t[rank] = my_kernel_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank = [round(v, 3) for v in t.tolist()]
     total_bytes, p_px, m_px = model_bytes(wl, plan, src_bytes_all)
     pipeline = {"model_bytes_per_step": total_bytes, "GBps": total_bytes / (ms_per_step / 1e3) / 1e9,
                 "frac_of_hbm_peak": total_bytes / (ms_per_step / 1e3) / 1e9 / peak}
@@ -373,6 +377,7 @@ def run_gpu_arm(args):
         "roofline": roofline,
         "pipeline": pipeline,
         "kernels": shares,
+        "per_rank_kernel_ms": per_rank,
         "host_ms_per_step": host_s / args.steps * 1e3,
         "host_enqueue_ms_per_step": enqueue_ms,
     }

@@ -132,8 +132,8 @@ int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int 
  *   p360_linear_collapse       stitcher.py:171-183 in the same gather form
  *   p360_paste_collapse        stitcher.py:160-168 in the same gather form
  * Nothing mosaic-sized is accumulated in HBM.  `patches` is a DEVICE array.
- * The collapse kernels produce mosaic rows [y_begin, y_end) (y_begin % 32 == 0;
- * y_end = H for the whole mosaic) so that callers can overlap the download of
+ * The collapse kernels produce mosaic rows [y_begin, y_end) (0 and H for the
+ * whole mosaic) so that callers can overlap the download or the NVLink send of
  * finished row bands with the computation of the next ones.
  */
 typedef struct p360_band_patch {

@@ -36,6 +36,12 @@ import torch
 from . import _lib, geometry as geo
 
 
+def band_edges(ya, yb, bands):
+    """[ya, yb) cut into ``bands`` row ranges with integer arithmetic only, so
+    that every rank derives identical cuts whatever its local row origin."""
+    return [(ya + k * (yb - ya) // bands, ya + (k + 1) * (yb - ya) // bands) for k in range(bands)]
+
+
 def _require_cuda(device):
     if not torch.cuda.is_available():
         raise RuntimeError("pano360_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -380,27 +386,35 @@ class Compositor:
                       self.stream)
         self._taps_key = n_levels
 
-    def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, bands=8):
-        """Launch a collapse kernel over the whole mosaic, or — when a pinned
-        host array is given — band by band with the download of each finished
-        band overlapping the computation of the next (side stream)."""
+    def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8):
+        """Launch a collapse kernel over rows ``rows`` (default: all) of the
+        mosaic buffer.  With ``out_host`` (pinned host array) or ``on_band``
+        (callback(y0, y1), e.g. an NVLink send) the rows are produced band by
+        band so that the transfer of each finished band overlaps the
+        computation of the next."""
         h, w = mosaic.shape[:2]
-        if out_host is None:
-            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), 0, h, w, self.stream)
+        ya, yb = (0, h) if rows is None else rows
+        if out_host is None and on_band is None:
+            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, w, self.stream)
             return
-        host = torch.from_numpy(out_host)
+        host = None if out_host is None else torch.from_numpy(out_host)
         main, side = torch.cuda.current_stream(self.device), self.copy_stream()
-        step = max(32, -(-h // bands + 31) // 32 * 32)
-        for y0 in range(0, h, step):
-            y1 = min(h, y0 + step)
-            _lib.call(fn, *head, _lib.ptr(mosaic), y0, y1, w, self.stream)
-            done = torch.cuda.Event()
-            done.record(main)
-            side.wait_event(done)
-            with torch.cuda.stream(side):
-                host[y0:y1].copy_(mosaic[y0:y1], non_blocking=True)
-        self._download = torch.cuda.Event()
-        self._download.record(side)
+        for y0, y1 in band_edges(ya, yb, bands):
+            if y1 <= y0:
+                continue
+            self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1, w,
+                         self.stream)
+            if on_band is not None:
+                on_band(y0, y1)
+            if host is not None:
+                done = torch.cuda.Event()
+                done.record(main)
+                side.wait_event(done)
+                with torch.cuda.stream(side):
+                    host[y0:y1].copy_(mosaic[y0:y1], non_blocking=True)
+        if host is not None:
+            self._download = torch.cuda.Event()
+            self._download.record(side)
 
     def finish_download(self):
         """Block until a banded download started by ``_collapse`` has landed."""
@@ -408,14 +422,16 @@ class Compositor:
             self._download.synchronize()
             self._download = None
 
-    def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None):
+    def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
+                        rows=None, on_band=None, mosaic=None, bands=8):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM."""
         h, w = shape
         if not 1 <= n_levels <= _lib.MAX_LEVELS:
             raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
-        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        if mosaic is None:
+            mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
             return mosaic.zero_()
         keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
@@ -467,31 +483,37 @@ class Compositor:
                         per.append(pool4[(2 * lvl * tot4 + o) * 4:][:h4 * w4 * 4].view(h4, w4, 4))
                     lows.append(per)
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
-                       (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host)
+                       (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
+                       rows, on_band, bands)
         self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows)
         return mosaic
 
-    def _pointwise(self, fn, name, patches, shape, out_host=None):
+    def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
+                   bands=8):
         h, w = shape
-        mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        if mosaic is None:
+            mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
             return mosaic.zero_()
         table = self._band_table(patches)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
-        self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host)
+        self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host,
+                       rows, on_band, bands)
         self._keep["collapse"] = (dev_table,)
         return mosaic
 
-    def blend_none(self, patches, shape, out_host=None):
+    def blend_none(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8):
         """stitcher.py:160-168 (last valid writer wins), gather form."""
-        return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host)
+        return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host, rows,
+                               on_band, mosaic, bands)
 
-    def blend_linear(self, patches, shape, out_host=None):
+    def blend_linear(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8):
         """stitcher.py:171-183, gather form."""
-        return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host)
+        return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host, rows,
+                               on_band, mosaic, bands)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""
@@ -503,13 +525,13 @@ class Compositor:
                       self.stream)
         return covered
 
-    def blend(self, kind, patches, shape, n_levels=5, out_host=None):
+    def blend(self, kind, patches, shape, n_levels=5, out_host=None, rows=None, on_band=None):
         if kind == "none":
-            return self.blend_none(patches, shape, out_host)
+            return self.blend_none(patches, shape, out_host, rows, on_band)
         if kind == "linear":
-            return self.blend_linear(patches, shape, out_host)
+            return self.blend_linear(patches, shape, out_host, rows, on_band)
         if kind == "multiband":
-            return self.blend_multiband(patches, shape, n_levels, out_host=out_host)
+            return self.blend_multiband(patches, shape, n_levels, out_host=out_host, rows=rows, on_band=on_band)
         raise ValueError(f"unknown blender {kind!r}")
 
     # -- whole path, device resident ------------------------------------------
@@ -520,12 +542,16 @@ class Compositor:
             return 0
         return geo.coarse_band_plan(n_levels)[0] + 4
 
-    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None):
+    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
+                  on_band=None, bands=8):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
-        those rows of the full composite).  ``out_host`` (pinned uint8 H x W x 3,
-        whole-mosaic mode only) receives the mosaic through a banded download
-        that overlaps the collapse; call ``finish_download`` before reading it."""
+        those rows of the full composite; only those rows are collapsed).
+        ``out_host`` (pinned uint8 H x W x 3, whole-mosaic mode only) receives
+        the mosaic through a banded download that overlaps the collapse; call
+        ``finish_download`` before reading it.  ``on_band(strip_rows, y0, y1)``
+        is called after the collapse of mosaic rows [y0, y1) has been launched
+        (``strip_rows`` = that part of the device result)."""
         halo = self.window_halo(kind, n_levels)
         if rows is None:
             ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
@@ -535,14 +561,29 @@ class Compositor:
             wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
             crops, tables = self.plan_crops(regions, plan, proj, rows=(wa, wb),
                                             row_align=4 if halo else 1, split_dilate=2 * halo)
+            out_host = None
         top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
         shape = (wb - top, plan.shape[1])
         state = self.new_owner_state(shape) if kind == "multiband" else None
         patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
-        if rows is not None:
-            out_host = None
+        holder = {}
+        band_cb = None
+        if on_band is not None:
+            def band_cb(y0, y1):
+                on_band(holder["mosaic"][y0:y1], y0 + top, y1 + top)
+        local = (ya - top, yb - top)
         if kind == "multiband":
-            strip = self.blend_multiband(patches, shape, n_levels, owner_state=state, out_host=out_host)
+            strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels,
+                                     owner_state=state, out_host=out_host, rows=local, on_band=band_cb,
+                                     bands=bands)
         else:
-            strip = self.blend(kind, patches, shape, n_levels, out_host)
-        return strip[ya - top:ya - top + (yb - ya)], patches
+            strip = self._blend_into(holder, self.blend_none if kind == "none" else self.blend_linear,
+                                     patches, shape, out_host=out_host, rows=local, on_band=band_cb,
+                                     bands=bands)
+        return strip[local[0]:local[1]], patches
+
+    def _blend_into(self, holder, blender, patches, shape, *args, **kwargs):
+        """Run a blender whose band callback needs to see the output buffer:
+        the buffer is allocated here and handed to the blender."""
+        holder["mosaic"] = torch.empty(tuple(shape) + (3,), dtype=torch.uint8, device=self.device)
+        return blender(patches, shape, *args, mosaic=holder["mosaic"], **kwargs)

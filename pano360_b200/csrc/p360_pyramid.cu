@@ -362,7 +362,7 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
     P360_REQUIRE(patches && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
     P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && W > 0, where);
-    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin && y_begin % 32 == 0, where);
+    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
     if (y_end == y_begin) return 0;
     const int H = y_end;
     auto bp = reinterpret_cast<const BandPatch *>(patches);
@@ -383,7 +383,7 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
 static int pointwise_collapse(const char *where, int mode, const p360_band_patch *patches, int n_patches,
                               uint8_t *out_u8, int y_begin, int y_end, int W, void *stream) {
     P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && W > 0, where);
-    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin && y_begin % 32 == 0, where);
+    P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
     if (y_end == y_begin) return 0;
     dim3 grid(cdiv(W, CT_X), cdiv(y_end - y_begin, CT_Y)), block(CT_X, 4);
     auto bp = reinterpret_cast<const BandPatch *>(patches);

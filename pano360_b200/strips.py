@@ -124,6 +124,51 @@ def gather_strips(strip, parts, shape, dst=0, group=None):
     return None
 
 
+def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,
+                     bands=4):
+    """Strip composite + gather, overlapped: every rank collapses its strip in
+    ``bands`` row bands and sends each band to rank 0 over NVLink as soon as it
+    is done, while the next band is being computed; rank 0 receives straight
+    into the rows of the full mosaic.  Returns the device mosaic on rank 0,
+    None elsewhere."""
+    from .compositor import band_edges
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return comp.composite(regions, src, plan, kind, n_levels, proj)[0]
+    h, w = plan.shape
+    rows = parts[rank]
+    if rank != 0:
+        works = []
+
+        def send_band(part, y0, y1):
+            works.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, part, 0, group)]))
+        if rows[1] > rows[0]:
+            comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, on_band=send_band, bands=bands)
+        for work in works:
+            work.wait()
+        return None
+    mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=comp.device)
+    if rows[1] > rows[0]:
+        strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
+        mosaic[rows[0]:rows[1]].copy_(strip)
+    works = []
+    for k in range(bands):
+        ops = []
+        for r in range(1, world):
+            a, b = parts[r]
+            if b <= a:
+                continue
+            y0, y1 = band_edges(a, b, bands)[k]
+            if y1 > y0:
+                ops.append(dist.P2POp(dist.irecv, mosaic[y0:y1], r, group))
+        if ops:
+            works.extend(dist.batch_isend_irecv(ops))
+    for work in works:
+        work.wait()
+    return mosaic
+
+
 def all_pair_statistics(comp, regions, src, group=None):
     """Exposure-gain statistics with the image pairs dealt round-robin over
     the ranks; the three sums per pair are all-reduced so that every rank
@@ -163,11 +208,7 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
         comp.set_gains(src, find_gains(overlaps, sizes))
-    if rows[1] > rows[0]:
-        strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
-    else:
-        strip = torch.empty((0, plan.shape[1], 3), dtype=torch.uint8, device=comp.device)
-    mosaic = gather_strips(strip, parts, plan.shape, 0, group)
+    mosaic = composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj, group)
     if rank != 0 or mosaic is None:
         return None
     if not to_host:
