@@ -4,8 +4,9 @@ One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The
 mosaic rows are split into contiguous ranges of equal estimated cost; every
 rank warps and blends only the images that overlap its rows (plus a halo of
 the largest blur radius, re-warped locally — the warp is pointwise, so no halo
-exchange is needed) and the uint8 strips are gathered on rank 0 in one grouped
-send/recv at the very end.  There is no other data-path collective.
+exchange is needed) and the uint8 strips are pushed band by band into rank 0's
+mosaic over NVLink (peer-mapped destination) while the rest of the strip is
+still being computed.  There is no other data-path collective.
 
 The reference has no distributed code; this module is the B200-side answer to
 its single-process ``stitch()`` (stitcher.py:274-327) for mosaics too large or
@@ -124,13 +125,54 @@ def gather_strips(strip, parts, shape, dst=0, group=None):
     return None
 
 
+class PeerMosaic:
+    """Rank 0's mosaic buffer mapped into every rank's address space over
+    NVLink / NVSwitch (torch symmetric memory): strips are written by DMA
+    straight into their rows of the destination, band by band, while the next
+    band is still being computed — no staging, no NCCL kernel."""
+
+    _cache = {}
+
+    def __init__(self, device, group):
+        self.device, self.group = device, group
+        self.capacity, self.handle, self.local = 0, None, None
+
+    @classmethod
+    def get(cls, device, group):
+        key = (str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(device, group)
+        return cls._cache[key]
+
+    def ensure(self, nbytes):
+        """Collective: (re)allocate the symmetric buffer when it is too small."""
+        if nbytes <= self.capacity:
+            return
+        import torch.distributed._symmetric_memory as symm
+        cap = (int(nbytes * 1.25) + (1 << 21) - 1) >> 21 << 21
+        self.local = symm.empty(cap, dtype=torch.uint8, device=self.device)
+        self.handle = symm.rendezvous(self.local, self.group if self.group is not None else dist.group.WORLD)
+        self.capacity = cap
+
+    def rows_of_rank0(self, h, w):
+        return self.handle.get_buffer(0, (h, w, 3), torch.uint8)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
+_peer_ok = True
+
+
 def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,
                      bands=4):
     """Strip composite + gather, overlapped: every rank collapses its strip in
-    ``bands`` row bands and sends each band to rank 0 over NVLink as soon as it
-    is done, while the next band is being computed; rank 0 receives straight
-    into the rows of the full mosaic.  Returns the device mosaic on rank 0,
-    None elsewhere."""
+    ``bands`` row bands and pushes each band into rank 0's mosaic over NVLink as
+    soon as it is done, while the next band is being computed.  Preferred
+    transport: peer-mapped destination (``PeerMosaic``, copy-engine DMA); if
+    symmetric memory cannot be set up, grouped NCCL send/recv.  Returns the
+    device mosaic on rank 0 (valid until the next call), None elsewhere."""
+    global _peer_ok
     from .compositor import band_edges
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -138,6 +180,35 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
         return comp.composite(regions, src, plan, kind, n_levels, proj)[0]
     h, w = plan.shape
     rows = parts[rank]
+    peer = None
+    if _peer_ok and comp.device.type == "cuda":
+        try:
+            peer = PeerMosaic.get(comp.device, group)
+            peer.ensure(h * w * 3)
+        except Exception as exc:                      # no symmetric memory on this system
+            import logging
+            logging.getLogger(__name__).warning("peer-mapped gather unavailable (%s); using NCCL send/recv", exc)
+            _peer_ok, peer = False, None
+    if peer is not None:
+        main, side = torch.cuda.current_stream(comp.device), comp.copy_stream()
+        dst = peer.rows_of_rank0(h, w)
+        peer.barrier()                                # rank 0 is done with the previous mosaic
+        if rows[1] > rows[0]:
+            if rank == 0:
+                strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
+                dst[rows[0]:rows[1]].copy_(strip)
+            else:
+                def push_band(part, y0, y1):
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    side.wait_event(done)
+                    with torch.cuda.stream(side):
+                        dst[y0:y1].copy_(part, non_blocking=True)
+                comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, on_band=push_band,
+                               bands=bands)
+                main.wait_stream(side)
+        peer.barrier()                                # every strip has landed
+        return dst if rank == 0 else None
     if rank != 0:
         works = []
 
