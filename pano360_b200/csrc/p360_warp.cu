@@ -70,9 +70,10 @@ __device__ __forceinline__ float blend4(float a, float b, float c, float d,
 }
 
 constexpr int WARP_BX = 64, WARP_BY = 4;
+constexpr int WARP_ROWS = 2;            // rows per thread (independent chains for latency hiding)
 
-__device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, int c, int r,
-                                           unsigned long long *keys, uint8_t *covered, int W) {
+// value of patch pixel (c, r): RGBA (alpha already masked) + invalid flag
+__device__ __forceinline__ float4 warp_compute(const WarpJob &s, const float *lut, int c, int r, bool &bad) {
     // p = K R (rx, ry, rz) in float64, k = 0, 1, 2 in order, then cast to
     // float32 (stitcher.py:303-306)
     const double rx = __ldg(s.ray_x + s.col0 + c), rz = __ldg(s.ray_z + s.col0 + c);
@@ -80,7 +81,7 @@ __device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, i
     const float px = (float)fma(s.kr[2], rz, fma(s.kr[1], ry, s.kr[0] * rx));
     const float py = (float)fma(s.kr[5], rz, fma(s.kr[4], ry, s.kr[3] * rx));
     const float pz = (float)fma(s.kr[8], rz, fma(s.kr[7], ry, s.kr[6] * rx));
-    bool bad = pz < 0.0f;                                        // stitcher.py:308
+    bad = pz < 0.0f;                                             // stitcher.py:308
     const float x = __fadd_rn(__fdiv_rn(px, pz), (float)(s.w / 2.0));   // stitcher.py:310
     const float y = __fadd_rn(__fdiv_rn(py, pz), (float)(s.h / 2.0));
     bad |= (x < 0.0f) | (x > (float)(s.w - 1)) | (y < 0.0f) | (y > (float)(s.h - 1));   // :311-312
@@ -106,6 +107,11 @@ __device__ __forceinline__ void warp_pixel(const WarpJob &s, const float *lut, i
     o.z = blend4(a.z, b.z, cc.z, d.z, w00, w01, w10, w11);
     o.w = blend4(a.w, b.w, cc.w, d.w, w00, w01, w10, w11);
     if (bad) o.w = 0.0f;                                         // stitcher.py:317
+    return o;
+}
+
+__device__ __forceinline__ void warp_commit(const WarpJob &s, int c, int r, const float4 &o, bool bad,
+                                            unsigned long long *keys, uint8_t *covered, int W) {
     const size_t idx = (size_t)r * s.pw + c;
     st_stream(s.out + idx, o);
     s.invalid[idx] = bad ? 1 : 0;
@@ -123,13 +129,27 @@ __global__ void __launch_bounds__(WARP_BX *WARP_BY)
 warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
     __shared__ float lut[256];
     const WarpJob &job = c_warp_jobs[blockIdx.z];
-    if ((int)(blockIdx.x * WARP_BX) >= job.pw || (int)(blockIdx.y * WARP_BY) >= job.ph) return;   // block-uniform
+    const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
+    if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
     const int tid = threadIdx.y * WARP_BX + threadIdx.x;
     lut[tid] = __ldg(job.lut + tid);
     __syncthreads();
-    const int c = blockIdx.x * WARP_BX + threadIdx.x, r = blockIdx.y * WARP_BY + threadIdx.y;
-    if (c >= job.pw || r >= job.ph) return;
-    warp_pixel(job, lut, c, r, keys, covered, W);
+    const int c = blockIdx.x * WARP_BX + threadIdx.x;
+    if (c >= job.pw) return;
+    // all gathers and arithmetic of the thread's rows first (independent
+    // chains in flight together), then the stores and the owner competition
+    float4 o[WARP_ROWS];
+    bool bad[WARP_ROWS];
+#pragma unroll
+    for (int k = 0; k < WARP_ROWS; ++k) {
+        const int r = min(r0 + threadIdx.y + k * WARP_BY, job.ph - 1);
+        o[k] = warp_compute(job, lut, c, r, bad[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < WARP_ROWS; ++k) {
+        const int r = r0 + threadIdx.y + k * WARP_BY;
+        if (r < job.ph) warp_commit(job, c, r, o[k], bad[k], keys, covered, W);
+    }
 }
 
 // u8 x 3 -> u8 x 4 (one aligned 32-bit word per source pixel for the gathers)
@@ -178,7 +198,7 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
         // stream-ordered: waits for the previous launch that still reads the table
         P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host + first, sizeof(WarpJob) * count, 0,
                                           cudaMemcpyHostToDevice, s), where);
-        dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY), count);
+        dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
         warp_batch_kernel<<<grid, block, 0, s>>>(reinterpret_cast<unsigned long long *>(owner_keys), covered, W);
         if (int e = check_launch(where)) return e;

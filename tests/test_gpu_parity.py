@@ -280,6 +280,44 @@ def test_blur_kernel_generic_taps(comp, ksize):
     assert np.abs(got - want).max() < 5e-6
 
 
+@pytest.mark.parametrize("ksizes", [(3, 15, 25), (17, 15, 19, 23), (27, 5), (33, 97)])
+def test_batched_blur_paths(comp, ksizes):
+    """p360_gauss_blur_batch: several images x several tap sets in one call.
+    ksize <= 25 takes the fused on-chip x+y kernel, wider sets the two-pass
+    kernels; both against a float64 NumPy convolution with REFLECT_101."""
+    import ctypes as C
+    import torch
+    from pano360_b200 import _lib
+    rng = np.random.default_rng(sum(ksizes))
+    shapes = [(70, 45), (33, 130), (5, 7), (64, 64)][:len(ksizes)]
+    jobs = np.zeros(len(ksizes), dtype=_lib.BLUR_JOB)
+    keep, wants = [], []
+    comp._taps_key = None                       # the slots are about to be overwritten
+    for slot, (ks, (h, w)) in enumerate(zip(ksizes, shapes)):
+        img = rng.random((h, w, 4), dtype=np.float32)
+        taps = rng.random(ks).astype(np.float32)
+        taps /= taps.sum()
+        _lib.call("p360_blur_set_taps", slot, taps.ctypes.data_as(C.POINTER(C.c_float)), ks, comp.stream)
+        dev = torch.from_numpy(img).to(comp.device)
+        out, tmp = torch.empty_like(dev), torch.empty_like(dev)
+        keep.append((dev, out, tmp))
+        jobs[slot] = (dev.data_ptr(), out.data_ptr(), tmp.data_ptr(), w, h, slot, 0)
+        r = ks // 2
+        rows, cols = np.pad(np.arange(h), r, mode="reflect"), np.pad(np.arange(w), r, mode="reflect")
+        if h == 1: rows = np.zeros(h + 2 * r, int)
+        mid = sum(np.float64(taps[t]) * img[:, cols[t:t + w]].astype(np.float64) for t in range(ks))
+        wants.append(sum(np.float64(taps[t]) * mid[rows[t:t + h]] for t in range(ks)))
+    # smaller slots than any previous test may have left: reset the rest to 1-tap kernels
+    one = np.ones(1, np.float32)
+    for slot in range(len(ksizes), _lib.MAX_LEVELS):
+        _lib.call("p360_blur_set_taps", slot, one.ctypes.data_as(C.POINTER(C.c_float)), 1, comp.stream)
+    dev_jobs = comp._table(jobs, "test_blur_jobs")
+    _lib.call("p360_gauss_blur_batch", _lib.ptr(dev_jobs), len(jobs), max(s[1] for s in shapes),
+              max(s[0] for s in shapes), comp.stream)
+    for (dev, out, tmp), want in zip(keep, wants):
+        assert np.abs(out.cpu().numpy() - want).max() < 5e-6
+
+
 def test_c_abi_reports_errors_without_aborting(comp):
     from pano360_b200 import _lib
     with pytest.raises(RuntimeError, match="p360_gauss_blur"):
