@@ -149,75 +149,6 @@ blur_v_batch_kernel(const BlurJob *__restrict__ jobs) {
     blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot]);
 }
 
-// ---- fused horizontal + vertical pass for short kernels ---------------------
-// The coarse-grid blurs of the band pipeline have ksize <= 25.  For those the
-// intermediate image never leaves the SM: a 32 x 32 output tile is staged with
-// its halo (reflection applied while staging), filtered along x into shared
-// memory and then along y into HBM — one read and one write per pixel of DRAM
-// traffic instead of two of each.  Same register-blocked FFMA2 inner loop.
-constexpr int F_T = 32;                       // outputs per tile edge
-constexpr int F_MAXR = 12;                    // largest radius handled here
-constexpr int F_IN = F_T + 2 * F_MAXR;        // staged rows / columns (max)
-constexpr int F_PITCH = 68;                   // input row pitch (float4), = 4 mod 8: conflict-free R-strided reads
-constexpr int F_MIDP = 36;                    // H-pass result row pitch (float4), = 4 mod 8
-constexpr size_t F_SMEM = sizeof(float4) * (size_t)F_IN * (F_PITCH + F_MIDP);
-
-__global__ void __launch_bounds__(128)
-blur_fused_batch_kernel(const BlurJob *__restrict__ jobs) {
-    extern __shared__ float4 smem[];
-    float4 *in = smem, *mid = smem + F_IN * F_PITCH;
-    const BlurJob &job = jobs[blockIdx.z];
-    const int w = job.w, h = job.h;
-    const int x0 = blockIdx.x * F_T, y0 = blockIdx.y * F_T;
-    if (x0 >= w || y0 >= h) return;                                   // block-uniform
-    const Taps &t = c_taps[job.slot];
-    const int r = t.ksize >> 1, nin = F_T + 2 * r;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float4 *src = job.in;
-    for (int ry = warp; ry < nin; ry += 4) {
-        const float4 *row = src + (size_t)reflect_101(y0 - r + ry, h) * w;
-        for (int rx = lane; rx < nin; rx += 32) in[ry * F_PITCH + h_phys(rx)] = __ldg(row + reflect_101(x0 - r + rx, w));
-    }
-    __syncthreads();
-    {   // along x: 4 threads x 8 outputs per row, 8 rows per warp pass
-        const int seg = lane & 3, sub = lane >> 2;
-        for (int g = warp; 8 * g < nin; g += 4) {
-            const int row = 8 * g + sub;
-            if (row < nin) {
-                float2 lo[R], hi[R];
-#pragma unroll
-                for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
-                const float4 *line = in + row * F_PITCH;
-                const int base = R * seg;
-                convolve_r(lo, hi, t, [&](int j, bool ok) {
-                    return ok ? line[h_phys(base + j)] : make_float4(0.f, 0.f, 0.f, 0.f);
-                });
-#pragma unroll
-                for (int i = 0; i < R; ++i)
-                    mid[row * F_MIDP + h_phys(base + i)] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
-            }
-        }
-    }
-    __syncthreads();
-    {   // along y: lanes along x, 8 output rows per warp
-        float2 lo[R], hi[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
-        const int base = R * warp, col = h_phys(lane);
-        convolve_r(lo, hi, t, [&](int j, bool ok) {
-            return ok ? mid[(base + j) * F_MIDP + col] : make_float4(0.f, 0.f, 0.f, 0.f);
-        });
-        const int x = x0 + lane;
-        if (x < w) {
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int y = y0 + base + i;
-                if (y < h) job.out[(size_t)y * w + x] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
-            }
-        }
-    }
-}
-
 inline void fill_taps(Taps &t, const float *taps_host, int ksize) {
     memset(&t, 0, sizeof(t));
     memcpy(t.k + R - 1, taps_host, sizeof(float) * ksize);
@@ -289,14 +220,6 @@ extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int 
     for (int i = 0; i < P360_MAX_LEVELS; ++i) ksize = g_slot_ksize[i] > ksize ? g_slot_ksize[i] : ksize;
     cudaStream_t s = (cudaStream_t)stream;
     auto bj = reinterpret_cast<const BlurJob *>(jobs);
-    if (ksize <= 2 * F_MAXR + 1) {              // short kernels: fused x+y pass, intermediate stays on chip
-        static size_t f_limit = 48 * 1024;
-        if (int e = ensure_smem(blur_fused_batch_kernel, F_SMEM, f_limit, where)) return e;
-        dim3 grid(cdiv(max_w, F_T), cdiv(max_h, F_T), n_jobs);
-        P360_REQUIRE(grid.y <= 65535, where);
-        blur_fused_batch_kernel<<<grid, 128, F_SMEM, s>>>(bj);
-        return check_launch(where);
-    }
     const int pitch = h_phys(H_SEG + ksize - 1) + 1;
     const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
     const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);

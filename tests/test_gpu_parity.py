@@ -217,6 +217,33 @@ def test_two_row_six_band_layout(st, restore_globals):
     assert_mosaic_close(got, rs.stitch(regs, "multiband", False, 6, 1e9))
 
 
+def test_full_size_cfg3_windows_and_properties(st, comp, restore_globals):
+    """BASELINE config 3 at FULL size (12 x 4000x3000, 6 bands, 6051 x 15316
+    mosaic, ~160 s on the reference's CPU path): windows of the GPU mosaic
+    against the oracle's exact window mode, plus size-independent properties
+    (coverage, determinism, linear blend == hat-weighted mean inside one image)."""
+    wl = synth.workload("cfg3")
+    regs = synth.make_views(wl)
+    st.MAX_RESOLUTION = wl.max_resolution
+    got = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
+    h, w = got.shape[:2]
+    assert (h, w) == geo.plan_mosaic(regs, True, 1e9).shape
+    for win in [(h // 2 - 100, h // 2 + 28, w // 2 - 150, w // 2 + 106),      # centre: 4 images meet
+                (0, 96, 2000, 2256),                                            # top mosaic edge
+                (h // 3, h // 3 + 96, 40, 296)]:                                # left edge of the first image
+        want = rs.stitch_window(regs, win, "multiband", False, wl.n_levels, 1e9)
+        assert_mosaic_close(got[win[0]:win[1], win[2]:win[3]], want, what=f"cfg3 window {win}")
+    again = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
+    assert np.array_equal(got, again)                                           # atomics notwithstanding
+    plan = geo.plan_mosaic(regs, False, 1e9)
+    none = st.stitch(regs, blender=st.no_blend)
+    win = (plan.shape[0] // 2 - 64, plan.shape[0] // 2 + 64, 3000, 3300)
+    want = rs.stitch_window(regs, win, "none", False, 5, 1e9)
+    assert np.array_equal(none[win[0]:win[1], win[2]:win[3]], want)
+    covered = (none.sum(axis=2) > 0).mean()
+    assert 0.6 < covered < 0.95
+
+
 def test_edge_cases(st, restore_globals):
     """Single image; images smaller than the blur radius; crop."""
     wl = synth.workload("cfg1", scale=16.0)          # 40 x 30 pixel views
@@ -282,9 +309,8 @@ def test_blur_kernel_generic_taps(comp, ksize):
 
 @pytest.mark.parametrize("ksizes", [(3, 15, 25), (17, 15, 19, 23), (27, 5), (33, 97)])
 def test_batched_blur_paths(comp, ksizes):
-    """p360_gauss_blur_batch: several images x several tap sets in one call.
-    ksize <= 25 takes the fused on-chip x+y kernel, wider sets the two-pass
-    kernels; both against a float64 NumPy convolution with REFLECT_101."""
+    """p360_gauss_blur_batch: several images x several tap sets in one call,
+    against a float64 NumPy convolution with REFLECT_101."""
     import ctypes as C
     import torch
     from pano360_b200 import _lib
