@@ -338,8 +338,15 @@ def run_gpu_arm(args):
         top = max(per_kernel, key=lambda k: per_kernel[k][0])
         t_ms, nbytes, count = per_kernel[top]
         achieved = nbytes / t_ms / 1e6                     # GB/s
+        traffic = None
+        try:           # ncu-measured DRAM bytes per launch of this kernel (1 GPU, same workload)
+            table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if world == 1 and args.scale == 1.0:
+                traffic = table.get(wl.name, {}).get(top)
+        except OSError:
+            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                     "launch_ms": t_ms / count, "algorithmic_bytes_per_launch": nbytes / count,
                     "share_of_step": t_ms / ms}
     # per-rank load (strip balance): traced kernel time of every rank, gathered on rank 0
