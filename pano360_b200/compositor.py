@@ -145,14 +145,14 @@ class Compositor:
         return rc
 
     # -- sources --------------------------------------------------------------
-    def pack_pixels(self, dev_img):
-        """u8 x 3 -> u8 x 4 on the device: one aligned 32-bit word per pixel,
-        so each bilinear tap of the warp is a single load."""
-        if dev_img.shape[2] == 4:
-            return dev_img
-        h, w = dev_img.shape[:2]
-        packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
-        _lib.call("p360_pack_rgbx", _lib.ptr(dev_img), _lib.ptr(packed), h * w, self.stream)
+    def pack_pixels(self, dev_img, hats):
+        """u8 x 3 -> {RGBX u32, alpha f32} on the device: one aligned 64-bit
+        word per pixel holds everything a bilinear tap of the warp needs."""
+        h, w, c = dev_img.shape
+        hat_y, hat_x = hats
+        packed = torch.empty((h, w, 8), dtype=torch.uint8, device=self.device)
+        _lib.call("p360_pack_rgbxa", _lib.ptr(dev_img), c, _lib.ptr(hat_y), _lib.ptr(hat_x), h, w,
+                  _lib.ptr(packed), self.stream)
         return packed
 
     def upload(self, regions, gains=None, need=None, overlap=False):
@@ -179,13 +179,16 @@ class Compositor:
                 if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
                 host = torch.from_numpy(np.ascontiguousarray(img))
+                if (h, w) not in src.hats:
+                    src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
+                    if overlap:
+                        side.wait_stream(main)               # hat tables were copied on the main stream
                 with torch.cuda.stream(side):
-                    src.pixels.append(self.pack_pixels(host.to(self.device, non_blocking=host.is_pinned())))
+                    dev_img = host.to(self.device, non_blocking=host.is_pinned())
+                    src.pixels.append(self.pack_pixels(dev_img, src.hats[(h, w)]))
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
-                if (h, w) not in src.hats:
-                    src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
             if gains is None:
                 lut0 = self._to_device(geo.sample_lut(None)) if lut0 is None else lut0
                 src.luts.append(lut0)

@@ -110,7 +110,7 @@ extern "C" int p360_pair_overlap_stats(const uint8_t *src_i, const uint8_t *src_
     using namespace p360;
     const char *where = "p360_pair_overlap_stats";
     P360_REQUIRE(src_i && src_j && lut && hat_y && hat_x && inv_hom_host && partial && out3, where);
-    P360_REQUIRE(h > 0 && w > 0 && (src_c == 3 || src_c == 4), where);
+    P360_REQUIRE(h > 0 && w > 0 && (src_c == 3 || src_c == 4 || src_c == 8), where);
     Hom inv;
     memcpy(inv.m, inv_hom_host, sizeof(inv.m));
     int nblocks = p360_pair_stats_blocks(h, w);

@@ -45,6 +45,14 @@ __device__ __forceinline__ float lut_at(const float *lut, uint32_t byte_offset) 
 __device__ __forceinline__ float4 sample(const WarpJob &s, const float *lut, int y, int x, double hy,
                                          double hx) {
     float4 v;
+    if (s.c == 8) {                                   // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
+        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(s.src) + (y * s.w + x));
+        v.x = lut_at(lut, (u.x << 2) & 0x3fc);        // byte k pre-scaled by sizeof(float)
+        v.y = lut_at(lut, (u.x >> 6) & 0x3fc);
+        v.z = lut_at(lut, (u.x >> 14) & 0x3fc);
+        v.w = __uint_as_float(u.y);
+        return v;
+    }
     if (s.c == 4) {
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(s.src) + (y * s.w + x));
         v.x = lut_at(lut, (u << 2) & 0x3fc);          // byte k pre-scaled by sizeof(float)
@@ -97,8 +105,11 @@ __device__ __forceinline__ float4 warp_compute(const WarpJob &s, const float *lu
     const float ax = (float)(sx & 31) * 0.03125f, ay = (float)(sy & 31) * 0.03125f;
     const float w00 = __fmul_rn(1.0f - ay, 1.0f - ax), w01 = __fmul_rn(1.0f - ay, ax);
     const float w10 = __fmul_rn(ay, 1.0f - ax), w11 = __fmul_rn(ay, ax);
-    const double hy0 = __ldg(s.hat_y + y0), hy1 = __ldg(s.hat_y + y1);
-    const double hx0 = __ldg(s.hat_x + x0), hx1 = __ldg(s.hat_x + x1);
+    double hy0 = 0.0, hy1 = 0.0, hx0 = 0.0, hx1 = 0.0;
+    if (s.c != 8) {                                              // alpha not pre-packed with the pixels
+        hy0 = __ldg(s.hat_y + y0); hy1 = __ldg(s.hat_y + y1);
+        hx0 = __ldg(s.hat_x + x0); hx1 = __ldg(s.hat_x + x1);
+    }
     const float4 a = sample(s, lut, y0, x0, hy0, hx0), b = sample(s, lut, y0, x1, hy0, hx1);
     const float4 cc = sample(s, lut, y1, x0, hy1, hx0), d = sample(s, lut, y1, x1, hy1, hx1);
     float4 o;
@@ -152,6 +163,22 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
     }
 }
 
+// u8 x 3 -> {RGBX u32, alpha f32}: one aligned 64-bit word per source pixel
+// holding everything a bilinear tap needs; alpha = float32(hat_y * hat_x) is
+// evaluated once per source pixel here instead of once per tap in the warp
+// (stitcher.py:257-263).
+__global__ void __launch_bounds__(256)
+pack_rgbxa_kernel(const uint8_t *__restrict__ src, int sc, const double *__restrict__ hat_y,
+                  const double *__restrict__ hat_x, int h, int w, uint2 *__restrict__ dst) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *p = src + ((size_t)y * w + x) * sc;
+    uint2 o;
+    o.x = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    o.y = __float_as_uint((float)(__ldg(hat_y + y) * __ldg(hat_x + x)));
+    dst[(size_t)y * w + x] = o;
+}
+
 // u8 x 3 -> u8 x 4 (one aligned 32-bit word per source pixel for the gathers)
 __global__ void __launch_bounds__(256)
 pack_rgbx_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, long long n) {
@@ -174,6 +201,18 @@ extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t
     return check_launch(where);
 }
 
+extern "C" int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
+                               int h, int w, uint8_t *dst_rgbxa, void *stream) {
+    using namespace p360;
+    const char *where = "p360_pack_rgbxa";
+    P360_REQUIRE(src && hat_y && hat_x && dst_rgbxa && h > 0 && w > 0 && h <= 65535, where);
+    P360_REQUIRE(src_c == 3 || src_c == 4, where);
+    P360_REQUIRE((reinterpret_cast<uintptr_t>(dst_rgbxa) & 7) == 0, where);
+    pack_rgbxa_kernel<<<dim3(cdiv(w, 256), h), 256, 0, (cudaStream_t)stream>>>(
+        src, src_c, hat_y, hat_x, h, w, reinterpret_cast<uint2 *>(dst_rgbxa));
+    return check_launch(where);
+}
+
 extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                                uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
     using namespace p360;
@@ -188,7 +227,8 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
             const p360_warp_job &j = jobs_host[k];
             P360_REQUIRE(j.src && j.lut && j.hat_y && j.hat_x && j.ray_x && j.ray_z && j.ray_y && j.out && j.invalid, where);
             P360_REQUIRE(j.h > 0 && j.w > 0 && j.h <= 32767 && j.w <= 32767 && j.pw >= 0 && j.ph >= 0, where);
-            P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0), where);
+            P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0) ||
+                         (j.c == 8 && (reinterpret_cast<uintptr_t>(j.src) & 7) == 0), where);
             P360_REQUIRE(aligned16(j.out), where);
             P360_REQUIRE(owner_keys == nullptr || (j.x0 >= 0 && j.y0 >= 0 && j.x0 + j.pw <= W), where);
             max_pw = j.pw > max_pw ? j.pw : max_pw;
