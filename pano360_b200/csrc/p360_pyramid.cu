@@ -202,7 +202,7 @@ __device__ __forceinline__ Pair2 expand_at(const float4 *__restrict__ p, int lw,
 constexpr int ROWS_PER_THREAD = CT_Y / 4;
 
 template <int L>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (L <= 5) ? 4 : 3)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
                           const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int row0,
@@ -211,6 +211,19 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
     const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
     int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
     n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+    {   // pull this tile's slice of every contributing patch (and of the owner keys) towards L2
+        // now: one 128-byte line per thread and patch, so that the gathers below find their
+        // streamed operands on chip instead of paying a DRAM round trip per patch iteration
+        const int tid = threadIdx.y * CT_X + threadIdx.x;
+        const int trow = ty0 + (tid >> 3), tcol = tx0 + 8 * (tid & 7);
+        if (trow < H && tcol < W) prefetch_l2(keys + (size_t)trow * W + tcol);
+        for (int it = 0; it < n_hit; ++it) {
+            const BandPatch &bp = patches[list[it]];
+            const int px = tcol - bp.x0, py = trow - bp.y0;
+            if ((unsigned)py < (unsigned)bp.ph && px > -8 && px < bp.pw)
+                prefetch_l2(bp.rgba + (size_t)py * bp.pw + max(px, 0));
+        }
+    }
     const int X = tx0 + threadIdx.x;
     if (X >= W) return;
     for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
