@@ -244,6 +244,43 @@ def test_full_size_cfg3_windows_and_properties(st, comp, restore_globals):
     assert 0.6 < covered <= 1.0
 
 
+def test_cli_with_reference_style_caches(st, tmp_path, monkeypatch, restore_globals):
+    """The drop-in CLI (stitcher.py:390-451): images on disk + the reference's
+    ba_<name>.pkl cache in the CWD -> same flags -> mosaic file, equal to the
+    oracle on the same regions.  The PKL names `bundle_adj.Image`, as the
+    reference writes it."""
+    import pickle
+    import sys
+    import types
+    regs = synth.make_views(synth.workload("cfg1", scale=4.0), noise=10.0)
+    img_dir = tmp_path / "room"
+    img_dir.mkdir()
+    for i, reg in enumerate(regs):
+        cv2.imwrite(str(img_dir / f"view{i}.png"), reg.img)
+    fake = types.ModuleType("bundle_adj")
+    fake.Image = type("Image", (), {"hom": lambda self: self.rot.T.dot(np.linalg.inv(self.intr)),
+                                    "proj": lambda self: self.intr.dot(self.rot)})
+    fake.Image.__module__ = "bundle_adj"
+    monkeypatch.setitem(sys.modules, "bundle_adj", fake)
+    objs = []
+    for reg in regs:
+        o = fake.Image()
+        o.img, o.rot, o.intr, o.range = reg.img, reg.rot, reg.intr, reg.range
+        objs.append(o)
+    monkeypatch.chdir(tmp_path)
+    with open("ba_room_s1.0.pkl", "wb") as fid:
+        pickle.dump(objs, fid, protocol=pickle.HIGHEST_PROTOCOL)
+    out = tmp_path / "pano.png"
+    for blend, extra in (("multiband", []), ("linear", ["-e"]), ("none", ["-c"])):
+        mosaic = st.main([str(img_dir), "-s", "1", "-b", blend, "-o", str(out), "--no-show"] + extra)
+        assert np.array_equal(cv2.imread(str(out)), mosaic)
+        want = rs.stitch(regs, blend, "-e" in extra, 5, 1400)
+        if "-c" in extra:
+            assert mosaic.shape[0] <= want.shape[0] and mosaic.shape[1] <= want.shape[1] and mosaic.min() >= 0
+        else:
+            assert_mosaic_close(mosaic, want, what=blend)
+
+
 def test_edge_cases(st, restore_globals):
     """Single image; images smaller than the blur radius; crop."""
     wl = synth.workload("cfg1", scale=16.0)          # 40 x 30 pixel views
