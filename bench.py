@@ -140,26 +140,59 @@ def run_reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a
+    background thread every 50 ms (cheaper than polling an nvidia-smi process,
+    which measurably stalls kernel launches); nvidia-smi -lms as a fallback."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread = index, None, None
+        self.samples, self.reasons, self.max_mhz, self.stop = [], set(), None, False
         self.path = tempfile.mktemp(prefix="p360_clocks_", suffix=".csv")
+
+    def _nvml_loop(self, nvml, handle):
+        while not self.stop:
+            try:
+                self.samples.append(float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)))
+                mask = nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def __enter__(self):
         try:
+            import threading
+            import pynvml as nvml
+            nvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.replace(",", "").isdigit() else self.index
+            handle = nvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nvml, handle), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
         return self
 
     def __exit__(self, *exc):
+        self.stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -168,24 +201,25 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            os.unlink(self.path)
-        except OSError:
-            return out
-        sm, reasons = [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            r = [c.strip() for c in r]
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+        sm, reasons = list(self.samples), set(self.reasons)
+        if self.thread is None:
+            out["source"] = "nvidia-smi"
             try:
-                sm.append(float(r[1]))
-                out["sm_max_mhz"] = float(r[2])
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+                rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+                os.unlink(self.path)
+            except OSError:
+                rows = []
+            for r in rows:
+                r = [c.strip() for c in r]
+                try:
+                    sm.append(float(r[1]))
+                    out["sm_max_mhz"] = float(r[2])
+                except (ValueError, IndexError):
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
         if sm:
             busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
             out["sm_mhz"] = float(np.median(busy))
