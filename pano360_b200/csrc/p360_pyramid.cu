@@ -236,6 +236,23 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         for (int l = 0; l < L; ++l) lo[l] = hi[l] = make_float2(0.f, 0.f);
         if (covered[mi] != 0) {
             const unsigned long long key = __ldg(keys + mi);
+            if (n_hit == 1 && L > 1) {
+                // Only one patch has non-zero weights anywhere in this tile.  Where it also
+                // owns the pixel every level weight is > 0, so sum_l band_l * w_l / w_l
+                // telescopes to the warped pixel itself (I - B0 + B0 - B1 + ... + B_{L-2}):
+                // skip the pyramid, exact up to float rounding (~1e-7).
+                const BandPatch &bp = patches[list[0]];
+                const int px = X - bp.x0, py = Y - bp.y0;
+                if ((unsigned)px < (unsigned)bp.pw && (unsigned)py < (unsigned)bp.ph &&
+                    key_is_owner(key, bp.index)) {
+                    const float4 pix = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
+                    uint8_t *o = out + mi * 3;
+                    o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.x, 0.f), 1.f)));
+                    o[1] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.y, 0.f), 1.f)));
+                    o[2] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.z, 0.f), 1.f)));
+                    continue;
+                }
+            }
             for (int it = 0; it < n_hit; ++it) {              // patch order = list order
                 const BandPatch &bp = patches[list[it]];
                 const int px = X - bp.x0, py = Y - bp.y0;
