@@ -110,7 +110,10 @@ typedef struct p360_blur_job {
     const float *in;
     float *out;
     float *tmp;
-    int32_t w, h, slot, reserved;
+    int32_t w, h, slot;
+    int32_t shift;                /* log2 of the coarse factor of this image (own != NULL)   */
+    const int32_t *own;           /* owned box of the patch (p360_band_patch.own) or NULL:    */
+    int32_t pad, grow;            /* blocks farther than `grow` px from it are skipped        */
 } p360_blur_job;
 
 int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp_rgba,
@@ -149,8 +152,17 @@ typedef struct p360_band_patch {
     int32_t w4, h4;                           /* f = 4 grid size (f = 2 grid: twice)    */
     int32_t pad;                              /* extension in full-res pixels           */
     int32_t index;                            /* id of this patch in the owner keys     */
+    int32_t own[4];                           /* box around the owned pixels (patch px), */
+                                              /* filled on the device by p360_owned_boxes; */
+                                              /* initialise to {MAX, MAX, MIN, MIN}       */
 } p360_band_patch;
 
+ /*  p360_owned_boxes        per patch, the (tile-granular) box around the pixels it owns,
+ *                           from the owner keys: weights vanish beyond the blur reach of
+ *                           that box, so reduce / blur / collapse skip everything farther
+ *                           away (exact: skipped values only ever meet zero weights)      */
+int p360_owned_boxes(const uint64_t *owner_keys, p360_band_patch *patches, int n_patches,
+                     int H, int W, void *stream);
 int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]);
 int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int max_w4,
                               int max_h4, const uint64_t *owner_keys, int W, void *stream);

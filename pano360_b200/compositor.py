@@ -377,6 +377,7 @@ class Compositor:
             rec["rgba"], rec["invalid"] = p.rgba.data_ptr(), p.invalid.data_ptr()
             rec["x0"], rec["y0"], rec["pw"], rec["ph"] = x0, y0, pw, ph
             rec["pad"], rec["index"] = pad, k
+            rec["own"] = (2 ** 31 - 1, 2 ** 31 - 1, -2 ** 31, -2 ** 31)      # grown on the device (p360_owned_boxes)
             if coarse:
                 rec["w4"], rec["h4"] = (pw + 2 * pad + 3) // 4, (ph + 2 * pad + 3) // 4
         return table
@@ -457,20 +458,26 @@ class Compositor:
             table["low"][:, 0] = b2 + np.uint64(2) * s2 + o2
             for lvl in range(1, len(plan)):
                 table["low"][:, lvl] = b4 + np.uint64(2 * lvl) * s4 + o4
+            self._set_taps(n_levels, plan)
+        dev_table = self._table(table, "band_table")
+        pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
+        if plan:
+            # which part of each patch can ever carry weight: box around its owned pixels
+            self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table), n,
+                         h, w, self.stream)
+            own_ptr = np.uint64(dev_table.data_ptr() + _lib.OWN_OFFSET) + \
+                np.uint64(_lib.BAND_PATCH.itemsize) * np.arange(n, dtype=np.uint64)
             jobs = np.zeros(n * len(plan), dtype=_lib.BLUR_JOB)
             for lvl in range(len(plan)):
                 sl = jobs[lvl * n:(lvl + 1) * n]
                 if lvl == 0:
                     sl["in"], sl["tmp"] = table["d2"], b2 + s2 + o2
-                    sl["w"], sl["h"] = 2 * table["w4"], 2 * table["h4"]
+                    sl["w"], sl["h"], sl["shift"] = 2 * table["w4"], 2 * table["h4"], 1
                 else:
                     sl["in"], sl["tmp"] = table["d4"], b4 + np.uint64(2 * lvl - 1) * s4 + o4
-                    sl["w"], sl["h"] = table["w4"], table["h4"]
+                    sl["w"], sl["h"], sl["shift"] = table["w4"], table["h4"], 2
                 sl["out"], sl["slot"] = table["low"][:, lvl], lvl
-            self._set_taps(n_levels, plan)
-        dev_table = self._table(table, "band_table")
-        pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
-        if plan:
+                sl["own"], sl["pad"], sl["grow"] = own_ptr, pad, 2 * pad + 4
             dev_jobs = self._table(jobs, "blur_jobs")
             self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
                          int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, self.stream)

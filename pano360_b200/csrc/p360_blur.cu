@@ -87,8 +87,17 @@ struct BlurJob {                       // == p360_blur_job
     const float4 *in;
     float4 *out;
     float4 *tmp;
-    int w, h, slot, reserved;
+    int w, h, slot;
+    int shift;                         // log2 coarse factor
+    const int *own;                    // owned box of the patch (or nullptr)
+    int pad, grow;
 };
+
+// is the coarse block [cx0, cx1) x [cy0, cy1) of this job within reach of the patch's owned box?
+__device__ __forceinline__ bool job_block_needed(const BlurJob &job, int cx0, int cy0, int cx1, int cy1) {
+    const int s = job.shift, p = job.pad;
+    return near_owned(job.own, job.grow, (cx0 << s) - p, (cy0 << s) - p, (cx1 << s) - p, (cy1 << s) - p);
+}
 static_assert(sizeof(BlurJob) == sizeof(p360_blur_job), "ABI struct mismatch");
 
 __constant__ Taps c_taps[P360_MAX_LEVELS];     // tap sets of the batched blurs (p360_blur_set_taps)
@@ -101,8 +110,11 @@ blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, i
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch) {
     const BlurJob &job = jobs[blockIdx.y];
-    const int blocks = ((job.w + H_SEG - 1) / H_SEG) * ((job.h + H_WARPS - 1) / H_WARPS);
+    const int nxb = (job.w + H_SEG - 1) / H_SEG;
+    const int blocks = nxb * ((job.h + H_WARPS - 1) / H_WARPS);
     if ((int)blockIdx.x >= blocks) return;
+    const int cx0 = ((int)blockIdx.x % nxb) * H_SEG, cy0 = ((int)blockIdx.x / nxb) * H_WARPS;
+    if (!job_block_needed(job, cx0, cy0, cx0 + H_SEG, cy0 + H_WARPS)) return;       // block-uniform
     blur_h_body(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
 }
 
@@ -146,6 +158,8 @@ __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_batch_kernel(const BlurJob *__restrict__ jobs) {
     const BlurJob &job = jobs[blockIdx.z];
     if ((int)(blockIdx.x * 32) >= job.w || (int)(blockIdx.y * V_ROWS) >= job.h) return;   // block-uniform
+    if (!job_block_needed(job, blockIdx.x * 32, blockIdx.y * V_ROWS, blockIdx.x * 32 + 32,
+                          blockIdx.y * V_ROWS + V_ROWS)) return;
     blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot]);
 }
 

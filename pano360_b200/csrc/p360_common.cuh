@@ -76,6 +76,18 @@ __device__ __forceinline__ void owner_compete(unsigned long long *keys, size_t m
     if (alpha > 0.0f) atomicMax(keys + mi, owner_key(alpha, patch));
 }
 
+// ---- owned boxes -------------------------------------------------------------
+// own = {x0, y0, x1, y1}: box (patch pixels) around the pixels a patch owns, written on the
+// device by p360_owned_boxes.  A patch has non-zero blend weights only within the reach of
+// the widest blur around that box, so every stage restricts itself to a dilation of it.
+// own == nullptr: no restriction.
+__device__ __forceinline__ bool near_owned(const int *own, int grow, int ax0, int ay0, int ax1, int ay1) {
+    if (own == nullptr) return true;
+    const int ox0 = __ldg(own), oy0 = __ldg(own + 1), ox1 = __ldg(own + 2), oy1 = __ldg(own + 3);
+    if (ox1 <= ox0 || oy1 <= oy0) return false;          // owns nothing
+    return ax0 < ox1 + grow && ax1 > ox0 - grow && ay0 < oy1 + grow && ay1 > oy0 - grow;
+}
+
 // Streaming (read-once / write-once) 128-bit accesses: keep L1 for the gathers.
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
     float4 r;

@@ -43,6 +43,7 @@ struct BandPatch {                      // == p360_band_patch
     int w4, h4;                         // size of the f = 4 grid (f = 2 grid is twice that)
     int pad;                            // extension R in full-res pixels (multiple of 4)
     int index;                          // id of this patch in the owner keys
+    int own[4];                         // box around the owned pixels (patch px), see p360_owned_boxes
 };
 static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
 
@@ -61,6 +62,9 @@ pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
     const int xe = blockIdx.x * 32 + lane;             // column in the extended frame
     if (cy >= h4 || (int)(blockIdx.x * 32) >= 4 * w4) return;   // warp-uniform
     const int pw = bp.pw, ph = bp.ph, pad = bp.pad, w2 = 2 * w4;
+    if (keys != nullptr &&       // nothing within the blur chain's reach of the owned box reads these cells
+        !near_owned(bp.own, 2 * pad + 4, (int)(blockIdx.x * 32) - pad, (int)(blockIdx.y * 32) - pad,
+                    (int)(blockIdx.x * 32) - pad + 32, (int)(blockIdx.y * 32) - pad + 32)) return;
     const float4 *rgba = bp.rgba;
     const bool live = xe < 4 * w4;
     const int sx = reflect_101(xe - pad, pw);
@@ -88,6 +92,43 @@ pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
     if (live && !(lane & 3)) bp.d4[(size_t)cy * w4 + (xe >> 2)] = scale4(q, 0.0625f);
 }
 
+// ---- owned boxes -------------------------------------------------------------
+// One block per 64 x 32 mosaic tile: which patches own a pixel here?  (shared bitmap, up to
+// 1024 patches.)  Each of them grows its box to this tile with four atomics.
+__global__ void __launch_bounds__(256)
+owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patches, int n_patches,
+                   int H, int W) {
+    __shared__ unsigned present[32];
+    const int tid = threadIdx.x;
+    if (tid < 32) present[tid] = 0u;
+    __syncthreads();
+    const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + 256 * i, x = tx0 + (idx & 63), y = ty0 + (idx >> 6);
+        if (x < W && y < H) {
+            const unsigned long long k = __ldg(keys + (size_t)y * W + x);
+            if (k != 0ull) {
+                const unsigned p = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+                if (p < (unsigned)n_patches && p < 1024u) atomicOr(&present[p >> 5], 1u << (p & 31));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        unsigned word = present[tid];
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            BandPatch &bp = patches[tid * 32 + bit];
+            atomicMin(&bp.own[0], max(tx0 - bp.x0, 0));
+            atomicMin(&bp.own[1], max(ty0 - bp.y0, 0));
+            atomicMax(&bp.own[2], min(tx0 + 64 - bp.x0, bp.pw));
+            atomicMax(&bp.own[3], min(ty0 + 32 - bp.y0, bp.ph));
+        }
+    }
+}
+
 // ---- tile lists -------------------------------------------------------------
 constexpr int CT_X = 64, CT_Y = 32;     // mosaic tile per block; block = 64 x 4 threads, 8 rows each
 constexpr int MAX_TILE_PATCHES = 1024;  // patches that may overlap one tile
@@ -95,6 +136,7 @@ constexpr int MAX_TILE_PATCHES = 1024;  // patches that may overlap one tile
 // Ordered list (patch order = accumulation order, stitcher.py:223) of the
 // patches whose box intersects this block's tile, built cooperatively in
 // shared memory with ballots so that no host-side tile lists are needed.
+template <bool SUPPORT>
 __device__ int build_tile_list(const BandPatch *__restrict__ patches, int n_patches,
                                int tx0, int ty0, int16_t *list) {
     __shared__ int warp_hits[8];
@@ -108,6 +150,8 @@ __device__ int build_tile_list(const BandPatch *__restrict__ patches, int n_patc
         if (t < n_patches) {
             const BandPatch &bp = patches[t];
             hit = bp.x0 < tx0 + CT_X && bp.x0 + bp.pw > tx0 && bp.y0 < ty0 + CT_Y && bp.y0 + bp.ph > ty0;
+            if (SUPPORT && hit)      // weights vanish farther than `pad` from the owned box
+                hit = near_owned(bp.own, bp.pad, tx0 - bp.x0, ty0 - bp.y0, tx0 + CT_X - bp.x0, ty0 + CT_Y - bp.y0);
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) warp_hits[warp] = __popc(ballot);
@@ -152,8 +196,11 @@ __device__ int cull_tile_list(const BandPatch *__restrict__ patches, int n_hit, 
         const int id = list[it];
         const BandPatch &bp = patches[id];
         const int lw = bp.w4 * (SHIFT == 1 ? 2 : 1);
-        const int px0 = max(tx0, bp.x0) - bp.x0, px1 = min(tx0 + CT_X, bp.x0 + bp.pw) - 1 - bp.x0;
-        const int py0 = max(ty0, bp.y0) - bp.y0, py1 = min(ty0 + CT_Y, bp.y0 + bp.ph) - 1 - bp.y0;
+        // tile ∩ patch box ∩ support (owned box grown by pad): only there were the levels computed
+        const int px0 = max(max(tx0 - bp.x0, 0), bp.own[0] - bp.pad);
+        const int px1 = min(min(tx0 + CT_X - bp.x0, bp.pw), bp.own[2] + bp.pad) - 1;
+        const int py0 = max(max(ty0 - bp.y0, 0), bp.own[1] - bp.pad);
+        const int py1 = min(min(ty0 + CT_Y - bp.y0, bp.ph), bp.own[3] + bp.pad) - 1;
         int ix0, ix1, iy0, iy1;
         float unused;
         coarse_coord<SHIFT>(bp.pad, px0, ix0, unused); coarse_coord<SHIFT>(bp.pad, px1, ix1, unused);
@@ -209,7 +256,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
-    int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
+    int n_hit = build_tile_list<(L > 1)>(patches, n_patches, tx0, ty0, list);
     n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
     {   // pull this tile's slice of every contributing patch (and of the owner keys) towards L2
         // now: one 128-byte line per thread and patch, so that the gathers below find their
@@ -257,6 +304,8 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                 const BandPatch &bp = patches[list[it]];
                 const int px = X - bp.x0, py = Y - bp.y0;
                 if ((unsigned)px >= (unsigned)bp.pw || (unsigned)py >= (unsigned)bp.ph) continue;
+                if (L > 1 && (px < bp.own[0] - bp.pad || px >= bp.own[2] + bp.pad ||
+                              py < bp.own[1] - bp.pad || py >= bp.own[3] + bp.pad)) continue;   // all weights 0
                 const float4 pix = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
                 Pair2 prev = to_pair(pix);
                 prev.hi.y = key_is_owner(key, bp.index) ? 1.0f : 0.0f;     // stitcher.py:207-208
@@ -313,7 +362,7 @@ pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           uint8_t *__restrict__ out, int row0, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
-    const int n_hit = build_tile_list(patches, n_patches, tx0, ty0, list);
+    const int n_hit = build_tile_list<false>(patches, n_patches, tx0, ty0, list);
     const int X = tx0 + threadIdx.x;
     if (X >= W) return;
     for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
@@ -362,6 +411,19 @@ int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long
 }  // namespace p360
 
 using namespace p360;
+
+extern "C" int p360_owned_boxes(const uint64_t *owner_keys, p360_band_patch *patches, int n_patches,
+                                int H, int W, void *stream) {
+    const char *where = "p360_owned_boxes";
+    P360_REQUIRE(owner_keys && patches && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && H > 0 && W > 0, where);
+    if (n_patches == 0) return 0;
+    dim3 grid(cdiv(W, 64), cdiv(H, 32));
+    P360_REQUIRE(grid.y <= 65535, where);
+    owned_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long *>(owner_keys), reinterpret_cast<BandPatch *>(patches),
+        n_patches, H, W);
+    return check_launch(where);
+}
 
 extern "C" int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]) {
     const char *where = "p360_pyramid_dims";
