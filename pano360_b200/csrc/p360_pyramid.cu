@@ -103,14 +103,30 @@ owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patch
     if (tid < 32) present[tid] = 0u;
     __syncthreads();
     const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 32;
+    // thread -> two adjacent keys (one 128-bit load) on 4 rows; runs of equal owners cost one
+    // shared-memory atomic
+    const int cx = tx0 + 2 * (tid & 31), ry = ty0 + (tid >> 5);
+    unsigned last = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int idx = tid + 256 * i, x = tx0 + (idx & 63), y = ty0 + (idx >> 6);
-        if (x < W && y < H) {
-            const unsigned long long k = __ldg(keys + (size_t)y * W + x);
-            if (k != 0ull) {
-                const unsigned p = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
-                if (p < (unsigned)n_patches && p < 1024u) atomicOr(&present[p >> 5], 1u << (p & 31));
+    for (int i = 0; i < 4; ++i) {
+        const int y = ry + 8 * i;
+        if (y >= H) break;
+        unsigned long long k2[2] = {0ull, 0ull};
+        const unsigned long long *src = keys + (size_t)y * W + cx;
+        if (cx + 1 < W && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(src));
+            k2[0] = v.x; k2[1] = v.y;
+        } else {
+            if (cx < W) k2[0] = __ldg(src);
+            if (cx + 1 < W) k2[1] = __ldg(src + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (k2[j] == 0ull) continue;
+            const unsigned p = 0xFFFFFFFFu - (unsigned)(k2[j] & 0xFFFFFFFFull);
+            if (p != last && p < (unsigned)n_patches && p < 1024u) {
+                atomicOr(&present[p >> 5], 1u << (p & 31));
+                last = p;
             }
         }
     }

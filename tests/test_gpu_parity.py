@@ -369,7 +369,7 @@ def test_batched_blur_paths(comp, ksizes):
         dev = torch.from_numpy(img).to(comp.device)
         out, tmp = torch.empty_like(dev), torch.empty_like(dev)
         keep.append((dev, out, tmp))
-        jobs[slot] = (dev.data_ptr(), out.data_ptr(), tmp.data_ptr(), w, h, slot, 0)
+        jobs[slot] = (dev.data_ptr(), out.data_ptr(), tmp.data_ptr(), w, h, slot, 0, 0, 0, 0)   # own = NULL: no restriction
         r = ks // 2
         rows, cols = np.pad(np.arange(h), r, mode="reflect"), np.pad(np.arange(w), r, mode="reflect")
         if h == 1: rows = np.zeros(h + 2 * r, int)
