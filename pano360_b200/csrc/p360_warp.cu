@@ -42,46 +42,21 @@ __device__ __forceinline__ float lut_at(const float *lut, uint32_t byte_offset) 
     return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(lut) + byte_offset);
 }
 
-__device__ __forceinline__ float4 sample(const WarpJob &s, const float *lut, int y, int x, double hy,
-                                         double hx) {
-    float4 v;
-    if (s.c == 8) {                                   // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
-        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(s.src) + (y * s.w + x));
-        v.x = lut_at(lut, (u.x << 2) & 0x3fc);        // byte k pre-scaled by sizeof(float)
-        v.y = lut_at(lut, (u.x >> 6) & 0x3fc);
-        v.z = lut_at(lut, (u.x >> 14) & 0x3fc);
-        v.w = __uint_as_float(u.y);
-        return v;
-    }
-    if (s.c == 4) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t *>(s.src) + (y * s.w + x));
-        v.x = lut_at(lut, (u << 2) & 0x3fc);          // byte k pre-scaled by sizeof(float)
-        v.y = lut_at(lut, (u >> 6) & 0x3fc);
-        v.z = lut_at(lut, (u >> 14) & 0x3fc);
-    } else {
-        const uint8_t *p = s.src + ((size_t)y * s.w + x) * s.c;
-        v.x = lut[__ldg(p)]; v.y = lut[__ldg(p + 1)]; v.z = lut[__ldg(p + 2)];
-    }
-    v.w = (float)(hy * hx);          // float32(hat_y * hat_x), stitcher.py:261
-    return v;
-}
+// ---- the warp of one pixel in three phases, so that the gathers of all the pixels a thread
+// handles can be in flight together (the kernel is bound by their latency otherwise) ---------
 
-// ((s00*w00 + s01*w01) + s10*w10) + s11*w11, separately rounded products and
-// sums: the exact evaluation order of OpenCV's remapBilinear float path.
-__device__ __forceinline__ float blend4(float a, float b, float c, float d,
-                                        float w00, float w01, float w10, float w11) {
-    float acc = __fmul_rn(a, w00);
-    acc = __fadd_rn(acc, __fmul_rn(b, w01));
-    acc = __fadd_rn(acc, __fmul_rn(c, w10));
-    acc = __fadd_rn(acc, __fmul_rn(d, w11));
-    return acc;
-}
+struct TapPlan {            // phase 1: where to sample and with which weights
+    int off00, off01, off10, off11;       // pixel offsets (y * w + x) of the four taps
+    float w00, w01, w10, w11;             // bilinear weights, products of 1/32 fractions (exact)
+    bool bad;
+};
 
-constexpr int WARP_BX = 64, WARP_BY = 4;
-constexpr int WARP_ROWS = 2;            // rows per thread (independent chains for latency hiding)
+struct RawTap {             // phase 2: what a tap returns before the LUT
+    uint32_t rgbx;
+    float alpha;
+};
 
-// value of patch pixel (c, r): RGBA (alpha already masked) + invalid flag
-__device__ __forceinline__ float4 warp_compute(const WarpJob &s, const float *lut, int c, int r, bool &bad) {
+__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r) {
     // p = K R (rx, ry, rz) in float64, k = 0, 1, 2 in order, then cast to
     // float32 (stitcher.py:303-306)
     const double rx = __ldg(s.ray_x + s.col0 + c), rz = __ldg(s.ray_z + s.col0 + c);
@@ -89,10 +64,11 @@ __device__ __forceinline__ float4 warp_compute(const WarpJob &s, const float *lu
     const float px = (float)fma(s.kr[2], rz, fma(s.kr[1], ry, s.kr[0] * rx));
     const float py = (float)fma(s.kr[5], rz, fma(s.kr[4], ry, s.kr[3] * rx));
     const float pz = (float)fma(s.kr[8], rz, fma(s.kr[7], ry, s.kr[6] * rx));
-    bad = pz < 0.0f;                                             // stitcher.py:308
+    TapPlan t;
+    t.bad = pz < 0.0f;                                           // stitcher.py:308
     const float x = __fadd_rn(__fdiv_rn(px, pz), (float)(s.w / 2.0));   // stitcher.py:310
     const float y = __fadd_rn(__fdiv_rn(py, pz), (float)(s.h / 2.0));
-    bad |= (x < 0.0f) | (x > (float)(s.w - 1)) | (y < 0.0f) | (y > (float)(s.h - 1));   // :311-312
+    t.bad |= (x < 0.0f) | (x > (float)(s.w - 1)) | (y < 0.0f) | (y > (float)(s.h - 1));   // :311-312
     const int sx = to_fixed5(x), sy = to_fixed5(y);
     const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);
     int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
@@ -102,24 +78,59 @@ __device__ __forceinline__ float4 warp_compute(const WarpJob &s, const float *lu
         x0 = reflect_fast(ix, s.w, inv_2w); x1 = reflect_fast(ix + 1, s.w, inv_2w);
         y0 = reflect_fast(iy, s.h, inv_2h); y1 = reflect_fast(iy + 1, s.h, inv_2h);
     }
+    t.off00 = y0 * s.w + x0; t.off01 = y0 * s.w + x1;
+    t.off10 = y1 * s.w + x0; t.off11 = y1 * s.w + x1;
     const float ax = (float)(sx & 31) * 0.03125f, ay = (float)(sy & 31) * 0.03125f;
-    const float w00 = __fmul_rn(1.0f - ay, 1.0f - ax), w01 = __fmul_rn(1.0f - ay, ax);
-    const float w10 = __fmul_rn(ay, 1.0f - ax), w11 = __fmul_rn(ay, ax);
-    double hy0 = 0.0, hy1 = 0.0, hx0 = 0.0, hx1 = 0.0;
-    if (s.c != 8) {                                              // alpha not pre-packed with the pixels
-        hy0 = __ldg(s.hat_y + y0); hy1 = __ldg(s.hat_y + y1);
-        hx0 = __ldg(s.hat_x + x0); hx1 = __ldg(s.hat_x + x1);
+    t.w00 = __fmul_rn(1.0f - ay, 1.0f - ax); t.w01 = __fmul_rn(1.0f - ay, ax);
+    t.w10 = __fmul_rn(ay, 1.0f - ax); t.w11 = __fmul_rn(ay, ax);
+    return t;
+}
+
+__device__ __forceinline__ RawTap load_tap(const WarpJob &s, int off) {
+    RawTap t;
+    if (s.c == 8) {                                   // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
+        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(s.src) + off);
+        t.rgbx = u.x;
+        t.alpha = __uint_as_float(u.y);
+        return t;
     }
-    const float4 a = sample(s, lut, y0, x0, hy0, hx0), b = sample(s, lut, y0, x1, hy0, hx1);
-    const float4 cc = sample(s, lut, y1, x0, hy1, hx0), d = sample(s, lut, y1, x1, hy1, hx1);
+    if (s.c == 4) {
+        t.rgbx = __ldg(reinterpret_cast<const uint32_t *>(s.src) + off);
+    } else {
+        const uint8_t *p = s.src + (size_t)off * 3;
+        t.rgbx = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
+    const int y = off / s.w, x = off - y * s.w;       // alpha not pre-packed: float32(hat_y * hat_x), stitcher.py:261
+    t.alpha = (float)(__ldg(s.hat_y + y) * __ldg(s.hat_x + x));
+    return t;
+}
+
+// ((s00*w00 + s01*w01) + s10*w10) + s11*w11, separately rounded products and
+// sums: the exact evaluation order of OpenCV's remapBilinear float path.
+__device__ __forceinline__ float blend4(float a, float b, float c, float d, const TapPlan &t) {
+    float acc = __fmul_rn(a, t.w00);
+    acc = __fadd_rn(acc, __fmul_rn(b, t.w01));
+    acc = __fadd_rn(acc, __fmul_rn(c, t.w10));
+    acc = __fadd_rn(acc, __fmul_rn(d, t.w11));
+    return acc;
+}
+
+// phase 3: LUT (u8 -> float exactly as the reference's float image holds it) + bilinear blend
+__device__ __forceinline__ float4 finish_pixel(const float *lut, const TapPlan &t, const RawTap (&q)[4]) {
     float4 o;
-    o.x = blend4(a.x, b.x, cc.x, d.x, w00, w01, w10, w11);
-    o.y = blend4(a.y, b.y, cc.y, d.y, w00, w01, w10, w11);
-    o.z = blend4(a.z, b.z, cc.z, d.z, w00, w01, w10, w11);
-    o.w = blend4(a.w, b.w, cc.w, d.w, w00, w01, w10, w11);
-    if (bad) o.w = 0.0f;                                         // stitcher.py:317
+    o.x = blend4(lut_at(lut, (q[0].rgbx << 2) & 0x3fc), lut_at(lut, (q[1].rgbx << 2) & 0x3fc),
+                 lut_at(lut, (q[2].rgbx << 2) & 0x3fc), lut_at(lut, (q[3].rgbx << 2) & 0x3fc), t);
+    o.y = blend4(lut_at(lut, (q[0].rgbx >> 6) & 0x3fc), lut_at(lut, (q[1].rgbx >> 6) & 0x3fc),
+                 lut_at(lut, (q[2].rgbx >> 6) & 0x3fc), lut_at(lut, (q[3].rgbx >> 6) & 0x3fc), t);
+    o.z = blend4(lut_at(lut, (q[0].rgbx >> 14) & 0x3fc), lut_at(lut, (q[1].rgbx >> 14) & 0x3fc),
+                 lut_at(lut, (q[2].rgbx >> 14) & 0x3fc), lut_at(lut, (q[3].rgbx >> 14) & 0x3fc), t);
+    o.w = blend4(q[0].alpha, q[1].alpha, q[2].alpha, q[3].alpha, t);
+    if (t.bad) o.w = 0.0f;                                       // stitcher.py:317
     return o;
 }
+
+constexpr int WARP_BX = 64, WARP_BY = 4;
+constexpr int WARP_ROWS = 4;            // rows per thread: 16 gathers in flight before the first use
 
 __device__ __forceinline__ void warp_commit(const WarpJob &s, int c, int r, const float4 &o, bool bad,
                                             unsigned long long *keys, uint8_t *covered, int W) {
@@ -147,19 +158,22 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
     __syncthreads();
     const int c = blockIdx.x * WARP_BX + threadIdx.x;
     if (c >= job.pw) return;
-    // all gathers and arithmetic of the thread's rows first (independent
-    // chains in flight together), then the stores and the owner competition
-    float4 o[WARP_ROWS];
-    bool bad[WARP_ROWS];
+    // coordinates of every row first, then all gathers back to back, then LUT + blend,
+    // then the stores and the owner competition
+    TapPlan plan[WARP_ROWS];
+    RawTap taps[WARP_ROWS][4];
+#pragma unroll
+    for (int k = 0; k < WARP_ROWS; ++k)
+        plan[k] = plan_taps(job, c, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1));
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
-        const int r = min(r0 + threadIdx.y + k * WARP_BY, job.ph - 1);
-        o[k] = warp_compute(job, lut, c, r, bad[k]);
+        taps[k][0] = load_tap(job, plan[k].off00); taps[k][1] = load_tap(job, plan[k].off01);
+        taps[k][2] = load_tap(job, plan[k].off10); taps[k][3] = load_tap(job, plan[k].off11);
     }
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
         const int r = r0 + threadIdx.y + k * WARP_BY;
-        if (r < job.ph) warp_commit(job, c, r, o[k], bad[k], keys, covered, W);
+        if (r < job.ph) warp_commit(job, c, r, finish_pixel(lut, plan[k], taps[k]), plan[k].bad, keys, covered, W);
     }
 }
 
