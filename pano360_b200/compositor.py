@@ -155,7 +155,7 @@ class Compositor:
                   _lib.ptr(packed), self.stream)
         return packed
 
-    def upload(self, regions, gains=None, need=None, overlap=False):
+    def upload(self, regions, gains=None, need=None, overlap=False, pack=True):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
@@ -185,7 +185,8 @@ class Compositor:
                         side.wait_stream(main)               # hat tables were copied on the main stream
                 with torch.cuda.stream(side):
                     dev_img = host.to(self.device, non_blocking=host.is_pinned())
-                    src.pixels.append(self.pack_pixels(dev_img, src.hats[(h, w)]))
+                    # pack=False keeps the uploaded u8 x 3 layout (the warp then evaluates alpha per tap)
+                    src.pixels.append(self.pack_pixels(dev_img, src.hats[(h, w)]) if pack else dev_img)
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)

@@ -86,9 +86,10 @@ __device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r) {
     return t;
 }
 
+template <bool PACKED>
 __device__ __forceinline__ RawTap load_tap(const WarpJob &s, int off) {
     RawTap t;
-    if (s.c == 8) {                                   // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
+    if (PACKED) {                                     // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
         const uint2 u = __ldg(reinterpret_cast<const uint2 *>(s.src) + off);
         t.rgbx = u.x;
         t.alpha = __uint_as_float(u.y);
@@ -132,12 +133,13 @@ __device__ __forceinline__ float4 finish_pixel(const float *lut, const TapPlan &
 constexpr int WARP_BX = 64, WARP_BY = 4;
 constexpr int WARP_ROWS = 4;            // rows per thread: 16 gathers in flight before the first use
 
+template <bool OWNER>
 __device__ __forceinline__ void warp_commit(const WarpJob &s, int c, int r, const float4 &o, bool bad,
                                             unsigned long long *keys, uint8_t *covered, int W) {
     const size_t idx = (size_t)r * s.pw + c;
     st_stream(s.out + idx, o);
     s.invalid[idx] = bad ? 1 : 0;
-    if (keys != nullptr) {
+    if (OWNER) {
         const size_t mi = (size_t)(r + s.y0) * W + (c + s.x0);
         owner_compete(keys, mi, o.w, s.patch);                   // stitcher.py:196-204
         if (!bad) covered[mi] = 1;                               // stitcher.py:233-234
@@ -147,6 +149,8 @@ __device__ __forceinline__ void warp_commit(const WarpJob &s, int c, int r, cons
 constexpr int WARP_JOBS_PER_LAUNCH = 128;
 __constant__ WarpJob c_warp_jobs[WARP_JOBS_PER_LAUNCH];   // block-uniform reads: no LSU traffic per pixel
 
+// PACKED: every job's source is in the 8-byte {RGBX, alpha} format; OWNER: owner keys wanted.
+template <bool PACKED, bool OWNER>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY)
 warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
     __shared__ float lut[256];
@@ -167,13 +171,14 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
         plan[k] = plan_taps(job, c, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1));
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
-        taps[k][0] = load_tap(job, plan[k].off00); taps[k][1] = load_tap(job, plan[k].off01);
-        taps[k][2] = load_tap(job, plan[k].off10); taps[k][3] = load_tap(job, plan[k].off11);
+        taps[k][0] = load_tap<PACKED>(job, plan[k].off00); taps[k][1] = load_tap<PACKED>(job, plan[k].off01);
+        taps[k][2] = load_tap<PACKED>(job, plan[k].off10); taps[k][3] = load_tap<PACKED>(job, plan[k].off11);
     }
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
         const int r = r0 + threadIdx.y + k * WARP_BY;
-        if (r < job.ph) warp_commit(job, c, r, finish_pixel(lut, plan[k], taps[k]), plan[k].bad, keys, covered, W);
+        if (r < job.ph)
+            warp_commit<OWNER>(job, c, r, finish_pixel(lut, plan[k], taps[k]), plan[k].bad, keys, covered, W);
     }
 }
 
@@ -237,6 +242,7 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
     for (int first = 0; first < n_jobs; first += WARP_JOBS_PER_LAUNCH) {
         const int count = n_jobs - first < WARP_JOBS_PER_LAUNCH ? n_jobs - first : WARP_JOBS_PER_LAUNCH;
         int max_pw = 0, max_ph = 0;
+        bool packed = true;
         for (int k = first; k < first + count; ++k) {
             const p360_warp_job &j = jobs_host[k];
             P360_REQUIRE(j.src && j.lut && j.hat_y && j.hat_x && j.ray_x && j.ray_z && j.ray_y && j.out && j.invalid, where);
@@ -245,6 +251,7 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                          (j.c == 8 && (reinterpret_cast<uintptr_t>(j.src) & 7) == 0), where);
             P360_REQUIRE(aligned16(j.out), where);
             P360_REQUIRE(owner_keys == nullptr || (j.x0 >= 0 && j.y0 >= 0 && j.x0 + j.pw <= W), where);
+            packed = packed && j.c == 8;
             max_pw = j.pw > max_pw ? j.pw : max_pw;
             max_ph = j.ph > max_ph ? j.ph : max_ph;
         }
@@ -254,7 +261,11 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                                           cudaMemcpyHostToDevice, s), where);
         dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
-        warp_batch_kernel<<<grid, block, 0, s>>>(reinterpret_cast<unsigned long long *>(owner_keys), covered, W);
+        auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
+        if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
+        else if (packed) warp_batch_kernel<true, false><<<grid, block, 0, s>>>(keys, covered, W);
+        else if (keys) warp_batch_kernel<false, true><<<grid, block, 0, s>>>(keys, covered, W);
+        else warp_batch_kernel<false, false><<<grid, block, 0, s>>>(keys, covered, W);
         if (int e = check_launch(where)) return e;
     }
     return 0;

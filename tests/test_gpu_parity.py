@@ -315,6 +315,22 @@ def test_row_window_equals_full_mosaic(st, comp, restore_globals):
             assert np.array_equal(strip.cpu().numpy(), full[rows[0]:rows[1]]), (kind, rows)
 
 
+def test_unpacked_source_layout_is_equivalent(comp, tiny4):
+    """K1 accepts the uploaded u8 x 3 pixels directly (alpha evaluated per tap
+    from the hat tables) or the packed {RGBX, alpha} words: identical patches."""
+    _, regs = tiny4
+    plan = geo.plan_mosaic(regs, True, 1400)
+    packed = comp.warp(regs, comp.upload(regs), plan)
+    raw = comp.warp(regs, comp.upload(regs, pack=False), plan)
+    for a, b in zip(packed, raw):
+        assert torch_equal(a.rgba, b.rgba) and torch_equal(a.invalid, b.invalid)
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
+
+
 def test_seam_split_is_exact(comp):
     """Dropping the all-invalid middle of seam-straddling boxes (SURVEY.md F10,
     H5) must not change a single output byte."""
