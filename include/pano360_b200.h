@@ -81,6 +81,9 @@ typedef struct p360_warp_job {
     int32_t x0, y0;
     int32_t col0, row0;
     int32_t patch;
+    float half_w, half_h;         /* float32(w / 2.0), float32(h / 2.0)                   */
+    float max_x, max_y;           /* float32(w - 1), float32(h - 1)                       */
+    float inv_2w, inv_2h;         /* 1 / (2 w), 1 / (2 h)                                 */
 } p360_warp_job;
 
 int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t n_pixels, void *stream);

@@ -49,14 +49,15 @@ MAX_LEVELS = 8
 WARP_JOB = np.dtype([("src", "u8"), ("lut", "u8"), ("hat_y", "u8"), ("hat_x", "u8"), ("ray_x", "u8"),
                      ("ray_z", "u8"), ("ray_y", "u8"), ("out", "u8"), ("invalid", "u8"), ("kr", "f8", (9,)),
                      ("h", "i4"), ("w", "i4"), ("c", "i4"), ("pw", "i4"), ("ph", "i4"), ("x0", "i4"),
-                     ("y0", "i4"), ("col0", "i4"), ("row0", "i4"), ("patch", "i4")])
+                     ("y0", "i4"), ("col0", "i4"), ("row0", "i4"), ("patch", "i4"), ("half_w", "f4"),
+                     ("half_h", "f4"), ("max_x", "f4"), ("max_y", "f4"), ("inv_2w", "f4"), ("inv_2h", "f4")])
 BLUR_JOB = np.dtype([("in", "u8"), ("out", "u8"), ("tmp", "u8"), ("w", "i4"), ("h", "i4"), ("slot", "i4"),
                      ("shift", "i4"), ("own", "u8"), ("pad", "i4"), ("grow", "i4")])
 BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "u8"),
                        ("low", "u8", (MAX_LEVELS - 1,)), ("x0", "i4"), ("y0", "i4"), ("pw", "i4"),
                        ("ph", "i4"), ("w4", "i4"), ("h4", "i4"), ("pad", "i4"), ("index", "i4"),
                        ("own", "i4", (4,))])
-assert WARP_JOB.itemsize == 184 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
+assert WARP_JOB.itemsize == 208 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
 OWN_OFFSET = BAND_PATCH.fields["own"][1]
 
 # entry points whose int return is a value, not a status

@@ -297,7 +297,9 @@ class Compositor:
             o = int(offs[k])
             jobs[k] = (pix.data_ptr(), src.luts[i].data_ptr(), hat_y.data_ptr(), hat_x.data_ptr(),
                        base_x, base_z, base_y, rgba_base + 16 * o, inv_base + o, k_r,
-                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, x0, ya, k)
+                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, x0, ya, k,
+                       np.float32(w / 2), np.float32(h / 2), np.float32(w - 1), np.float32(h - 1),
+                       np.float32(1.0) / np.float32(2 * w), np.float32(1.0) / np.float32(2 * h))
             patches.append(DevicePatch(rgba_pool[4 * o:4 * (o + pw * ph)].view(ph, pw, 4),
                                        inv_pool[o:o + pw * ph].view(ph, pw),
                                        (x0 - ox, ya - oy, x1 - ox, yb - oy), i))

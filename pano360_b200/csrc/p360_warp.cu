@@ -24,6 +24,9 @@ struct WarpJob {                 // == p360_warp_job
     int x0, y0;                  // position in the (window) mosaic
     int col0, row0;              // absolute mosaic column / row of the patch origin (ray tables)
     int patch;                   // id in the owner map
+    float half_w, half_h;        // float32(w / 2), float32(h / 2)          (stitcher.py:310)
+    float max_x, max_y;          // float32(w - 1), float32(h - 1)          (stitcher.py:311-312)
+    float inv_2w, inv_2h;        // 1 / (2w), 1 / (2h): reflection period reciprocals
 };
 static_assert(sizeof(WarpJob) == sizeof(p360_warp_job), "ABI struct mismatch");
 
@@ -66,17 +69,16 @@ __device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r) {
     const float pz = (float)fma(s.kr[8], rz, fma(s.kr[7], ry, s.kr[6] * rx));
     TapPlan t;
     t.bad = pz < 0.0f;                                           // stitcher.py:308
-    const float x = __fadd_rn(__fdiv_rn(px, pz), (float)(s.w / 2.0));   // stitcher.py:310
-    const float y = __fadd_rn(__fdiv_rn(py, pz), (float)(s.h / 2.0));
-    t.bad |= (x < 0.0f) | (x > (float)(s.w - 1)) | (y < 0.0f) | (y > (float)(s.h - 1));   // :311-312
+    const float x = __fadd_rn(__fdiv_rn(px, pz), s.half_w);      // stitcher.py:310
+    const float y = __fadd_rn(__fdiv_rn(py, pz), s.half_h);
+    t.bad |= (x < 0.0f) | (x > s.max_x) | (y < 0.0f) | (y > s.max_y);   // :311-312
     const int sx = to_fixed5(x), sy = to_fixed5(y);
     const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);
     int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
     if ((unsigned)ix >= (unsigned)(s.w - 1) || (unsigned)iy >= (unsigned)(s.h - 1)) {
         // a tap falls outside the image: BORDER_REFLECT (cv2.remap at stitcher.py:315-316)
-        const float inv_2w = 1.0f / (2.0f * s.w), inv_2h = 1.0f / (2.0f * s.h);
-        x0 = reflect_fast(ix, s.w, inv_2w); x1 = reflect_fast(ix + 1, s.w, inv_2w);
-        y0 = reflect_fast(iy, s.h, inv_2h); y1 = reflect_fast(iy + 1, s.h, inv_2h);
+        x0 = reflect_fast(ix, s.w, s.inv_2w); x1 = reflect_fast(ix + 1, s.w, s.inv_2w);
+        y0 = reflect_fast(iy, s.h, s.inv_2h); y1 = reflect_fast(iy + 1, s.h, s.inv_2h);
     }
     t.off00 = y0 * s.w + x0; t.off01 = y0 * s.w + x1;
     t.off10 = y1 * s.w + x0; t.off11 = y1 * s.w + x1;
