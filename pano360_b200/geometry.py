@@ -94,6 +94,7 @@ class MosaicPlan:
     ranges: list              # per image (min, max) angles
     border_theta: list = None # per image sorted longitudes of the border samples
     _rays: tuple = None       # cached (ray_x[W], ray_z[W], ray_y[H]) of proj2hom
+    _runs: dict = None        # cached active_column_runs results
 
     def rays(self, proj=SphProj):
         """``proj2hom`` evaluated once per mosaic column / row (it is separable:
@@ -134,7 +135,7 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
             bottom = np.maximum(bottom - PATCH_PAD, np.int32([0, 0]))
             top = np.minimum(top + PATCH_PAD, limit)
         boxes.append((int(bottom[0]), int(bottom[1]), int(top[0]), int(top[1])))
-    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples])
+    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples], None, {})
 
 
 def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
@@ -153,6 +154,9 @@ def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     multiple of ``align`` columns from the box origin.  Returns
     [(x0, x1), ...] inside the box, in ascending order; a single run equal to
     the box if no split."""
+    cached = plan._runs.get((index, box, dilate, margin, align)) if plan._runs is not None else None
+    if cached is not None:
+        return cached
     x0, y0, x1, y1 = box
     theta = plan.border_theta[index]
     gaps = np.diff(theta)
@@ -164,9 +168,12 @@ def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     right_start = x0 + (right_start - x0) // align * align
     # only worth (and only safe) when the gap dwarfs both the sampling step and the dilation
     if right_start - left_end < max(256, 4 * dilate) or gaps[k] < 20 * np.median(gaps):
-        return [(x0, x1)]
-    runs = [(x0, left_end), (right_start, x1)]
-    return [(a, b) for a, b in runs if b > a]
+        runs = [(x0, x1)]
+    else:
+        runs = [(a, b) for a, b in [(x0, left_end), (right_start, x1)] if b > a]
+    if plan._runs is not None:
+        plan._runs[(index, box, dilate, margin, align)] = runs
+    return runs
 
 
 def inverse_map_tables(region, box, plan, proj=SphProj):

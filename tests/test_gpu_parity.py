@@ -286,6 +286,21 @@ def test_cli_with_reference_style_caches(st, tmp_path, monkeypatch, restore_glob
             assert_mosaic_close(mosaic, want, what=blend)
 
 
+def test_many_small_views(st, restore_globals):
+    """150 views on a dense ring: more patches than one K1 launch holds (128)
+    and long per-tile patch lists; every blender against the oracle."""
+    from dataclasses import replace
+    wl = synth.workload("cfg1", scale=8.0)
+    n = 150
+    wl = replace(wl, yaws=tuple(0.04 * (i - n / 2) for i in range(n)),
+                 pitches=tuple(0.15 * ((i % 3) - 1) for i in range(n)))
+    regs = synth.make_views(wl, noise=5.0)
+    st.MAX_RESOLUTION = 10 ** 9
+    for blend in ("none", "linear", "multiband"):
+        got = st.stitch(regs, blender=st.BLENDERS[blend])
+        assert_mosaic_close(got, rs.stitch(regs, blend, False, 5, 1e9), what=blend)
+
+
 def test_edge_cases(st, restore_globals):
     """Single image; images smaller than the blur radius; crop."""
     wl = synth.workload("cfg1", scale=16.0)          # 40 x 30 pixel views
