@@ -142,9 +142,12 @@ int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int 
  *   p360_linear_collapse       stitcher.py:171-183 in the same gather form
  *   p360_paste_collapse        stitcher.py:160-168 in the same gather form
  * Nothing mosaic-sized is accumulated in HBM.  `patches` is a DEVICE array.
- * The collapse kernels produce mosaic rows [y_begin, y_end) (0 and H for the
- * whole mosaic) so that callers can overlap the download or the NVLink send of
- * finished row bands with the computation of the next ones.
+ * The collapse kernels produce rows [y_begin, y_end) of the output buffer (0 and
+ * H for the whole mosaic) so that callers can overlap the download or the NVLink
+ * send of finished row bands with the computation of the next ones.  row_origin
+ * is the absolute mosaic row of buffer row 0 (0 unless the buffer is a strip):
+ * work tiles are anchored at absolute rows, which makes the result independent
+ * of how the mosaic is cut into strips and bands.
  */
 typedef struct p360_band_patch {
     const float *rgba;                        /* full-res patch                         */
@@ -171,11 +174,12 @@ int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int
                               int max_h4, const uint64_t *owner_keys, int W, void *stream);
 int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                             const uint64_t *owner_keys, const uint8_t *covered,
-                            uint8_t *out_u8, int y_begin, int y_end, int W, void *stream);
+                            uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
+                            void *stream);
 int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                         int y_begin, int y_end, int W, void *stream);
+                         int y_begin, int y_end, int row_origin, int W, void *stream);
 int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                        int y_begin, int y_end, int W, void *stream);
+                        int y_begin, int y_end, int row_origin, int W, void *stream);
 
 /* ---- K8: pair overlap statistics for exposure gains (stitcher.py:48-63) ---
  * For every pixel of image i: fixed-point perspective map into image j

@@ -35,9 +35,9 @@ SIGNATURES = {
     "p360_owned_boxes": [_vp, _vp, _i, _i, _i, _vp],
     "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
     "p360_pyramid_reduce_batch": [_vp, _i, _i, _i, _vp, _i, _vp],
-    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
-    "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _vp],
-    "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _vp],
+    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],

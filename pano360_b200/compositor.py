@@ -393,7 +393,8 @@ class Compositor:
                       self.stream)
         self._taps_key = n_levels
 
-    def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8):
+    def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8,
+                  row_origin=0):
         """Launch a collapse kernel over rows ``rows`` (default: all) of the
         mosaic buffer.  With ``out_host`` (pinned host array) or ``on_band``
         (callback(y0, y1), e.g. an NVLink send) the rows are produced band by
@@ -402,15 +403,15 @@ class Compositor:
         h, w = mosaic.shape[:2]
         ya, yb = (0, h) if rows is None else rows
         if out_host is None and on_band is None:
-            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, w, self.stream)
+            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
         main, side = torch.cuda.current_stream(self.device), self.copy_stream()
         for y0, y1 in band_edges(ya, yb, bands):
             if y1 <= y0:
                 continue
-            self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1, w,
-                         self.stream)
+            self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1,
+                         row_origin, w, self.stream)
             if on_band is not None:
                 on_band(y0, y1)
             if host is not None:
@@ -430,7 +431,7 @@ class Compositor:
             self._download = None
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
-                        rows=None, on_band=None, mosaic=None, bands=8):
+                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM."""
@@ -497,14 +498,14 @@ class Compositor:
                     lows.append(per)
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
-                       rows, on_band, bands)
+                       rows, on_band, bands, row_origin)
         self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows)
         return mosaic
 
     def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
-                   bands=8):
+                   bands=8, row_origin=0):
         h, w = shape
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
@@ -514,19 +515,21 @@ class Compositor:
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host,
-                       rows, on_band, bands)
+                       rows, on_band, bands, row_origin)
         self._keep["collapse"] = (dev_table,)
         return mosaic
 
-    def blend_none(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8):
+    def blend_none(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
+                   row_origin=0):
         """stitcher.py:160-168 (last valid writer wins), gather form."""
         return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands)
+                               on_band, mosaic, bands, row_origin)
 
-    def blend_linear(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8):
+    def blend_linear(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
+                     row_origin=0):
         """stitcher.py:171-183, gather form."""
         return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands)
+                               on_band, mosaic, bands, row_origin)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""
@@ -588,11 +591,11 @@ class Compositor:
         if kind == "multiband":
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels,
                                      owner_state=state, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands)
+                                     bands=bands, row_origin=top)
         else:
             strip = self._blend_into(holder, self.blend_none if kind == "none" else self.blend_linear,
                                      patches, shape, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands)
+                                     bands=bands, row_origin=top)
         return strip[local[0]:local[1]], patches
 
     def _blend_into(self, holder, blender, patches, shape, *args, **kwargs):

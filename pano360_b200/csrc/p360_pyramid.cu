@@ -268,10 +268,13 @@ template <int L>
 __global__ void __launch_bounds__(256, (L <= 5) ? 4 : 3)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
-                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int row0,
-                          int H, int W) {
+                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
+                          int y_begin, int H, int W) {
+    // Tiles are anchored at absolute mosaic rows (first_tile_row may be < y_begin, even < 0):
+    // whether a tile takes the single-contributor shortcut must not depend on how the
+    // mosaic was cut into strips or row bands.
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
+    const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
     int n_hit = build_tile_list<(L > 1)>(patches, n_patches, tx0, ty0, list);
     n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
     {   // pull this tile's slice of every contributing patch (and of the owner keys) towards L2
@@ -279,7 +282,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         // streamed operands on chip instead of paying a DRAM round trip per patch iteration
         const int tid = threadIdx.y * CT_X + threadIdx.x;
         const int trow = ty0 + (tid >> 3), tcol = tx0 + 8 * (tid & 7);
-        if (trow < H && tcol < W) prefetch_l2(keys + (size_t)trow * W + tcol);
+        if (trow >= 0 && trow < H && tcol < W) prefetch_l2(keys + (size_t)trow * W + tcol);
         for (int it = 0; it < n_hit; ++it) {
             const BandPatch &bp = patches[list[it]];
             const int px = tcol - bp.x0, py = trow - bp.y0;
@@ -292,6 +295,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
     for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
         const int Y = ty0 + threadIdx.y + 4 * sub;
         if (Y >= H) break;
+        if (Y < y_begin) continue;
         const size_t mi = (size_t)Y * W + X;
         // per level: lo = (sum band.x*w, sum band.y*w), hi = (sum band.z*w, sum w)
         float2 lo[L], hi[L];
@@ -375,15 +379,16 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
-                          uint8_t *__restrict__ out, int row0, int H, int W) {
+                          uint8_t *__restrict__ out, int first_tile_row, int y_begin, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int tx0 = blockIdx.x * CT_X, ty0 = row0 + blockIdx.y * CT_Y;
+    const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
     const int n_hit = build_tile_list<false>(patches, n_patches, tx0, ty0, list);
     const int X = tx0 + threadIdx.x;
     if (X >= W) return;
     for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
         const int Y = ty0 + threadIdx.y + 4 * sub;
         if (Y >= H) break;
+        if (Y < y_begin) continue;
         const size_t mi = (size_t)Y * W + X;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, wsum = 0.f;
         for (int it = 0; it < n_hit; ++it) {
@@ -417,10 +422,19 @@ pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 }
 
 template <int L>
+inline int first_tile(int y_begin, int row_origin) {     // absolute-row-aligned tile containing y_begin
+    int phase = (y_begin + row_origin) % CT_Y;
+    if (phase < 0) phase += CT_Y;
+    return y_begin - phase;
+}
+
+template <int L>
 int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
-                    const uint8_t *covered, uint8_t *out, int y0, int y1, int W, cudaStream_t s) {
-    dim3 grid(cdiv(W, CT_X), cdiv(y1 - y0, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, y0, y1, W);
+                    const uint8_t *covered, uint8_t *out, int y0, int y1, int row_origin, int W,
+                    cudaStream_t s) {
+    const int first = first_tile(y0, row_origin);
+    dim3 grid(cdiv(W, CT_X), cdiv(y1 - first, CT_Y)), block(CT_X, 4);
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1, W);
     return check_launch("p360_multiband_collapse");
 }
 
@@ -465,7 +479,8 @@ extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_p
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                                        const uint64_t *owner_keys, const uint8_t *covered,
-                                       uint8_t *out_u8, int y_begin, int y_end, int W, void *stream) {
+                                       uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
+                                       void *stream) {
     const char *where = "p360_multiband_collapse";
     P360_REQUIRE(patches && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
@@ -477,37 +492,40 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
     auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
-        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, W, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
     }
 }
 
 static int pointwise_collapse(const char *where, int mode, const p360_band_patch *patches, int n_patches,
-                              uint8_t *out_u8, int y_begin, int y_end, int W, void *stream) {
+                              uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W, void *stream) {
     P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && W > 0, where);
     P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
     if (y_end == y_begin) return 0;
-    dim3 grid(cdiv(W, CT_X), cdiv(y_end - y_begin, CT_Y)), block(CT_X, 4);
+    const int first = first_tile(y_begin, row_origin);
+    dim3 grid(cdiv(W, CT_X), cdiv(y_end - first, CT_Y)), block(CT_X, 4);
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     if (mode == 0)
-        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, y_begin, y_end, W);
+        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, first, y_begin, y_end, W);
     else
-        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, y_begin, y_end, W);
+        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, first, y_begin, y_end, W);
     return check_launch(where);
 }
 
 extern "C" int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                                    int y_begin, int y_end, int W, void *stream) {
-    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, y_begin, y_end, W, stream);
+                                    int y_begin, int y_end, int row_origin, int W, void *stream) {
+    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, y_begin, y_end,
+                              row_origin, W, stream);
 }
 
 extern "C" int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
-                                   int y_begin, int y_end, int W, void *stream) {
-    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, y_begin, y_end, W, stream);
+                                   int y_begin, int y_end, int row_origin, int W, void *stream) {
+    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, y_begin, y_end,
+                              row_origin, W, stream);
 }
