@@ -76,10 +76,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m pano360_b200.build` "
-            "(pano360_b200 has no CPU fallback)")
+    from . import build as _build
+    if _build.stale():                   # missing, or older than csrc/ or the header: never run stale kernels
+        try:
+            _build.build()
+        except Exception as exc:
+            raise RuntimeError(
+                f"{LIB_PATH} is missing or out of date and could not be rebuilt ({exc}); build it with "
+                "`python -m pano360_b200.build` (pano360_b200 has no CPU fallback)") from exc
     lib = C.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -421,7 +421,6 @@ pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
     }
 }
 
-template <int L>
 inline int first_tile(int y_begin, int row_origin) {     // absolute-row-aligned tile containing y_begin
     int phase = (y_begin + row_origin) % CT_Y;
     if (phase < 0) phase += CT_Y;
