@@ -182,19 +182,24 @@ int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *
                         int y_begin, int y_end, int row_origin, int W, void *stream);
 
 /* ---- K8: pair overlap statistics for exposure gains (stitcher.py:48-63) ---
- * For every pixel of image i: fixed-point perspective map into image j
- * (cv2.warpPerspective semantics, zero destination), overlap = warped alpha
- * != 0.  out[0] = overlap count, out[1] = sum of image-i rgb over the overlap,
- * out[2] = sum of warped image-j rgb.  inv_hom_host: 9 float64, the INVERSE of
- * the i<-j homography in un-centred pixel coordinates.  partial: scratch of
- * at least 3 * p360_pair_stats_blocks(h, w) float64.
+ * For every pair (i, j) and every pixel of image i: fixed-point perspective map
+ * into image j (cv2.warpPerspective semantics, zero destination), overlap =
+ * warped alpha != 0.  out[3*p + 0] = overlap count of pair p, [3*p + 1] = sum of
+ * image-i rgb over the overlap, [3*p + 2] = sum of warped image-j rgb.  All
+ * images share h, w, src_c (as in the reference).  `jobs` is a DEVICE array;
+ * inv = INVERSE of the i <- j homography in un-centred pixel coordinates.
+ * partial: scratch of at least 3 * n_pairs * p360_pair_stats_blocks(h, w) float64.
  */
+typedef struct p360_pair_job {
+    const uint8_t *src_i;
+    const uint8_t *src_j;
+    double inv[9];
+} p360_pair_job;
+
 int p360_pair_stats_blocks(int h, int w);
-int p360_pair_overlap_stats(const uint8_t *src_i, const uint8_t *src_j,
-                            int h, int w, int src_c, const float *lut,
-                            const double *hat_y, const double *hat_x,
-                            const double *inv_hom_host, double *partial,
-                            double *out3, void *stream);
+int p360_pair_overlap_stats(const p360_pair_job *jobs, int n_pairs, int h, int w, int src_c,
+                            const float *lut, const double *hat_y, const double *hat_x,
+                            double *partial, double *out, void *stream);
 
 /* ---- valid-area mask for the crop stage (stitcher.py:266-271) -------------*/
 int p360_cover_update(const uint8_t *invalid, int pw, int ph, int x0, int y0,

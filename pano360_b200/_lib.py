@@ -39,7 +39,7 @@ SIGNATURES = {
     "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "p360_pair_stats_blocks": [_i, _i],
-    "p360_pair_overlap_stats": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp],
+    "p360_pair_overlap_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
 }
 MAX_LEVELS = 8
@@ -57,6 +57,8 @@ BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "
                        ("low", "u8", (MAX_LEVELS - 1,)), ("x0", "i4"), ("y0", "i4"), ("pw", "i4"),
                        ("ph", "i4"), ("w4", "i4"), ("h4", "i4"), ("pad", "i4"), ("index", "i4"),
                        ("own", "i4", (4,))])
+PAIR_JOB = np.dtype([("src_i", "u8"), ("src_j", "u8"), ("inv", "f8", (9,))])
+assert PAIR_JOB.itemsize == 88
 assert WARP_JOB.itemsize == 208 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
 OWN_OFFSET = BAND_PATCH.fields["own"][1]
 

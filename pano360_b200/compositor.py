@@ -219,16 +219,17 @@ class Compositor:
         lut0 = self._to_device(geo.sample_lut(None))
         hat_y, hat_x = src.hats[(h, w)]
         nblocks = _lib.call("p360_pair_stats_blocks", h, w)
-        partial = torch.empty(3 * nblocks, dtype=torch.float64, device=self.device)
-        out = torch.zeros((len(todo), 3), dtype=torch.float64, device=self.device)
+        jobs = np.zeros(len(todo), dtype=_lib.PAIR_JOB)
         for k, (i, j, inv) in enumerate(todo):
             if src.shapes[i] != (h, w) or src.shapes[j] != (h, w):
                 raise ValueError("exposure equalisation needs equally sized images (as the reference)")
-            inv_c = (C.c_double * 9)(*inv.ravel())
-            self._traced("K8_pair_overlap_stats", 6 * h * w, "p360_pair_overlap_stats",
-                         _lib.ptr(src.pixels[i]), _lib.ptr(src.pixels[j]), h, w, src.pixels[i].shape[2],
-                         _lib.ptr(lut0), _lib.ptr(hat_y), _lib.ptr(hat_x), inv_c, _lib.ptr(partial),
-                         out[k].data_ptr(), self.stream)
+            jobs[k] = (src.pixels[i].data_ptr(), src.pixels[j].data_ptr(), inv.ravel())
+        dev_jobs = self._table(jobs, "pair_jobs")
+        partial = torch.empty(3 * nblocks * len(todo), dtype=torch.float64, device=self.device)
+        out = torch.empty((len(todo), 3), dtype=torch.float64, device=self.device)
+        self._traced("K8_pair_overlap_stats", 6 * h * w * len(todo), "p360_pair_overlap_stats",
+                     _lib.ptr(dev_jobs), len(todo), h, w, src.pixels[todo[0][0]].shape[2], _lib.ptr(lut0),
+                     _lib.ptr(hat_y), _lib.ptr(hat_x), _lib.ptr(partial), _lib.ptr(out), self.stream)
         sums = out.cpu().numpy()
         for (i, j, _), (cnt, s_i, s_j) in zip(todo, sums):
             sizes[i, j] = sizes[j, i] = cnt

@@ -4,12 +4,18 @@
 // SURVEY.md F7), then takes the overlap count and two mean intensities.  Here
 // nothing is materialised: every thread maps one pixel of i, samples j, and
 // the three sums are reduced with warp shuffles -> one partial per block ->
-// a fixed-order final pass (deterministic).
+// a fixed-order final pass (deterministic).  All pairs of a panorama run in one
+// launch (grid.y = pair).
 #include "p360_common.cuh"
 
 namespace p360 {
 
-struct Hom { double m[9]; };
+struct PairJob {                     // == p360_pair_job
+    const uint8_t *src_i;            // image i (destination frame)
+    const uint8_t *src_j;            // image j (warped into i's frame)
+    double inv[9];                   // INVERSE of the i <- j homography, un-centred pixel coordinates
+};
+static_assert(sizeof(PairJob) == sizeof(p360_pair_job), "ABI struct mismatch");
 
 constexpr int GB = 256;
 constexpr int GAIN_PIX_PER_THREAD = 4;
@@ -25,12 +31,17 @@ __device__ __forceinline__ int sat_round_int(double v) {     // saturate_cast<in
     return __double2int_rn(v);
 }
 
+// grid = (blocks per image, pairs): every pair of the panorama in one launch.
 __global__ void __launch_bounds__(GB)
-pair_stats_kernel(const uint8_t *__restrict__ src_i, const uint8_t *__restrict__ src_j,
-                  int h, int w, int sc, const float *__restrict__ lut,
+pair_stats_kernel(const PairJob *__restrict__ jobs, int h, int w, int sc, const float *__restrict__ lut,
                   const double *__restrict__ hat_y, const double *__restrict__ hat_x,
-                  Hom inv, double *__restrict__ partial) {
+                  double *__restrict__ partial) {
     __shared__ double red[3][GB / 32];
+    const PairJob &job = jobs[blockIdx.y];
+    const uint8_t *src_i = job.src_i, *src_j = job.src_j;
+    double m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = job.inv[k];
     double cnt = 0.0, sum_i = 0.0, sum_j = 0.0;
     long long n = (long long)h * w;
     long long base = ((long long)blockIdx.x * GB) * GAIN_PIX_PER_THREAD + threadIdx.x;
@@ -39,12 +50,13 @@ pair_stats_kernel(const uint8_t *__restrict__ src_i, const uint8_t *__restrict__
         long long p = base + (long long)it * GB;
         if (p >= n) break;
         int y = (int)(p / w), x = (int)(p - (long long)y * w);
-        // WarpPerspectiveInvoker: X = saturate<int>(rint(32 * X0 / W0)), double
-        double xd = inv.m[0] * x + inv.m[1] * y + inv.m[2];
-        double yd = inv.m[3] * x + inv.m[4] * y + inv.m[5];
-        double wd = inv.m[6] * x + inv.m[7] * y + inv.m[8];
+        // WarpPerspectiveInvoker: X = saturate<int>(rint(32 * X0 / W0)), double, products and
+        // sums separately rounded like the compiled C++ (no FMA contraction)
+        double xd = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
+        double yd = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
+        double wd = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), m[8]);
         wd = wd != 0.0 ? 32.0 / wd : 0.0;
-        int fx = sat_round_int(xd * wd), fy = sat_round_int(yd * wd);
+        int fx = sat_round_int(__dmul_rn(xd, wd)), fy = sat_round_int(__dmul_rn(yd, wd));
         int ix = sat16(fx >> 5), iy = sat16(fy >> 5);
         if (ix < 0 || ix > w - 1 || iy < 0 || iy > h - 1) continue;   // destination untouched (zero)
         int ix1 = min(ix + 1, w - 1), iy1 = min(iy + 1, h - 1);        // right/bottom taps replicate
@@ -80,19 +92,20 @@ pair_stats_kernel(const uint8_t *__restrict__ src_i, const uint8_t *__restrict__
     if (threadIdx.x < 3) {
         double s = 0.0;
         for (int k = 0; k < GB / 32; ++k) s += red[threadIdx.x][k];
-        partial[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
     }
 }
 
 __global__ void pair_stats_final_kernel(const double *__restrict__ partial, int nblocks,
-                                        double *__restrict__ out3) {
-    // 3 warps, one per statistic; lane-strided partial sums then a shuffle tree:
-    // the order is fixed by nblocks alone, so the result is reproducible.
+                                        double *__restrict__ out) {
+    // one block of 3 warps per pair, one warp per statistic; lane-strided partial sums then a
+    // shuffle tree: the order is fixed by nblocks alone, so the result is reproducible.
     int stat = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double *mine = partial + (size_t)blockIdx.x * nblocks * 3;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * 3 + stat];
+    for (int b = lane; b < nblocks; b += 32) s += mine[(size_t)b * 3 + stat];
     s = warp_sum(s);
-    if (lane == 0) out3[stat] = s;
+    if (lane == 0) out[(size_t)blockIdx.x * 3 + stat] = s;
 }
 
 }  // namespace p360
@@ -103,20 +116,20 @@ extern "C" int p360_pair_stats_blocks(int h, int w) {
     return (int)cdiv((long long)h * w, (long long)GB * GAIN_PIX_PER_THREAD);
 }
 
-extern "C" int p360_pair_overlap_stats(const uint8_t *src_i, const uint8_t *src_j, int h, int w,
-                                       int src_c, const float *lut, const double *hat_y,
-                                       const double *hat_x, const double *inv_hom_host,
-                                       double *partial, double *out3, void *stream) {
+extern "C" int p360_pair_overlap_stats(const p360_pair_job *jobs, int n_pairs, int h, int w, int src_c,
+                                       const float *lut, const double *hat_y, const double *hat_x,
+                                       double *partial, double *out, void *stream) {
     using namespace p360;
     const char *where = "p360_pair_overlap_stats";
-    P360_REQUIRE(src_i && src_j && lut && hat_y && hat_x && inv_hom_host && partial && out3, where);
+    P360_REQUIRE(jobs && lut && hat_y && hat_x && partial && out, where);
+    P360_REQUIRE(n_pairs >= 0 && n_pairs <= 65535, where);
     P360_REQUIRE(h > 0 && w > 0 && (src_c == 3 || src_c == 4 || src_c == 8), where);
-    Hom inv;
-    memcpy(inv.m, inv_hom_host, sizeof(inv.m));
+    if (n_pairs == 0) return 0;
     int nblocks = p360_pair_stats_blocks(h, w);
     cudaStream_t s = (cudaStream_t)stream;
-    pair_stats_kernel<<<nblocks, GB, 0, s>>>(src_i, src_j, h, w, src_c, lut, hat_y, hat_x, inv, partial);
+    pair_stats_kernel<<<dim3(nblocks, n_pairs), GB, 0, s>>>(reinterpret_cast<const PairJob *>(jobs), h, w, src_c,
+                                                            lut, hat_y, hat_x, partial);
     if (int e = check_launch(where)) return e;
-    pair_stats_final_kernel<<<1, 96, 0, s>>>(partial, nblocks, out3);
+    pair_stats_final_kernel<<<n_pairs, 96, 0, s>>>(partial, nblocks, out);
     return check_launch(where);
 }

@@ -180,6 +180,59 @@ def test_c_abi_exports_every_declared_symbol():
     assert rc == -22 and "p360_gauss_blur" in _lib.last_error()
 
 
+def test_job_records_match_the_header(tmp_path):
+    """The NumPy mirrors of the job records (filled on the host, shipped as raw
+    bytes) have exactly the layout the C header declares: compile a probe
+    against include/pano360_b200.h with gcc and compare sizes and offsets."""
+    import subprocess
+    records = {"p360_warp_job": _lib.WARP_JOB, "p360_blur_job": _lib.BLUR_JOB,
+               "p360_band_patch": _lib.BAND_PATCH, "p360_pair_job": _lib.PAIR_JOB}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "pano360_b200.h"', "int main(void) {"]
+    for cname, dtype in records.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for field in dtype.names:
+            lines.append(f'printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = {}
+    for line in filter(None, out):
+        cname, field, value = line.split()
+        seen[(cname, field)] = int(value)
+    for cname, dtype in records.items():
+        assert seen[(cname, "size")] == dtype.itemsize, cname
+        for field in dtype.names:
+            assert seen[(cname, field)] == dtype.fields[field][1], (cname, field)
+
+
+def test_band_edges_are_translation_invariant():
+    from pano360_b200.compositor import band_edges
+    for ya, yb, bands in [(0, 1103, 4), (57, 1160, 4), (10, 13, 8), (5, 5, 3)]:
+        cuts = band_edges(ya, yb, bands)
+        assert cuts[0][0] == ya and cuts[-1][1] == yb and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        shifted = band_edges(ya + 1000, yb + 1000, bands)
+        assert [(a + 1000, b + 1000) for a, b in cuts] == shifted
+
+
+def test_active_column_runs_split_only_seam_straddlers():
+    wl = synth.workload("cfg4")
+    regs = synth.camera_only(wl)
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    total = 0
+    for i, box in enumerate(plan.boxes):
+        runs = geo.active_column_runs(i, box, plan, dilate=120)
+        wide = box[2] - box[0] > 20000
+        assert len(runs) == (2 if wide else 1)
+        assert runs[0][0] == box[0] and runs[-1][1] == box[2]
+        if wide:
+            assert (runs[1][0] - box[0]) % 4 == 0            # coarse-grid phase preserved
+        total += sum(b - a for a, b in runs) * (box[3] - box[1])
+    assert total < 0.56 * sum((b[2] - b[0]) * (b[3] - b[1]) for b in plan.boxes)
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "pano360_b200")
     for fname in os.listdir(pkg):
