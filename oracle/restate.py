@@ -343,14 +343,15 @@ def build_patches(regions, blend="none", equalize_gains=False, max_resolution=14
     reflections still happen at true box edges) and slices are returned in
     window coordinates."""
     pl = plan(regions, blend, max_resolution, proj)
-    rgba = [rgba_with_weights(r.img) for r in regions]
+    lazy = window is not None and not equalize_gains      # only convert the images the window touches
+    rgba = [None if lazy else rgba_with_weights(r.img) for r in regions]
     if equalize_gains:
         equalize(regions, rgba, backend)
     patches = []
-    for reg, src, box in zip(regions, rgba, pl.boxes):
+    for k, (reg, box) in enumerate(zip(regions, pl.boxes)):
         x0, y0, x1, y1 = box
         if window is None:
-            warped, invalid = warp_region(src, reg, box, pl, proj, backend)
+            warped, invalid = warp_region(rgba[k], reg, box, pl, proj, backend)
             patches.append((warped, invalid, np.s_[y0:y1, x0:x1]))
             continue
         wy0, wy1, wx0, wx1 = window
@@ -358,6 +359,7 @@ def build_patches(regions, blend="none", equalize_gains=False, max_resolution=14
         cx0, cx1 = max(x0, wx0 - halo), min(x1, wx1 + halo)
         if cy0 >= cy1 or cx0 >= cx1:
             continue
+        src = rgba[k] if rgba[k] is not None else rgba_with_weights(reg.img)
         sub = (cx0, y0, cx1, y1)
         warped, invalid = warp_region(src, reg, sub, pl, proj, backend, rows=(cy0 - y0, cy1 - y0))
         oy, ox = wy0 - halo, wx0 - halo

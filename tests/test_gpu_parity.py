@@ -301,6 +301,27 @@ def test_many_small_views(st, restore_globals):
         assert_mosaic_close(got, rs.stitch(regs, blend, False, 5, 1e9), what=blend)
 
 
+def test_full_size_cfg4_windows(st, restore_globals):
+    """The benchmark workload itself — BASELINE config 4, 36 x 4000x3000 views on a
+    full ring, 8819 x 31654 mosaic, which the reference cannot hold in RAM (~85 GiB):
+    windows of the GPU mosaic against the oracle's exact window mode, at the +-pi seam
+    (full-width seam-straddling boxes, split on the GPU), in the middle, and at the
+    bottom edge."""
+    wl = synth.workload("cfg4")
+    regs = synth.make_views(wl)
+    st.MAX_RESOLUTION = wl.max_resolution
+    got = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
+    h, w = got.shape[:2]
+    assert (h, w) == geo.plan_mosaic(regs, True, 1e9).shape and h > 8000 and w > 30000
+    for win in [(h // 2 - 64, h // 2 + 64, 0, 256),                      # left end of the ring (theta = -pi)
+                (h // 2 - 64, h // 2 + 64, w - 256, w),                  # right end (theta = +pi)
+                (h // 3 - 48, h // 3 + 48, w // 2 - 128, w // 2 + 128),  # interior seam crossing
+                (h - 96, h, w // 4, w // 4 + 256)]:                      # bottom edge
+        want = rs.stitch_window(regs, win, "multiband", False, wl.n_levels, 1e9)
+        assert_mosaic_close(got[win[0]:win[1], win[2]:win[3]], want, what=f"cfg4 window {win}")
+    assert (got.sum(axis=2) > 0).mean() > 0.9
+
+
 def test_edge_cases(st, restore_globals):
     """Single image; images smaller than the blur radius; crop."""
     wl = synth.workload("cfg1", scale=16.0)          # 40 x 30 pixel views
