@@ -51,15 +51,44 @@ def _require_cuda(device):
     return dev
 
 
-@dataclass
 class DevicePatch:
     """One warped image resident in HBM.  Unpacks like the reference's patch
-    triple ``(warped, mask, irange)`` (stitcher.py:318-319)."""
+    triple ``(warped, mask, irange)`` (stitcher.py:318-319).
 
-    rgba: torch.Tensor        # [ph, pw, 4] float32
-    invalid: torch.Tensor     # [ph, pw] uint8 (1 = masked)
-    box: tuple                # (x0, y0, x1, y1) in mosaic pixels
-    index: int = 0            # source image number
+    Patches produced by the warp live back to back in two pools; the tensor
+    views ``rgba`` ([ph, pw, 4] float32) and ``invalid`` ([ph, pw] uint8, 1 =
+    masked) are only materialised when somebody asks for them — the kernels
+    work from the raw device addresses."""
+
+    __slots__ = ("box", "index", "rgba_ptr", "invalid_ptr", "_rgba", "_invalid", "_pools", "_offset")
+
+    def __init__(self, rgba=None, invalid=None, box=(0, 0, 0, 0), index=0, pools=None, offset=0):
+        self.box, self.index = tuple(box), index
+        self._rgba, self._invalid, self._pools, self._offset = rgba, invalid, pools, offset
+        if pools is None:
+            self.rgba_ptr, self.invalid_ptr = rgba.data_ptr(), invalid.data_ptr()
+        else:
+            self.rgba_ptr = pools[0].data_ptr() + 16 * offset
+            self.invalid_ptr = pools[1].data_ptr() + offset
+
+    @property
+    def shape(self):
+        x0, y0, x1, y1 = self.box
+        return y1 - y0, x1 - x0
+
+    @property
+    def rgba(self):
+        if self._rgba is None:
+            ph, pw = self.shape
+            self._rgba = self._pools[0][4 * self._offset:4 * (self._offset + ph * pw)].view(ph, pw, 4)
+        return self._rgba
+
+    @property
+    def invalid(self):
+        if self._invalid is None:
+            ph, pw = self.shape
+            self._invalid = self._pools[1][self._offset:self._offset + ph * pw].view(ph, pw)
+        return self._invalid
 
     @property
     def irange(self):
@@ -278,7 +307,12 @@ class Compositor:
         if not crops:
             return []
         ray_x, ray_z, ray_y = tables
-        dev_rays = self._to_device(np.concatenate([ray_x, ray_z, ray_y]), pinned_key="rays")
+        cached = self._keep.get("rays")
+        if cached is not None and cached[0] is ray_x:          # same plan as last time: tables already on the device
+            dev_rays = cached[1]
+        else:
+            dev_rays = self._to_device(np.concatenate([ray_x, ray_z, ray_y]), pinned_key="rays")
+            self._keep["rays"] = (ray_x, dev_rays)
         base_x = dev_rays.data_ptr()
         base_z, base_y = base_x + 8 * len(ray_x), base_x + 8 * (len(ray_x) + len(ray_z))
         ox, oy = origin
@@ -301,9 +335,8 @@ class Compositor:
                        h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, x0, ya, k,
                        np.float32(w / 2), np.float32(h / 2), np.float32(w - 1), np.float32(h - 1),
                        np.float32(1.0) / np.float32(2 * w), np.float32(1.0) / np.float32(2 * h))
-            patches.append(DevicePatch(rgba_pool[4 * o:4 * (o + pw * ph)].view(ph, pw, 4),
-                                       inv_pool[o:o + pw * ph].view(ph, pw),
-                                       (x0 - ox, ya - oy, x1 - ox, yb - oy), i))
+            patches.append(DevicePatch(box=(x0 - ox, ya - oy, x1 - ox, yb - oy), index=i,
+                                       pools=(rgba_pool, inv_pool), offset=o))
         if owner_state is None:
             keys = covered = None
             width, per_px = 0, 17
@@ -345,8 +378,8 @@ class Compositor:
         keys, covered = self.new_owner_state(shape)
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
-            self._traced("K2_owner_update", 30 * pw * ph, "p360_owner_update", _lib.ptr(p.rgba),
-                         _lib.ptr(p.invalid), pw, ph, x0, y0, k, _lib.ptr(keys), _lib.ptr(covered),
+            self._traced("K2_owner_update", 30 * pw * ph, "p360_owner_update", p.rgba_ptr,
+                         p.invalid_ptr, pw, ph, x0, y0, k, _lib.ptr(keys), _lib.ptr(covered),
                          shape[1], self.stream)
         return keys, covered
 
@@ -378,7 +411,7 @@ class Compositor:
         for k, p in enumerate(patches):
             pw, ph, x0, y0 = self._args(p)
             rec = table[k]
-            rec["rgba"], rec["invalid"] = p.rgba.data_ptr(), p.invalid.data_ptr()
+            rec["rgba"], rec["invalid"] = p.rgba_ptr, p.invalid_ptr
             rec["x0"], rec["y0"], rec["pw"], rec["ph"] = x0, y0, pw, ph
             rec["pad"], rec["index"] = pad, k
             rec["own"] = (2 ** 31 - 1, 2 ** 31 - 1, -2 ** 31, -2 ** 31)      # grown on the device (p360_owned_boxes)
@@ -538,7 +571,7 @@ class Compositor:
         covered = torch.zeros((h, w), dtype=torch.uint8, device=self.device)
         for p in patches:
             pw, ph, x0, y0 = self._args(p)
-            _lib.call("p360_cover_update", _lib.ptr(p.invalid), pw, ph, x0, y0, _lib.ptr(covered), w,
+            _lib.call("p360_cover_update", p.invalid_ptr, pw, ph, x0, y0, _lib.ptr(covered), w,
                       self.stream)
         return covered
 
