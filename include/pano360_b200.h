@@ -46,10 +46,10 @@ int  p360_device_info(int device, int32_t out_host[4]);
  * One launch warps every patch of a composite (up to 128 per launch; the job
  * records are staged in constant memory): `jobs_host` is a HOST array whose
  * pointer members are device pointers.
- *   src         u8, h x w x c bytes per pixel: c = 3 (as uploaded), c = 4 (one
- *               aligned word per pixel, p360_pack_rgbx) or c = 8 ({RGBX u32,
- *               alpha f32} per pixel, p360_pack_rgbxa: alpha = float32(hat_y *
- *               hat_x) evaluated once per source pixel, not once per tap)
+ *   src         u8, h x w x c bytes per pixel: c = 3 or 4 (as uploaded; a 4th
+ *               channel is ignored) or c = 8 ({RGBX u32, alpha f32} per pixel,
+ *               p360_pack_rgbxa: alpha = float32(hat_y * hat_x) evaluated once
+ *               per source pixel, not once per tap)
  *   lut         256 float32: value of a u8 sample (u8/255, optionally
  *               gain-scaled and clipped, stitcher.py:65-66)
  *   hat_y/hat_x float64 tables of `_hat(h)` / `_hat(w)` (stitcher.py:251-254)
@@ -86,7 +86,6 @@ typedef struct p360_warp_job {
     float inv_2w, inv_2h;         /* 1 / (2 w), 1 / (2 h)                                 */
 } p360_warp_job;
 
-int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t n_pixels, void *stream);
 int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
                     int h, int w, uint8_t *dst_rgbxa, void *stream);
 int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,

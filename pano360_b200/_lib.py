@@ -24,7 +24,6 @@ SIGNATURES = {
     "p360_version": [],
     "p360_last_error": [C.c_char_p, _i],
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
-    "p360_pack_rgbx": [_vp, _vp, _i64, _vp],
     "p360_pack_rgbxa": [_vp, _i, _vp, _vp, _i, _i, _vp, _vp],
     "p360_warp_batch": [_vp, _i, _vp, _vp, _i, _vp],
     "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
@@ -67,7 +66,7 @@ _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
-_LAUNCHES = {"p360_pack_rgbx": 1, "p360_pack_rgbxa": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
+_LAUNCHES = {"p360_pack_rgbxa": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
              "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1, "p360_owned_boxes": 1,
              "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
              "p360_pair_overlap_stats": 2, "p360_cover_update": 1}

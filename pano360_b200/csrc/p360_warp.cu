@@ -200,27 +200,7 @@ pack_rgbxa_kernel(const uint8_t *__restrict__ src, int sc, const double *__restr
     dst[(size_t)y * w + x] = o;
 }
 
-// u8 x 3 -> u8 x 4 (one aligned 32-bit word per source pixel for the gathers)
-__global__ void __launch_bounds__(256)
-pack_rgbx_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, long long n) {
-    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t *p = src + i * 3;
-    dst[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-}
-
 }  // namespace p360
-
-extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, uint8_t *dst_rgbx, int64_t n_pixels, void *stream) {
-    using namespace p360;
-    const char *where = "p360_pack_rgbx";
-    P360_REQUIRE(src_rgb && dst_rgbx && n_pixels >= 0, where);
-    P360_REQUIRE((reinterpret_cast<uintptr_t>(dst_rgbx) & 3) == 0, where);
-    if (n_pixels == 0) return 0;
-    pack_rgbx_kernel<<<cdiv(n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(
-        src_rgb, reinterpret_cast<uint32_t *>(dst_rgbx), (long long)n_pixels);
-    return check_launch(where);
-}
 
 extern "C" int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
                                int h, int w, uint8_t *dst_rgbxa, void *stream) {

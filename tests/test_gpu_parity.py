@@ -360,6 +360,13 @@ def test_unpacked_source_layout_is_equivalent(comp, tiny4):
     raw = comp.warp(regs, comp.upload(regs, pack=False), plan)
     for a, b in zip(packed, raw):
         assert torch_equal(a.rgba, b.rgba) and torch_equal(a.invalid, b.invalid)
+    # 4-channel uint8 sources (4th channel ignored), packed and as uploaded
+    from pano360_b200.camera import Image
+    four = [Image(np.ascontiguousarray(np.dstack([r.img, np.full(r.img.shape[:2], 77, np.uint8)])), r.rot, r.intr)
+            for r in regs]
+    for pack in (True, False):
+        for a, b in zip(packed, comp.warp(four, comp.upload(four, pack=pack), plan)):
+            assert torch_equal(a.rgba, b.rgba) and torch_equal(a.invalid, b.invalid)
 
 
 def torch_equal(a, b):
