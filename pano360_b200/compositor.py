@@ -2,14 +2,15 @@
 for allocation, streams and copies only) and sequences the sm_100a kernels of
 ``libpano360_b200.so`` through the C ABI.
 
-A whole composite is five launches, whatever the number of images: one warp
-over every patch (K1, grid.z = patch), one reduce, one horizontal and one
-vertical coarse blur over every (patch, level) job, one output-stationary
-collapse.  Per-patch parameters travel in small device tables.
+A whole multiband composite is six launches, whatever the number of images:
+one warp over every patch (K1, grid.z = patch, owner competition fused), one
+owned-box pass over the owner keys, one reduce, one horizontal and one vertical
+coarse blur over every (patch, level) job, one output-stationary collapse.
+Per-patch parameters travel in small job tables.
 
 Data layout in HBM
 ------------------
-* source image      u8  [h][w][4]            RGBX, packed on device from the u8x3 upload
+* source image      {u32 RGBX, f32 alpha} [h][w]   packed on device from the u8x3 upload
 * sample LUT        f32 [256] per image      u8 -> float value (gain folded in)
 * hat tables        f64 [h], [w]             shared by images of equal size
 * ray tables        f64 [W], [W], [H]        proj2hom per mosaic column (x, z) / row (y); K*R per patch
