@@ -459,6 +459,13 @@ class Compositor:
             self._download = torch.cuda.Event()
             self._download.record(side)
 
+    def release(self):
+        """Drop the references that keep the last composite's pools alive (patch
+        pool, coarse levels, job tables); the memory goes back to torch's caching
+        allocator.  Call only after the work that uses them has been waited for."""
+        for key in ("warp", "bands", "collapse"):
+            self._keep.pop(key, None)
+
     def finish_download(self):
         """Block until a banded download started by ``_collapse`` has landed."""
         if self._download is not None:

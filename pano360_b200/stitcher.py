@@ -208,6 +208,8 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     if crop:
         logging.debug("Cropping...")
         mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))
+    del patches
+    comp.release()          # everything has been waited for (the mosaic is on the host)
     return mosaic
 
 

@@ -285,4 +285,6 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     if not to_host:
         return mosaic
     from .stitcher import _download
-    return _download(mosaic, out)
+    host = _download(mosaic, out)
+    comp.release()
+    return host
