@@ -1,0 +1,116 @@
+"""The GPU parity tests, re-run in the CPU tier against the kernels' own source compiled for
+the host (tests/emul: every CUDA thread a fiber, barriers and warp collectives emulated).
+
+What this checks without a GPU: the job tables the host code builds, the launch sequence,
+and the logic of every kernel, against the same golden fixtures and oracle comparisons as
+``-m gpu``.  What it cannot check: anything about timing, and the few float expressions
+nvcc contracts to FMA on its own (multiband only; within the same tolerance).
+
+Only the small cases are re-run here — the whole CPU suite has to stay within minutes.
+The sm_100a build remains the only thing the package loads (tests/emul/harness.py patches
+the binding from the outside).
+"""
+import pytest
+
+from . import test_gpu_parity as gpu
+from .emul import harness
+
+
+@pytest.fixture()
+def comp(monkeypatch):
+    return harness.install(monkeypatch)
+
+
+@pytest.fixture()
+def st(comp):
+    from pano360_b200 import stitcher
+    return stitcher
+
+
+tiny4 = gpu.tiny4
+restore_globals = gpu.restore_globals
+
+# the same test bodies, collected here without the gpu mark and bound to the fixtures above
+test_golden_tiny4 = gpu.test_golden_tiny4
+test_golden_levels_and_resolution_cap = gpu.test_golden_levels_and_resolution_cap
+test_inputs_are_not_mutated = gpu.test_inputs_are_not_mutated
+test_warp_stage_matches_reference_patches = gpu.test_warp_stage_matches_reference_patches
+test_gains_match_reference = gpu.test_gains_match_reference
+test_blur_stage_matches_cv2 = gpu.test_blur_stage_matches_cv2
+test_owner_map_matches_oracle = gpu.test_owner_map_matches_oracle
+test_coarse_levels_track_the_reference_blurs = gpu.test_coarse_levels_track_the_reference_blurs
+test_blenders_accept_reference_style_patches = gpu.test_blenders_accept_reference_style_patches
+test_foreign_blender_gets_numpy_patches = gpu.test_foreign_blender_gets_numpy_patches
+test_oracle_seeded_cfg1_half = gpu.test_oracle_seeded_cfg1_half
+test_golden_cfg1_full_size = gpu.test_golden_cfg1_full_size
+test_golden_ring12_seam_straddlers = gpu.test_golden_ring12_seam_straddlers
+test_two_row_six_band_layout = gpu.test_two_row_six_band_layout
+test_many_small_views = gpu.test_many_small_views
+test_edge_cases = gpu.test_edge_cases
+test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
+test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
+test_seam_split_is_exact = gpu.test_seam_split_is_exact
+test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
+test_batched_blur_paths = gpu.test_batched_blur_paths
+
+
+def test_c_abi_error_path(comp):
+    from pano360_b200 import _lib
+    with pytest.raises(RuntimeError, match="p360_gauss_blur"):
+        _lib.call("p360_gauss_blur", None, None, None, 4, 4, None, 3, None)
+
+
+def test_barrier_misuse_is_detected():
+    """The emulation aborts on a barrier not every live thread reaches; its own sanity check
+    here is that a well-formed run leaves no fiber behind (a hang would time the test out)."""
+    import numpy as np
+    import torch
+    from pano360_b200 import _lib
+    lib = harness._load_library()
+    keys = torch.zeros(64 * 33, dtype=torch.int64)
+    owner = torch.empty(64 * 33, dtype=torch.int32)
+    assert lib.p360_owner_decode(keys.data_ptr(), owner.data_ptr(), keys.numel(), None) == 0
+    assert np.all(owner.numpy() == -1)
+    assert set(_lib.SIGNATURES) <= {n for n in dir(lib) if n.startswith("p360_")} | set(_lib.SIGNATURES)
+
+
+# ---- the multi-rank path end to end: strips over gloo, kernels on the host -------------------
+def _strip_worker(rank, world, port, golden, kind, equalize, out_path):
+    import os
+
+    import numpy as np
+    import torch.distributed as dist
+
+    from pano360_b200 import strips
+    from .conftest import load_golden, regions_from_golden
+    patcher = pytest.MonkeyPatch()
+    comp = harness.install(patcher)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), P360_EMUL_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        regs = regions_from_golden(load_golden(golden))
+        mosaic = strips.stitch_strips(comp, regs, kind, n_levels=5, equalize=equalize)
+        assert (mosaic is not None) == (rank == 0)
+        if rank == 0:
+            np.save(out_path, mosaic)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+        patcher.undo()
+
+
+@pytest.mark.parametrize("golden,kind,equalize,world", [("tiny4", "multiband", False, 2), ("tiny4", "linear", True, 2),
+                                                        ("ring12", "multiband", True, 3), ("tiny4", "none", False, 2)])
+def test_strips_over_gloo_equal_single_rank(st, tmp_path, golden, kind, equalize, world):
+    """stitch_strips on 2-3 ranks (row strips with halo, banded sends to rank 0, pair statistics
+    all-reduced) gives the bytes of the single-rank stitch — SURVEY.md §8(e)."""
+    import numpy as np
+    import torch.multiprocessing as mp
+
+    from .conftest import load_golden, regions_from_golden
+    from .test_strips_gloo import _free_port
+    regs = regions_from_golden(load_golden(golden))
+    want = st.stitch(regs, blender=st.BLENDERS[kind], equalize=equalize)
+    out = str(tmp_path / "mosaic.npy")
+    mp.spawn(_strip_worker, args=(world, _free_port(), golden, kind, equalize, out), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), want)
