@@ -113,17 +113,19 @@ typedef struct p360_blur_job {
     float *out;
     float *tmp;
     int32_t w, h, slot;
-    int32_t shift;                /* log2 of the coarse factor of this image (own != NULL)   */
-    const int32_t *own;           /* owned box of the patch (p360_band_patch.own) or NULL:    */
-    int32_t pad, grow;            /* blocks farther than `grow` px from it are skipped        */
+    int32_t shift;                /* log2 of the coarse factor of this image (patch != NULL)  */
+    const struct p360_band_patch *patch;   /* DEVICE record of the patch this image belongs to, */
+                                  /* or NULL: blocks nobody reads are skipped (seam-band maps  */
+    int32_t pad, grow;            /* if given, else farther than `grow` px from patch->own)    */
 } p360_blur_job;
 
 int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp_rgba,
                     int pw, int ph, const float *taps_host, int ksize,
                     void *stream);
 int p360_blur_set_taps(int slot, const float *taps_host, int ksize, void *stream);
+struct p360_tile_maps;
 int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int max_h,
-                          void *stream);
+                          const struct p360_tile_maps *maps_host, void *stream);
 
 /* ---- reduced-resolution band pipeline + output-stationary blenders ----------
  * The blurs of stitcher.py:226 are evaluated on coarse grids (f = 2 for level
@@ -168,13 +170,45 @@ typedef struct p360_band_patch {
  *                           away (exact: skipped values only ever meet zero weights)      */
 int p360_owned_boxes(const uint64_t *owner_keys, p360_band_patch *patches, int n_patches,
                      int H, int W, void *stream);
+
+/* Seam-band maps: bitmaps over the 64 x 32 mosaic tiles, one bit per patch, `words` =
+ * ceil(n_patches / 32) uint32 per tile, tile rows anchored at absolute mosaic rows
+ * (row0 = -((row_origin mod 32 + 32) mod 32), tiles_y = ceil((H - row0) / 32),
+ * tiles_x = ceil(W / 64)).  The weights of stitcher.py:207-232 are non-zero only within
+ * the blur reach of an owner seam; everywhere else the multiband sum telescopes to the
+ * owner's warped pixel.  p360_tile_maps_build fills, from the owner keys:
+ *   present  patches that own a pixel of the tile (also grows p360_band_patch.own)
+ *   cand     patches that own a pixel within reach_x / reach_y tiles: the candidates for
+ *            non-zero weight in the tile;  multi = more than one candidate, or one and a
+ *            valid pixel nobody owns (alpha == 0): the tile is not just its owner's pixels
+ *   need     candidates of the multi tiles within reach: where coarse levels are consumed
+ * reduce / blur run only the blocks whose tiles carry the patch's `need` bit (a scan compacts
+ * them into `work`, a persistent grid consumes the list: an empty block of a dense grid costs
+ * as much as a small busy one), the collapse takes its patch list from `cand`.  Results are identical with and without maps (maps_host == NULL).
+ */
+typedef struct p360_tile_maps {
+    uint32_t *present, *cand, *need;          /* DEVICE [tiles_y][tiles_x][words]       */
+    uint8_t *multi;                           /* DEVICE [tiles_y][tiles_x]              */
+    uint32_t *work;                           /* DEVICE scratch, 2 * work_cap uint32: the list  */
+    int32_t *work_count;                      /* of blocks a reduce / blur pass has to run (+ its */
+                                              /* length); work_cap >= blocks of the largest grid */
+    int32_t tiles_x, tiles_y, words;
+    int32_t row0;
+    int32_t reach_x, reach_y;                 /* ceil(pad / 64), ceil(pad / 32)          */
+    int32_t work_cap;
+    int32_t reserved;
+} p360_tile_maps;
+int p360_tile_maps_build(const uint64_t *owner_keys, const uint8_t *covered,
+                         p360_band_patch *patches, int n_patches, int H, int W,
+                         const p360_tile_maps *maps_host, void *stream);
 int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]);
 int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int max_w4,
-                              int max_h4, const uint64_t *owner_keys, int W, void *stream);
+                              int max_h4, const uint64_t *owner_keys, int W,
+                              const p360_tile_maps *maps_host, void *stream);
 int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                             const uint64_t *owner_keys, const uint8_t *covered,
                             uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
-                            void *stream);
+                            const p360_tile_maps *maps_host, void *stream);
 int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
                          int y_begin, int y_end, int row_origin, int W, void *stream);
 int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,

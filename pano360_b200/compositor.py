@@ -29,6 +29,7 @@ at true patch edges wherever they influence rows inside the window.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -126,6 +127,9 @@ class Compositor:
         self._copy = None      # side stream for uploads / downloads that overlap the kernels
         self._download = None
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
+        # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
+        # blur reach.  Bit-identical output; off until measured on the B200.
+        self.seam_maps = os.environ.get("P360_SEAM_MAPS", "0") == "1"
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -420,6 +424,30 @@ class Compositor:
                 rec["w4"], rec["h4"] = (pw + 2 * pad + 3) // 4, (ph + 2 * pad + 3) // 4
         return table
 
+    def _tile_maps(self, table, n_blurs, h, w, pad, row_origin):
+        """Device bitmaps of p360_tile_maps (one bit per patch and 64 x 32 tile, tile rows on
+        absolute mosaic rows), the scratch for the compacted block lists of reduce / blur, and the
+        host record that names them."""
+        n = len(table)
+        row0 = -(row_origin % 32)
+        tiles_x, tiles_y, words = -(-w // 64), -(-(h - row0) // 32), -(-n // 32)
+        cells = tiles_x * tiles_y
+        w4, h4 = int(table["w4"].max()), int(table["h4"].max())
+        cap = max(-(-4 * w4 // 32) * -(-h4 // 8) * n,                      # reduce blocks
+                  -(-2 * w4 // 256) * -(-2 * h4 // 4) * n * n_blurs,      # horizontal blur blocks
+                  -(-2 * w4 // 32) * -(-2 * h4 // 64) * n * n_blurs)      # vertical blur blocks
+        bits = torch.empty(2 + 2 * cap + 3 * cells * words, dtype=torch.int32, device=self.device)
+        multi = torch.empty(cells, dtype=torch.uint8, device=self.device)
+        maps = np.zeros(1, dtype=_lib.TILE_MAPS)
+        base = bits.data_ptr()
+        maps["work_count"], maps["work"], maps["work_cap"] = base, base + 8, cap      # work: 8-byte items
+        base += 8 + 8 * cap
+        maps["present"], maps["cand"], maps["need"] = base, base + 4 * cells * words, base + 8 * cells * words
+        maps["multi"] = multi.data_ptr()
+        maps["tiles_x"], maps["tiles_y"], maps["words"], maps["row0"] = tiles_x, tiles_y, words, row0
+        maps["reach_x"], maps["reach_y"] = -(-pad // 64), -(-pad // 32)
+        return maps, (bits, multi)
+
     def _set_taps(self, n_levels, plan):
         if self._taps_key == n_levels:
             return
@@ -429,7 +457,7 @@ class Compositor:
         self._taps_key = n_levels
 
     def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8,
-                  row_origin=0):
+                  row_origin=0, tail=()):
         """Launch a collapse kernel over rows ``rows`` (default: all) of the
         mosaic buffer.  With ``out_host`` (pinned host array) or ``on_band``
         (callback(y0, y1), e.g. an NVLink send) the rows are produced band by
@@ -438,7 +466,7 @@ class Compositor:
         h, w = mosaic.shape[:2]
         ya, yb = (0, h) if rows is None else rows
         if out_host is None and on_band is None:
-            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, self.stream)
+            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, *tail, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
         main, side = torch.cuda.current_stream(self.device), self.copy_stream()
@@ -446,7 +474,7 @@ class Compositor:
             if y1 <= y0:
                 continue
             self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1,
-                         row_origin, w, self.stream)
+                         row_origin, w, *tail, self.stream)
             if on_band is not None:
                 on_band(y0, y1)
             if host is not None:
@@ -507,11 +535,17 @@ class Compositor:
             self._set_taps(n_levels, plan)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
+        maps = None
         if plan:
             # which part of each patch can ever carry weight: box around its owned pixels
-            self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table), n,
-                         h, w, self.stream)
-            own_ptr = np.uint64(dev_table.data_ptr() + _lib.OWN_OFFSET) + \
+            if self.seam_maps:
+                maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
+                self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
+                             _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)
+            else:
+                self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table),
+                             n, h, w, self.stream)
+            patch_ptr = np.uint64(dev_table.data_ptr()) + \
                 np.uint64(_lib.BAND_PATCH.itemsize) * np.arange(n, dtype=np.uint64)
             jobs = np.zeros(n * len(plan), dtype=_lib.BLUR_JOB)
             for lvl in range(len(plan)):
@@ -523,14 +557,18 @@ class Compositor:
                     sl["in"], sl["tmp"] = table["d4"], b4 + np.uint64(2 * lvl - 1) * s4 + o4
                     sl["w"], sl["h"], sl["shift"] = table["w4"], table["h4"], 2
                 sl["out"], sl["slot"] = table["low"][:, lvl], lvl
-                sl["own"], sl["pad"], sl["grow"] = own_ptr, pad, 2 * pad + 4
+                sl["patch"], sl["pad"], sl["grow"] = patch_ptr, pad, 2 * pad + 4
             dev_jobs = self._table(jobs, "blur_jobs")
             self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
-                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, self.stream)
+                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w,
+                         None if maps is None else maps.ctypes.data, self.stream)
             coarse_px = int(4 * tot4 + (len(plan) - 1) * tot4)
             self._traced("K3_gauss_blur", 32 * coarse_px, "p360_gauss_blur_batch", _lib.ptr(dev_jobs),
-                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()), self.stream)
-            self._keep["bands"] = (pool2, pool4, dev_jobs)
+                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()),
+                         None if maps is None else maps.ctypes.data, self.stream)
+            if maps is not None:
+                _lib.launch_count += 3          # the scan kernels that compact the block lists
+            self._keep["bands"] = (pool2, pool4, dev_jobs, maps, maps_keep if maps is not None else None)
             if stages is not None:
                 for k in range(n):
                     w4, h4, o = int(table["w4"][k]), int(table["h4"][k]), int(off4[k])
@@ -540,7 +578,8 @@ class Compositor:
                     lows.append(per)
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
-                       rows, on_band, bands, row_origin)
+                       rows, on_band, bands, row_origin,
+                       tail=(None if maps is None else maps.ctypes.data,))
         self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows)

@@ -44,11 +44,25 @@ __device__ __forceinline__ void convolve_r(float2 (&lo)[R], float2 (&hi)[R], con
     }
 }
 
+// The batched kernels skip blocks nobody reads, so a block that does run may stage cells that
+// were never written (stale memory).  Those cells only ever meet zero taps or outputs that are
+// themselves unread — unless they hold NaN / Inf, where 0 * x != 0.  FINITE clamps what is
+// staged to +-1e30 (fmaxf / fminf drop NaN); written data lies in [0, 1] and is unaffected.
+template <bool FINITE>
+__device__ __forceinline__ float4 staged(float4 v) {
+    if (FINITE) {
+        v.x = fminf(fmaxf(v.x, -1e30f), 1e30f); v.y = fminf(fmaxf(v.y, -1e30f), 1e30f);
+        v.z = fminf(fmaxf(v.z, -1e30f), 1e30f); v.w = fminf(fmaxf(v.w, -1e30f), 1e30f);
+    }
+    return v;
+}
+
 // ---- horizontal ------------------------------------------------------------
 constexpr int H_WARPS = 4;             // rows per block (one warp per row)
 constexpr int H_SEG = 32 * R;          // outputs per warp
 __host__ __device__ __forceinline__ int h_phys(int q) { return q + (q >> 3); }   // 1 pad slot per 8: lane stride 9
 
+template <bool FINITE>
 __device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float4 *__restrict__ out,
                                             int pw, int ph, int pitch, const Taps &t, int block) {
     extern __shared__ float4 smem[];
@@ -61,7 +75,7 @@ __device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float
     const int r = t.ksize >> 1;
     const float4 *src = in + (size_t)row * pw;
     const int nq = H_SEG + t.ksize - 1;
-    for (int q = lane; q < nq; q += 32) tile[h_phys(q)] = __ldg(src + reflect_101(xb - r + q, pw));
+    for (int q = lane; q < nq; q += 32) tile[h_phys(q)] = staged<FINITE>(__ldg(src + reflect_101(xb - r + q, pw)));
     __syncwarp();
     float2 lo[R], hi[R];
 #pragma unroll
@@ -89,14 +103,22 @@ struct BlurJob {                       // == p360_blur_job
     float4 *tmp;
     int w, h, slot;
     int shift;                         // log2 coarse factor
-    const int *own;                    // owned box of the patch (or nullptr)
+    const BandPatch *patch;            // the patch this coarse image belongs to (or nullptr: no skipping)
     int pad, grow;
 };
 
-// is the coarse block [cx0, cx1) x [cy0, cy1) of this job within reach of the patch's owned box?
-__device__ __forceinline__ bool job_block_needed(const BlurJob &job, int cx0, int cy0, int cx1, int cy1) {
+// Does anybody read the coarse block [cx0, cx1) x [cy0, cy1) of this job?  With seam-band maps:
+// a tile under it carries the patch's `need` bit; else: it lies within reach of the owned box.
+__device__ __forceinline__ bool job_block_needed(const BlurJob &job, const TileMaps &maps,
+                                                 int cx0, int cy0, int cx1, int cy1) {
+    if (job.patch == nullptr) return true;
     const int s = job.shift, p = job.pad;
-    return near_owned(job.own, job.grow, (cx0 << s) - p, (cy0 << s) - p, (cx1 << s) - p, (cy1 << s) - p);
+    const int xa = (cx0 << s) - p, ya = (cy0 << s) - p, xb = (cx1 << s) - p, yb = (cy1 << s) - p;   // patch px
+    if (maps.need != nullptr) {
+        const int x0 = __ldg(&job.patch->x0), y0 = __ldg(&job.patch->y0);
+        return tiles_test(maps, maps.need, __ldg(&job.patch->index), xa + x0, ya + y0, xb + x0, yb + y0);
+    }
+    return near_owned(job.patch->own, job.grow, xa, ya, xb, yb);
 }
 static_assert(sizeof(BlurJob) == sizeof(p360_blur_job), "ABI struct mismatch");
 
@@ -104,35 +126,63 @@ __constant__ Taps c_taps[P360_MAX_LEVELS];     // tap sets of the batched blurs 
 
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
-    blur_h_body(in, out, pw, ph, pitch, t, blockIdx.x);
+    blur_h_body<false>(in, out, pw, ph, pitch, t, blockIdx.x);
+}
+
+// block `b` of a job's horizontal grid: exists and is read by somebody?
+__device__ __forceinline__ bool h_block_needed(const BlurJob &job, const TileMaps &maps, int b) {
+    const int nxb = (job.w + H_SEG - 1) / H_SEG;
+    if (b >= nxb * ((job.h + H_WARPS - 1) / H_WARPS)) return false;
+    const int cx0 = (b % nxb) * H_SEG, cy0 = (b / nxb) * H_WARPS;
+    return job_block_needed(job, maps, cx0, cy0, cx0 + H_SEG, cy0 + H_WARPS);
 }
 
 __global__ void __launch_bounds__(32 * H_WARPS)
-blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch) {
+blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     const BlurJob &job = jobs[blockIdx.y];
-    const int nxb = (job.w + H_SEG - 1) / H_SEG;
-    const int blocks = nxb * ((job.h + H_WARPS - 1) / H_WARPS);
-    if ((int)blockIdx.x >= blocks) return;
-    const int cx0 = ((int)blockIdx.x % nxb) * H_SEG, cy0 = ((int)blockIdx.x / nxb) * H_WARPS;
-    if (!job_block_needed(job, cx0, cy0, cx0 + H_SEG, cy0 + H_WARPS)) return;       // block-uniform
-    blur_h_body(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
+    if (!h_block_needed(job, maps, blockIdx.x)) return;                               // block-uniform
+    blur_h_body<true>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
+}
+
+// With seam-band maps: the needed blocks of the dense grids are compacted into a work list by
+// one thread per block, and persistent grids walk the list (see reduce_scan_kernel).
+__global__ void __launch_bounds__(256)
+blur_h_scan_kernel(const BlurJob *__restrict__ jobs, int n_jobs, int gx, TileMaps maps) {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)gx * n_jobs) return;
+    const int b = (int)(t % gx), j = (int)(t / gx);
+    if (!h_block_needed(jobs[j], maps, b)) return;
+    const int at = atomicAdd(maps.work_count, 1);
+    if (at < maps.work_cap) maps.work[at] = make_uint2((unsigned)j, (unsigned)b);
+}
+
+__global__ void __launch_bounds__(32 * H_WARPS)
+blur_h_list_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
+    const int n = min(*maps.work_count, maps.work_cap);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint2 item = maps.work[i];
+        const BlurJob &job = jobs[item.x];
+        blur_h_body<true>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], (int)item.y);
+        __syncwarp();                   // the warp's tile is restaged by the next item
+    }
 }
 
 // ---- vertical --------------------------------------------------------------
 constexpr int V_WARPS = 8;
 constexpr int V_ROWS = V_WARPS * R;    // output rows per block, 32 columns wide
 
+template <bool FINITE>
 __device__ __forceinline__ void blur_v_body(const float4 *__restrict__ in, float4 *__restrict__ out,
-                                            int pw, int ph, const Taps &t) {
+                                            int pw, int ph, const Taps &t, int bxi, int byi) {
     extern __shared__ float4 smem[];   // [V_ROWS + ksize - 1][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + lane;
-    const int yb = blockIdx.y * V_ROWS;
+    const int x = bxi * 32 + lane;
+    const int yb = byi * V_ROWS;
     const int r = t.ksize >> 1;
     const int nq = V_ROWS + t.ksize - 1;
     const int xs = min(x, pw - 1);
     for (int q = warp; q < nq; q += V_WARPS)
-        smem[q * 32 + lane] = __ldg(in + (size_t)reflect_101(yb - r + q, ph) * pw + xs);
+        smem[q * 32 + lane] = staged<FINITE>(__ldg(in + (size_t)reflect_101(yb - r + q, ph) * pw + xs));
     __syncthreads();
     float2 lo[R], hi[R];
 #pragma unroll
@@ -151,16 +201,41 @@ __device__ __forceinline__ void blur_v_body(const float4 *__restrict__ in, float
 
 __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
-    blur_v_body(in, out, pw, ph, t);
+    blur_v_body<false>(in, out, pw, ph, t, blockIdx.x, blockIdx.y);
+}
+
+__device__ __forceinline__ bool v_block_needed(const BlurJob &job, const TileMaps &maps, int bxi, int byi) {
+    if (bxi * 32 >= job.w || byi * V_ROWS >= job.h) return false;
+    return job_block_needed(job, maps, bxi * 32, byi * V_ROWS, bxi * 32 + 32, byi * V_ROWS + V_ROWS);
 }
 
 __global__ void __launch_bounds__(32 * V_WARPS)
-blur_v_batch_kernel(const BlurJob *__restrict__ jobs) {
+blur_v_batch_kernel(const BlurJob *__restrict__ jobs, TileMaps maps) {
     const BlurJob &job = jobs[blockIdx.z];
-    if ((int)(blockIdx.x * 32) >= job.w || (int)(blockIdx.y * V_ROWS) >= job.h) return;   // block-uniform
-    if (!job_block_needed(job, blockIdx.x * 32, blockIdx.y * V_ROWS, blockIdx.x * 32 + 32,
-                          blockIdx.y * V_ROWS + V_ROWS)) return;
-    blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot]);
+    if (!v_block_needed(job, maps, blockIdx.x, blockIdx.y)) return;                   // block-uniform
+    blur_v_body<true>(job.tmp, job.out, job.w, job.h, c_taps[job.slot], blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(256)
+blur_v_scan_kernel(const BlurJob *__restrict__ jobs, int n_jobs, int gx, int gy, TileMaps maps) {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)gx * gy * n_jobs) return;
+    const int bxi = (int)(t % gx), byi = (int)((t / gx) % gy), j = (int)(t / ((long long)gx * gy));
+    if (!v_block_needed(jobs[j], maps, bxi, byi)) return;
+    const int at = atomicAdd(maps.work_count, 1);
+    if (at < maps.work_cap) maps.work[at] = make_uint2((unsigned)j, (unsigned)bxi | ((unsigned)byi << 16));
+}
+
+__global__ void __launch_bounds__(32 * V_WARPS)
+blur_v_list_kernel(const BlurJob *__restrict__ jobs, TileMaps maps) {
+    const int n = min(*maps.work_count, maps.work_cap);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint2 item = maps.work[i];
+        const BlurJob &job = jobs[item.x];
+        blur_v_body<true>(job.tmp, job.out, job.w, job.h, c_taps[job.slot], (int)(item.y & 0xffffu),
+                          (int)(item.y >> 16));
+        __syncthreads();                // the staged tile is replaced by the next item
+    }
 }
 
 inline void fill_taps(Taps &t, const float *taps_host, int ksize) {
@@ -225,9 +300,17 @@ extern "C" int p360_blur_set_taps(int slot, const float *taps_host, int ksize, v
 }
 
 extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int max_h,
-                                     void *stream) {
+                                     const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
     const char *where = "p360_gauss_blur_batch";
+    TileMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (maps_host != nullptr) {
+        memcpy(&maps, maps_host, sizeof(maps));
+        P360_REQUIRE(maps.need && maps.work && maps.work_count && maps.work_cap > 0, where);
+        P360_REQUIRE((reinterpret_cast<uintptr_t>(maps.work) & 7) == 0, where);
+        P360_REQUIRE(maps.tiles_x > 0 && maps.tiles_y > 0 && maps.words > 0, where);
+    }
     P360_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= 65535 && max_w >= 0 && max_h >= 0, where);
     if (n_jobs == 0 || max_w == 0 || max_h == 0) return 0;
     int ksize = 1;
@@ -240,10 +323,29 @@ extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int 
     static size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
     if (int e = ensure_smem(blur_h_batch_kernel, smem_h, h_limit, where)) return e;
     if (int e = ensure_smem(blur_v_batch_kernel, smem_v, v_limit, where)) return e;
-    blur_h_batch_kernel<<<dim3(cdiv(max_w, H_SEG) * cdiv(max_h, H_WARPS), n_jobs), 32 * H_WARPS, smem_h, s>>>(bj, pitch);
-    if (int e = check_launch(where)) return e;
+    const unsigned h_blocks = cdiv(max_w, H_SEG) * cdiv(max_h, H_WARPS);
     dim3 grid_v(cdiv(max_w, 32), cdiv(max_h, V_ROWS), n_jobs);
     P360_REQUIRE(grid_v.y <= 65535, where);
-    blur_v_batch_kernel<<<grid_v, 32 * V_WARPS, smem_v, s>>>(bj);
+    if (maps_host == nullptr) {
+        blur_h_batch_kernel<<<dim3(h_blocks, n_jobs), 32 * H_WARPS, smem_h, s>>>(bj, pitch, maps);
+        if (int e = check_launch(where)) return e;
+        blur_v_batch_kernel<<<grid_v, 32 * V_WARPS, smem_v, s>>>(bj, maps);
+        return check_launch(where);
+    }
+    // compacted work lists, persistent grids
+    static size_t hl_limit = 48 * 1024, vl_limit = 48 * 1024;
+    if (int e = ensure_smem(blur_h_list_kernel, smem_h, hl_limit, where)) return e;
+    if (int e = ensure_smem(blur_v_list_kernel, smem_v, vl_limit, where)) return e;
+    const long long h_cand = (long long)h_blocks * n_jobs, v_cand = (long long)grid_v.x * grid_v.y * n_jobs;
+    P360_REQUIRE(h_cand <= maps.work_cap && v_cand <= maps.work_cap && grid_v.x <= 65535, where);
+    P360_CUDA(cudaMemsetAsync(maps.work_count, 0, sizeof(int), s), where);
+    blur_h_scan_kernel<<<cdiv(h_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)h_blocks, maps);
+    if (int e = check_launch(where)) return e;
+    blur_h_list_kernel<<<persistent_blocks(8), 32 * H_WARPS, smem_h, s>>>(bj, pitch, maps);
+    if (int e = check_launch(where)) return e;
+    P360_CUDA(cudaMemsetAsync(maps.work_count, 0, sizeof(int), s), where);
+    blur_v_scan_kernel<<<cdiv(v_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)grid_v.x, (int)grid_v.y, maps);
+    if (int e = check_launch(where)) return e;
+    blur_v_list_kernel<<<persistent_blocks(4), 32 * V_WARPS, smem_v, s>>>(bj, maps);
     return check_launch(where);
 }

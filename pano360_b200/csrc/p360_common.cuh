@@ -88,6 +88,70 @@ __device__ __forceinline__ bool near_owned(const int *own, int grow, int ax0, in
     return ax0 < ox1 + grow && ax1 > ox0 - grow && ay0 < oy1 + grow && ay1 > oy0 - grow;
 }
 
+// ---- the per-patch record shared by reduce, blur and the collapse kernels -----
+struct BandPatch {                      // == p360_band_patch
+    const float4 *rgba;                 // full-res patch; alpha is replaced by (owner == index) for multiband
+    const uint8_t *invalid;             // ph x pw mask (linear / paste only)
+    float4 *d2, *d4;                    // reduce outputs (f = 2, f = 4)
+    const float4 *low[P360_MAX_LEVELS - 1];   // blurred coarse image of level l (level 0: f = 2, others f = 4)
+    int x0, y0, pw, ph;                 // box in (window) mosaic pixels
+    int w4, h4;                         // size of the f = 4 grid (f = 2 grid is twice that)
+    int pad;                            // extension R in full-res pixels (multiple of 4)
+    int index;                          // id of this patch in the owner keys
+    int own[4];                         // box around the owned pixels (patch px), see p360_owned_boxes
+};
+static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
+
+// ---- seam-band maps -------------------------------------------------------------
+// Bitmaps over the 64 x 32 mosaic tiles, one bit per patch (p360_tile_maps_build):
+//   present  patches that own a pixel of the tile
+//   cand     patches that own a pixel within the blur reach of the tile: the only ones
+//            that can carry weight there (one bit set: the tile is its owner's pixels)
+//   need     patches whose coarse levels are read within the blur chain's reach of the
+//            tile: everything else of reduce / blur is never consumed
+// maps.need == nullptr: no maps, the owned boxes decide.
+constexpr int TILE_X = 64, TILE_Y = 32;
+struct TileMaps {                       // == p360_tile_maps
+    uint32_t *present, *cand, *need;
+    uint8_t *multi;                     // per tile: more than one candidate
+    uint2 *work;                        // compacted list of the blocks a pass has to run
+    int *work_count;
+    int tiles_x, tiles_y, words;
+    int row0;                           // window row of tile row 0 (<= 0; tiles sit on absolute mosaic rows)
+    int reach_x, reach_y;               // blur reach in tiles
+    int work_cap;
+    int reserved;
+};
+
+// Persistent grids over a work list: blocks per SM x SMs (cached per process).
+inline int persistent_blocks(int per_sm) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148 * per_sm;
+        sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    }
+    return sms * per_sm;
+}
+static_assert(sizeof(TileMaps) == sizeof(p360_tile_maps), "ABI struct mismatch");
+
+// Is `patch`'s bit set in any tile of `map` that the window-mosaic box [xa, xb) x [ya, yb)
+// touches?  Boxes beyond the mosaic (reflected extension) count for the nearest edge tile.
+// Every thread of a block evaluates this on the same arguments: the outcome is block-uniform.
+__device__ __forceinline__ bool tiles_test(const TileMaps &m, const uint32_t *map, int patch,
+                                           int xa, int ya, int xb, int yb) {
+    const int tx0 = min(max(xa >> 6, 0), m.tiles_x - 1), tx1 = min(max((xb - 1) >> 6, 0), m.tiles_x - 1);
+    const int ty0 = min(max((ya - m.row0) >> 5, 0), m.tiles_y - 1);
+    const int ty1 = min(max((yb - 1 - m.row0) >> 5, 0), m.tiles_y - 1);
+    const int word = patch >> 5;
+    const uint32_t bit = 1u << (patch & 31);
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx)
+            if (__ldg(map + ((size_t)ty * m.tiles_x + tx) * m.words + word) & bit) return true;
+    return false;
+}
+
 // Streaming (read-once / write-once) 128-bit accesses: keep L1 for the gathers.
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
     float4 r;

@@ -33,38 +33,29 @@ __device__ __forceinline__ float4 scale4(const float4 &v, float s) {
     return make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
 }
 
-// ---- the per-patch record shared by reduce and the collapse kernels --------
-struct BandPatch {                      // == p360_band_patch
-    const float4 *rgba;                 // full-res patch; alpha is replaced by (owner == index) for multiband
-    const uint8_t *invalid;             // ph x pw mask (linear / paste only)
-    float4 *d2, *d4;                    // reduce outputs (f = 2, f = 4)
-    const float4 *low[P360_MAX_LEVELS - 1];   // blurred coarse image of level l (level 0: f = 2, others f = 4)
-    int x0, y0, pw, ph;                 // box in (window) mosaic pixels
-    int w4, h4;                         // size of the f = 4 grid (f = 2 grid is twice that)
-    int pad;                            // extension R in full-res pixels (multiple of 4)
-    int index;                          // id of this patch in the owner keys
-    int own[4];                         // box around the owned pixels (patch px), see p360_owned_boxes
-};
-static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch");
-
 // ---- reduce ----------------------------------------------------------------
 // Block = 8 warps; warp w of block (bx, by) produces coarse row 8*by + w of D4
 // (two rows of D2) for 32 full-resolution columns: lanes run along x, so each
 // of the four row loads is one coalesced 512-byte request; 2x2 and 4x4 sums
 // are finished with xor-shuffles.  grid.z = patch.
-__global__ void __launch_bounds__(256)
-pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
-                      const unsigned long long *__restrict__ keys, int W) {
-    const BandPatch &bp = patches[blockIdx.z];
+// Does anybody read what block (bxi, byi) of this patch's reduce grid produces?
+__device__ __forceinline__ bool reduce_block_needed(const BandPatch &bp, int bxi, int byi, bool owners,
+                                                    const TileMaps &maps) {
+    const int bx0 = bxi * 32 - bp.pad, by0 = byi * 32 - bp.pad;           // block in patch pixels
+    if (maps.need != nullptr)    // no seam within the blur chain's reach reads these cells
+        return tiles_test(maps, maps.need, bp.index, bx0 + bp.x0, by0 + bp.y0, bx0 + bp.x0 + 32, by0 + bp.y0 + 32);
+    // nothing within the blur chain's reach of the owned box reads these cells
+    return !owners || near_owned(bp.own, 2 * bp.pad + 4, bx0, by0, bx0 + 32, by0 + 32);
+}
+
+__device__ __forceinline__ void reduce_block(const BandPatch &bp, int bxi, int byi,
+                                             const unsigned long long *__restrict__ keys, int W) {
     const int w4 = bp.w4, h4 = bp.h4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cy = blockIdx.y * 8 + warp;              // D4 row
-    const int xe = blockIdx.x * 32 + lane;             // column in the extended frame
-    if (cy >= h4 || (int)(blockIdx.x * 32) >= 4 * w4) return;   // warp-uniform
+    const int cy = byi * 8 + warp;                     // D4 row
+    const int xe = bxi * 32 + lane;                    // column in the extended frame
+    if (cy >= h4 || bxi * 32 >= 4 * w4) return;        // warp-uniform
     const int pw = bp.pw, ph = bp.ph, pad = bp.pad, w2 = 2 * w4;
-    if (keys != nullptr &&       // nothing within the blur chain's reach of the owned box reads these cells
-        !near_owned(bp.own, 2 * pad + 4, (int)(blockIdx.x * 32) - pad, (int)(blockIdx.y * 32) - pad,
-                    (int)(blockIdx.x * 32) - pad + 32, (int)(blockIdx.y * 32) - pad + 32)) return;
     const float4 *rgba = bp.rgba;
     const bool live = xe < 4 * w4;
     const int sx = reflect_101(xe - pad, pw);
@@ -92,17 +83,57 @@ pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
     if (live && !(lane & 3)) bp.d4[(size_t)cy * w4 + (xe >> 2)] = scale4(q, 0.0625f);
 }
 
+// dense grid: grid.z = patch, every block decides for itself
+__global__ void __launch_bounds__(256)
+pyramid_reduce_kernel(const BandPatch *__restrict__ patches,
+                      const unsigned long long *__restrict__ keys, int W, TileMaps maps) {
+    const BandPatch &bp = patches[blockIdx.z];
+    if (!reduce_block_needed(bp, blockIdx.x, blockIdx.y, keys != nullptr, maps)) return;   // block-uniform
+    reduce_block(bp, blockIdx.x, blockIdx.y, keys, W);
+}
+
+// Seam-band maps leave a few percent of a dense grid busy, and an empty block costs about as
+// much as a busy one here.  So: one THREAD per block of the dense grid appends the needed ones
+// to a work list, and a persistent grid walks the list.
+__global__ void __launch_bounds__(256)
+reduce_scan_kernel(const BandPatch *__restrict__ patches, int n_patches, int gx, int gy, TileMaps maps) {
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)gx * gy * n_patches) return;
+    const int bxi = (int)(t % gx), byi = (int)((t / gx) % gy), p = (int)(t / ((long long)gx * gy));
+    const BandPatch &bp = patches[p];
+    if (byi * 8 >= bp.h4 || bxi * 32 >= 4 * bp.w4) return;
+    if (!reduce_block_needed(bp, bxi, byi, true, maps)) return;
+    const int at = atomicAdd(maps.work_count, 1);
+    if (at < maps.work_cap) maps.work[at] = make_uint2((unsigned)p, (unsigned)bxi | ((unsigned)byi << 16));
+}
+
+__global__ void __launch_bounds__(256)
+pyramid_reduce_list_kernel(const BandPatch *__restrict__ patches,
+                           const unsigned long long *__restrict__ keys, int W, TileMaps maps) {
+    const int n = min(*maps.work_count, maps.work_cap);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint2 item = maps.work[i];
+        reduce_block(patches[item.x], (int)(item.y & 0xffffu), (int)(item.y >> 16), keys, W);
+    }
+}
+
 // ---- owned boxes -------------------------------------------------------------
 // One block per 64 x 32 mosaic tile: which patches own a pixel here?  (shared bitmap, up to
 // 1024 patches.)  Each of them grows its box to this tile with four atomics.
+// With `present_out` the bitmap is also kept per tile (seam-band maps); tile rows then start
+// at window row `row0` (<= 0) so that they sit on absolute mosaic rows.
 __global__ void __launch_bounds__(256)
 owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patches, int n_patches,
-                   int H, int W) {
+                   int H, int W, int row0, uint32_t *__restrict__ present_out, int words,
+                   const uint8_t *__restrict__ covered, uint8_t *__restrict__ unowned_out) {
     __shared__ unsigned present[32];
+    __shared__ unsigned unowned;         // a valid pixel nobody owns (alpha == 0 everywhere): the tile is not
+                                         // simply its owner's pixels
     const int tid = threadIdx.x;
     if (tid < 32) present[tid] = 0u;
+    if (tid == 0) unowned = 0u;
     __syncthreads();
-    const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 32;
+    const int tx0 = blockIdx.x * 64, ty0 = row0 + (int)blockIdx.y * 32;
     // thread -> two adjacent keys (one 128-bit load) on 4 rows; runs of equal owners cost one
     // shared-memory atomic
     const int cx = tx0 + 2 * (tid & 31), ry = ty0 + (tid >> 5);
@@ -111,6 +142,7 @@ owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patch
     for (int i = 0; i < 4; ++i) {
         const int y = ry + 8 * i;
         if (y >= H) break;
+        if (y < 0) continue;
         unsigned long long k2[2] = {0ull, 0ull};
         const unsigned long long *src = keys + (size_t)y * W + cx;
         if (cx + 1 < W && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
@@ -122,7 +154,10 @@ owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patch
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            if (k2[j] == 0ull) continue;
+            if (k2[j] == 0ull) {
+                if (covered != nullptr && cx + j < W && covered[(size_t)y * W + cx + j] != 0) unowned = 1u;
+                continue;
+            }
             const unsigned p = 0xFFFFFFFFu - (unsigned)(k2[j] & 0xFFFFFFFFull);
             if (p != last && p < (unsigned)n_patches && p < 1024u) {
                 atomicOr(&present[p >> 5], 1u << (p & 31));
@@ -131,6 +166,9 @@ owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patch
         }
     }
     __syncthreads();
+    if (present_out != nullptr && tid < words)
+        present_out[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * words + tid] = present[tid];
+    if (unowned_out != nullptr && tid == 0) unowned_out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = (uint8_t)unowned;
     if (tid < 32) {
         unsigned word = present[tid];
         while (word) {
@@ -138,10 +176,51 @@ owned_boxes_kernel(const unsigned long long *__restrict__ keys, BandPatch *patch
             word &= word - 1;
             BandPatch &bp = patches[tid * 32 + bit];
             atomicMin(&bp.own[0], max(tx0 - bp.x0, 0));
-            atomicMin(&bp.own[1], max(ty0 - bp.y0, 0));
+            atomicMin(&bp.own[1], max(max(ty0, 0) - bp.y0, 0));
             atomicMax(&bp.own[2], min(tx0 + 64 - bp.x0, bp.pw));
             atomicMax(&bp.own[3], min(ty0 + 32 - bp.y0, bp.ph));
         }
+    }
+}
+
+// ---- seam-band maps ------------------------------------------------------------
+// cand(T) = OR of present over the tiles within blur reach of T; multi(T) = |cand(T)| > 1.
+// One thread per tile.
+__global__ void __launch_bounds__(256)
+tile_candidates_kernel(TileMaps m) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int x0 = max(tx - m.reach_x, 0), x1 = min(tx + m.reach_x, m.tiles_x - 1);
+    const int y0 = max(ty - m.reach_y, 0), y1 = min(ty + m.reach_y, m.tiles_y - 1);
+    int count = 0;
+    for (int w = 0; w < m.words; ++w) {
+        uint32_t bits = 0u;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) bits |= __ldg(m.present + ((size_t)y * m.tiles_x + x) * m.words + w);
+        m.cand[(size_t)t * m.words + w] = bits;
+        count += __popc(bits);
+    }
+    // on entry multi[t] = "holds a valid pixel nobody owns": such a tile is blended in full too
+    m.multi[t] = (count > 1 || (count == 1 && m.multi[t] != 0)) ? 1 : 0;
+}
+
+// need(T) = OR of cand over the multi tiles within blur reach of T.
+__global__ void __launch_bounds__(256)
+tile_needs_kernel(TileMaps m) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int x0 = max(tx - m.reach_x, 0), x1 = min(tx + m.reach_x, m.tiles_x - 1);
+    const int y0 = max(ty - m.reach_y, 0), y1 = min(ty + m.reach_y, m.tiles_y - 1);
+    for (int w = 0; w < m.words; ++w) {
+        uint32_t bits = 0u;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const size_t n = (size_t)y * m.tiles_x + x;
+                if (m.multi[n]) bits |= m.cand[n * m.words + w];
+            }
+        m.need[(size_t)t * m.words + w] = bits;
     }
 }
 
@@ -184,6 +263,30 @@ __device__ int build_tile_list(const BandPatch *__restrict__ patches, int n_patc
         }
         __syncthreads();
     }
+    return total;
+}
+
+// The same list from the tile's candidate bitmap (seam-band maps); ascending bits = patch order.
+__device__ int tile_list_from_maps(const BandPatch *__restrict__ patches, int n_patches, const TileMaps &m,
+                                   size_t tile, int tx0, int ty0, int16_t *list) {
+    __shared__ int total;
+    if (threadIdx.y == 0 && threadIdx.x == 0) {
+        int n = 0;
+        for (int w = 0; w < m.words; ++w) {
+            uint32_t bits = __ldg(m.cand + tile * m.words + w);
+            while (bits) {
+                const int t = 32 * w + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (t >= n_patches) break;
+                const BandPatch &bp = patches[t];
+                if (bp.x0 < tx0 + CT_X && bp.x0 + bp.pw > tx0 && bp.y0 < ty0 + CT_Y && bp.y0 + bp.ph > ty0 &&
+                    near_owned(bp.own, bp.pad, tx0 - bp.x0, ty0 - bp.y0, tx0 + CT_X - bp.x0, ty0 + CT_Y - bp.y0))
+                    list[n++] = (int16_t)t;
+            }
+        }
+        total = n;
+    }
+    __syncthreads();
     return total;
 }
 
@@ -269,14 +372,23 @@ __global__ void __launch_bounds__(256, (L <= 5) ? 4 : 3)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
                           const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
-                          int y_begin, int H, int W) {
+                          int y_begin, int H, int W, TileMaps maps) {
     // Tiles are anchored at absolute mosaic rows (first_tile_row may be < y_begin, even < 0):
     // whether a tile takes the single-contributor shortcut must not depend on how the
     // mosaic was cut into strips or row bands.
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
-    int n_hit = build_tile_list<(L > 1)>(patches, n_patches, tx0, ty0, list);
-    n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+    int n_hit;
+    if (maps.cand != nullptr) {
+        // a single candidate: every valid pixel of the tile is its own (p360_tile_maps_build), no
+        // coarse level is read and none was computed here — nothing to cull either
+        const size_t tile = (size_t)((ty0 - maps.row0) >> 5) * maps.tiles_x + blockIdx.x;
+        n_hit = tile_list_from_maps(patches, n_patches, maps, tile, tx0, ty0, list);
+        if (n_hit > 1 || __ldg(maps.multi + tile) != 0) n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+    } else {
+        n_hit = build_tile_list<(L > 1)>(patches, n_patches, tx0, ty0, list);
+        n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+    }
     {   // pull this tile's slice of every contributing patch (and of the owner keys) towards L2
         // now: one 128-byte line per thread and patch, so that the gathers below find their
         // streamed operands on chip instead of paying a DRAM round trip per patch iteration
@@ -430,16 +542,31 @@ inline int first_tile(int y_begin, int row_origin) {     // absolute-row-aligned
 template <int L>
 int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
                     const uint8_t *covered, uint8_t *out, int y0, int y1, int row_origin, int W,
-                    cudaStream_t s) {
+                    const TileMaps &maps, cudaStream_t s) {
     const int first = first_tile(y0, row_origin);
     dim3 grid(cdiv(W, CT_X), cdiv(y1 - first, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1, W);
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1, W,
+                                                        maps);
     return check_launch("p360_multiband_collapse");
 }
 
 }  // namespace p360
 
 using namespace p360;
+
+static TileMaps device_maps(const p360_tile_maps *maps_host) {
+    TileMaps m;
+    memset(&m, 0, sizeof(m));
+    if (maps_host != nullptr) memcpy(&m, maps_host, sizeof(m));
+    return m;
+}
+static bool maps_ok(const p360_tile_maps *m) {
+    return m == nullptr || (m->present && m->cand && m->need && m->multi && m->work && m->work_count &&
+                            (reinterpret_cast<uintptr_t>(m->work) & 7) == 0 &&
+                            m->work_cap > 0 && m->tiles_x > 0 && m->tiles_y > 0 &&
+                            m->words > 0 && m->words <= 32 && m->row0 <= 0 && m->row0 > -32 &&
+                            m->reach_x >= 0 && m->reach_y >= 0);
+}
 
 extern "C" int p360_owned_boxes(const uint64_t *owner_keys, p360_band_patch *patches, int n_patches,
                                 int H, int W, void *stream) {
@@ -450,7 +577,27 @@ extern "C" int p360_owned_boxes(const uint64_t *owner_keys, p360_band_patch *pat
     P360_REQUIRE(grid.y <= 65535, where);
     owned_boxes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const unsigned long long *>(owner_keys), reinterpret_cast<BandPatch *>(patches),
-        n_patches, H, W);
+        n_patches, H, W, 0, nullptr, 0, nullptr, nullptr);
+    return check_launch(where);
+}
+
+extern "C" int p360_tile_maps_build(const uint64_t *owner_keys, const uint8_t *covered, p360_band_patch *patches,
+                                    int n_patches, int H, int W, const p360_tile_maps *maps_host, void *stream) {
+    const char *where = "p360_tile_maps_build";
+    P360_REQUIRE(owner_keys && covered && patches && maps_host && maps_ok(maps_host), where);
+    P360_REQUIRE(n_patches > 0 && n_patches <= MAX_TILE_PATCHES && H > 0 && W > 0, where);
+    const TileMaps m = device_maps(maps_host);
+    P360_REQUIRE(m.words == (n_patches + 31) / 32 && m.tiles_x == (int)cdiv(W, TILE_X) &&
+                 m.tiles_y == (int)cdiv(H - m.row0, TILE_Y) && m.tiles_y <= 65535, where);
+    cudaStream_t s = (cudaStream_t)stream;
+    owned_boxes_kernel<<<dim3(m.tiles_x, m.tiles_y), 256, 0, s>>>(
+        reinterpret_cast<const unsigned long long *>(owner_keys), reinterpret_cast<BandPatch *>(patches),
+        n_patches, H, W, m.row0, m.present, m.words, covered, m.multi);
+    if (int e = check_launch(where)) return e;
+    const unsigned blocks = cdiv((long long)m.tiles_x * m.tiles_y, 256);
+    tile_candidates_kernel<<<blocks, 256, 0, s>>>(m);
+    if (int e = check_launch(where)) return e;
+    tile_needs_kernel<<<blocks, 256, 0, s>>>(m);
     return check_launch(where);
 }
 
@@ -463,24 +610,45 @@ extern "C" int p360_pyramid_dims(int pw, int ph, int pad, int32_t out_host[4]) {
 }
 
 extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int max_w4,
-                                         int max_h4, const uint64_t *owner_keys, int W, void *stream) {
+                                         int max_h4, const uint64_t *owner_keys, int W,
+                                         const p360_tile_maps *maps_host, void *stream) {
     const char *where = "p360_pyramid_reduce_batch";
     P360_REQUIRE(patches && n_patches >= 0 && n_patches <= 65535 && max_w4 >= 0 && max_h4 >= 0, where);
     P360_REQUIRE(owner_keys == nullptr || W > 0, where);
+    P360_REQUIRE(maps_ok(maps_host) && (maps_host == nullptr || owner_keys != nullptr), where);
     if (n_patches == 0 || max_w4 == 0 || max_h4 == 0) return 0;
     dim3 grid(cdiv(4 * max_w4, 32), cdiv(max_h4, 8), n_patches);
     P360_REQUIRE(grid.y <= 65535, where);
-    pyramid_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const BandPatch *>(patches),
-        reinterpret_cast<const unsigned long long *>(owner_keys), W);
+    auto bp = reinterpret_cast<const BandPatch *>(patches);
+    auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
+    cudaStream_t s = (cudaStream_t)stream;
+    const TileMaps maps = device_maps(maps_host);
+    if (maps_host == nullptr) {
+        pyramid_reduce_kernel<<<grid, 256, 0, s>>>(bp, keys, W, maps);
+        return check_launch(where);
+    }
+    const long long blocks = (long long)grid.x * grid.y * grid.z;
+    P360_REQUIRE(blocks <= maps.work_cap && grid.x <= 65535, where);
+    P360_CUDA(cudaMemsetAsync(maps.work_count, 0, sizeof(int), s), where);
+    reduce_scan_kernel<<<cdiv(blocks, 256), 256, 0, s>>>(bp, n_patches, (int)grid.x, (int)grid.y, maps);
+    if (int e = check_launch(where)) return e;
+    pyramid_reduce_list_kernel<<<persistent_blocks(8), 256, 0, s>>>(bp, keys, W, maps);
     return check_launch(where);
 }
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                                        const uint64_t *owner_keys, const uint8_t *covered,
                                        uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
-                                       void *stream) {
+                                       const p360_tile_maps *maps_host, void *stream) {
     const char *where = "p360_multiband_collapse";
+    P360_REQUIRE(maps_ok(maps_host), where);
+    const TileMaps maps = device_maps(maps_host);
+    if (maps_host != nullptr) {         // the maps' tile grid must be the collapse's
+        int phase = row_origin % 32;
+        if (phase < 0) phase += 32;
+        P360_REQUIRE(maps.row0 == -phase && maps.tiles_x == (int)cdiv(W, TILE_X) &&
+                     y_end <= maps.row0 + 32 * maps.tiles_y, where);
+    }
     P360_REQUIRE(patches && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
     P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && W > 0, where);
@@ -491,14 +659,14 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
     auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
-        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
     }
 }
 

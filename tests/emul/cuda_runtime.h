@@ -66,6 +66,8 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     *p = cudaDeviceProp{(int)std::thread::hardware_concurrency(), 0, 0, 0};
     return cudaSuccess;
 }
+inline cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *p, int value, size_t n, cudaStream_t) { memset(p, value, n); return cudaSuccess; }
 template <class K>
 inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 template <class T>

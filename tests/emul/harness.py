@@ -82,5 +82,19 @@ def install(monkeypatch):
         return torch.from_numpy(np.array(array, copy=True, order="C"))
 
     monkeypatch.setattr(compositor.Compositor, "_to_device", to_host_tensor)
+
+    # Fresh host allocations are zero pages, which would hide reads of memory no kernel wrote;
+    # the GPU's caching allocator hands out stale data.  Poison every torch.empty instead.
+    real_empty = torch.empty
+
+    def poisoned_empty(*args, **kwargs):
+        t = real_empty(*args, **kwargs)
+        if t.is_floating_point():
+            t.fill_(float("nan"))
+        elif t.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+            t.fill_(0x5B)
+        return t
+
+    monkeypatch.setattr(torch, "empty", poisoned_empty)
     monkeypatch.setattr(stitcher, "_compositors", {})
     return compositor.Compositor()

@@ -391,6 +391,39 @@ def test_seam_split_is_exact(comp):
         assert np.array_equal(a, b), kind
 
 
+def _seam_map_cases():
+    yield "tiny4", regions_from_golden(load_golden("tiny4")), 5
+    yield "ring12", regions_from_golden(load_golden("ring12")), 6
+    yield "cfg1/2", synth.make_views(synth.workload("cfg1", scale=2.0), noise=20.0), 5
+    yield "two rows", synth.make_views(synth.workload("cfg3", scale=8.0), noise=10.0), 3
+    from dataclasses import replace
+    many = replace(synth.workload("cfg1", scale=8.0), yaws=tuple(0.04 * (i - 35) for i in range(70)),
+                   pitches=tuple(0.15 * ((i % 3) - 1) for i in range(70)))
+    yield "70 small views", synth.make_views(many, noise=5.0), 2
+
+
+def test_seam_band_maps_are_exact(comp):
+    """Restricting reduce / blur to the seam bands and taking the collapse lists from the tile
+    bitmaps (p360_tile_maps_build) must not change a single byte, for whole mosaics and for
+    row windows — and has to leave most of a mosaic to the single-owner shortcut."""
+    saved = comp.seam_maps
+    try:
+        for name, regs, levels in _seam_map_cases():
+            plan = geo.plan_mosaic(regs, True, 1e9)
+            src = comp.upload(regs)
+            h = plan.shape[0]
+            for rows in (None, (h // 3 + 5, 2 * h // 3 + 1)):
+                comp.seam_maps = False
+                want = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+                comp.seam_maps = True
+                got = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+                assert np.array_equal(got, want), (name, rows)
+                maps = comp._keep["bands"][3]
+                assert maps is not None and int(maps["words"][0]) == -(-len(comp._keep["warp"][3]) // 32)
+    finally:
+        comp.seam_maps = saved
+
+
 @pytest.mark.parametrize("ksize", [1, 3, 15, 33, 97, 129])
 def test_blur_kernel_generic_taps(comp, ksize):
     """K3 with arbitrary odd tap counts against a float64 NumPy convolution."""
@@ -428,7 +461,7 @@ def test_batched_blur_paths(comp, ksizes):
         dev = torch.from_numpy(img).to(comp.device)
         out, tmp = torch.empty_like(dev), torch.empty_like(dev)
         keep.append((dev, out, tmp))
-        jobs[slot] = (dev.data_ptr(), out.data_ptr(), tmp.data_ptr(), w, h, slot, 0, 0, 0, 0)   # own = NULL: no restriction
+        jobs[slot] = (dev.data_ptr(), out.data_ptr(), tmp.data_ptr(), w, h, slot, 0, 0, 0, 0)   # patch = NULL: no restriction
         r = ks // 2
         rows, cols = np.pad(np.arange(h), r, mode="reflect"), np.pad(np.arange(w), r, mode="reflect")
         if h == 1: rows = np.zeros(h + 2 * r, int)
@@ -440,7 +473,7 @@ def test_batched_blur_paths(comp, ksizes):
         _lib.call("p360_blur_set_taps", slot, one.ctypes.data_as(C.POINTER(C.c_float)), 1, comp.stream)
     dev_jobs = comp._table(jobs, "test_blur_jobs")
     _lib.call("p360_gauss_blur_batch", _lib.ptr(dev_jobs), len(jobs), max(s[1] for s in shapes),
-              max(s[0] for s in shapes), comp.stream)
+              max(s[0] for s in shapes), None, comp.stream)
     for (dev, out, tmp), want in zip(keep, wants):
         assert np.abs(out.cpu().numpy() - want).max() < 5e-6
 

@@ -50,6 +50,7 @@ test_edge_cases = gpu.test_edge_cases
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
+test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
 test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
 
