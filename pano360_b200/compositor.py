@@ -38,6 +38,9 @@ import torch
 from . import _lib, geometry as geo
 
 
+SEAM_MAPS_MIN_PIXELS = 1 << 22      # mosaic (or strip) size from which the seam-band maps are used
+
+
 def band_edges(ya, yb, bands):
     """[ya, yb) cut into ``bands`` row ranges with integer arithmetic only, so
     that every rank derives identical cuts whatever its local row origin."""
@@ -128,8 +131,9 @@ class Compositor:
         self._download = None
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
         # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
-        # blur reach.  Bit-identical output; off until measured on the B200.
-        self.seam_maps = os.environ.get("P360_SEAM_MAPS", "0") == "1"
+        # blur reach.  Bit-identical output either way; None = on for mosaics large enough for the
+        # extra launches to pay (B200, cfg4: 15.9 -> 13.2 ms), P360_SEAM_MAPS=0/1 forces it.
+        self.seam_maps = {"0": False, "1": True}.get(os.environ.get("P360_SEAM_MAPS", ""))
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -538,7 +542,7 @@ class Compositor:
         maps = None
         if plan:
             # which part of each patch can ever carry weight: box around its owned pixels
-            if self.seam_maps:
+            if self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS:
                 maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
                 self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
                              _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)

@@ -39,13 +39,37 @@ def main():
         tiles_x, tiles_y, words = int(maps["tiles_x"][0]), int(maps["tiles_y"][0]), int(maps["words"][0])
         row0 = int(maps["row0"][0])
         cells = tiles_x * tiles_y
-        planes = bits.numpy().view(np.uint32).reshape(3, tiles_y, tiles_x, words)
+        cap = int(maps["work_cap"][0])
+        flat = bits.numpy().view(np.uint32)
+        print(f"last work list (vertical blur): {int(flat[0])} blocks of a {cap}-block scratch")
+        planes = flat[2 + 2 * cap:].reshape(3, tiles_y, tiles_x, words)
         cand, need = planes[1], planes[2]
         multi = multi.numpy().reshape(tiles_y, tiles_x)
         n_cand = sum(np.bitwise_count(cand[..., w]).astype(np.int64) for w in range(words))
         print(f"{args.workload} / {args.scale:g}: mosaic {plan.shape[0]}x{plan.shape[1]}, {len(table)} patches, "
               f"{cells} tiles: {100 * np.mean(n_cand == 0):.1f}% empty, {100 * np.mean((n_cand >= 1) & (multi == 0)):.1f}% "
               f"single owner (shortcut), {100 * np.mean(multi != 0):.1f}% blended")
+        def blocks_hit(has, xs, ys, bw, bh):
+            """grid of blocks at window px (xs, ys), bw x bh px each: which touch a tile with the bit set?"""
+            cs = np.zeros((tiles_y + 1, tiles_x + 1), np.int64)
+            cs[1:, 1:] = has.astype(np.int64).cumsum(0).cumsum(1)
+            xa, xb = np.clip(xs >> 6, 0, tiles_x - 1), np.clip((xs + bw - 1) >> 6, 0, tiles_x - 1) + 1
+            ya, yb = np.clip((ys - row0) >> 5, 0, tiles_y - 1), np.clip((ys + bh - 1 - row0) >> 5, 0, tiles_y - 1) + 1
+            return (cs[yb][:, xb] - cs[ya][:, xb] - cs[yb][:, xa] + cs[ya][:, xa]) > 0
+
+        blur = {"H f=2": [0, 0], "V f=2": [0, 0], "H f=4": [0, 0], "V f=4": [0, 0]}
+        for k, rec in enumerate(table):
+            pad, w4, h4 = int(rec["pad"]), int(rec["w4"]), int(rec["h4"])
+            has = (need[..., k >> 5] >> np.uint32(k & 31)) & 1
+            for f, cw, ch in ((2, 2 * w4, 2 * h4), (4, w4, h4)):
+                for name, bw, bh in (("H", 256, 4), ("V", 32, 64)):
+                    xs = np.arange(-(-cw // bw)) * bw * f - pad + int(rec["x0"])
+                    ys = np.arange(-(-ch // bh)) * bh * f - pad + int(rec["y0"])
+                    hit = blocks_hit(has, xs, ys, bw * f, bh * f)
+                    blur[f"{name} f={f}"][0] += int(hit.sum())
+                    blur[f"{name} f={f}"][1] += hit.size
+        for name, (run, tot) in blur.items():
+            print(f"blur blocks {name}: {run} of {tot} ({100 * run / max(tot, 1):.1f}%)")
         run_own = run_maps = total = 0
         for k, rec in enumerate(table):
             pad, w4, h4 = int(rec["pad"]), int(rec["w4"]), int(rec["h4"])
