@@ -76,6 +76,7 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda device: None)
     monkeypatch.setattr(compositor, "_require_cuda", lambda device: torch.device("cpu"))
 
     def to_host_tensor(self, array, pinned_key=None):

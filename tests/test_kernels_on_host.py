@@ -55,6 +55,13 @@ test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
 
 
+def test_smoke_entry_point(comp, capsys):
+    """__graft_entry__.smoke() — what the driver runs first on the GPU box — end to end."""
+    import __graft_entry__
+    __graft_entry__.smoke()
+    assert "smoke multiband" in capsys.readouterr().out
+
+
 def test_c_abi_error_path(comp):
     from pano360_b200 import _lib
     with pytest.raises(RuntimeError, match="p360_gauss_blur"):
