@@ -127,7 +127,8 @@ class Compositor:
         self._pinned = {}
         self._taps_key = None
         self._keep = {}
-        self._copy = None      # side stream for uploads / downloads that overlap the kernels
+        self._copy = None      # side streams for uploads / downloads that overlap the kernels
+        self._down = None
         self._download = None
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
         # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
@@ -161,9 +162,17 @@ class Compositor:
         return host.to(self.device)
 
     def copy_stream(self):
+        """Side stream of the uploads (and of the NVLink pushes of strips.py)."""
         if self._copy is None:
             self._copy = torch.cuda.Stream(self.device)
         return self._copy
+
+    def download_stream(self):
+        """Side stream of the banded mosaic downloads: its own stream, so that device -> host
+        copies are not queued behind uploads still in flight (PCIe is full duplex)."""
+        if self._down is None:
+            self._down = torch.cuda.Stream(self.device)
+        return self._down
 
     def _table(self, records, key):
         """Structured job table -> device bytes."""
@@ -193,27 +202,28 @@ class Compositor:
                   _lib.ptr(packed), self.stream)
         return packed
 
-    def upload(self, regions, gains=None, need=None, overlap=False, pack=True):
+    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
         ``overlap`` the copies (and the RGBX packing) run on a side stream and
         every image gets a ``ready`` event, so the warp of the first images
-        starts while the last ones are still crossing PCIe."""
-        src = DeviceSources([], [])
+        starts while the last ones are still crossing PCIe.  ``order`` (a
+        permutation of the indices) is the order in which the copies are issued."""
+        n = len(regions)
+        src = DeviceSources([None] * n, [None] * n)
+        src.shapes = [reg.img.shape[:2] for reg in regions]
         lut0 = None
         main = torch.cuda.current_stream(self.device)
         side = self.copy_stream() if overlap else main
         if overlap:
-            src.ready = [None] * len(regions)
+            src.ready = [None] * n
             side.wait_stream(main)
-        for i, reg in enumerate(regions):
+        for i in (range(n) if order is None else order):
+            reg = regions[i]
             img = reg.img
             h, w = img.shape[:2]
-            src.shapes.append((h, w))
-            if need is not None and i not in need:
-                src.pixels.append(None)
-            else:
+            if need is None or i in need:
                 if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
                 host = torch.from_numpy(np.ascontiguousarray(img))
@@ -224,15 +234,15 @@ class Compositor:
                 with torch.cuda.stream(side):
                     dev_img = host.to(self.device, non_blocking=host.is_pinned())
                     # pack=False keeps the uploaded u8 x 3 layout (the warp then evaluates alpha per tap)
-                    src.pixels.append(self.pack_pixels(dev_img, src.hats[(h, w)]) if pack else dev_img)
+                    src.pixels[i] = self.pack_pixels(dev_img, src.hats[(h, w)]) if pack else dev_img
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
             if gains is None:
                 lut0 = self._to_device(geo.sample_lut(None)) if lut0 is None else lut0
-                src.luts.append(lut0)
+                src.luts[i] = lut0
             else:
-                src.luts.append(self._to_device(geo.sample_lut(gains[i])))
+                src.luts[i] = self._to_device(geo.sample_lut(gains[i]))
         return src
 
     def set_gains(self, src, gains):
@@ -364,7 +374,8 @@ class Compositor:
                 b = a
                 while b < n and crops[b][0] <= last:
                     b += 1
-                main.wait_event(src.ready[max(c[0] for c in crops[a:b])])
+                for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
+                    main.wait_event(src.ready[i])
                 _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
                           _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
                 a = b
@@ -473,7 +484,7 @@ class Compositor:
             self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, *tail, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
-        main, side = torch.cuda.current_stream(self.device), self.copy_stream()
+        main, side = torch.cuda.current_stream(self.device), self.download_stream()
         for y0, y1 in band_edges(ya, yb, bands):
             if y1 <= y0:
                 continue
@@ -485,8 +496,8 @@ class Compositor:
                 done = torch.cuda.Event()
                 done.record(main)
                 side.wait_event(done)
-                with torch.cuda.stream(side):
-                    host[y0:y1].copy_(mosaic[y0:y1], non_blocking=True)
+                with torch.cuda.stream(side):       # buffer row y is mosaic row y + row_origin
+                    host[y0 + row_origin:y1 + row_origin].copy_(mosaic[y0:y1], non_blocking=True)
         if host is not None:
             self._download = torch.cuda.Event()
             self._download.record(side)
@@ -495,7 +506,7 @@ class Compositor:
         """Drop the references that keep the last composite's pools alive (patch
         pool, coarse levels, job tables); the memory goes back to torch's caching
         allocator.  Call only after the work that uses them has been waited for."""
-        for key in ("warp", "bands", "collapse"):
+        for key in ("warp", "bands", "collapse", "streamed"):
             self._keep.pop(key, None)
 
     def finish_download(self):
@@ -636,33 +647,41 @@ class Compositor:
         raise ValueError(f"unknown blender {kind!r}")
 
     # -- whole path, device resident ------------------------------------------
-    def window_halo(self, kind, n_levels):
-        """Rows of context a row window needs on each side: the reach of the
-        widest coarse blur (reduce + blur + expand), 0 for pointwise blenders."""
+    def blur_reach(self, kind, n_levels):
+        """Reach of the widest coarse blur (reduce + blur + expand) in pixels, 0 for
+        pointwise blenders."""
         if kind != "multiband" or n_levels < 2:
             return 0
         return geo.coarse_band_plan(n_levels)[0] + 4
+
+    def window_halo(self, kind, n_levels):
+        """Rows of context a row window needs on each side: the blur reach, plus one collapse
+        tile.  The collapse decides per 64 x 32 tile (anchored at absolute rows) which patches
+        carry weight and whether the tile is a single owner's pixels; a tile straddling the
+        window edge must see true data on all its rows, or the decision — and with it the last
+        bit of a pixel — would depend on where the window was cut."""
+        reach = self.blur_reach(kind, n_levels)
+        return reach + 32 if reach else 0
 
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
                   on_band=None, bands=8):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
         those rows of the full composite; only those rows are collapsed).
-        ``out_host`` (pinned uint8 H x W x 3, whole-mosaic mode only) receives
-        the mosaic through a banded download that overlaps the collapse; call
-        ``finish_download`` before reading it.  ``on_band(strip_rows, y0, y1)``
+        ``out_host`` (pinned uint8 H x W x 3: the WHOLE mosaic, also in window
+        mode) receives the rows produced through a banded download that overlaps
+        the collapse; call ``finish_download`` before reading it.  ``on_band(strip_rows, y0, y1)``
         is called after the collapse of mosaic rows [y0, y1) has been launched
         (``strip_rows`` = that part of the device result)."""
-        halo = self.window_halo(kind, n_levels)
+        halo, reach = self.window_halo(kind, n_levels), self.blur_reach(kind, n_levels)
         if rows is None:
             ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
-            crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * halo)
+            crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
         else:
             ya, yb = rows
             wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
             crops, tables = self.plan_crops(regions, plan, proj, rows=(wa, wb),
-                                            row_align=4 if halo else 1, split_dilate=2 * halo)
-            out_host = None
+                                            row_align=4 if halo else 1, split_dilate=2 * reach)
         top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
         shape = (wb - top, plan.shape[1])
         state = self.new_owner_state(shape) if kind == "multiband" else None
@@ -682,6 +701,45 @@ class Compositor:
                                      patches, shape, out_host=out_host, rows=local, on_band=band_cb,
                                      bands=bands, row_origin=top)
         return strip[local[0]:local[1]], patches
+
+    def streamed_windows(self, plan, kind, n_levels, windows=3):
+        """Plan of ``composite_streamed``: the order in which to upload the images (top edge
+        first) and row windows [ya, yb) of the mosaic with the number of uploads each one has
+        to wait for — window k needs nothing beyond the first ``count_k`` images."""
+        n = len(plan.boxes)
+        height = plan.shape[0]
+        halo = self.window_halo(kind, n_levels)
+        order = sorted(range(n), key=lambda i: (plan.boxes[i][1], i))
+        rank = {i: r for r, i in enumerate(order)}
+        last = np.zeros(height, dtype=np.int64)           # per mosaic row: rank of the last upload it needs
+        for i, (x0, y0, x1, y1) in enumerate(plan.boxes):
+            if x1 > x0 and y1 > y0:
+                a, b = max(0, y0 - halo), min(height, y1 + halo)
+                last[a:b] = np.maximum(last[a:b], rank[i])
+        last = np.maximum.accumulate(last)                # windows are prefixes of the upload order
+        cuts = [0]
+        for k in range(1, windows):
+            y = int(np.searchsorted(last, -(-k * n // windows) - 1, side="right"))   # rows done with k/windows of the images
+            if y > cuts[-1] and y < height:
+                cuts.append(y)
+        cuts.append(height)
+        return order, [(a, b, int(last[b - 1]) + 1) for a, b in zip(cuts, cuts[1:]) if b > a]
+
+    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=3, bands=4):
+        """Upload + composite + download with both PCIe directions busy: the images are uploaded
+        top edge first, and as soon as the images a row window of the mosaic depends on have
+        arrived that window is composited (exactly the bytes of the whole composite, see
+        ``composite``) and downloaded, while the uploads for the windows below continue on their
+        own stream.  ``out_host``: pinned uint8 H x W x 3.  Call ``finish_download`` afterwards."""
+        order, wins = self.streamed_windows(plan, kind, n_levels, windows)
+        src = self.upload(regions, overlap=True, order=order)
+        strips = []
+        for ya, yb, _ in wins:
+            strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, rows=(ya, yb), out_host=out_host,
+                                      bands=bands)
+            strips.append(strip)          # the download stream still reads it: keep it allocated
+        self._keep["streamed"] = (strips, src)
+        return src
 
     def _blend_into(self, holder, blender, patches, shape, *args, **kwargs):
         """Run a blender whose band callback needs to see the output buffer:

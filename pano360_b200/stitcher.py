@@ -37,6 +37,11 @@ from .geometry import CylProj, SphProj  # noqa: F401  (module globals, looked up
 
 MAX_RESOLUTION = 1400
 
+# Row windows of the streamed end-to-end pipeline (Compositor.composite_streamed); 0 = off.
+# Opt-in until it has been timed on the B200: P360_STREAM_WINDOWS=3.
+STREAM_WINDOWS = int(os.environ.get("P360_STREAM_WINDOWS", "0"))
+STREAM_MIN_PIXELS = 1 << 24
+
 _compositors = {}
 
 
@@ -186,14 +191,26 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     comp = _compositor()
     kind = _blend_kind(blender)
     proj = globals()["SphProj"]            # honours `stitcher.SphProj = stitcher.CylProj`
-    src = comp.upload(regions, overlap=not equalize)       # warp starts while late images still upload
-    if equalize:
-        comp.set_gains(src, equalize_gains(regions, src))
-    plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
-                           max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
     levels = 5
     if kind == "multiband":
         levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
+    plan = None
+    if STREAM_WINDOWS and kind is not None and not equalize and not crop and out is not None:
+        plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
+                               max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
+        if _is_pinned_out(out, plan.shape) and plan.shape[0] * plan.shape[1] >= STREAM_MIN_PIXELS:
+            # both PCIe directions at once: row windows are composited and downloaded while the
+            # images of the windows below are still being uploaded
+            comp.composite_streamed(regions, plan, kind, levels, proj, out, windows=STREAM_WINDOWS)
+            comp.finish_download()
+            comp.release()
+            return out
+    src = comp.upload(regions, overlap=not equalize)       # warp starts while late images still upload
+    if equalize:
+        comp.set_gains(src, equalize_gains(regions, src))
+    if plan is None:
+        plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
+                               max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
     if kind is None:                       # foreign blender: the reference's one-box-per-image NumPy triples
         patches = comp.warp(regions, src, plan, proj)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)

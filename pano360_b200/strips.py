@@ -22,11 +22,12 @@ from . import geometry as geo
 
 
 def blur_halo(kind, n_levels):
-    """Rows of context a strip needs above and below: the radius of the widest
-    Gaussian the blender applies (stitcher.py:218, :226)."""
+    """Rows of context a strip needs above and below: the reach of the widest
+    Gaussian the blender applies (stitcher.py:218, :226) plus one collapse tile
+    (``Compositor.window_halo``) plus the alignment slack of cropped tops."""
     if kind != "multiband" or n_levels < 2:
         return 0
-    return geo.coarse_band_plan(n_levels)[0] + 4 + 3     # + alignment slack of cropped tops
+    return geo.coarse_band_plan(n_levels)[0] + 4 + 32 + 3
 
 
 def row_costs(plan, kind="multiband", n_levels=5):

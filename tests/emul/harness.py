@@ -89,6 +89,7 @@ def install(monkeypatch):
     real_empty = torch.empty
 
     def poisoned_empty(*args, **kwargs):
+        kwargs.pop("pin_memory", None)             # no page-locked memory without a driver
         t = real_empty(*args, **kwargs)
         if t.is_floating_point():
             t.fill_(float("nan"))
@@ -97,5 +98,7 @@ def install(monkeypatch):
         return t
 
     monkeypatch.setattr(torch, "empty", poisoned_empty)
+    monkeypatch.setattr(stitcher, "_is_pinned_out", lambda out, shape: (
+        out is not None and out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == tuple(shape) + (3,)))
     monkeypatch.setattr(stitcher, "_compositors", {})
     return compositor.Compositor()

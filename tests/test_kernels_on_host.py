@@ -48,11 +48,36 @@ test_two_row_six_band_layout = gpu.test_two_row_six_band_layout
 test_many_small_views = gpu.test_many_small_views
 test_edge_cases = gpu.test_edge_cases
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
+test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
 test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
+
+
+def test_streamed_windows_pipeline(st, monkeypatch, restore_globals):
+    """(Host build only until the stream / event choreography has run on a B200; then it moves to
+    test_gpu_parity.py.)  The opt-in end-to-end pipeline that overlaps the two PCIe directions (uploads ordered top
+    edge first, row windows composited and downloaded as their images arrive) returns the bytes
+    of the plain stitch, for every blender and window count."""
+    import torch
+    regs = gpu.synth.make_views(gpu.synth.workload("cfg3", scale=8.0), noise=10.0)
+    st.MAX_RESOLUTION = 10 ** 9
+    monkeypatch.setattr(st, "STREAM_MIN_PIXELS", 0)
+    for kind in ("multiband", "linear", "none"):
+        monkeypatch.setattr(st, "STREAM_WINDOWS", 0)
+        want = st.stitch(regs, blender=st.BLENDERS[kind])
+        for windows in (2, 4):
+            monkeypatch.setattr(st, "STREAM_WINDOWS", windows)
+            out = torch.empty(want.shape, dtype=torch.uint8, pin_memory=True).numpy()
+            out[:] = 7
+            got = st.stitch(regs, blender=st.BLENDERS[kind], out=out)
+            assert got is out and gpu.np.array_equal(got, want), (kind, windows)
+    comp = st._compositor()
+    order, wins = comp.streamed_windows(gpu.geo.plan_mosaic(regs, True, 1e9), "multiband", 5, 3)
+    assert sorted(order) == list(range(len(regs))) and wins[0][0] == 0 and wins[-1][2] == len(regs)
+    assert all(a[1] == b[0] and a[2] <= b[2] for a, b in zip(wins, wins[1:])) and len(wins) >= 2
 
 
 def test_smoke_entry_point(comp, capsys):
