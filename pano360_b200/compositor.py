@@ -463,6 +463,53 @@ class Compositor:
         maps["reach_x"], maps["reach_y"] = -(-pad // 64), -(-pad // 32)
         return maps, (bits, multi)
 
+    def _coarse_layout(self, table, n_blurs):
+        """HBM for the coarse levels of every patch, back to back: on the f = 2 grid the reduce
+        output, the horizontal-pass scratch and the blurred level 0; on the f = 4 grid the reduce
+        output and (scratch, blurred level) for every level >= 1.  Fills the pointer fields of the
+        patch table; returns the pools and the per-level (in, tmp, out) pointer arrays."""
+        cells = table["w4"].astype(np.int64) * table["h4"]                # f = 4 cells per patch
+        first = np.concatenate([[0], np.cumsum(cells)]).astype(np.uint64)
+        total = int(first[-1])
+        pool2 = torch.empty(3 * 4 * total * 4, dtype=torch.float32, device=self.device)
+        pool4 = torch.empty((1 + 2 * (n_blurs - 1)) * total * 4, dtype=torch.float32, device=self.device)
+        base2, base4 = np.uint64(pool2.data_ptr()), np.uint64(pool4.data_ptr())
+        plane2, plane4 = np.uint64(16 * 4 * total), np.uint64(16 * total)      # bytes per plane
+        at2, at4 = np.uint64(64) * first[:-1], np.uint64(16) * first[:-1]      # byte offset of each patch
+        table["d2"], table["d4"] = base2 + at2, base4 + at4
+        levels = [(table["d2"], base2 + plane2 + at2, base2 + np.uint64(2) * plane2 + at2)]
+        for lvl in range(1, n_blurs):
+            levels.append((table["d4"], base4 + np.uint64(2 * lvl - 1) * plane4 + at4,
+                           base4 + np.uint64(2 * lvl) * plane4 + at4))
+        for lvl, (_, _, out) in enumerate(levels):
+            table["low"][:, lvl] = out
+        return {"pool2": pool2, "pool4": pool4, "levels": levels, "cells": total, "first": first}
+
+    def _blur_jobs(self, table, layout, dev_table, pad):
+        """One p360_blur_job per (level, patch): level 0 on the f = 2 grid, the others on f = 4."""
+        n = len(table)
+        patch_ptr = np.uint64(dev_table.data_ptr()) + np.uint64(_lib.BAND_PATCH.itemsize) * np.arange(n, dtype=np.uint64)
+        jobs = np.zeros(n * len(layout["levels"]), dtype=_lib.BLUR_JOB)
+        for lvl, (src, tmp, out) in enumerate(layout["levels"]):
+            sl = jobs[lvl * n:(lvl + 1) * n]
+            scale = 2 if lvl == 0 else 1
+            sl["in"], sl["tmp"], sl["out"], sl["slot"] = src, tmp, out, lvl
+            sl["w"], sl["h"], sl["shift"] = scale * table["w4"], scale * table["h4"], 1 if lvl == 0 else 2
+            sl["patch"], sl["pad"], sl["grow"] = patch_ptr, pad, 2 * pad + 4
+        return jobs
+
+    def _level_views(self, table, layout):
+        """Per patch, tensor views of its blurred coarse levels (stage-level tests)."""
+        pool2, pool4, total = layout["pool2"], layout["pool4"], layout["cells"]
+        lows = []
+        for k in range(len(table)):
+            w4, h4, o = int(table["w4"][k]), int(table["h4"][k]), int(layout["first"][k])
+            per = [pool2[(2 * 4 * total + 4 * o) * 4:][:4 * h4 * w4 * 4].view(2 * h4, 2 * w4, 4)]
+            for lvl in range(1, len(layout["levels"])):
+                per.append(pool4[(2 * lvl * total + o) * 4:][:h4 * w4 * 4].view(h4, w4, 4))
+            lows.append(per)
+        return lows
+
     def _set_taps(self, n_levels, plan):
         if self._taps_key == n_levels:
             return
@@ -531,70 +578,38 @@ class Compositor:
         pad, plan = geo.coarse_band_plan(n_levels)
         table = self._band_table(patches, pad, coarse=True)
         n = len(patches)
-        lows = []
+        lows, maps = [], None
+        layout = self._coarse_layout(table, len(plan)) if plan else None
         if plan:
-            c4 = table["w4"].astype(np.int64) * table["h4"]           # f=4 cells per patch
-            off4 = np.concatenate([[0], np.cumsum(c4)]).astype(np.uint64)
-            tot4 = int(off4[-1])
-            # pools: f=2 grid: d2, tmp, low0; f=4 grid: d4 + (tmp, low) per level >= 1
-            pool2 = torch.empty(3 * 4 * tot4 * 4, dtype=torch.float32, device=self.device)
-            pool4 = torch.empty((1 + 2 * (len(plan) - 1)) * tot4 * 4, dtype=torch.float32, device=self.device)
-            b2, b4 = np.uint64(pool2.data_ptr()), np.uint64(pool4.data_ptr())
-            s2, s4 = np.uint64(16 * 4 * tot4), np.uint64(16 * tot4)   # bytes per full plane
-            o2, o4 = np.uint64(64) * off4[:-1], np.uint64(16) * off4[:-1]
-            table["d2"] = b2 + o2
-            table["d4"] = b4 + o4
-            table["low"][:, 0] = b2 + np.uint64(2) * s2 + o2
-            for lvl in range(1, len(plan)):
-                table["low"][:, lvl] = b4 + np.uint64(2 * lvl) * s4 + o4
             self._set_taps(n_levels, plan)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
-        maps = None
         if plan:
-            # which part of each patch can ever carry weight: box around its owned pixels
+            # where can a patch carry weight at all: seam-band bitmaps, or the box around its owned pixels
             if self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS:
                 maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
                 self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
                              _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)
             else:
+                maps_keep = None
                 self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table),
                              n, h, w, self.stream)
-            patch_ptr = np.uint64(dev_table.data_ptr()) + \
-                np.uint64(_lib.BAND_PATCH.itemsize) * np.arange(n, dtype=np.uint64)
-            jobs = np.zeros(n * len(plan), dtype=_lib.BLUR_JOB)
-            for lvl in range(len(plan)):
-                sl = jobs[lvl * n:(lvl + 1) * n]
-                if lvl == 0:
-                    sl["in"], sl["tmp"] = table["d2"], b2 + s2 + o2
-                    sl["w"], sl["h"], sl["shift"] = 2 * table["w4"], 2 * table["h4"], 1
-                else:
-                    sl["in"], sl["tmp"] = table["d4"], b4 + np.uint64(2 * lvl - 1) * s4 + o4
-                    sl["w"], sl["h"], sl["shift"] = table["w4"], table["h4"], 2
-                sl["out"], sl["slot"] = table["low"][:, lvl], lvl
-                sl["patch"], sl["pad"], sl["grow"] = patch_ptr, pad, 2 * pad + 4
+            maps_ptr = None if maps is None else maps.ctypes.data
+            jobs = self._blur_jobs(table, layout, dev_table, pad)
             dev_jobs = self._table(jobs, "blur_jobs")
             self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
-                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w,
-                         None if maps is None else maps.ctypes.data, self.stream)
-            coarse_px = int(4 * tot4 + (len(plan) - 1) * tot4)
+                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, maps_ptr, self.stream)
+            coarse_px = int((4 + len(plan) - 1) * layout["cells"])
             self._traced("K3_gauss_blur", 32 * coarse_px, "p360_gauss_blur_batch", _lib.ptr(dev_jobs),
-                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()),
-                         None if maps is None else maps.ctypes.data, self.stream)
+                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()), maps_ptr, self.stream)
             if maps is not None:
                 _lib.launch_count += 3          # the scan kernels that compact the block lists
-            self._keep["bands"] = (pool2, pool4, dev_jobs, maps, maps_keep if maps is not None else None)
+            self._keep["bands"] = (layout["pool2"], layout["pool4"], dev_jobs, maps, maps_keep)
             if stages is not None:
-                for k in range(n):
-                    w4, h4, o = int(table["w4"][k]), int(table["h4"][k]), int(off4[k])
-                    per = [pool2[(2 * 4 * tot4 + 4 * o) * 4:][:4 * h4 * w4 * 4].view(2 * h4, 2 * w4, 4)]
-                    for lvl in range(1, len(plan)):
-                        per.append(pool4[(2 * lvl * tot4 + o) * 4:][:h4 * w4 * 4].view(h4, w4, 4))
-                    lows.append(per)
+                lows = self._level_views(table, layout)
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
-                       rows, on_band, bands, row_origin,
-                       tail=(None if maps is None else maps.ctypes.data,))
+                       rows, on_band, bands, row_origin, tail=(None if maps is None else maps.ctypes.data,))
         self._keep["collapse"] = (dev_table, keys, covered)
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows)

@@ -107,14 +107,25 @@ struct Block {
     const std::function<void()> *body = nullptr;
 };
 
-inline Block &block() {
-    static thread_local Block *b = nullptr;
-    if (!b) {
-        b = new Block();
-        b->stacks = static_cast<char *>(aligned_alloc(64, STACK_BYTES * MAX_THREADS));
-        b->dyn_smem = static_cast<char *>(aligned_alloc(64, DYN_SMEM_BYTES));
+struct BlockOwner {              // one per OS thread; workers of a launch end with it, so free what they touched
+    Block *b = nullptr;
+    ~BlockOwner() {
+        if (b) {
+            free(b->stacks);
+            free(b->dyn_smem);
+            delete b;
+        }
     }
-    return *b;
+};
+
+inline Block &block() {
+    static thread_local BlockOwner owner;
+    if (!owner.b) {
+        owner.b = new Block();
+        owner.b->stacks = static_cast<char *>(aligned_alloc(64, STACK_BYTES * MAX_THREADS));
+        owner.b->dyn_smem = static_cast<char *>(aligned_alloc(64, DYN_SMEM_BYTES));
+    }
+    return *owner.b;
 }
 inline void *dyn_smem() { return block().dyn_smem; }
 

@@ -135,6 +135,8 @@ def main():
                 if not isinstance(exc, AssertionError):
                     traceback.print_exc()
             done += 1
+            if done % 25 == 0:
+                print(f"... {done} cases, {len(failures)} failures, {time.time() - t0:.0f} s", flush=True)
     finally:
         patcher.undo()
     print(f"{done} cases, {len(failures)} failures, {time.time() - t0:.0f} s")
