@@ -379,12 +379,15 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
     int n_hit;
+    bool pure = false;      // every valid pixel of the tile belongs to list[0]: the owner keys are not needed
     if (maps.cand != nullptr) {
         // a single candidate: every valid pixel of the tile is its own (p360_tile_maps_build), no
         // coarse level is read and none was computed here — nothing to cull either
         const size_t tile = (size_t)((ty0 - maps.row0) >> 5) * maps.tiles_x + blockIdx.x;
         n_hit = tile_list_from_maps(patches, n_patches, maps, tile, tx0, ty0, list);
-        if (n_hit > 1 || __ldg(maps.multi + tile) != 0) n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+        const bool blended = __ldg(maps.multi + tile) != 0;
+        if (n_hit > 1 || blended) n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
+        pure = L > 1 && n_hit == 1 && !blended;
     } else {
         n_hit = build_tile_list<(L > 1)>(patches, n_patches, tx0, ty0, list);
         n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
@@ -394,7 +397,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         // streamed operands on chip instead of paying a DRAM round trip per patch iteration
         const int tid = threadIdx.y * CT_X + threadIdx.x;
         const int trow = ty0 + (tid >> 3), tcol = tx0 + 8 * (tid & 7);
-        if (trow >= 0 && trow < H && tcol < W) prefetch_l2(keys + (size_t)trow * W + tcol);
+        if (!pure && trow >= 0 && trow < H && tcol < W) prefetch_l2(keys + (size_t)trow * W + tcol);
         for (int it = 0; it < n_hit; ++it) {
             const BandPatch &bp = patches[list[it]];
             const int px = tcol - bp.x0, py = trow - bp.y0;
@@ -414,7 +417,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 #pragma unroll
         for (int l = 0; l < L; ++l) lo[l] = hi[l] = make_float2(0.f, 0.f);
         if (covered[mi] != 0) {
-            const unsigned long long key = __ldg(keys + mi);
+            const unsigned long long key = pure ? 0ull : __ldg(keys + mi);
             if (n_hit == 1 && L > 1) {
                 // Only one patch has non-zero weights anywhere in this tile.  Where it also
                 // owns the pixel every level weight is > 0, so sum_l band_l * w_l / w_l
@@ -423,7 +426,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                 const BandPatch &bp = patches[list[0]];
                 const int px = X - bp.x0, py = Y - bp.y0;
                 if ((unsigned)px < (unsigned)bp.pw && (unsigned)py < (unsigned)bp.ph &&
-                    key_is_owner(key, bp.index)) {
+                    (pure || key_is_owner(key, bp.index))) {
                     const float4 pix = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
                     uint8_t *o = out + mi * 3;
                     o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.x, 0.f), 1.f)));
@@ -432,7 +435,8 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                     continue;
                 }
             }
-            for (int it = 0; it < n_hit; ++it) {              // patch order = list order
+            // (a valid pixel of a pure tile lies inside its owner's box and was written above)
+            for (int it = 0; it < (pure ? 0 : n_hit); ++it) {     // patch order = list order
                 const BandPatch &bp = patches[list[it]];
                 const int px = X - bp.x0, py = Y - bp.y0;
                 if ((unsigned)px >= (unsigned)bp.pw || (unsigned)py >= (unsigned)bp.ph) continue;

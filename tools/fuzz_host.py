@@ -15,6 +15,7 @@ import os
 import sys
 import time
 import traceback
+from dataclasses import replace
 
 import numpy as np
 import pytest
@@ -29,8 +30,10 @@ from tests.emul import harness  # noqa: E402
 
 
 def random_case(rng):
-    n = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 12]))
+    n = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 12, 12, 40, 70]))           # 40 / 70: multi-word tile bitmaps
     width, height = int(rng.integers(17, 260)), int(rng.integers(13, 200))
+    if n >= 40:
+        width, height = int(rng.integers(17, 90)), int(rng.integers(13, 70))
     focal = float(rng.uniform(0.6, 2.5) * max(width, height))
     layout = rng.choice(["ring", "arc", "grid", "scatter"])
     if layout == "ring":                      # full circle: boxes straddle the +-pi seam
@@ -50,11 +53,16 @@ def random_case(rng):
     wl = synth.Workload("fuzz", width, height, focal, tuple(float(v) for v in yaws), tuple(float(v) for v in pitches),
                         "multiband", 5, False, (256, 512), 1e9, int(rng.integers(1 << 30)), int(rng.integers(1 << 30)))
     regs = synth.make_views(wl, noise=float(rng.choice([0.0, 5.0, 40.0])))
+    mixed = n > 1 and rng.random() < 0.25
+    if mixed:                                 # every other view at another size (and focal length)
+        w2, h2 = int(rng.integers(17, 200)), int(rng.integers(13, 160))
+        other = synth.make_views(replace(wl, width=w2, height=h2, focal=wl.focal * w2 / width), noise=5.0)
+        regs = [other[i] if i % 2 else regs[i] for i in range(n)]
     if rng.random() < 0.5:                    # roll + shuffled list order
         regs = [Image(r.img, rotation_to_mat([0.0, 0.0, float(rng.uniform(-0.5, 0.5))]) @ r.rot, r.intr) for r in regs]
         regs = [regs[i] for i in rng.permutation(n)]
     return dict(regs=regs, blend=str(rng.choice(["none", "linear", "multiband", "multiband"])),
-                equalize=bool(rng.random() < 0.3), levels=int(rng.choice([1, 2, 3, 5, 5, 6, 8])),
+                equalize=bool(rng.random() < 0.3) and not mixed, levels=int(rng.choice([1, 2, 3, 5, 5, 6, 8])),
                 cylindrical=bool(rng.random() < 0.25), cap=float(rng.choice([1e9, 1e9, 1400, 300])),
                 maps=[None, True, False][int(rng.integers(3))], layout=str(layout))
 

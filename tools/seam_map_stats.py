@@ -57,19 +57,23 @@ def main():
             ya, yb = np.clip((ys - row0) >> 5, 0, tiles_y - 1), np.clip((ys + bh - 1 - row0) >> 5, 0, tiles_y - 1) + 1
             return (cs[yb][:, xb] - cs[ya][:, xb] - cs[yb][:, xa] + cs[ya][:, xa]) > 0
 
-        blur = {"H f=2": [0, 0], "V f=2": [0, 0], "H f=4": [0, 0], "V f=4": [0, 0]}
+        # the kernels' block shapes (coarse cells) first, then alternatives worth measuring
+        shapes = [("H", 256, 4), ("V", 32, 64), ("H", 64, 4), ("H", 64, 16), ("H", 128, 8), ("V", 32, 32), ("V", 16, 64)]
+        blur = {}
         for k, rec in enumerate(table):
             pad, w4, h4 = int(rec["pad"]), int(rec["w4"]), int(rec["h4"])
             has = (need[..., k >> 5] >> np.uint32(k & 31)) & 1
             for f, cw, ch in ((2, 2 * w4, 2 * h4), (4, w4, h4)):
-                for name, bw, bh in (("H", 256, 4), ("V", 32, 64)):
+                for name, bw, bh in shapes:
                     xs = np.arange(-(-cw // bw)) * bw * f - pad + int(rec["x0"])
                     ys = np.arange(-(-ch // bh)) * bh * f - pad + int(rec["y0"])
                     hit = blocks_hit(has, xs, ys, bw * f, bh * f)
-                    blur[f"{name} f={f}"][0] += int(hit.sum())
-                    blur[f"{name} f={f}"][1] += hit.size
-        for name, (run, tot) in blur.items():
-            print(f"blur blocks {name}: {run} of {tot} ({100 * run / max(tot, 1):.1f}%)")
+                    acc = blur.setdefault((name, bw, bh, f), [0, 0])
+                    acc[0] += int(hit.sum()) * bw * bh
+                    acc[1] += cw * ch
+        for (name, bw, bh, f), (run, tot) in blur.items():
+            print(f"blur {name} blocks of {bw}x{bh} cells, f={f}: {run / 1e6:.1f} of {tot / 1e6:.1f} Mcells "
+                  f"({100 * run / max(tot, 1):.1f}%)")
         run_own = run_maps = total = 0
         for k, rec in enumerate(table):
             pad, w4, h4 = int(rec["pad"]), int(rec["w4"]), int(rec["h4"])
