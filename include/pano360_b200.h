@@ -196,7 +196,8 @@ typedef struct p360_tile_maps {
     int32_t row0;
     int32_t reach_x, reach_y;                 /* ceil(pad / 64), ceil(pad / 32)          */
     int32_t work_cap;
-    int32_t reserved;
+    int32_t h_rows;                           /* 4: horizontal blur in 64-cell segments x 16 rows */
+                                              /* per block instead of 256 x 4 (0 / 1)             */
 } p360_tile_maps;
 int p360_tile_maps_build(const uint64_t *owner_keys, const uint8_t *covered,
                          p360_band_patch *patches, int n_patches, int H, int W,

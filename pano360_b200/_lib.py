@@ -59,7 +59,7 @@ BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "
                        ("own", "i4", (4,))])
 TILE_MAPS = np.dtype([("present", "u8"), ("cand", "u8"), ("need", "u8"), ("multi", "u8"), ("work", "u8"),
                       ("work_count", "u8"), ("tiles_x", "i4"), ("tiles_y", "i4"), ("words", "i4"), ("row0", "i4"),
-                      ("reach_x", "i4"), ("reach_y", "i4"), ("work_cap", "i4"), ("reserved", "i4")])
+                      ("reach_x", "i4"), ("reach_y", "i4"), ("work_cap", "i4"), ("h_rows", "i4")])
 PAIR_JOB = np.dtype([("src_i", "u8"), ("src_j", "u8"), ("inv", "f8", (9,))])
 assert PAIR_JOB.itemsize == 88
 assert WARP_JOB.itemsize == 208 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136

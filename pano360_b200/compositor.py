@@ -135,6 +135,9 @@ class Compositor:
         # blur reach.  Bit-identical output either way; None = on for mosaics large enough for the
         # extra launches to pay (B200, cfg4: 15.9 -> 13.2 ms), P360_SEAM_MAPS=0/1 forces it.
         self.seam_maps = {"0": False, "1": True}.get(os.environ.get("P360_SEAM_MAPS", ""))
+        # horizontal blur of the block lists in 64-cell instead of 256-cell segments (4 rows per
+        # warp): halves the cells run at cfg4 (tools/seam_map_stats.py); to be timed on the B200
+        self.blur_h_rows = 4 if os.environ.get("P360_BLUR_H_ROWS", "1") == "4" else 1
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -449,7 +452,8 @@ class Compositor:
         cells = tiles_x * tiles_y
         w4, h4 = int(table["w4"].max()), int(table["h4"].max())
         cap = max(-(-4 * w4 // 32) * -(-h4 // 8) * n,                      # reduce blocks
-                  -(-2 * w4 // 256) * -(-2 * h4 // 4) * n * n_blurs,      # horizontal blur blocks
+                  -(-2 * w4 // 256) * -(-2 * h4 // 4) * n * n_blurs,      # horizontal blur blocks (256 x 4 cells)
+                  -(-2 * w4 // 64) * -(-2 * h4 // 16) * n * n_blurs,      # ... in 64 x 16 blocks
                   -(-2 * w4 // 32) * -(-2 * h4 // 64) * n * n_blurs)      # vertical blur blocks
         bits = torch.empty(2 + 2 * cap + 3 * cells * words, dtype=torch.int32, device=self.device)
         multi = torch.empty(cells, dtype=torch.uint8, device=self.device)
@@ -461,6 +465,7 @@ class Compositor:
         maps["multi"] = multi.data_ptr()
         maps["tiles_x"], maps["tiles_y"], maps["words"], maps["row0"] = tiles_x, tiles_y, words, row0
         maps["reach_x"], maps["reach_y"] = -(-pad // 64), -(-pad // 32)
+        maps["h_rows"] = self.blur_h_rows
         return maps, (bits, multi)
 
     def _coarse_layout(self, table, n_blurs):

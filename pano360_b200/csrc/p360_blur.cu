@@ -62,38 +62,48 @@ constexpr int H_WARPS = 4;             // rows per block (one warp per row)
 constexpr int H_SEG = 32 * R;          // outputs per warp
 __host__ __device__ __forceinline__ int h_phys(int q) { return q + (q >> 3); }   // 1 pad slot per 8: lane stride 9
 
-template <bool FINITE>
+// ROWS rows per warp, H_SEG / ROWS outputs on each (ROWS = 1: one 256-wide segment per warp;
+// ROWS = 4: four 64-wide ones, for the block lists of the seam-band maps, where a 1024-pixel
+// segment across a 200-pixel seam band is mostly wasted work).  pitch = h_phys(segment + ksize - 1) + 1.
+template <bool FINITE, int ROWS>
 __device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float4 *__restrict__ out,
                                             int pw, int ph, int pitch, const Taps &t, int block) {
+    constexpr int LPR = 32 / ROWS, SEG = H_SEG / ROWS;   // lanes, outputs per row
     extern __shared__ float4 smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nxb = (pw + H_SEG - 1) / H_SEG;
-    const int row = (block / nxb) * H_WARPS + warp;
-    const int xb = (block % nxb) * H_SEG;
-    if (row >= ph) return;                              // warp-uniform, no block barrier below
-    float4 *tile = smem + (size_t)warp * pitch;
+    const int sub = lane / LPR, lr = lane % LPR;
+    const int nxb = (pw + SEG - 1) / SEG;
+    const int row = ((block / nxb) * H_WARPS + warp) * ROWS + sub;
+    const int xb = (block % nxb) * SEG;
+    if (ROWS == 1 && row >= ph) return;                  // warp-uniform, no block barrier below
+    const bool live = row < ph;                          // ROWS > 1: rows of a warp end separately
+    float4 *tile = smem + ((size_t)warp * ROWS + sub) * pitch;
     const int r = t.ksize >> 1;
-    const float4 *src = in + (size_t)row * pw;
-    const int nq = H_SEG + t.ksize - 1;
-    for (int q = lane; q < nq; q += 32) tile[h_phys(q)] = staged<FINITE>(__ldg(src + reflect_101(xb - r + q, pw)));
+    const float4 *src = in + (size_t)(live ? row : 0) * pw;
+    const int nq = SEG + t.ksize - 1;
+    if (live)
+        for (int q = lr; q < nq; q += LPR) tile[h_phys(q)] = staged<FINITE>(__ldg(src + reflect_101(xb - r + q, pw)));
     __syncwarp();
     float2 lo[R], hi[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
-    const int base = R * lane;
-    convolve_r(lo, hi, t, [&](int j, bool ok) {
-        return ok ? tile[h_phys(base + j)] : make_float4(0.f, 0.f, 0.f, 0.f);
-    });
+    const int base = R * lr;
+    if (live)
+        convolve_r(lo, hi, t, [&](int j, bool ok) {
+            return ok ? tile[h_phys(base + j)] : make_float4(0.f, 0.f, 0.f, 0.f);
+        });
     __syncwarp();
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-        tile[h_phys(base + i)] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
+        for (int i = 0; i < R; ++i)
+            tile[h_phys(base + i)] = make_float4(lo[i].x, lo[i].y, hi[i].x, hi[i].y);
+    }
     __syncwarp();
-    float4 *dst = out + (size_t)row * pw + xb;
+    float4 *dst = out + (size_t)(live ? row : 0) * pw + xb;
 #pragma unroll
     for (int c = 0; c < R; ++c) {
-        const int x = c * 32 + lane;
-        if (xb + x < pw) dst[x] = tile[h_phys(x)];
+        const int x = c * LPR + lr;
+        if (live && xb + x < pw) dst[x] = tile[h_phys(x)];
     }
 }
 
@@ -126,44 +136,49 @@ __constant__ Taps c_taps[P360_MAX_LEVELS];     // tap sets of the batched blurs 
 
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
-    blur_h_body<false>(in, out, pw, ph, pitch, t, blockIdx.x);
+    blur_h_body<false, 1>(in, out, pw, ph, pitch, t, blockIdx.x);
 }
 
-// block `b` of a job's horizontal grid: exists and is read by somebody?
+// block `b` of a job's horizontal grid (H_SEG / ROWS cells x H_WARPS * ROWS rows): exists and is
+// read by somebody?
+template <int ROWS>
 __device__ __forceinline__ bool h_block_needed(const BlurJob &job, const TileMaps &maps, int b) {
-    const int nxb = (job.w + H_SEG - 1) / H_SEG;
-    if (b >= nxb * ((job.h + H_WARPS - 1) / H_WARPS)) return false;
-    const int cx0 = (b % nxb) * H_SEG, cy0 = (b / nxb) * H_WARPS;
-    return job_block_needed(job, maps, cx0, cy0, cx0 + H_SEG, cy0 + H_WARPS);
+    constexpr int SEG = H_SEG / ROWS, BROWS = H_WARPS * ROWS;
+    const int nxb = (job.w + SEG - 1) / SEG;
+    if (b >= nxb * ((job.h + BROWS - 1) / BROWS)) return false;
+    const int cx0 = (b % nxb) * SEG, cy0 = (b / nxb) * BROWS;
+    return job_block_needed(job, maps, cx0, cy0, cx0 + SEG, cy0 + BROWS);
 }
 
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     const BlurJob &job = jobs[blockIdx.y];
-    if (!h_block_needed(job, maps, blockIdx.x)) return;                               // block-uniform
-    blur_h_body<true>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
+    if (!h_block_needed<1>(job, maps, blockIdx.x)) return;                            // block-uniform
+    blur_h_body<true, 1>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
 }
 
 // With seam-band maps: the needed blocks of the dense grids are compacted into a work list by
 // one thread per block, and persistent grids walk the list (see reduce_scan_kernel).
+template <int ROWS>
 __global__ void __launch_bounds__(256)
 blur_h_scan_kernel(const BlurJob *__restrict__ jobs, int n_jobs, int gx, TileMaps maps) {
     const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
     if (t >= (long long)gx * n_jobs) return;
     const int b = (int)(t % gx), j = (int)(t / gx);
-    if (!h_block_needed(jobs[j], maps, b)) return;
+    if (!h_block_needed<ROWS>(jobs[j], maps, b)) return;
     const int at = atomicAdd(maps.work_count, 1);
     if (at < maps.work_cap) maps.work[at] = make_uint2((unsigned)j, (unsigned)b);
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_list_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     const int n = min(*maps.work_count, maps.work_cap);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         const BlurJob &job = jobs[item.x];
-        blur_h_body<true>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], (int)item.y);
-        __syncwarp();                   // the warp's tile is restaged by the next item
+        blur_h_body<true, ROWS>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], (int)item.y);
+        __syncwarp();                   // the warp's tiles are restaged by the next item
     }
 }
 
@@ -332,16 +347,28 @@ extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int 
         blur_v_batch_kernel<<<grid_v, 32 * V_WARPS, smem_v, s>>>(bj, maps);
         return check_launch(where);
     }
-    // compacted work lists, persistent grids
-    static size_t hl_limit = 48 * 1024, vl_limit = 48 * 1024;
-    if (int e = ensure_smem(blur_h_list_kernel, smem_h, hl_limit, where)) return e;
+    // compacted work lists, persistent grids; the horizontal pass in 64-cell segments if asked for
+    const bool narrow = maps.h_rows == 4;
+    const int seg = narrow ? H_SEG / 4 : H_SEG, brows = narrow ? H_WARPS * 4 : H_WARPS;
+    const int pitch_l = h_phys(seg + ksize - 1) + 1;
+    const size_t smem_l = sizeof(float4) * pitch_l * (narrow ? 4 : 1) * H_WARPS;
+    static size_t hl_limit = 48 * 1024, hn_limit = 48 * 1024, vl_limit = 48 * 1024;
+    if (int e = narrow ? ensure_smem(blur_h_list_kernel<4>, smem_l, hn_limit, where)
+                       : ensure_smem(blur_h_list_kernel<1>, smem_l, hl_limit, where)) return e;
     if (int e = ensure_smem(blur_v_list_kernel, smem_v, vl_limit, where)) return e;
-    const long long h_cand = (long long)h_blocks * n_jobs, v_cand = (long long)grid_v.x * grid_v.y * n_jobs;
+    const unsigned hl_blocks = cdiv(max_w, seg) * cdiv(max_h, brows);
+    const long long h_cand = (long long)hl_blocks * n_jobs, v_cand = (long long)grid_v.x * grid_v.y * n_jobs;
     P360_REQUIRE(h_cand <= maps.work_cap && v_cand <= maps.work_cap && grid_v.x <= 65535, where);
     P360_CUDA(cudaMemsetAsync(maps.work_count, 0, sizeof(int), s), where);
-    blur_h_scan_kernel<<<cdiv(h_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)h_blocks, maps);
-    if (int e = check_launch(where)) return e;
-    blur_h_list_kernel<<<persistent_blocks(8), 32 * H_WARPS, smem_h, s>>>(bj, pitch, maps);
+    if (narrow) {
+        blur_h_scan_kernel<4><<<cdiv(h_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)hl_blocks, maps);
+        if (int e = check_launch(where)) return e;
+        blur_h_list_kernel<4><<<persistent_blocks(8), 32 * H_WARPS, smem_l, s>>>(bj, pitch_l, maps);
+    } else {
+        blur_h_scan_kernel<1><<<cdiv(h_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)hl_blocks, maps);
+        if (int e = check_launch(where)) return e;
+        blur_h_list_kernel<1><<<persistent_blocks(8), 32 * H_WARPS, smem_l, s>>>(bj, pitch_l, maps);
+    }
     if (int e = check_launch(where)) return e;
     P360_CUDA(cudaMemsetAsync(maps.work_count, 0, sizeof(int), s), where);
     blur_v_scan_kernel<<<cdiv(v_cand, 256), 256, 0, s>>>(bj, n_jobs, (int)grid_v.x, (int)grid_v.y, maps);

@@ -120,7 +120,7 @@ struct TileMaps {                       // == p360_tile_maps
     int row0;                           // window row of tile row 0 (<= 0; tiles sit on absolute mosaic rows)
     int reach_x, reach_y;               // blur reach in tiles
     int work_cap;
-    int reserved;
+    int h_rows;                         // 4: horizontal blur lists in 64-cell segments (else 256)
 };
 
 // Persistent grids over a work list: blocks per SM x SMs (cached per process).

@@ -21,6 +21,7 @@ def main(comp=None):
     ap.add_argument("workload", nargs="?", default="cfg4")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--h-rows", type=int, default=1, help="4: horizontal blur lists in 64-cell segments")
     args = ap.parse_args()
     t0 = time.time()
     import torch
@@ -33,6 +34,7 @@ def main(comp=None):
         r.img = img
     plan = geo.plan_mosaic(regs, wl.blend == "multiband", 1e9)
     comp = comp or Compositor()
+    comp.blur_h_rows = args.h_rows
     src = comp.upload(regs)
     out = {"workload": args.workload, "scale": args.scale, "mosaic": list(plan.shape), "setup_s": round(time.time() - t0, 1)}
     mosaics = {}
