@@ -110,6 +110,7 @@ def test_barrier_misuse_is_detected():
 # ---- the multi-rank path end to end: strips over gloo, kernels on the host -------------------
 def _strip_worker(rank, world, port, golden, kind, equalize, out_path):
     import os
+    os.environ["P360_SEAM_MAPS"] = "1" if rank % 2 else "0"      # ranks may differ: the bytes do not
 
     import numpy as np
     import torch.distributed as dist
