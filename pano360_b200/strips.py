@@ -35,9 +35,14 @@ def row_costs(plan, kind="multiband", n_levels=5):
     equal-height strips are unbalanced: 12/12/24/24/24/24/12/12 images)."""
     height = plan.shape[0]
     cost = np.zeros(height + 1, dtype=np.float64)
-    for x0, y0, x1, y1 in plan.boxes:
-        cost[max(y0, 0)] += x1 - x0
-        cost[min(y1, height)] -= x1 - x0
+    reach = geo.coarse_band_plan(n_levels)[0] + 4 if kind == "multiband" and n_levels > 1 else 0
+    for i, (x0, y0, x1, y1) in enumerate(plan.boxes):
+        if x1 <= x0 or y1 <= y0:
+            continue
+        # columns actually warped: seam-straddling boxes span the mosaic but are mostly empty
+        width = sum(b - a for a, b in geo.active_column_runs(i, (x0, y0, x1, y1), plan, dilate=2 * reach))
+        cost[max(y0, 0)] += width
+        cost[min(y1, height)] -= width
     per_row = np.cumsum(cost[:-1])
     return per_row + plan.shape[1] * 0.25      # mosaic-sized passes (owner, collapse)
 

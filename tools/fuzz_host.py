@@ -94,6 +94,21 @@ def run_case(st, comp, case):
     return got
 
 
+def run_blender_api(st, case):
+    """The drop-in blender functions on the oracle's own NumPy patches (external patches take the
+    owner-update kernel instead of the fused competition of the warp)."""
+    regs, blend = case["regs"], case["blend"]
+    proj = "cylindrical" if case["cylindrical"] else "spherical"
+    patches, pl = rs.build_patches(regs, blend, False, case["cap"], proj)
+    want = rs.BLENDERS[blend]([(w.copy(), m.copy(), s) for w, m, s in patches], pl.shape)
+    got = st.BLENDERS[blend](patches, pl.shape)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    if blend == "multiband":
+        assert diff.max() <= 2 and psnr(got, want) >= 45.0, ("blender api", int(diff.max()), psnr(got, want))
+    else:
+        assert diff.max() == 0, ("blender api", blend, int(diff.max()))
+
+
 def run_windows(comp, case, whole, rng):
     """Random row windows of the same composite against the whole mosaic (no gains: the window
     API takes the sources as uploaded)."""
@@ -137,6 +152,8 @@ def main():
                 whole = run_case(st, comp, case)
                 if whole is not None:
                     run_windows(comp, case, whole, rng)
+                if not case["equalize"] and rng.random() < 0.3:
+                    run_blender_api(st, case)
             except Exception as exc:                              # keep going: collect every failure
                 failures.append((tag, exc))
                 print("FAIL", tag, "->", repr(exc)[:300], flush=True)
