@@ -148,3 +148,29 @@ def test_strips_over_gloo_equal_single_rank(st, tmp_path, golden, kind, equalize
     out = str(tmp_path / "mosaic.npy")
     mp.spawn(_strip_worker, args=(world, _free_port(), golden, kind, equalize, out), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
+
+
+def test_random_rigs_against_the_oracle(st, comp, restore_globals):
+    """A fixed slice of tools/fuzz_host.py (random view counts, odd sizes, rings across the +-pi
+    seam, steep pitches, roll, band counts, projections, forced seam-band maps, random row
+    windows, the blender API on external patches); the full campaign runs from the tool."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_host", os.path.join(os.path.dirname(__file__), "..", "tools", "fuzz_host.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    saved = comp.seam_maps
+    try:
+        for seed in range(900, 916):
+            rng = np.random.default_rng(seed)
+            case = fuzz.random_case(rng)
+            whole = fuzz.run_case(st, comp, case)
+            if whole is not None:
+                fuzz.run_windows(comp, case, whole, rng)
+                if not case["equalize"]:
+                    fuzz.run_blender_api(st, case)
+    finally:
+        comp.seam_maps = saved
