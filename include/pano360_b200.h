@@ -88,8 +88,25 @@ typedef struct p360_warp_job {
 
 int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
                     int h, int w, uint8_t *dst_rgbxa, void *stream);
+struct p360_tile_maps;
 int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
-                    uint64_t *owner_keys, uint8_t *covered, int W, void *stream);
+                    uint64_t *owner_keys, uint8_t *covered, int W,
+                    const struct p360_tile_maps *gate_host, void *stream);
+
+/* Optional gate for p360_warp_batch (multiband with seam-band maps only): most of what a warp
+ * produces is never read — a patch's pixels matter where it owns them and within the blur reach
+ * of a seam it takes part in.  Ownership is arg-max of alpha = hat_y(v) * hat_x(u), a function of
+ * the geometry alone: p360_warp_gate_build bounds alpha of every patch on every 64 x 32 tile by
+ * interval arithmetic (ray tables -> K R ray -> source position -> alpha), keeps as candidates
+ * the patches no other patch dominates on the whole tile (gate->cand), and dilates them by
+ * gate->reach_x / reach_y tiles (gate->need): p360_warp_batch then skips the blocks of a patch
+ * over tiles where its bit is clear.  jobs_dev = DEVICE copy of the job table passed to
+ * p360_warp_batch (patch = position); tile grid as for p360_tile_maps_build; only cand, need,
+ * tiles_x, tiles_y, words, row0, reach_x, reach_y of the record are used.  The reach must cover
+ * everything downstream reads: twice the blur reach of the seam-band maps, one tile for block
+ * overhang, and the reflection at patch edges. */
+int p360_warp_gate_build(const p360_warp_job *jobs_dev, int n_jobs, int H, int W,
+                         const struct p360_tile_maps *gate_host, void *stream);
 
 /* ---- K2: owner map for externally supplied patches (stitcher.py:196-208) ---
  * p360_owner_update: the same competition for one already-warped patch (the

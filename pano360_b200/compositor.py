@@ -138,6 +138,9 @@ class Compositor:
         # horizontal blur of the block lists in 64-cell instead of 256-cell segments (4 rows per
         # warp): halves the cells run at cfg4 (tools/seam_map_stats.py); to be timed on the B200
         self.blur_h_rows = 4 if os.environ.get("P360_BLUR_H_ROWS", "1") == "4" else 1
+        # gate the warp by geometric ownership bounds (p360_warp_gate_build): at cfg4 only 60 % of
+        # the warped blocks are ever read.  Byte-identical on the host build; to be timed on the B200
+        self.warp_gate = os.environ.get("P360_WARP_GATE", "0") == "1"
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -321,7 +324,27 @@ class Compositor:
         return (torch.zeros((h, w), dtype=torch.int64, device=self.device),
                 torch.zeros((h, w), dtype=torch.uint8, device=self.device))
 
-    def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
+    def _warp_gate(self, jobs, shape, row_origin, pad):
+        """Run bitmap for the warp: which (patch, tile) pairs can produce anything that is read."""
+        h, w = shape
+        n = len(jobs)
+        row0 = -(row_origin % 32)
+        tiles_x, tiles_y, words = -(-w // 64), -(-(h - row0) // 32), -(-n // 32)
+        cells = tiles_x * tiles_y
+        bits = torch.empty(2 * cells * words, dtype=torch.int32, device=self.device)
+        gate = np.zeros(1, dtype=_lib.TILE_MAPS)
+        gate["cand"], gate["need"] = bits.data_ptr(), bits.data_ptr() + 4 * cells * words
+        gate["tiles_x"], gate["tiles_y"], gate["words"], gate["row0"] = tiles_x, tiles_y, words, row0
+        # everything downstream reads lies within: twice the blur reach of an owned tile (seam-band
+        # maps), one tile of block overhang, and the reflection at (real or cut) patch edges
+        rx, ry = -(-pad // 64), -(-pad // 32)
+        gate["reach_x"], gate["reach_y"] = 2 * rx + 1 + -(-2 * pad // 64), 2 * ry + 1 + -(-2 * pad // 32)
+        dev_jobs = self._table(jobs, "warp_jobs")
+        self._traced("K0_warp_gate", 208 * n, "p360_warp_gate_build", _lib.ptr(dev_jobs), n, h, w,
+                     gate.ctypes.data, self.stream)
+        return gate, (bits, dev_jobs)
+
+    def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None, gate_pad=None):
         """K1 over every crop in ONE launch.  Boxes of the returned patches
         are relative to ``origin`` (x, y).  With ``owner_state = (keys,
         covered)`` (mosaic-sized, zeroed) the owner-map competition is fused
@@ -359,15 +382,19 @@ class Compositor:
                        np.float32(1.0) / np.float32(2 * w), np.float32(1.0) / np.float32(2 * h))
             patches.append(DevicePatch(box=(x0 - ox, ya - oy, x1 - ox, yb - oy), index=i,
                                        pools=(rgba_pool, inv_pool), offset=o))
+        gate = gate_keep = None
         if owner_state is None:
             keys = covered = None
             width, per_px = 0, 17
         else:
             keys, covered = owner_state
             width, per_px = keys.shape[1], 30
+            if gate_pad is not None:
+                gate, gate_keep = self._warp_gate(jobs, tuple(keys.shape), oy, gate_pad)
+        gate_ptr = None if gate is None else gate.ctypes.data
         if src.ready is None:
             self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", jobs.ctypes.data, n,
-                         _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+                         _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
         else:                  # uploads in flight: warp image groups as they arrive
             main = torch.cuda.current_stream(self.device)
             group = max(1, -(-len(src.ready) // 8))
@@ -380,9 +407,9 @@ class Compositor:
                 for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
                     main.wait_event(src.ready[i])
                 _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
-                          _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+                          _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
                 a = b
-        self._keep["warp"] = (dev_rays, rgba_pool, inv_pool, jobs)
+        self._keep["warp"] = (dev_rays, rgba_pool, inv_pool, jobs, gate, gate_keep)
         return patches
 
     def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
@@ -568,7 +595,7 @@ class Compositor:
             self._download = None
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
-                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0):
+                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM."""
@@ -591,7 +618,9 @@ class Compositor:
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         if plan:
             # where can a patch carry weight at all: seam-band bitmaps, or the box around its owned pixels
-            if self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS:
+            if use_maps is None:      # (a gated warp leaves pixels unwritten that only the maps know to skip)
+                use_maps = self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS
+            if use_maps:
                 maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
                 self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
                              _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)
@@ -684,7 +713,7 @@ class Compositor:
         return reach + 32 if reach else 0
 
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8):
+                  on_band=None, bands=8, gate=None):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
         those rows of the full composite; only those rows are collapsed).
@@ -705,7 +734,10 @@ class Compositor:
         top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
         shape = (wb - top, plan.shape[1])
         state = self.new_owner_state(shape) if kind == "multiband" else None
-        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+        # (callers that read the patches themselves afterwards — the crop mask — pass gate=False)
+        gated = (self.warp_gate if gate is None else gate) and kind == "multiband" and n_levels > 1
+        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state,
+                                  gate_pad=geo.coarse_band_plan(n_levels)[0] if gated else None)
         holder = {}
         band_cb = None
         if on_band is not None:
@@ -715,7 +747,7 @@ class Compositor:
         if kind == "multiband":
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels,
                                      owner_state=state, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands, row_origin=top)
+                                     bands=bands, row_origin=top, use_maps=True if gated else None)
         else:
             strip = self._blend_into(holder, self.blend_none if kind == "none" else self.blend_linear,
                                      patches, shape, out_host=out_host, rows=local, on_band=band_cb,

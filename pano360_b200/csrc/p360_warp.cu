@@ -153,12 +153,9 @@ __constant__ WarpJob c_warp_jobs[WARP_JOBS_PER_LAUNCH];   // block-uniform reads
 
 // PACKED: every job's source is in the 8-byte {RGBX, alpha} format; OWNER: owner keys wanted.
 template <bool PACKED, bool OWNER>
-__global__ void __launch_bounds__(WARP_BX *WARP_BY)
-warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
-    __shared__ float lut[256];
-    const WarpJob &job = c_warp_jobs[blockIdx.z];
+__device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsigned long long *__restrict__ keys,
+                                           uint8_t *__restrict__ covered, int W) {
     const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
-    if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
     const int tid = threadIdx.y * WARP_BX + threadIdx.x;
     lut[tid] = __ldg(job.lut + tid);
     __syncthreads();
@@ -181,6 +178,131 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
         const int r = r0 + threadIdx.y + k * WARP_BY;
         if (r < job.ph)
             warp_commit<OWNER>(job, c, r, finish_pixel(lut, plan[k], taps[k]), plan[k].bad, keys, covered, W);
+    }
+}
+
+template <bool PACKED, bool OWNER>
+__global__ void __launch_bounds__(WARP_BX *WARP_BY)
+warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
+    __shared__ float lut[256];
+    const WarpJob &job = c_warp_jobs[blockIdx.z];
+    const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
+    if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
+    warp_block<PACKED, OWNER>(job, lut, keys, covered, W);
+}
+
+// The same with a gate: gate.need = "run" bitmap of p360_warp_gate_build; blocks of a patch over
+// tiles where its bit is clear produce nothing anybody reads and are skipped.
+template <bool PACKED>
+__global__ void __launch_bounds__(WARP_BX *WARP_BY)
+warp_batch_gated_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W, TileMaps gate) {
+    __shared__ float lut[256];
+    const WarpJob &job = c_warp_jobs[blockIdx.z];
+    const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
+    if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
+    const int bx = job.x0 + (int)(blockIdx.x * WARP_BX), by = job.y0 + r0;
+    if (!tiles_test(gate, gate.need, job.patch, bx, by, bx + WARP_BX, by + WARP_BY * WARP_ROWS)) return;   // block-uniform
+    warp_block<PACKED, true>(job, lut, keys, covered, W);
+}
+
+// ---- K0: who can own a pixel of a tile?  (geometry only, before anything is sampled) ---------
+// Ownership is arg-max of alpha = hat_y(v) * hat_x(u).  Interval arithmetic over a 64 x 32 tile —
+// ray tables -> K R ray -> (u, v) -> alpha — bounds alpha of every patch on the tile; a patch whose
+// upper bound lies below another patch's lower bound can never win there.  Every true owner is a
+// candidate (tools/gate_bounds.py checks it against the owner keys on random rigs); at cfg4 92 % of
+// the tiles keep a single candidate.
+struct Interval { double lo, hi; };
+__device__ __forceinline__ Interval scaled(double k, Interval v) {
+    const double a = k * v.lo, b = k * v.hi;
+    return Interval{fmin(a, b), fmax(a, b)};
+}
+__device__ __forceinline__ Interval table_range(const double *__restrict__ t, int a, int b) {   // t[a .. b)
+    Interval r{t[a], t[a]};
+    for (int i = a + 1; i < b; ++i) { r.lo = fmin(r.lo, t[i]); r.hi = fmax(r.hi, t[i]); }
+    return r;
+}
+// hat over source coordinates [lo, hi] clipped to [0, size - 1]: lower bound of the interpolated
+// table (concave: the smaller end, at the surrounding integers), upper bound of its envelope
+__device__ __forceinline__ void hat_range(double lo, double hi, int size, double &mn, double &mx,
+                                          bool &any_valid, bool &all_valid) {
+    any_valid = hi >= 0.0 && lo <= size - 1.0;
+    all_valid = lo >= 0.0 && hi <= size - 1.0;
+    const double a = fmin(fmax(lo, 0.0), size - 1.0), b = fmin(fmax(hi, 0.0), size - 1.0), c = 0.5 * size;
+    mx = (a <= c && b >= c) ? 0.5 : fmax(0.5 - fabs(a - c) / size, 0.5 - fabs(b - c) / size);
+    const double la = fmin(0.5 - fabs(floor(a) - c) / size, 0.5 - fabs(ceil(a) - c) / size);
+    const double lb = fmin(0.5 - fabs(floor(b) - c) / size, 0.5 - fabs(ceil(b) - c) / size);
+    mn = fmin(la, lb);
+}
+// alpha bounds of one patch on one tile; false if the patch has no valid pixel there
+__device__ __forceinline__ bool alpha_range(const WarpJob &j, Interval rx, Interval ry, Interval rz,
+                                            double &a_min, double &a_max) {
+    Interval p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const Interval x = scaled(j.kr[3 * k], rx), y = scaled(j.kr[3 * k + 1], ry), z = scaled(j.kr[3 * k + 2], rz);
+        p[k] = Interval{x.lo + y.lo + z.lo, x.hi + y.hi + z.hi};
+    }
+    if (p[2].hi <= 0.0) return false;                      // behind the camera
+    if (p[2].lo <= 1e-9) { a_min = 0.0; a_max = 0.25; return true; }   // partly behind: anything goes
+    const double slack = 1.0 / 32 + 1e-3;                  // fixed-point sampling + float32 quotient
+    double u0 = fmin(fmin(p[0].lo / p[2].lo, p[0].lo / p[2].hi), fmin(p[0].hi / p[2].lo, p[0].hi / p[2].hi));
+    double u1 = fmax(fmax(p[0].lo / p[2].lo, p[0].lo / p[2].hi), fmax(p[0].hi / p[2].lo, p[0].hi / p[2].hi));
+    double v0 = fmin(fmin(p[1].lo / p[2].lo, p[1].lo / p[2].hi), fmin(p[1].hi / p[2].lo, p[1].hi / p[2].hi));
+    double v1 = fmax(fmax(p[1].lo / p[2].lo, p[1].lo / p[2].hi), fmax(p[1].hi / p[2].lo, p[1].hi / p[2].hi));
+    double xn, xx, yn, yx;
+    bool x_any, x_all, y_any, y_all;
+    hat_range(u0 + 0.5 * j.w - slack, u1 + 0.5 * j.w + slack, j.w, xn, xx, x_any, x_all);
+    hat_range(v0 + 0.5 * j.h - slack, v1 + 0.5 * j.h + slack, j.h, yn, yx, y_any, y_all);
+    if (!(x_any && y_any)) return false;
+    a_max = xx * yx * (1.0 + 1e-5);
+    a_min = (x_all && y_all) ? xn * yn * (1.0 - 1e-5) : 0.0;
+    return true;
+}
+
+// one thread per tile; jobs = DEVICE copy of the warp jobs (patch id = position)
+__global__ void __launch_bounds__(128)
+warp_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int W, TileMaps m) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int xa = tx * TILE_X, xb = min(xa + TILE_X, W);
+    const int ya = max(m.row0 + ty * TILE_Y, 0), yb = min(m.row0 + ty * TILE_Y + TILE_Y, H);
+    for (int w = 0; w < m.words; ++w) m.cand[(size_t)t * m.words + w] = 0u;
+    if (yb <= ya || n_jobs == 0) return;
+    // the ray tables are shared by all jobs: absolute mosaic column / row = col0 - x0 + x, row0 - y0 + y
+    const WarpJob &j0 = jobs[0];
+    const int dc = j0.col0 - j0.x0, dr = j0.row0 - j0.y0;
+    const Interval rx = table_range(j0.ray_x, xa + dc, xb + dc), rz = table_range(j0.ray_z, xa + dc, xb + dc);
+    const Interval ry = table_range(j0.ray_y, ya + dr, yb + dr);
+    double best_min = 0.0;
+    for (int k = 0; k < n_jobs; ++k) {
+        const WarpJob &j = jobs[k];
+        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.y0 >= yb || j.y0 + j.ph <= ya) continue;
+        double a_min, a_max;
+        if (alpha_range(j, rx, ry, rz, a_min, a_max)) best_min = fmax(best_min, a_min);
+    }
+    for (int k = 0; k < n_jobs; ++k) {
+        const WarpJob &j = jobs[k];
+        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.y0 >= yb || j.y0 + j.ph <= ya) continue;
+        double a_min, a_max;
+        if (alpha_range(j, rx, ry, rz, a_min, a_max) && a_max >= best_min)
+            m.cand[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
+    }
+}
+
+// need(T) = OR of cand over the tiles within reach_x / reach_y of T
+__global__ void __launch_bounds__(256)
+tile_dilate_kernel(TileMaps m) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int x0 = max(tx - m.reach_x, 0), x1 = min(tx + m.reach_x, m.tiles_x - 1);
+    const int y0 = max(ty - m.reach_y, 0), y1 = min(ty + m.reach_y, m.tiles_y - 1);
+    for (int w = 0; w < m.words; ++w) {
+        uint32_t bits = 0u;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) bits |= __ldg(m.cand + ((size_t)y * m.tiles_x + x) * m.words + w);
+        m.need[(size_t)t * m.words + w] = bits;
     }
 }
 
@@ -214,11 +336,36 @@ extern "C" int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_
     return check_launch(where);
 }
 
+extern "C" int p360_warp_gate_build(const p360_warp_job *jobs_dev, int n_jobs, int H, int W,
+                                    const p360_tile_maps *gate_host, void *stream) {
+    using namespace p360;
+    const char *where = "p360_warp_gate_build";
+    P360_REQUIRE(jobs_dev && gate_host && n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0, where);
+    TileMaps m;
+    memcpy(&m, gate_host, sizeof(m));
+    P360_REQUIRE(m.cand && m.need && m.words == (n_jobs + 31) / 32 && m.row0 <= 0 && m.row0 > -TILE_Y, where);
+    P360_REQUIRE(m.tiles_x == (int)cdiv(W, TILE_X) && m.tiles_y == (int)cdiv(H - m.row0, TILE_Y), where);
+    P360_REQUIRE(m.reach_x >= 0 && m.reach_y >= 0, where);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long tiles = (long long)m.tiles_x * m.tiles_y;
+    warp_candidates_kernel<<<cdiv(tiles, 128), 128, 0, s>>>(reinterpret_cast<const WarpJob *>(jobs_dev), n_jobs, H, W, m);
+    if (int e = check_launch(where)) return e;
+    tile_dilate_kernel<<<cdiv(tiles, 256), 256, 0, s>>>(m);
+    return check_launch(where);
+}
+
 extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
-                               uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
+                               uint64_t *owner_keys, uint8_t *covered, int W,
+                               const p360_tile_maps *gate_host, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_batch";
     P360_REQUIRE(jobs_host && n_jobs >= 0, where);
+    TileMaps gate;
+    memset(&gate, 0, sizeof(gate));
+    if (gate_host != nullptr) {
+        memcpy(&gate, gate_host, sizeof(gate));
+        P360_REQUIRE(gate.need && gate.tiles_x > 0 && gate.tiles_y > 0 && gate.words > 0 && owner_keys, where);
+    }
     P360_REQUIRE(owner_keys == nullptr || (covered != nullptr && W > 0), where);
     cudaStream_t s = (cudaStream_t)stream;
     for (int first = 0; first < n_jobs; first += WARP_JOBS_PER_LAUNCH) {
@@ -244,7 +391,9 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
         dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
         auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
-        if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
+        if (gate_host != nullptr && packed) warp_batch_gated_kernel<true><<<grid, block, 0, s>>>(keys, covered, W, gate);
+        else if (gate_host != nullptr) warp_batch_gated_kernel<false><<<grid, block, 0, s>>>(keys, covered, W, gate);
+        else if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
         else if (packed) warp_batch_kernel<true, false><<<grid, block, 0, s>>>(keys, covered, W);
         else if (keys) warp_batch_kernel<false, true><<<grid, block, 0, s>>>(keys, covered, W);
         else warp_batch_kernel<false, false><<<grid, block, 0, s>>>(keys, covered, W);

@@ -216,7 +216,8 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
     else:
         banded = out if _is_pinned_out(out, plan.shape) else None
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded,
+                                             gate=False if crop else None)
         if banded is not None:
             comp.finish_download()
             mosaic = out

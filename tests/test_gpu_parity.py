@@ -351,6 +351,35 @@ def test_row_window_equals_full_mosaic(st, comp, restore_globals):
             assert np.array_equal(strip.cpu().numpy(), full[rows[0]:rows[1]]), (kind, rows)
 
 
+def test_warp_gate_is_exact_and_conservative(comp):
+    """(Host build only until it has run on a B200.)  Gating the warp by the geometric ownership
+    bounds of p360_warp_gate_build must not change a byte — whole mosaics and row windows — and
+    every tile's true owners must be among its candidates."""
+    if comp.device.type == "cuda":
+        pytest.skip("warp gate: verified on the host build of the kernels; GPU run pending")
+    saved = comp.warp_gate
+    try:
+        for name, regs, levels in _seam_map_cases():
+            plan = geo.plan_mosaic(regs, True, 1e9)
+            src = comp.upload(regs)
+            h = plan.shape[0]
+            for rows in (None, (h // 3 + 5, 2 * h // 3 + 1)):
+                comp.warp_gate = False
+                want = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+                comp.warp_gate = True
+                got = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+                assert np.array_equal(got, want), (name, rows)
+                gate, (bits, _) = comp._keep["warp"][4], comp._keep["warp"][5]
+                tiles, words = int(gate["tiles_x"][0]) * int(gate["tiles_y"][0]), int(gate["words"][0])
+                cand = bits.cpu().numpy().view(np.uint32)[:tiles * words].reshape(tiles, words)
+                present = comp._keep["bands"][4][0].cpu().numpy().view(np.uint32)
+                cap = int(comp._keep["bands"][3]["work_cap"][0])
+                present = present[2 + 2 * cap:][:tiles * words].reshape(tiles, words)
+                assert not np.any(present & ~cand), (name, rows)              # conservative
+    finally:
+        comp.warp_gate = saved
+
+
 def test_row_windows_cut_anywhere(comp):
     """Windows whose edges fall anywhere inside the 64 x 32 collapse tiles, on the three-row ring
     of the benchmark layout at 1/8 scale.  (618, 1105) once differed from the whole mosaic by one

@@ -52,6 +52,7 @@ test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
+test_warp_gate_is_exact_and_conservative = gpu.test_warp_gate_is_exact_and_conservative
 test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
 
@@ -162,7 +163,7 @@ def test_random_rigs_against_the_oracle(st, comp, restore_globals):
         "fuzz_host", os.path.join(os.path.dirname(__file__), "..", "tools", "fuzz_host.py"))
     fuzz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fuzz)
-    saved = comp.seam_maps
+    saved = comp.seam_maps, comp.warp_gate
     try:
         for seed in range(900, 916):
             rng = np.random.default_rng(seed)
@@ -173,4 +174,4 @@ def test_random_rigs_against_the_oracle(st, comp, restore_globals):
                 if not case["equalize"]:
                     fuzz.run_blender_api(st, case)
     finally:
-        comp.seam_maps = saved
+        comp.seam_maps, comp.warp_gate = saved

@@ -74,6 +74,22 @@ def main():
         for (name, bw, bh, f), (run, tot) in blur.items():
             print(f"blur {name} blocks of {bw}x{bh} cells, f={f}: {run / 1e6:.1f} of {tot / 1e6:.1f} Mcells "
                   f"({100 * run / max(tot, 1):.1f}%)")
+        # upper bound for gating the warp itself: blocks (64 x 16 px) of a patch whose pixels anybody
+        # reads = tiles where it owns a pixel or is reduced / blended, grown by one tile for the
+        # overhang of reduce blocks and reflections
+        from scipy.ndimage import maximum_filter
+        present = planes[0]
+        k1_run = k1_tot = 0
+        for k, rec in enumerate(table):
+            bit = np.uint32(k & 31)
+            used = (((present[..., k >> 5] | need[..., k >> 5]) >> bit) & 1).astype(bool)
+            used = maximum_filter(used, size=(3, 3), mode="constant")
+            xs = np.arange(-(-int(rec["pw"]) // 64)) * 64 + int(rec["x0"])
+            ys = np.arange(-(-int(rec["ph"]) // 16)) * 16 + int(rec["y0"])
+            hit = blocks_hit(used, xs, ys, 64, 16)
+            k1_run += int(hit.sum())
+            k1_tot += hit.size
+        print(f"warp blocks (64x16 px) whose output is ever read: {k1_run} of {k1_tot} ({100 * k1_run / k1_tot:.1f}%)")
         run_own = run_maps = total = 0
         for k, rec in enumerate(table):
             pad, w4, h4 = int(rec["pad"]), int(rec["w4"]), int(rec["h4"])
