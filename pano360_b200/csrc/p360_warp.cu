@@ -278,6 +278,9 @@ warp_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int 
     for (int k = 0; k < n_jobs; ++k) {
         const WarpJob &j = jobs[k];
         if (j.x0 >= xb || j.x0 + j.pw <= xa || j.y0 >= yb || j.y0 + j.ph <= ya) continue;
+        // a patch only dominates a tile it covers completely: beyond its box it has no pixels,
+        // however large alpha would be there (boxes end where the reference's ranges end)
+        if (j.x0 > xa || j.x0 + j.pw < xb || j.y0 > ya || j.y0 + j.ph < yb) continue;
         double a_min, a_max;
         if (alpha_range(j, rx, ry, rz, a_min, a_max)) best_min = fmax(best_min, a_min);
     }

@@ -175,3 +175,47 @@ def test_random_rigs_against_the_oracle(st, comp, restore_globals):
                     fuzz.run_blender_api(st, case)
     finally:
         comp.seam_maps, comp.warp_gate = saved
+
+
+def test_warp_gate_candidates_at_full_scale(comp):
+    """K0 alone on the benchmark geometry at FULL size (one thread per tile, no pixels needed)
+    against the NumPy statement of the same interval arithmetic (tools/gate_bounds.py), plus the
+    case that once broke it: at the right end of the ring image 24's box ends at column 31640,
+    inside the last tile column, although the image itself continues (it wraps) — it must not
+    out-bid the crop of image 35 that owns the columns beyond."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    import torch
+
+    from pano360_b200 import _lib
+    spec = importlib.util.spec_from_file_location(
+        "gate_bounds", os.path.join(os.path.dirname(__file__), "..", "tools", "gate_bounds.py"))
+    gb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gb)
+    wl = gpu.synth.workload("cfg4")
+    regs = gpu.synth.make_views(wl, only=set())          # the benchmark's cameras, pixel-free stubs
+    plan = gpu.geo.plan_mosaic(regs, True, 1e9)
+    pad = gpu.geo.coarse_band_plan(5)[0]
+    crops, (ray_x, ray_z, ray_y) = comp.plan_crops(regs, plan, split_dilate=2 * (pad + 4))
+    rays = torch.from_numpy(np.concatenate([ray_x, ray_z, ray_y]))
+    base = rays.data_ptr()
+    jobs = np.zeros(len(crops), dtype=_lib.WARP_JOB)
+    for k, (i, x0, y0, x1, y1, k_r) in enumerate(crops):
+        h, w = regs[i].img.shape[:2]
+        jobs[k]["ray_x"], jobs[k]["ray_z"], jobs[k]["ray_y"] = base, base + 8 * len(ray_x), base + 8 * (len(ray_x) + len(ray_z))
+        jobs[k]["kr"], jobs[k]["h"], jobs[k]["w"] = k_r, h, w
+        jobs[k]["pw"], jobs[k]["ph"], jobs[k]["x0"], jobs[k]["y0"] = x1 - x0, y1 - y0, x0, y0
+        jobs[k]["col0"], jobs[k]["row0"], jobs[k]["patch"] = x0, y0, k
+    gate, (bits, _) = comp._warp_gate(jobs, plan.shape, 0, pad)
+    tx, ty, words = int(gate["tiles_x"][0]), int(gate["tiles_y"][0]), int(gate["words"][0])
+    device = bits.numpy().view(np.uint32)[:tx * ty * words].reshape(ty, tx, words)
+    want = gb.candidates(regs, plan, crops=[c[:5] for c in crops])
+    got = np.stack([((device[..., k >> 5] >> np.uint32(k & 31)) & 1).astype(bool) for k in range(len(crops))])
+    assert got.shape == want.shape
+    assert np.mean(got != want) < 1e-4 and not np.any(want & ~got & (want.sum(0) == 1)[None])
+    crop41 = [k for k, c in enumerate(crops) if c[0] == 35 and c[3] == plan.shape[1]][0]
+    assert got[crop41, 198, 494]
+    single = (got.sum(0) == 1).mean()
+    assert single > 0.85, single            # the bound is tight: most tiles have one possible owner

@@ -94,12 +94,20 @@ def alpha_bounds(reg, box, plan, proj=geo.SphProj):
     inside = np.zeros((ty, tx), bool)
     inside[max(y0, 0) // TY:-(-min(y1, height) // TY), max(x0, 0) // TX:-(-min(x1, width) // TX)] = True
     any_valid &= inside
-    return np.where(any_valid & all_valid & inside, a_min, 0.0), np.where(any_valid, a_max, 0.0), any_valid
+    # a patch only dominates a tile it covers completely: beyond its box it has no pixels
+    txa, tya = np.arange(tx) * TX, np.arange(ty) * TY
+    cols = (x0 <= txa) & (x1 >= np.minimum(txa + TX, width))
+    rows = (y0 <= tya) & (y1 >= np.minimum(tya + TY, height))
+    full = rows[:, None] & cols[None, :]
+    return np.where(any_valid & all_valid & full, a_min, 0.0), np.where(any_valid, a_max, 0.0), any_valid
 
 
-def candidates(regs, plan, proj=geo.SphProj):
-    """bool [n, tiles_y, tiles_x]: patch may own a pixel of the tile."""
-    bounds = [alpha_bounds(r, b, plan, proj) for r, b in zip(regs, plan.boxes)]
+def candidates(regs, plan, proj=geo.SphProj, crops=None):
+    """bool [n, tiles_y, tiles_x]: patch may own a pixel of the tile.  ``crops`` = [(image, x0, y0,
+    x1, y1), ...] replaces the boxes of the plan (seam-split pieces, row windows)."""
+    if crops is None:
+        crops = [(i,) + tuple(b) for i, b in enumerate(plan.boxes)]
+    bounds = [alpha_bounds(regs[c[0]], tuple(c[1:5]), plan, proj) for c in crops]
     best_min = np.max([b[0] for b in bounds], axis=0)
     return np.stack([b[2] & (b[1] >= best_min) for b in bounds])
 
