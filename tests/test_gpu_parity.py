@@ -393,7 +393,7 @@ def test_row_windows_cut_anywhere(comp):
     h = plan.shape[0]
     rng = np.random.default_rng(11)
     cuts = [(618, 1105), (284, 618), (0, 33), (h - 31, h)]
-    cuts += [tuple(sorted(rng.choice(h, 2, replace=False))) for _ in range(5)]
+    cuts += [tuple(sorted(rng.choice(h, 2, replace=False))) for _ in range(3)]
     for ya, yb in cuts:
         strip = comp.composite(regs, src, plan, "multiband", 5, rows=(int(ya), int(yb)))[0].cpu().numpy()
         assert np.array_equal(strip, full[ya:yb]), (ya, yb)
