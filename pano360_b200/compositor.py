@@ -38,7 +38,10 @@ import torch
 from . import _lib, geometry as geo
 
 
-SEAM_MAPS_MIN_PIXELS = 1 << 22      # mosaic (or strip) size from which the seam-band maps are used
+# Mosaic (or strip) size from which the seam-band maps are used.  Measured only at cfg4 (279 Mpix:
+# 15.9 -> 13.2 ms); the five extra launches and the persistent grids are not free, so the 1-8 Mpix
+# panoramas of cfg1 / cfg5 (0.2-0.5 ms per composite) keep the dense path until they are measured.
+SEAM_MAPS_MIN_PIXELS = 1 << 24
 
 
 def band_edges(ya, yb, bands):
