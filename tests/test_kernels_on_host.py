@@ -44,6 +44,7 @@ test_foreign_blender_gets_numpy_patches = gpu.test_foreign_blender_gets_numpy_pa
 test_oracle_seeded_cfg1_half = gpu.test_oracle_seeded_cfg1_half
 test_golden_cfg1_full_size = gpu.test_golden_cfg1_full_size
 test_golden_ring12_seam_straddlers = gpu.test_golden_ring12_seam_straddlers
+test_cli_with_reference_style_caches = gpu.test_cli_with_reference_style_caches
 test_two_row_six_band_layout = gpu.test_two_row_six_band_layout
 test_many_small_views = gpu.test_many_small_views
 test_edge_cases = gpu.test_edge_cases
