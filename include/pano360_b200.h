@@ -103,8 +103,8 @@ int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
  * over tiles where its bit is clear.  jobs_dev = DEVICE copy of the job table passed to
  * p360_warp_batch (patch = position); tile grid as for p360_tile_maps_build; only cand, need,
  * tiles_x, tiles_y, words, row0, reach_x, reach_y of the record are used.  The reach must cover
- * everything downstream reads: twice the blur reach of the seam-band maps, one tile for block
- * overhang, and the reflection at patch edges. */
+ * everything downstream reads: twice the blur reach of the seam-band maps plus one tile for
+ * block overhang (reflections at patch edges stay within that). */
 int p360_warp_gate_build(const p360_warp_job *jobs_dev, int n_jobs, int H, int W,
                          const struct p360_tile_maps *gate_host, void *stream);
 

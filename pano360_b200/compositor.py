@@ -338,10 +338,13 @@ class Compositor:
         gate = np.zeros(1, dtype=_lib.TILE_MAPS)
         gate["cand"], gate["need"] = bits.data_ptr(), bits.data_ptr() + 4 * cells * words
         gate["tiles_x"], gate["tiles_y"], gate["words"], gate["row0"] = tiles_x, tiles_y, words, row0
-        # everything downstream reads lies within: twice the blur reach of an owned tile (seam-band
-        # maps), one tile of block overhang, and the reflection at (real or cut) patch edges
+        # everything downstream reads lies within twice the blur reach (in tiles) of a tile the patch
+        # owns a pixel of — a needed coarse block is that close by construction of the seam-band maps,
+        # and what it reads by reflection at a (real or cut) patch edge is the mirror image of a
+        # position outside the box: no farther from the owned tile than that position — plus one
+        # tile for blocks that overhang the tile they were needed for
         rx, ry = -(-pad // 64), -(-pad // 32)
-        gate["reach_x"], gate["reach_y"] = 2 * rx + 1 + -(-2 * pad // 64), 2 * ry + 1 + -(-2 * pad // 32)
+        gate["reach_x"], gate["reach_y"] = 2 * rx + 1, 2 * ry + 1
         dev_jobs = self._table(jobs, "warp_jobs")
         self._traced("K0_warp_gate", 208 * n, "p360_warp_gate_build", _lib.ptr(dev_jobs), n, h, w,
                      gate.ctypes.data, self.stream)
