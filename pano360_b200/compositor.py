@@ -395,7 +395,7 @@ class Compositor:
         else:
             keys, covered = owner_state
             width, per_px = keys.shape[1], 30
-            if gate_pad is not None:
+            if gate_pad is not None and n <= 1024:          # (the tile bitmaps hold 1024 patches)
                 gate, gate_keep = self._warp_gate(jobs, tuple(keys.shape), oy, gate_pad)
         gate_ptr = None if gate is None else gate.ctypes.data
         if src.ready is None:
