@@ -372,22 +372,36 @@ class Compositor:
         offs = np.concatenate([[0], np.cumsum(sizes)])
         rgba_pool = torch.empty(int(offs[-1]) * 4, dtype=torch.float32, device=self.device)
         inv_pool = torch.empty(int(offs[-1]), dtype=torch.uint8, device=self.device)
-        jobs = np.zeros(n, dtype=_lib.WARP_JOB)
-        patches = []
         rgba_base, inv_base = rgba_pool.data_ptr(), inv_pool.data_ptr()
-        for k, (i, x0, ya, x1, yb, k_r) in enumerate(crops):
-            pw, ph = x1 - x0, yb - ya
+        # the job table column by column (per-image constants looked up once per image, not per crop)
+        image = np.array([c[0] for c in crops], dtype=np.int64)
+        box = np.array([c[1:5] for c in crops], dtype=np.int64).reshape(n, 4)          # x0, ya, x1, yb
+        per_image = {}
+        for i in set(image.tolist()):
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
             pix = src.pixels[i]
-            o = int(offs[k])
-            jobs[k] = (pix.data_ptr(), src.luts[i].data_ptr(), hat_y.data_ptr(), hat_x.data_ptr(),
-                       base_x, base_z, base_y, rgba_base + 16 * o, inv_base + o, k_r,
-                       h, w, pix.shape[2], pw, ph, x0 - ox, ya - oy, x0, ya, k,
-                       np.float32(w / 2), np.float32(h / 2), np.float32(w - 1), np.float32(h - 1),
-                       np.float32(1.0) / np.float32(2 * w), np.float32(1.0) / np.float32(2 * h))
-            patches.append(DevicePatch(box=(x0 - ox, ya - oy, x1 - ox, yb - oy), index=i,
-                                       pools=(rgba_pool, inv_pool), offset=o))
+            per_image[i] = (pix.data_ptr(), src.luts[i].data_ptr(), hat_y.data_ptr(), hat_x.data_ptr(), h, w, pix.shape[2])
+        consts = np.array([per_image[i] for i in image.tolist()], dtype=np.uint64).reshape(n, 7)
+        hs, ws = consts[:, 4].astype(np.int64), consts[:, 5].astype(np.int64)
+        jobs = np.zeros(n, dtype=_lib.WARP_JOB)
+        jobs["src"], jobs["lut"], jobs["hat_y"], jobs["hat_x"] = consts[:, 0], consts[:, 1], consts[:, 2], consts[:, 3]
+        jobs["ray_x"], jobs["ray_z"], jobs["ray_y"] = base_x, base_z, base_y
+        jobs["out"] = np.uint64(rgba_base) + np.uint64(16) * offs[:-1].astype(np.uint64)
+        jobs["invalid"] = np.uint64(inv_base) + offs[:-1].astype(np.uint64)
+        jobs["kr"] = np.stack([c[5] for c in crops])
+        jobs["h"], jobs["w"], jobs["c"] = hs, ws, consts[:, 6]
+        jobs["pw"], jobs["ph"] = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
+        jobs["x0"], jobs["y0"], jobs["col0"], jobs["row0"] = box[:, 0] - ox, box[:, 1] - oy, box[:, 0], box[:, 1]
+        jobs["patch"] = np.arange(n)
+        jobs["half_w"], jobs["half_h"] = (ws / 2).astype(np.float32), (hs / 2).astype(np.float32)
+        jobs["max_x"], jobs["max_y"] = (ws - 1).astype(np.float32), (hs - 1).astype(np.float32)
+        jobs["inv_2w"] = np.float32(1.0) / (2 * ws).astype(np.float32)
+        jobs["inv_2h"] = np.float32(1.0) / (2 * hs).astype(np.float32)
+        pools = (rgba_pool, inv_pool)
+        patches = [DevicePatch(box=(int(b[0]) - ox, int(b[1]) - oy, int(b[2]) - ox, int(b[3]) - oy), index=int(i),
+                               pools=pools, offset=int(o))
+                   for i, b, o in zip(image, box, offs[:-1])]
         gate = gate_keep = None
         if owner_state is None:
             keys = covered = None
@@ -463,16 +477,17 @@ class Compositor:
 
     def _band_table(self, patches, pad=0, coarse=False):
         """p360_band_patch records (+ coarse-grid sizes) for a patch list."""
-        table = np.zeros(len(patches), dtype=_lib.BAND_PATCH)
-        for k, p in enumerate(patches):
-            pw, ph, x0, y0 = self._args(p)
-            rec = table[k]
-            rec["rgba"], rec["invalid"] = p.rgba_ptr, p.invalid_ptr
-            rec["x0"], rec["y0"], rec["pw"], rec["ph"] = x0, y0, pw, ph
-            rec["pad"], rec["index"] = pad, k
-            rec["own"] = (2 ** 31 - 1, 2 ** 31 - 1, -2 ** 31, -2 ** 31)      # grown on the device (p360_owned_boxes)
-            if coarse:
-                rec["w4"], rec["h4"] = (pw + 2 * pad + 3) // 4, (ph + 2 * pad + 3) // 4
+        n = len(patches)
+        table = np.zeros(n, dtype=_lib.BAND_PATCH)
+        boxes = np.array([p.box for p in patches], dtype=np.int64).reshape(n, 4)      # column-wise: no per-record Python
+        table["rgba"] = [p.rgba_ptr for p in patches]
+        table["invalid"] = [p.invalid_ptr for p in patches]
+        table["x0"], table["y0"] = boxes[:, 0], boxes[:, 1]
+        table["pw"], table["ph"] = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+        table["pad"], table["index"] = pad, np.arange(n)
+        table["own"] = (2 ** 31 - 1, 2 ** 31 - 1, -2 ** 31, -2 ** 31)                  # grown on the device (p360_owned_boxes)
+        if coarse:
+            table["w4"], table["h4"] = (table["pw"] + 2 * pad + 3) // 4, (table["ph"] + 2 * pad + 3) // 4
         return table
 
     def _tile_maps(self, table, n_blurs, h, w, pad, row_origin):

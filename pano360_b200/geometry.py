@@ -7,6 +7,7 @@ reference does it: projections (stitcher.py:73-104), per-image angular range
 from __future__ import annotations
 
 from dataclasses import dataclass
+from functools import lru_cache
 
 import numpy as np
 
@@ -207,6 +208,7 @@ def band_sigma(level):
     return float(np.sqrt(2 * level + 1.0) * 4)
 
 
+@lru_cache(maxsize=None)
 def coarse_band_plan(n_levels):
     """How the blurs of levels 0 .. L-2 are evaluated on coarse grids
     (csrc/p360_pyramid.cu): level 0 on the f = 2 grid, higher levels on the
@@ -224,6 +226,8 @@ def coarse_band_plan(n_levels):
         taps = gaussian_taps(np.sqrt(sigma * sigma - (f * f - 1) / 12.0 - f * f / 6.0) / f)
         levels.append((shift, taps))
         pad = max(pad, f * ((len(taps) - 1) // 2 + 2))
+    for _, taps in levels:
+        taps.setflags(write=False)          # cached: shared by every caller
     return (pad + 3) // 4 * 4, levels
 
 
