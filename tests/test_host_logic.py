@@ -186,7 +186,8 @@ def test_job_records_match_the_header(tmp_path):
     against include/pano360_b200.h with gcc and compare sizes and offsets."""
     import subprocess
     records = {"p360_warp_job": _lib.WARP_JOB, "p360_blur_job": _lib.BLUR_JOB,
-               "p360_band_patch": _lib.BAND_PATCH, "p360_pair_job": _lib.PAIR_JOB}
+               "p360_band_patch": _lib.BAND_PATCH, "p360_pair_job": _lib.PAIR_JOB,
+               "p360_tile_maps": _lib.TILE_MAPS}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "pano360_b200.h"', "int main(void) {"]
     for cname, dtype in records.items():
         lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
