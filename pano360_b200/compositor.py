@@ -70,14 +70,15 @@ class DevicePatch:
 
     __slots__ = ("box", "index", "rgba_ptr", "invalid_ptr", "_rgba", "_invalid", "_pools", "_offset")
 
-    def __init__(self, rgba=None, invalid=None, box=(0, 0, 0, 0), index=0, pools=None, offset=0):
+    def __init__(self, rgba=None, invalid=None, box=(0, 0, 0, 0), index=0, pools=None, offset=0, bases=None):
         self.box, self.index = tuple(box), index
         self._rgba, self._invalid, self._pools, self._offset = rgba, invalid, pools, offset
         if pools is None:
             self.rgba_ptr, self.invalid_ptr = rgba.data_ptr(), invalid.data_ptr()
         else:
-            self.rgba_ptr = pools[0].data_ptr() + 16 * offset
-            self.invalid_ptr = pools[1].data_ptr() + offset
+            bases = bases or (pools[0].data_ptr(), pools[1].data_ptr())
+            self.rgba_ptr = bases[0] + 16 * offset
+            self.invalid_ptr = bases[1] + offset
 
     @property
     def shape(self):
@@ -307,6 +308,10 @@ class Compositor:
         the same image index.
         Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R)], tables =
         the per-mosaic-column / per-row ray tables of the projection."""
+        key = (id(regions), len(regions), proj, rows, row_align, split_dilate)
+        cached = plan._crops.get(key) if plan._crops is not None else None
+        if cached is not None:                       # same regions, same plan, same window as last time
+            return cached, plan.rays(proj)
         crops = []
         for i, (reg, box) in enumerate(zip(regions, plan.boxes)):
             x0, y0, x1, y1 = box
@@ -319,6 +324,8 @@ class Compositor:
             k_r = np.ascontiguousarray(reg.proj(), dtype=np.float64).ravel()
             for cx0, cx1 in runs:
                 crops.append((i, cx0, ya, cx1, yb, k_r))
+        if plan._crops is not None:
+            plan._crops[key] = crops
         return crops, plan.rays(proj)
 
     def new_owner_state(self, shape):
@@ -398,10 +405,9 @@ class Compositor:
         jobs["max_x"], jobs["max_y"] = (ws - 1).astype(np.float32), (hs - 1).astype(np.float32)
         jobs["inv_2w"] = np.float32(1.0) / (2 * ws).astype(np.float32)
         jobs["inv_2h"] = np.float32(1.0) / (2 * hs).astype(np.float32)
-        pools = (rgba_pool, inv_pool)
-        patches = [DevicePatch(box=(int(b[0]) - ox, int(b[1]) - oy, int(b[2]) - ox, int(b[3]) - oy), index=int(i),
-                               pools=pools, offset=int(o))
-                   for i, b, o in zip(image, box, offs[:-1])]
+        pools, bases = (rgba_pool, inv_pool), (rgba_base, inv_base)
+        patches = [DevicePatch(box=(b[0] - ox, b[1] - oy, b[2] - ox, b[3] - oy), index=i, pools=pools, offset=o, bases=bases)
+                   for i, b, o in zip(image.tolist(), box.tolist(), offs[:-1].tolist())]
         gate = gate_keep = None
         if owner_state is None:
             keys = covered = None

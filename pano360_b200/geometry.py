@@ -96,6 +96,7 @@ class MosaicPlan:
     border_theta: list = None # per image sorted longitudes of the border samples
     _rays: tuple = None       # cached (ray_x[W], ray_z[W], ray_y[H]) of proj2hom
     _runs: dict = None        # cached active_column_runs results
+    _crops: dict = None       # cached Compositor.plan_crops results
 
     def rays(self, proj=SphProj):
         """``proj2hom`` evaluated once per mosaic column / row (it is separable:
@@ -136,7 +137,7 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
             bottom = np.maximum(bottom - PATCH_PAD, np.int32([0, 0]))
             top = np.minimum(top + PATCH_PAD, limit)
         boxes.append((int(bottom[0]), int(bottom[1]), int(top[0]), int(top[1])))
-    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples], None, {})
+    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples], None, {}, {})
 
 
 def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
