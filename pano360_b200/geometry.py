@@ -65,7 +65,7 @@ def image_range_border(shape, hom, proj=SphProj):
     ring[3 * n:4 * n, 0], ring[3 * n:4 * n, 1] = along_x, h
     ring -= np.array([w / 2, h / 2, 0])
     ang = proj.hom2proj(hom.dot(ring.T).T)
-    return np.min(ang, axis=0), np.max(ang, axis=0), np.sort(ang[:, 0])
+    return np.min(ang, axis=0), np.max(ang, axis=0), np.sort(ang[:, 0]), ang[:, 0].reshape(4, n).copy()
 
 
 def image_range_corners(shape, hom, proj=SphProj):
@@ -97,6 +97,7 @@ class MosaicPlan:
     _rays: tuple = None       # cached (ray_x[W], ray_z[W], ray_y[H]) of proj2hom
     _runs: dict = None        # cached active_column_runs results
     _crops: dict = None       # cached Compositor.plan_crops results
+    border_sides: list = None # per image 4 x BORDER_SAMPLES longitudes in order along each image side
 
     def rays(self, proj=SphProj):
         """``proj2hom`` evaluated once per mosaic column / row (it is separable:
@@ -137,7 +138,8 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
             bottom = np.maximum(bottom - PATCH_PAD, np.int32([0, 0]))
             top = np.minimum(top + PATCH_PAD, limit)
         boxes.append((int(bottom[0]), int(bottom[1]), int(top[0]), int(top[1])))
-    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples], None, {}, {})
+    return MosaicPlan(shape, resolution, lo, boxes, ranges, [s[2] for s in samples], None, {}, {},
+                      [s[3] for s in samples])
 
 
 def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
@@ -168,8 +170,19 @@ def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     left_end, right_start = min(left_end, x1), max(right_start, x0)
     # keep coarse grids anchored at the second run in phase with those of the whole box
     right_start = x0 + (right_start - x0) // align * align
+    # The gap between two sorted samples is empty only if the border itself does not cross it
+    # between samples: a footprint that contains (or passes close to) a pole of the projection
+    # covers a wide range of longitudes with a few border samples — neighbours along a side then
+    # lie on both sides of the gap.  (Across the +-pi seam they differ by more than pi: the short
+    # arc between them runs through the seam, not through the gap.)
+    crossed = False
+    if plan.border_sides is not None:
+        side = plan.border_sides[index]
+        a, b = side[:, :-1], side[:, 1:]
+        lo_s, hi_s = np.minimum(a, b), np.maximum(a, b)
+        crossed = bool(np.any((hi_s - lo_s <= np.pi) & (lo_s <= theta[k]) & (hi_s >= theta[k + 1])))
     # only worth (and only safe) when the gap dwarfs both the sampling step and the dilation
-    if right_start - left_end < max(256, 4 * dilate) or gaps[k] < 20 * np.median(gaps):
+    if crossed or right_start - left_end < max(256, 4 * dilate) or gaps[k] < 20 * np.median(gaps):
         runs = [(x0, x1)]
     else:
         runs = [(a, b) for a, b in [(x0, left_end), (right_start, x1)] if b > a]

@@ -380,6 +380,24 @@ def test_warp_gate_is_exact_and_conservative(comp):
         comp.warp_gate = saved
 
 
+def test_view_over_the_pole(st, restore_globals):
+    """A ring of views plus one looking (almost) straight up: its footprint contains the pole of
+    the projection, its box spans the whole mosaic width and nothing of it may be dropped."""
+    from dataclasses import replace
+    wl = replace(synth.workload("cfg1", scale=4.0), yaws=(-1.0, 0.0, 1.0, 2.0, 3.0, -2.0, 0.3),
+                 pitches=(0.0,) * 6 + (1.25,), focal=110.0)
+    regs = synth.make_views(wl, noise=5.0)
+    for name, proj in (("spherical", st.SphProj), ("cylindrical", st.CylProj)):
+        st.SphProj = proj
+        for blend in ("none", "linear", "multiband"):
+            got = st.stitch(regs, blender=st.BLENDERS[blend])
+            want = rs.stitch(regs, blend, False, 5, 1400, proj=name)
+            if blend == "multiband":
+                assert_mosaic_close(got, want, what=f"{name}/{blend}")
+            else:
+                assert np.array_equal(got, want), (name, blend)
+
+
 def test_row_windows_cut_anywhere(comp):
     """Windows whose edges fall anywhere inside the 64 x 32 collapse tiles, on the three-row ring
     of the benchmark layout at 1/8 scale.  (618, 1105) once differed from the whole mosaic by one

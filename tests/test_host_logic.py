@@ -250,3 +250,22 @@ def test_missing_gpu_fails_loudly():
     regs = synth.make_views(synth.workload("cfg1", scale=8.0))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         stitcher.stitch(regs, stitcher.multiband_blend)
+
+
+def test_no_seam_split_when_the_border_crosses_the_gap():
+    """tools/fuzz_host.py seed 2900468: 70 small views, cylindrical; view 62 looks so steeply up
+    that its footprint winds around the pole.  Its border samples leave a 384-column gap in
+    longitude although the footprint covers those columns (330 765 valid pixels): neighbouring
+    samples along one side lie on both sides of the gap, so the box must stay whole — while the
+    seam-straddling views of the same rig are still split."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_host", os.path.join(ROOT, "tools", "fuzz_host.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    case = fuzz.random_case(np.random.default_rng(2900468))
+    regs = case["regs"]
+    assert case["cylindrical"] and len(regs) == 70
+    plan = geo.plan_mosaic(regs, False, 1e9, geo.CylProj)
+    runs = [geo.active_column_runs(i, b, plan, dilate=0) for i, b in enumerate(plan.boxes)]
+    assert runs[62] == [(plan.boxes[62][0], plan.boxes[62][2])]
+    assert sum(len(r) == 2 for r in runs) >= 5

@@ -50,6 +50,7 @@ test_many_small_views = gpu.test_many_small_views
 test_edge_cases = gpu.test_edge_cases
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
+test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
