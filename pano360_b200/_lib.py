@@ -73,7 +73,8 @@ _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
 _LAUNCHES = {"p360_pack_rgbxa": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
-             "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,   # +1 scan kernel per pass with maps "p360_owned_boxes": 1,
+             "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,
+             "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_warp_gate_build": 2,
              "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
              "p360_pair_overlap_stats": 2, "p360_cover_update": 1}

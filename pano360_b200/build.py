@@ -24,8 +24,14 @@ def nvcc():
 
 
 def stale():
+    """Missing, or older than a source.  A library that exists where nvcc does not (a snapshot
+    copied to a box without the toolkit) is never declared stale: it cannot be rebuilt there and
+    copying does not preserve mtimes reliably."""
     if not os.path.exists(LIB):
         return True
+    if not os.path.exists(nvcc()) and not any(
+            os.access(os.path.join(d, "nvcc"), os.X_OK) for d in os.environ.get("PATH", "").split(os.pathsep) if d):
+        return False
     built = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "pano360_b200.h"))
@@ -38,10 +44,21 @@ def build(force=False, verbose=False):
     cmd = [nvcc()] + NVCC_FLAGS
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    # One builder at a time (N ranks of a torchrun may all find the library stale), and the
+    # library appears atomically: built next to it, then renamed over it.
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not stale():          # somebody else built it while we waited
+            return LIB
+        tmp = f"{LIB}.{os.getpid()}.tmp"
+        full = cmd + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+        res = subprocess.run(full, capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError("nvcc failed:\n" + " ".join(full) + "\n" + res.stdout + res.stderr)
+        os.replace(tmp, LIB)
     if verbose:
         print(res.stderr)
     return LIB

@@ -140,11 +140,12 @@ class Compositor:
         # extra launches to pay (B200, cfg4: 15.9 -> 13.2 ms), P360_SEAM_MAPS=0/1 forces it.
         self.seam_maps = {"0": False, "1": True}.get(os.environ.get("P360_SEAM_MAPS", ""))
         # horizontal blur of the block lists in 64-cell instead of 256-cell segments (4 rows per
-        # warp): halves the cells run at cfg4 (tools/seam_map_stats.py); to be timed on the B200
-        self.blur_h_rows = 4 if os.environ.get("P360_BLUR_H_ROWS", "1") == "4" else 1
+        # warp): halves the cells run at cfg4 (tools/seam_map_stats.py).  B200, cfg4: K3 2.56 ->
+        # 1.53 ms, byte-identical (profiles/r02_probe_switches.log); P360_BLUR_H_ROWS=1 for the old lists
+        self.blur_h_rows = 1 if os.environ.get("P360_BLUR_H_ROWS", "4") == "1" else 4
         # gate the warp by geometric ownership bounds (p360_warp_gate_build): at cfg4 only 60 % of
-        # the warped blocks are ever read.  Byte-identical on the host build; to be timed on the B200
-        self.warp_gate = os.environ.get("P360_WARP_GATE", "0") == "1"
+        # the warped blocks are ever read.  B200, cfg4: K1 5.75 -> 4.21 ms + 0.14 ms K0, byte-identical
+        self.warp_gate = os.environ.get("P360_WARP_GATE", "1") == "1"
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -587,15 +588,17 @@ class Compositor:
         h, w = mosaic.shape[:2]
         ya, yb = (0, h) if rows is None else rows
         if out_host is None and on_band is None:
-            self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, *tail, self.stream)
+            if fn is not None:
+                self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, *tail, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
         main, side = torch.cuda.current_stream(self.device), self.download_stream()
         for y0, y1 in band_edges(ya, yb, bands):
             if y1 <= y0:
                 continue
-            self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1,
-                         row_origin, w, *tail, self.stream)
+            if fn is not None:             # (None: the rows are already final, e.g. a blank window)
+                self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1,
+                             row_origin, w, *tail, self.stream)
             if on_band is not None:
                 on_band(y0, y1)
             if host is not None:
@@ -607,6 +610,14 @@ class Compositor:
         if host is not None:
             self._download = torch.cuda.Event()
             self._download.record(side)
+
+    def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin):
+        """A mosaic (or row window) no image touches: zeros — through the same banded path as a
+        collapse, so that ``out_host`` receives its rows and ``on_band`` fires for every band
+        (a strip that falls into a gap between images must still send its bands)."""
+        mosaic.zero_()
+        self._collapse("blank", 0, None, (), mosaic, out_host, rows, on_band, bands, row_origin)
+        return mosaic
 
     def release(self):
         """Drop the references that keep the last composite's pools alive (patch
@@ -631,8 +642,8 @@ class Compositor:
             raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        if not patches:
-            return mosaic.zero_()
+        if not patches:      # nothing lands here: still produce (and download / hand on) every band
+            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
         keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
         pad, plan = geo.coarse_band_plan(n_levels)
         table = self._band_table(patches, pad, coarse=True)
@@ -682,7 +693,7 @@ class Compositor:
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
-            return mosaic.zero_()
+            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
         table = self._band_table(patches)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())

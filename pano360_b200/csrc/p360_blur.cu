@@ -259,12 +259,20 @@ inline void fill_taps(Taps &t, const float *taps_host, int ksize) {
     t.ksize = ksize;
 }
 
-// dynamic shared memory opt-in above 48 KB, remembered per kernel
+// dynamic shared memory opt-in above 48 KB, remembered per kernel AND per device (the attribute
+// is per device; one process may drive several GPUs)
+struct SmemLimit {
+    size_t bytes[64];
+    SmemLimit() { for (size_t &b : bytes) b = 48 * 1024; }
+};
 template <class K>
-int ensure_smem(K kernel, size_t bytes, size_t &limit, const char *where) {
-    if (bytes > limit) {
+int ensure_smem(K kernel, size_t bytes, SmemLimit &limit, const char *where) {
+    int dev = 0;
+    P360_CUDA(cudaGetDevice(&dev), where);
+    size_t &have = limit.bytes[dev & 63];
+    if (bytes > have) {
         P360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), where);
-        limit = bytes;
+        have = bytes;
     }
     return 0;
 }
@@ -290,7 +298,7 @@ extern "C" int p360_gauss_blur(const float *in_rgba, float *out_rgba, float *tmp
     const int pitch = h_phys(H_SEG + ksize - 1) + 1;
     const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
     const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);
-    static size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
+    static SmemLimit h_limit, v_limit;
     if (int e = ensure_smem(blur_h_kernel, smem_h, h_limit, where)) return e;
     if (int e = ensure_smem(blur_v_kernel, smem_v, v_limit, where)) return e;
     blur_h_kernel<<<cdiv(pw, H_SEG) * cdiv(ph, H_WARPS), 32 * H_WARPS, smem_h, s>>>(in, tmp, pw, ph, pitch, t);
@@ -335,7 +343,7 @@ extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int 
     const int pitch = h_phys(H_SEG + ksize - 1) + 1;
     const size_t smem_h = sizeof(float4) * pitch * H_WARPS;
     const size_t smem_v = sizeof(float4) * 32 * (V_ROWS + ksize - 1);
-    static size_t h_limit = 48 * 1024, v_limit = 48 * 1024;
+    static SmemLimit h_limit, v_limit;
     if (int e = ensure_smem(blur_h_batch_kernel, smem_h, h_limit, where)) return e;
     if (int e = ensure_smem(blur_v_batch_kernel, smem_v, v_limit, where)) return e;
     const unsigned h_blocks = cdiv(max_w, H_SEG) * cdiv(max_h, H_WARPS);
@@ -352,7 +360,7 @@ extern "C" int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int 
     const int seg = narrow ? H_SEG / 4 : H_SEG, brows = narrow ? H_WARPS * 4 : H_WARPS;
     const int pitch_l = h_phys(seg + ksize - 1) + 1;
     const size_t smem_l = sizeof(float4) * pitch_l * (narrow ? 4 : 1) * H_WARPS;
-    static size_t hl_limit = 48 * 1024, hn_limit = 48 * 1024, vl_limit = 48 * 1024;
+    static SmemLimit hl_limit, hn_limit, vl_limit;
     if (int e = narrow ? ensure_smem(blur_h_list_kernel<4>, smem_l, hn_limit, where)
                        : ensure_smem(blur_h_list_kernel<1>, smem_l, hl_limit, where)) return e;
     if (int e = ensure_smem(blur_v_list_kernel, smem_v, vl_limit, where)) return e;

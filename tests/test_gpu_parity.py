@@ -351,12 +351,37 @@ def test_row_window_equals_full_mosaic(st, comp, restore_globals):
             assert np.array_equal(strip.cpu().numpy(), full[rows[0]:rows[1]]), (kind, rows)
 
 
+def test_window_without_any_image(comp):
+    """A row window (a strip of the multi-GPU path) that falls into a gap between images still
+    produces its rows: zeros in the device strip, in ``out_host`` and through ``on_band``."""
+    import torch
+    from dataclasses import replace
+    wl = replace(synth.workload("cfg1", scale=8.0), yaws=(0.0, 0.0), pitches=(-1.0, 1.0), focal=220.0)
+    regs = synth.make_views(wl, noise=5.0)
+    for kind in ("multiband", "linear", "none"):
+        plan = geo.plan_mosaic(regs, kind == "multiband", 1e9)
+        h = plan.shape[0]
+        gap = (plan.boxes[0][3] + 100, plan.boxes[1][1] - 100) if plan.boxes[0][1] < plan.boxes[1][1] else \
+              (plan.boxes[1][3] + 100, plan.boxes[0][1] - 100)
+        assert 0 < gap[0] < gap[1] < h, (plan.boxes, h)
+        src = comp.upload(regs)
+        host = torch.full(plan.shape + (3,), 7, dtype=torch.uint8)
+        if comp.device.type == "cuda":
+            host = host.pin_memory()
+        seen = []
+        strip, _ = comp.composite(regs, src, plan, kind, 5, rows=gap, out_host=host.numpy(),
+                                  on_band=lambda part, y0, y1: seen.append((y0, y1, int(part.sum()))), bands=3)
+        comp.finish_download()
+        assert strip.shape[0] == gap[1] - gap[0] and int(strip.sum()) == 0
+        assert not host[gap[0]:gap[1]].any() and bool((host[:gap[0]] == 7).all()) and bool((host[gap[1]:] == 7).all())
+        assert [s[:2] for s in seen] == [tuple(e) for e in __import__("pano360_b200.compositor", fromlist=["x"]).band_edges(gap[0], gap[1], 3)]
+        assert all(s[2] == 0 for s in seen)
+
+
 def test_warp_gate_is_exact_and_conservative(comp):
-    """(Host build only until it has run on a B200.)  Gating the warp by the geometric ownership
-    bounds of p360_warp_gate_build must not change a byte — whole mosaics and row windows — and
-    every tile's true owners must be among its candidates."""
-    if comp.device.type == "cuda":
-        pytest.skip("warp gate: verified on the host build of the kernels; GPU run pending")
+    """Gating the warp by the geometric ownership bounds of p360_warp_gate_build must not change a
+    byte — whole mosaics and row windows — and every tile's true owners must be among its
+    candidates."""
     saved = comp.warp_gate
     try:
         for name, regs, levels in _seam_map_cases():
@@ -481,9 +506,8 @@ def test_seam_band_maps_are_exact(comp):
                 comp.seam_maps = False
                 want = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
                 comp.seam_maps = True
-                # horizontal blur lists in 256-cell segments, and (host build only until it has run on
-                # a B200) in 64-cell ones
-                for h_rows in ((1,) if comp.device.type == "cuda" else (1, 4)):
+                # horizontal blur lists in 256-cell segments and in 64-cell ones
+                for h_rows in (1, 4):
                     comp.blur_h_rows = h_rows
                     got = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
                     assert np.array_equal(got, want), (name, rows, h_rows)

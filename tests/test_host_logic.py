@@ -269,3 +269,14 @@ def test_no_seam_split_when_the_border_crosses_the_gap():
     runs = [geo.active_column_runs(i, b, plan, dilate=0) for i, b in enumerate(plan.boxes)]
     assert runs[62] == [(plan.boxes[62][0], plan.boxes[62][2])]
     assert sum(len(r) == 2 for r in runs) >= 5
+
+
+def test_every_launching_entry_point_is_counted():
+    """bench.py's gpu_launches is summed from _lib._LAUNCHES: an entry point that launches kernels
+    and is missing there silently undercounts (a trailing comment once swallowed one)."""
+    from pano360_b200 import _lib
+    no_kernel = {"p360_version", "p360_last_error", "p360_device_info", "p360_pyramid_dims",
+                 "p360_pair_stats_blocks", "p360_blur_set_taps"}
+    missing = set(_lib.SIGNATURES) - no_kernel - set(_lib._LAUNCHES)
+    assert not missing, missing
+    assert all(v >= 1 for v in _lib._LAUNCHES.values())

@@ -55,6 +55,7 @@ test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_e
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
 test_warp_gate_is_exact_and_conservative = gpu.test_warp_gate_is_exact_and_conservative
+test_window_without_any_image = gpu.test_window_without_any_image
 test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
 
