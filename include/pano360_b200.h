@@ -84,29 +84,51 @@ typedef struct p360_warp_job {
     float half_w, half_h;         /* float32(w / 2.0), float32(h / 2.0)                   */
     float max_x, max_y;           /* float32(w - 1), float32(h - 1)                       */
     float inv_2w, inv_2h;         /* 1 / (2 w), 1 / (2 h)                                 */
+    int32_t ty0, ty1;             /* rows of the image's TRUE box in window coordinates (y0 / ph may */
+                                  /* be cropped to a row window; the seam plan must not depend on it) */
 } p360_warp_job;
 
 int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
                     int h, int w, uint8_t *dst_rgbxa, void *stream);
 struct p360_tile_maps;
+struct p360_band_patch;
+/* gate_host (optional): a seam plan; blocks of a patch over tiles without its `wneed` bit are skipped. */
 int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
                     uint64_t *owner_keys, uint8_t *covered, int W,
                     const struct p360_tile_maps *gate_host, void *stream);
 
-/* Optional gate for p360_warp_batch (multiband with seam-band maps only): most of what a warp
- * produces is never read — a patch's pixels matter where it owns them and within the blur reach
- * of a seam it takes part in.  Ownership is arg-max of alpha = hat_y(v) * hat_x(u), a function of
- * the geometry alone: p360_warp_gate_build bounds alpha of every patch on every 64 x 32 tile by
- * interval arithmetic (ray tables -> K R ray -> source position -> alpha), keeps as candidates
- * the patches no other patch dominates on the whole tile (gate->cand), and dilates them by
- * gate->reach_x / reach_y tiles (gate->need): p360_warp_batch then skips the blocks of a patch
- * over tiles where its bit is clear.  jobs_dev = DEVICE copy of the job table passed to
- * p360_warp_batch (patch = position); tile grid as for p360_tile_maps_build; only cand, need,
- * tiles_x, tiles_y, words, row0, reach_x, reach_y of the record are used.  The reach must cover
- * everything downstream reads: twice the blur reach of the seam-band maps plus one tile for
- * block overhang (reflections at patch edges stay within that). */
-int p360_warp_gate_build(const p360_warp_job *jobs_dev, int n_jobs, int H, int W,
-                         const struct p360_tile_maps *gate_host, void *stream);
+/* ---- K0 + K1d: the seam plan and the direct tiles (multiband, >= 2 bands) -----------------
+ * Ownership (stitcher.py:196-204) is arg-max of alpha = hat_y(v) * hat_x(u): a function of the
+ * geometry alone.  p360_seam_plan_build bounds alpha of every patch on every 64 x 32 mosaic tile
+ * by interval arithmetic (ray tables -> K R ray -> source position -> alpha) and fills the tile
+ * bitmaps of p360_tile_maps BEFORE anything is sampled:
+ *   present  patches no other patch dominates on the whole tile: every true owner is among them
+ *            (also grows p360_band_patch.own of patches_dev, may be NULL)
+ *   cand     `present` within reach_x / reach_y tiles, restricted to patches whose box meets the
+ *            tile: the only patches with non-zero blend weights there.  multi = more than one.
+ *            A tile with ONE candidate is that patch's warped pixels wherever it is valid (the
+ *            sum over the bands of stitcher.py:224-238 telescopes) and zero elsewhere
+ *   need     candidates of the multi tiles within reach: where coarse levels are consumed
+ *   wneed    candidates of the multi tiles within reach + 1 tile, plus `present` of every tile
+ *            that close to a multi tile: where float pixels and owner keys are consumed
+ * Tiles are evaluated on their full extent against the TRUE boxes (ty0 / ty1) in absolute rows
+ * (buffer row 0 = mosaic row abs_row0, mosaic height mosaic_h), so that a row window plans every
+ * tile that lies with its reach inside the window exactly like the whole mosaic does.
+ * jobs_dev = DEVICE copy of the job table (patch = position), at most 1024 jobs.
+ *
+ * p360_warp_direct then writes every non-multi tile of rows [y_begin, y_end) of the uint8 mosaic
+ * straight from the source images (one block per tile, rows staged in shared memory and stored
+ * as aligned 128-bit words), clears owner_keys / covered on the tiles with a `wneed` bit (neither
+ * buffer needs initialising) and, if want_covered, records the valid mask of the tiles it writes
+ * (stitcher.py:266-271).  p360_warp_batch with the same record as gate warps float RGBA only
+ * where `wneed` asks for it, and p360_multiband_collapse writes only the multi tiles.
+ * packed: every job's src is in the c = 8 layout. */
+int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
+                         int H, int W, int abs_row0, int mosaic_h,
+                         const struct p360_tile_maps *maps_host, void *stream);
+int p360_warp_direct(const p360_warp_job *jobs_dev, int n_jobs, int packed, uint64_t *owner_keys,
+                     uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
+                     int want_covered, const struct p360_tile_maps *maps_host, void *stream);
 
 /* ---- K2: owner map for externally supplied patches (stitcher.py:196-208) ---
  * p360_owner_update: the same competition for one already-warped patch (the
@@ -209,6 +231,8 @@ typedef struct p360_tile_maps {
     uint32_t *work;                           /* DEVICE scratch, 2 * work_cap uint32: the list  */
     int32_t *work_count;                      /* of blocks a reduce / blur pass has to run (+ its */
                                               /* length); work_cap >= blocks of the largest grid */
+    uint32_t *wneed;                          /* seam plan only (else NULL): where float pixels and  */
+                                              /* owner keys are wanted, see p360_seam_plan_build     */
     int32_t tiles_x, tiles_y, words;
     int32_t row0;
     int32_t reach_x, reach_y;                 /* ceil(pad / 64), ceil(pad / 32)          */

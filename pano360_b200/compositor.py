@@ -143,9 +143,12 @@ class Compositor:
         # warp): halves the cells run at cfg4 (tools/seam_map_stats.py).  B200, cfg4: K3 2.56 ->
         # 1.53 ms, byte-identical (profiles/r02_probe_switches.log); P360_BLUR_H_ROWS=1 for the old lists
         self.blur_h_rows = 1 if os.environ.get("P360_BLUR_H_ROWS", "4") == "1" else 4
-        # gate the warp by geometric ownership bounds (p360_warp_gate_build): at cfg4 only 60 % of
-        # the warped blocks are ever read.  B200, cfg4: K1 5.75 -> 4.21 ms + 0.14 ms K0, byte-identical
-        self.warp_gate = os.environ.get("P360_WARP_GATE", "1") == "1"
+        # seam plan (p360_seam_plan_build): ownership is geometric, so before anything is sampled the
+        # mosaic tiles are split into solo tiles — written straight from the sources as uint8
+        # (p360_warp_direct) — and the seam zone, the only place where float patches, owner keys and
+        # coarse levels exist.  P360_DIRECT=0: every patch warped to float, maps from the owner keys.
+        self.direct = os.environ.get("P360_DIRECT", "1") == "1"
+        self.last_covered = None
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -307,7 +310,7 @@ class Compositor:
         all-invalid middle of seam-straddling boxes is dropped
         (``geometry.active_column_runs``): such an image yields two crops with
         the same image index.
-        Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R)], tables =
+        Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R, true y0, true y1)], tables =
         the per-mosaic-column / per-row ray tables of the projection."""
         key = (id(regions), len(regions), proj, rows, row_align, split_dilate)
         cached = plan._crops.get(key) if plan._crops is not None else None
@@ -324,7 +327,7 @@ class Compositor:
                 geo.active_column_runs(i, box, plan, dilate=split_dilate)
             k_r = np.ascontiguousarray(reg.proj(), dtype=np.float64).ravel()
             for cx0, cx1 in runs:
-                crops.append((i, cx0, ya, cx1, yb, k_r))
+                crops.append((i, cx0, ya, cx1, yb, k_r, y0, y1))
         if plan._crops is not None:
             plan._crops[key] = crops
         return crops, plan.rays(proj)
@@ -335,36 +338,9 @@ class Compositor:
         return (torch.zeros((h, w), dtype=torch.int64, device=self.device),
                 torch.zeros((h, w), dtype=torch.uint8, device=self.device))
 
-    def _warp_gate(self, jobs, shape, row_origin, pad):
-        """Run bitmap for the warp: which (patch, tile) pairs can produce anything that is read."""
-        h, w = shape
-        n = len(jobs)
-        row0 = -(row_origin % 32)
-        tiles_x, tiles_y, words = -(-w // 64), -(-(h - row0) // 32), -(-n // 32)
-        cells = tiles_x * tiles_y
-        bits = torch.empty(2 * cells * words, dtype=torch.int32, device=self.device)
-        gate = np.zeros(1, dtype=_lib.TILE_MAPS)
-        gate["cand"], gate["need"] = bits.data_ptr(), bits.data_ptr() + 4 * cells * words
-        gate["tiles_x"], gate["tiles_y"], gate["words"], gate["row0"] = tiles_x, tiles_y, words, row0
-        # everything downstream reads lies within twice the blur reach (in tiles) of a tile the patch
-        # owns a pixel of — a needed coarse block is that close by construction of the seam-band maps,
-        # and what it reads by reflection at a (real or cut) patch edge is the mirror image of a
-        # position outside the box: no farther from the owned tile than that position — plus one
-        # tile for blocks that overhang the tile they were needed for
-        rx, ry = -(-pad // 64), -(-pad // 32)
-        gate["reach_x"], gate["reach_y"] = 2 * rx + 1, 2 * ry + 1
-        dev_jobs = self._table(jobs, "warp_jobs")
-        self._traced("K0_warp_gate", 208 * n, "p360_warp_gate_build", _lib.ptr(dev_jobs), n, h, w,
-                     gate.ctypes.data, self.stream)
-        return gate, (bits, dev_jobs)
-
-    def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None, gate_pad=None):
-        """K1 over every crop in ONE launch.  Boxes of the returned patches
-        are relative to ``origin`` (x, y).  With ``owner_state = (keys,
-        covered)`` (mosaic-sized, zeroed) the owner-map competition is fused
-        into the warp; patch k of the returned list is known as k there."""
-        if not crops:
-            return []
+    def _warp_jobs(self, src, crops, tables, origin=(0, 0)):
+        """Host side of K1: the job table (one p360_warp_job per crop), the patch pools and the
+        patches.  Returns (jobs, patches, keep) — ``keep`` holds what the launches reference."""
         ray_x, ray_z, ray_y = tables
         cached = self._keep.get("rays")
         if cached is not None and cached[0] is ray_x:          # same plan as last time: tables already on the device
@@ -384,6 +360,7 @@ class Compositor:
         # the job table column by column (per-image constants looked up once per image, not per crop)
         image = np.array([c[0] for c in crops], dtype=np.int64)
         box = np.array([c[1:5] for c in crops], dtype=np.int64).reshape(n, 4)          # x0, ya, x1, yb
+        true_rows = np.array([c[6:8] for c in crops], dtype=np.int64).reshape(n, 2)
         per_image = {}
         for i in set(image.tolist()):
             h, w = src.shapes[i]
@@ -401,6 +378,7 @@ class Compositor:
         jobs["h"], jobs["w"], jobs["c"] = hs, ws, consts[:, 6]
         jobs["pw"], jobs["ph"] = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
         jobs["x0"], jobs["y0"], jobs["col0"], jobs["row0"] = box[:, 0] - ox, box[:, 1] - oy, box[:, 0], box[:, 1]
+        jobs["ty0"], jobs["ty1"] = true_rows[:, 0] - oy, true_rows[:, 1] - oy
         jobs["patch"] = np.arange(n)
         jobs["half_w"], jobs["half_h"] = (ws / 2).astype(np.float32), (hs / 2).astype(np.float32)
         jobs["max_x"], jobs["max_y"] = (ws - 1).astype(np.float32), (hs - 1).astype(np.float32)
@@ -409,34 +387,46 @@ class Compositor:
         pools, bases = (rgba_pool, inv_pool), (rgba_base, inv_base)
         patches = [DevicePatch(box=(b[0] - ox, b[1] - oy, b[2] - ox, b[3] - oy), index=i, pools=pools, offset=o, bases=bases)
                    for i, b, o in zip(image.tolist(), box.tolist(), offs[:-1].tolist())]
-        gate = gate_keep = None
+        return jobs, patches, (dev_rays, rgba_pool, inv_pool, int(offs[-1]))
+
+    def _launch_warp(self, src, crops, jobs, keys, covered, width, gate_ptr, per_px, pixels):
+        """K1 over the job table: one launch, or — while uploads are still in flight — one per
+        group of images as they arrive."""
+        n = len(jobs)
+        if src.ready is None:
+            self._traced("K1_warp", per_px * pixels, "p360_warp_batch", jobs.ctypes.data, n,
+                         _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
+            return
+        main = torch.cuda.current_stream(self.device)
+        group = max(1, -(-len(src.ready) // 8))
+        a = 0
+        while a < n:
+            last = (crops[a][0] // group + 1) * group - 1          # last image of this group
+            b = a
+            while b < n and crops[b][0] <= last:
+                b += 1
+            for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
+                main.wait_event(src.ready[i])
+            _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
+                      _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
+            a = b
+
+    def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
+        """K1 over every crop in ONE launch.  Boxes of the returned patches
+        are relative to ``origin`` (x, y).  With ``owner_state = (keys,
+        covered)`` (mosaic-sized, zeroed) the owner-map competition is fused
+        into the warp; patch k of the returned list is known as k there."""
+        if not crops:
+            return []
+        jobs, patches, keep = self._warp_jobs(src, crops, tables, origin)
         if owner_state is None:
             keys = covered = None
             width, per_px = 0, 17
         else:
             keys, covered = owner_state
             width, per_px = keys.shape[1], 30
-            if gate_pad is not None and n <= 1024:          # (the tile bitmaps hold 1024 patches)
-                gate, gate_keep = self._warp_gate(jobs, tuple(keys.shape), oy, gate_pad)
-        gate_ptr = None if gate is None else gate.ctypes.data
-        if src.ready is None:
-            self._traced("K1_warp", per_px * int(offs[-1]), "p360_warp_batch", jobs.ctypes.data, n,
-                         _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
-        else:                  # uploads in flight: warp image groups as they arrive
-            main = torch.cuda.current_stream(self.device)
-            group = max(1, -(-len(src.ready) // 8))
-            a = 0
-            while a < n:
-                last = (crops[a][0] // group + 1) * group - 1          # last image of this group
-                b = a
-                while b < n and crops[b][0] <= last:
-                    b += 1
-                for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
-                    main.wait_event(src.ready[i])
-                _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
-                          _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
-                a = b
-        self._keep["warp"] = (dev_rays, rgba_pool, inv_pool, jobs, gate, gate_keep)
+        self._launch_warp(src, crops, jobs, keys, covered, width, None, per_px, keep[3])
+        self._keep["warp"] = keep[:3] + (jobs,)
         return patches
 
     def warp(self, regions, src, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
@@ -497,7 +487,7 @@ class Compositor:
             table["w4"], table["h4"] = (table["pw"] + 2 * pad + 3) // 4, (table["ph"] + 2 * pad + 3) // 4
         return table
 
-    def _tile_maps(self, table, n_blurs, h, w, pad, row_origin):
+    def _tile_maps(self, table, n_blurs, h, w, pad, row_origin, seam_plan=False):
         """Device bitmaps of p360_tile_maps (one bit per patch and 64 x 32 tile, tile rows on
         absolute mosaic rows), the scratch for the compacted block lists of reduce / blur, and the
         host record that names them."""
@@ -510,13 +500,15 @@ class Compositor:
                   -(-2 * w4 // 256) * -(-2 * h4 // 4) * n * n_blurs,      # horizontal blur blocks (256 x 4 cells)
                   -(-2 * w4 // 64) * -(-2 * h4 // 16) * n * n_blurs,      # ... in 64 x 16 blocks
                   -(-2 * w4 // 32) * -(-2 * h4 // 64) * n * n_blurs)      # vertical blur blocks
-        bits = torch.empty(2 + 2 * cap + 3 * cells * words, dtype=torch.int32, device=self.device)
+        bits = torch.empty(2 + 2 * cap + 4 * cells * words, dtype=torch.int32, device=self.device)
         multi = torch.empty(cells, dtype=torch.uint8, device=self.device)
         maps = np.zeros(1, dtype=_lib.TILE_MAPS)
         base = bits.data_ptr()
         maps["work_count"], maps["work"], maps["work_cap"] = base, base + 8, cap      # work: 8-byte items
         base += 8 + 8 * cap
         maps["present"], maps["cand"], maps["need"] = base, base + 4 * cells * words, base + 8 * cells * words
+        if seam_plan:
+            maps["wneed"] = base + 12 * cells * words
         maps["multi"] = multi.data_ptr()
         maps["tiles_x"], maps["tiles_y"], maps["words"], maps["row0"] = tiles_x, tiles_y, words, row0
         maps["reach_x"], maps["reach_y"] = -(-pad // 64), -(-pad // 32)
@@ -623,7 +615,8 @@ class Compositor:
         """Drop the references that keep the last composite's pools alive (patch
         pool, coarse levels, job tables); the memory goes back to torch's caching
         allocator.  Call only after the work that uses them has been waited for."""
-        for key in ("warp", "bands", "collapse", "streamed"):
+        self.last_covered = None
+        for key in ("warp", "bands", "collapse", "streamed", "seam"):
             self._keep.pop(key, None)
 
     def finish_download(self):
@@ -633,10 +626,14 @@ class Compositor:
             self._download = None
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
-                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None):
+                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None, seam=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
-        in list order, so no mosaic-sized accumulator ever touches HBM."""
+        in list order, so no mosaic-sized accumulator ever touches HBM.
+
+        ``seam`` (from ``composite``): the patches have NOT been warped yet — the seam plan
+        decides from the geometry which tiles are one patch's pixels (written straight from the
+        sources as uint8) and warps float patches only in the seam zone."""
         h, w = shape
         if not 1 <= n_levels <= _lib.MAX_LEVELS:
             raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
@@ -644,7 +641,6 @@ class Compositor:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:      # nothing lands here: still produce (and download / hand on) every band
             return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
-        keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
         pad, plan = geo.coarse_band_plan(n_levels)
         table = self._band_table(patches, pad, coarse=True)
         n = len(patches)
@@ -654,18 +650,47 @@ class Compositor:
             self._set_taps(n_levels, plan)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
+        if seam is not None:
+            # K0: plan the tiles; K1d: solo tiles straight to uint8 (+ clears the zone's keys);
+            # K1: float patches in the seam zone only
+            assert plan, "the seam plan needs at least two bands"
+            jobs, crops, src = seam["jobs"], seam["crops"], seam["src"]
+            maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin, seam_plan=True)
+            dev_wjobs = self._table(jobs, "warp_jobs")
+            self._traced("K0_seam_plan", 216 * n, "p360_seam_plan_build", _lib.ptr(dev_wjobs), n, _lib.ptr(dev_table),
+                         h, w, row_origin, seam["mosaic_h"], maps.ctypes.data, self.stream)
+            keys = torch.empty((h, w), dtype=torch.int64, device=self.device)       # cleared where they are used
+            covered = torch.empty((h, w), dtype=torch.uint8, device=self.device)
+            if src.ready is not None:          # direct tiles read whichever image owns them: all uploads first
+                main = torch.cuda.current_stream(self.device)
+                for i in sorted({c[0] for c in crops}):
+                    main.wait_event(src.ready[i])
+            ya, yb = (0, h) if rows is None else rows
+            packed = int(bool(np.all(jobs["c"] == 8)))
+            self._traced("K1d_warp_direct", 3 * w * (yb - ya), "p360_warp_direct", _lib.ptr(dev_wjobs), n, packed,
+                         _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
+                         int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
+            ready, src.ready = src.ready, None                   # (already waited for)
+            try:
+                self._launch_warp(src, crops, jobs, keys, covered, w, maps.ctypes.data, 30, seam["pixels"])
+            finally:
+                src.ready = ready
+            self._keep["seam"] = (dev_wjobs,)
+        else:
+            keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
         if plan:
             # where can a patch carry weight at all: seam-band bitmaps, or the box around its owned pixels
-            if use_maps is None:      # (a gated warp leaves pixels unwritten that only the maps know to skip)
-                use_maps = self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS
-            if use_maps:
-                maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
-                self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
-                             _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)
-            else:
-                maps_keep = None
-                self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table),
-                             n, h, w, self.stream)
+            if seam is None:
+                if use_maps is None:
+                    use_maps = self.seam_maps if self.seam_maps is not None else h * w >= SEAM_MAPS_MIN_PIXELS
+                if use_maps:
+                    maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin)
+                    self._traced("K2b_tile_maps", 9 * h * w, "p360_tile_maps_build", _lib.ptr(keys), _lib.ptr(covered),
+                                 _lib.ptr(dev_table), n, h, w, maps.ctypes.data, self.stream)
+                else:
+                    maps_keep = None
+                    self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table),
+                                 n, h, w, self.stream)
             maps_ptr = None if maps is None else maps.ctypes.data
             jobs = self._blur_jobs(table, layout, dev_table, pad)
             dev_jobs = self._table(jobs, "blur_jobs")
@@ -683,8 +708,9 @@ class Compositor:
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
                        rows, on_band, bands, row_origin, tail=(None if maps is None else maps.ctypes.data,))
         self._keep["collapse"] = (dev_table, keys, covered)
+        self.last_covered = covered
         if stages is not None:
-            stages.update(keys=keys, covered=covered, lows=lows)
+            stages.update(keys=keys, covered=covered, lows=lows, maps=maps)
         return mosaic
 
     def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
@@ -750,8 +776,30 @@ class Compositor:
         reach = self.blur_reach(kind, n_levels)
         return reach + 32 if reach else 0
 
+    def window_margin(self, kind, n_levels):
+        """Upper bound of the rows beyond [ya, yb) that ``window_rows`` (plus the alignment of
+        cropped patch tops) may ask for: which images a window depends on."""
+        halo = self.window_halo(kind, n_levels)
+        if not halo:
+            return 0
+        return max(halo, 32 * -(-geo.coarse_band_plan(n_levels)[0] // 32) + 31) + 3
+
+    def window_rows(self, rows, kind, n_levels, height):
+        """Rows [wa, wb) a row window [ya, yb) has to warp: the halo on both sides, widened to
+        whole 32-row tiles so that every tile the seam plan consults for a tile of the window
+        (the blur reach, in tiles) lies completely inside — the plan then cannot depend on where
+        the window was cut."""
+        ya, yb = rows
+        halo = self.window_halo(kind, n_levels)
+        wa, wb = ya - halo, yb + halo
+        if halo:
+            reach_y = -(-geo.coarse_band_plan(n_levels)[0] // 32)
+            wa = min(wa, 32 * (ya // 32 - reach_y))
+            wb = max(wb, 32 * ((yb - 1) // 32 + reach_y + 1))
+        return max(0, wa), min(height, wb)
+
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8, gate=None):
+                  on_band=None, bands=8, direct=None, want_covered=False):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
         those rows of the full composite; only those rows are collapsed).
@@ -759,37 +807,47 @@ class Compositor:
         mode) receives the rows produced through a banded download that overlaps
         the collapse; call ``finish_download`` before reading it.  ``on_band(strip_rows, y0, y1)``
         is called after the collapse of mosaic rows [y0, y1) has been launched
-        (``strip_rows`` = that part of the device result)."""
-        halo, reach = self.window_halo(kind, n_levels), self.blur_reach(kind, n_levels)
+        (``strip_rows`` = that part of the device result).  ``want_covered``: keep the union of
+        valid pixels of the rows produced in ``last_covered`` (crop stage, stitcher.py:266-271)."""
+        reach = self.blur_reach(kind, n_levels)
         if rows is None:
             ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
             crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
         else:
             ya, yb = rows
-            wa, wb = max(0, ya - halo), min(plan.shape[0], yb + halo)
+            wa, wb = self.window_rows(rows, kind, n_levels, plan.shape[0])
             crops, tables = self.plan_crops(regions, plan, proj, rows=(wa, wb),
-                                            row_align=4 if halo else 1, split_dilate=2 * reach)
+                                            row_align=4 if reach else 1, split_dilate=2 * reach)
         top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
         shape = (wb - top, plan.shape[1])
-        state = self.new_owner_state(shape) if kind == "multiband" else None
-        # (callers that read the patches themselves afterwards — the crop mask — pass gate=False)
-        gated = (self.warp_gate if gate is None else gate) and kind == "multiband" and n_levels > 1
-        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state,
-                                  gate_pad=geo.coarse_band_plan(n_levels)[0] if gated else None)
         holder = {}
         band_cb = None
         if on_band is not None:
             def band_cb(y0, y1):
                 on_band(holder["mosaic"][y0:y1], y0 + top, y1 + top)
         local = (ya - top, yb - top)
+        use_plan = (self.direct if direct is None else direct) and kind == "multiband" and n_levels > 1 \
+            and 0 < len(crops) <= 1024                         # (the tile bitmaps hold 1024 patches)
+        if use_plan:
+            jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(0, top))
+            self._keep["warp"] = keep[:3] + (jobs,)
+            seam = {"jobs": jobs, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": keep[3],
+                    "want_covered": want_covered}
+            strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels, out_host=out_host,
+                                     rows=local, on_band=band_cb, bands=bands, row_origin=top, seam=seam)
+            return strip[local[0]:local[1]], patches
+        state = self.new_owner_state(shape) if kind == "multiband" else None
+        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
         if kind == "multiband":
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels,
                                      owner_state=state, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands, row_origin=top, use_maps=True if gated else None)
+                                     bands=bands, row_origin=top)
         else:
             strip = self._blend_into(holder, self.blend_none if kind == "none" else self.blend_linear,
                                      patches, shape, out_host=out_host, rows=local, on_band=band_cb,
                                      bands=bands, row_origin=top)
+            if want_covered:
+                self.last_covered = self.covered_mask(patches, shape)
         return strip[local[0]:local[1]], patches
 
     def streamed_windows(self, plan, kind, n_levels, windows=3):
@@ -798,7 +856,7 @@ class Compositor:
         to wait for — window k needs nothing beyond the first ``count_k`` images."""
         n = len(plan.boxes)
         height = plan.shape[0]
-        halo = self.window_halo(kind, n_levels)
+        halo = self.window_margin(kind, n_levels)
         order = sorted(range(n), key=lambda i: (plan.boxes[i][1], i))
         rank = {i: r for r, i in enumerate(order)}
         last = np.zeros(height, dtype=np.int64)           # per mosaic row: rank of the last upload it needs

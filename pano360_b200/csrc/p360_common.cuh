@@ -110,12 +110,16 @@ static_assert(sizeof(BandPatch) == sizeof(p360_band_patch), "ABI struct mismatch
 //   need     patches whose coarse levels are read within the blur chain's reach of the
 //            tile: everything else of reduce / blur is never consumed
 // maps.need == nullptr: no maps, the owned boxes decide.
+// The same bitmaps are also built from the geometry alone, before anything is sampled
+// (p360_seam_plan_build, p360_warp.cu): supersets of the ones above, plus `wneed`.
 constexpr int TILE_X = 64, TILE_Y = 32;
 struct TileMaps {                       // == p360_tile_maps
     uint32_t *present, *cand, *need;
     uint8_t *multi;                     // per tile: more than one candidate
     uint2 *work;                        // compacted list of the blocks a pass has to run
     int *work_count;
+    uint32_t *wneed;                    // seam plan only (p360_seam_plan_build): where float pixels are wanted;
+                                        // non-null also says: solo tiles were written by p360_warp_direct
     int tiles_x, tiles_y, words;
     int row0;                           // window row of tile row 0 (<= 0; tiles sit on absolute mosaic rows)
     int reach_x, reach_y;               // blur reach in tiles

@@ -27,6 +27,8 @@ struct WarpJob {                 // == p360_warp_job
     float half_w, half_h;        // float32(w / 2), float32(h / 2)          (stitcher.py:310)
     float max_x, max_y;          // float32(w - 1), float32(h - 1)          (stitcher.py:311-312)
     float inv_2w, inv_2h;        // 1 / (2w), 1 / (2h): reflection period reciprocals
+    int ty0, ty1;                // rows of the image's TRUE box in window coordinates (a row window crops
+                                 // y0 / ph; the seam plan must not depend on where the window was cut)
 };
 static_assert(sizeof(WarpJob) == sizeof(p360_warp_job), "ABI struct mismatch");
 
@@ -191,8 +193,8 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
     warp_block<PACKED, OWNER>(job, lut, keys, covered, W);
 }
 
-// The same with a gate: gate.need = "run" bitmap of p360_warp_gate_build; blocks of a patch over
-// tiles where its bit is clear produce nothing anybody reads and are skipped.
+// The same with a gate: gate.wneed = "float pixels wanted" bitmap of p360_seam_plan_build; blocks
+// of a patch over tiles where its bit is clear produce nothing anybody reads and are skipped.
 template <bool PACKED>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY)
 warp_batch_gated_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W, TileMaps gate) {
@@ -201,16 +203,30 @@ warp_batch_gated_kernel(unsigned long long *__restrict__ keys, uint8_t *__restri
     const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
     if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
     const int bx = job.x0 + (int)(blockIdx.x * WARP_BX), by = job.y0 + r0;
-    if (!tiles_test(gate, gate.need, job.patch, bx, by, bx + WARP_BX, by + WARP_BY * WARP_ROWS)) return;   // block-uniform
+    if (!tiles_test(gate, gate.wneed, job.patch, bx, by, bx + WARP_BX, by + WARP_BY * WARP_ROWS)) return;   // block-uniform
     warp_block<PACKED, true>(job, lut, keys, covered, W);
 }
 
-// ---- K0: who can own a pixel of a tile?  (geometry only, before anything is sampled) ---------
+// ---- K0: the seam plan — who can own a pixel of a tile?  (geometry only, before anything is
+// sampled) ----------------------------------------------------------------------------------
 // Ownership is arg-max of alpha = hat_y(v) * hat_x(u).  Interval arithmetic over a 64 x 32 tile —
 // ray tables -> K R ray -> (u, v) -> alpha — bounds alpha of every patch on the tile; a patch whose
 // upper bound lies below another patch's lower bound can never win there.  Every true owner is a
 // candidate (tools/gate_bounds.py checks it against the owner keys on random rigs); at cfg4 92 % of
-// the tiles keep a single candidate.
+// the tiles keep a single candidate.  Everything downstream is planned from these bitmaps:
+//   present  candidates for owning a pixel of the tile
+//   cand     candidates within the blur reach whose box meets the tile: the only patches that can
+//            carry weight there.  One bit set ("solo"): the multiband sum telescopes to that
+//            patch's warped pixel on the whole tile -> p360_warp_direct writes uint8 straight into
+//            the mosaic and nothing else ever touches the tile.  More ("multi"): full blend.
+//   need     candidates of the multi tiles within reach: where coarse levels are consumed
+//   wneed    where float pixels / owner keys are consumed: candidates of the multi tiles within
+//            reach + one tile (block overhang; mirror images at patch edges are no farther from
+//            the consuming tile than the position they stand for), plus — in every such tile —
+//            all its own `present` patches, so that the owner keys are right wherever they are read
+// Tiles are evaluated on their full extent in absolute mosaic rows against the images' TRUE boxes,
+// so the plan of a row window agrees with the plan of the whole mosaic on every tile that lies
+// (with its reach) inside the window.
 struct Interval { double lo, hi; };
 __device__ __forceinline__ Interval scaled(double k, Interval v) {
     const double a = k * v.lo, b = k * v.hi;
@@ -259,15 +275,20 @@ __device__ __forceinline__ bool alpha_range(const WarpJob &j, Interval rx, Inter
     return true;
 }
 
-// one thread per tile; jobs = DEVICE copy of the warp jobs (patch id = position)
+// one thread per tile; jobs = DEVICE copy of the warp jobs (patch id = position).  [0, H) are the
+// rows of the window buffer, [-abs_row0, mosaic_h - abs_row0) those of the whole mosaic in the
+// same coordinates.  Also grows the `own` boxes of the band patches (box around the tiles a patch
+// may own a pixel of, clipped to its cropped box).
 __global__ void __launch_bounds__(128)
-warp_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int W, TileMaps m) {
+seam_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, BandPatch *patches, int H, int W,
+                       int abs_row0, int mosaic_h, TileMaps m) {
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= m.tiles_x * m.tiles_y) return;
     const int tx = t % m.tiles_x, ty = t / m.tiles_x;
     const int xa = tx * TILE_X, xb = min(xa + TILE_X, W);
-    const int ya = max(m.row0 + ty * TILE_Y, 0), yb = min(m.row0 + ty * TILE_Y + TILE_Y, H);
-    for (int w = 0; w < m.words; ++w) m.cand[(size_t)t * m.words + w] = 0u;
+    const int ta = m.row0 + ty * TILE_Y;                                     // tile rows (window coordinates)
+    const int ya = max(ta, -abs_row0), yb = min(ta + TILE_Y, mosaic_h - abs_row0);   // ... inside the mosaic
+    for (int w = 0; w < m.words; ++w) m.present[(size_t)t * m.words + w] = 0u;
     if (yb <= ya || n_jobs == 0) return;
     // the ray tables are shared by all jobs: absolute mosaic column / row = col0 - x0 + x, row0 - y0 + y
     const WarpJob &j0 = jobs[0];
@@ -277,36 +298,217 @@ warp_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int 
     double best_min = 0.0;
     for (int k = 0; k < n_jobs; ++k) {
         const WarpJob &j = jobs[k];
-        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.y0 >= yb || j.y0 + j.ph <= ya) continue;
+        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
         // a patch only dominates a tile it covers completely: beyond its box it has no pixels,
         // however large alpha would be there (boxes end where the reference's ranges end)
-        if (j.x0 > xa || j.x0 + j.pw < xb || j.y0 > ya || j.y0 + j.ph < yb) continue;
+        if (j.x0 > xa || j.x0 + j.pw < xb || j.ty0 > ya || j.ty1 < yb) continue;
         double a_min, a_max;
         if (alpha_range(j, rx, ry, rz, a_min, a_max)) best_min = fmax(best_min, a_min);
     }
     for (int k = 0; k < n_jobs; ++k) {
         const WarpJob &j = jobs[k];
-        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.y0 >= yb || j.y0 + j.ph <= ya) continue;
+        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
         double a_min, a_max;
-        if (alpha_range(j, rx, ry, rz, a_min, a_max) && a_max >= best_min)
-            m.cand[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
+        if (alpha_range(j, rx, ry, rz, a_min, a_max) && a_max >= best_min) {
+            m.present[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
+            if (patches != nullptr) {
+                BandPatch &bp = patches[j.patch];
+                atomicMin(&bp.own[0], max(xa - bp.x0, 0));
+                atomicMin(&bp.own[1], max(max(ta, 0) - bp.y0, 0));
+                atomicMax(&bp.own[2], min(xa + TILE_X - bp.x0, bp.pw));
+                atomicMax(&bp.own[3], min(ta + TILE_Y - bp.y0, bp.ph));
+            }
+        }
     }
 }
 
-// need(T) = OR of cand over the tiles within reach_x / reach_y of T
+// cand(T) = present dilated by the blur reach, restricted to the patches whose (true) box meets T;
+// multi(T) = |cand(T)| > 1.  One thread per tile.
 __global__ void __launch_bounds__(256)
-tile_dilate_kernel(TileMaps m) {
+seam_cand_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int W, TileMaps m) {
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= m.tiles_x * m.tiles_y) return;
     const int tx = t % m.tiles_x, ty = t / m.tiles_x;
     const int x0 = max(tx - m.reach_x, 0), x1 = min(tx + m.reach_x, m.tiles_x - 1);
     const int y0 = max(ty - m.reach_y, 0), y1 = min(ty + m.reach_y, m.tiles_y - 1);
+    const int xa = tx * TILE_X, xb = min(xa + TILE_X, W), ta = m.row0 + ty * TILE_Y;
+    int count = 0;
     for (int w = 0; w < m.words; ++w) {
         uint32_t bits = 0u;
         for (int y = y0; y <= y1; ++y)
-            for (int x = x0; x <= x1; ++x) bits |= __ldg(m.cand + ((size_t)y * m.tiles_x + x) * m.words + w);
-        m.need[(size_t)t * m.words + w] = bits;
+            for (int x = x0; x <= x1; ++x) bits |= __ldg(m.present + ((size_t)y * m.tiles_x + x) * m.words + w);
+        uint32_t keep = 0u;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int k = 32 * w + b;
+            if (k >= n_jobs) break;
+            const WarpJob &j = jobs[k];
+            if (j.x0 < xb && j.x0 + j.pw > xa && j.ty0 < ta + TILE_Y && j.ty1 > ta) keep |= 1u << b;
+        }
+        m.cand[(size_t)t * m.words + w] = keep;
+        count += __popc(keep);
     }
+    m.multi[t] = count > 1 ? 1 : 0;
+}
+
+// need(T) = OR of cand over the multi tiles within the blur reach of T;  wneed(T) = the same over
+// reach + 1 tile, plus present(T) itself if there is any multi tile that close.
+__global__ void __launch_bounds__(256)
+seam_need_kernel(TileMaps m) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int x0 = max(tx - m.reach_x - 1, 0), x1 = min(tx + m.reach_x + 1, m.tiles_x - 1);
+    const int y0 = max(ty - m.reach_y - 1, 0), y1 = min(ty + m.reach_y + 1, m.tiles_y - 1);
+    bool zone = false;
+    for (int y = y0; y <= y1 && !zone; ++y)
+        for (int x = x0; x <= x1; ++x)
+            if (m.multi[(size_t)y * m.tiles_x + x]) { zone = true; break; }
+    for (int w = 0; w < m.words; ++w) {
+        uint32_t near = 0u, wide = 0u;
+        if (zone) {
+            for (int y = y0; y <= y1; ++y)
+                for (int x = x0; x <= x1; ++x) {
+                    const size_t n = (size_t)y * m.tiles_x + x;
+                    if (!m.multi[n]) continue;
+                    const uint32_t bits = __ldg(m.cand + n * m.words + w);
+                    wide |= bits;
+                    if (x - tx <= m.reach_x && tx - x <= m.reach_x && y - ty <= m.reach_y && ty - y <= m.reach_y) near |= bits;
+                }
+            wide |= __ldg(m.present + (size_t)t * m.words + w);
+        }
+        m.need[(size_t)t * m.words + w] = near;
+        m.wneed[(size_t)t * m.words + w] = wide;
+    }
+}
+
+// ---- K1d: direct tiles ------------------------------------------------------------------------
+// One block per 64 x 32 mosaic tile.  A solo tile (one candidate) is that patch's warped pixels
+// wherever it is valid, truncated to uint8 like the blender's last line (stitcher.py:240-241), and
+// zero elsewhere — exactly what the multiband sum telescopes to; the tile never exists as float
+// RGBA, owner keys or coarse levels.  Tiles inside the seam zone get their owner keys / covered
+// bytes cleared here (the float warp that follows competes into them); multi tiles are left to
+// the collapse.  Rows are staged in shared memory at the byte phase of their destination, so that
+// the mosaic is written with aligned 128-bit stores whatever W is.
+constexpr int DT_PITCH = 3 * TILE_X + 16 + 16;          // 192 bytes of pixels + alignment phase (+ bank skew)
+
+template <bool PACKED>
+__device__ __forceinline__ uint32_t load_rgbx(const WarpJob &s, int off) {
+    if (PACKED) return __ldg(reinterpret_cast<const uint32_t *>(s.src) + 2 * (size_t)off);
+    if (s.c == 4) return __ldg(reinterpret_cast<const uint32_t *>(s.src) + off);
+    const uint8_t *p = s.src + (size_t)off * 3;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+}
+
+__device__ __forceinline__ uint8_t to_u8(float v) {      // (255 * clip(v, 0, 1)).astype(uint8)
+    return (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(v, 0.f), 1.f)));
+}
+
+// store `n` bytes staged at row[phase ...] to dst (dst & 15 == phase): bytes up to the first
+// 16-byte boundary, aligned 128-bit words, bytes after the last one.  `lanes` threads cooperate.
+__device__ __forceinline__ void store_row_bytes(uint8_t *dst, const uint8_t *row, int n, int lane, int lanes) {
+    const int phase = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
+    const int head = min((16 - phase) & 15, n);
+    const int body = (n - head) >> 4, tail = n - head - (body << 4);
+    const uint8_t *src = row + phase;
+    for (int i = lane; i < head; i += lanes) dst[i] = src[i];
+    for (int i = lane; i < body; i += lanes)
+        *reinterpret_cast<uint4 *>(dst + head + 16 * i) = *reinterpret_cast<const uint4 *>(src + head + 16 * i);
+    for (int i = lane; i < tail; i += lanes) dst[head + 16 * body + i] = src[head + 16 * body + i];
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+warp_direct_kernel(const WarpJob *__restrict__ jobs, int n_jobs, unsigned long long *__restrict__ keys,
+                   uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
+                   int y_begin, int y_end, int H, int W, int want_covered, TileMaps m) {
+    __align__(16) __shared__ uint8_t rows[TILE_Y][DT_PITCH];
+    __align__(16) __shared__ WarpJob job;
+    __shared__ float lut[256];
+    __shared__ int who;
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int tx0 = blockIdx.x * TILE_X, ty0 = first_tile_row + blockIdx.y * TILE_Y;
+    const size_t tile = (size_t)((ty0 - m.row0) >> 5) * m.tiles_x + blockIdx.x;
+    if (tid == 0) {
+        int single = -1;
+        bool zone = false;
+        for (int w = 0; w < m.words; ++w) {
+            const uint32_t c = __ldg(m.cand + tile * m.words + w);
+            if (c && single < 0) single = 32 * w + __ffs(c) - 1;
+            zone |= __ldg(m.wneed + tile * m.words + w) != 0u;
+        }
+        // bit 30: seam zone, bit 29: multi; low bits: the candidate (0x1fffffff: none)
+        who = (single < 0 ? 0x1fffffff : single) | (zone ? 1 << 30 : 0) | (__ldg(m.multi + tile) ? 1 << 29 : 0);
+    }
+    __syncthreads();
+    const bool zone = who & (1 << 30), multi = who & (1 << 29);
+    const int cand = who & 0x1fffffff;
+    const int X = tx0 + threadIdx.x;
+    if (zone && X < W) {            // the float warp competes into these keys next
+        for (int sub = 0; sub < TILE_Y / 4; ++sub) {
+            const int Y = ty0 + threadIdx.y + 4 * sub;
+            if (Y < 0 || Y >= H) continue;
+            keys[(size_t)Y * W + X] = 0ull;
+            covered[(size_t)Y * W + X] = 0;
+        }
+    }
+    if (multi) return;                                   // block-uniform: the collapse writes this tile
+    const bool have = cand < n_jobs;
+    if (have) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(jobs + cand);
+        if (tid < (int)(sizeof(WarpJob) / 4)) reinterpret_cast<uint32_t *>(&job)[tid] = __ldg(src + tid);
+    }
+    __syncthreads();
+    if (have) lut[tid] = __ldg(job.lut + tid);
+    __syncthreads();
+    const int ncols = min(TILE_X, W - tx0);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        // four rows per thread and pass: all coordinates, then all gathers, then LUT + blend
+        TapPlan plan[WARP_ROWS];
+        uint32_t taps[WARP_ROWS][4];
+        bool live[WARP_ROWS];
+#pragma unroll
+        for (int k = 0; k < WARP_ROWS; ++k) {
+            const int Y = ty0 + 16 * half + threadIdx.y + 4 * k;
+            const int c = have ? X - job.x0 : -1, r = have ? Y - job.y0 : -1;
+            live[k] = have && Y >= y_begin && Y < y_end && X < W &&
+                      (unsigned)c < (unsigned)job.pw && (unsigned)r < (unsigned)job.ph;
+            if (live[k]) plan[k] = plan_taps(job, c, r);
+        }
+#pragma unroll
+        for (int k = 0; k < WARP_ROWS; ++k) {
+            if (!live[k]) continue;
+            taps[k][0] = load_rgbx<PACKED>(job, plan[k].off00); taps[k][1] = load_rgbx<PACKED>(job, plan[k].off01);
+            taps[k][2] = load_rgbx<PACKED>(job, plan[k].off10); taps[k][3] = load_rgbx<PACKED>(job, plan[k].off11);
+        }
+#pragma unroll
+        for (int k = 0; k < WARP_ROWS; ++k) {
+            const int ry = 16 * half + threadIdx.y + 4 * k, Y = ty0 + ry;
+            if (Y < y_begin || Y >= y_end || X >= W) continue;
+            uint8_t b0 = 0, b1 = 0, b2 = 0;
+            const bool valid = live[k] && !plan[k].bad;
+            if (valid) {
+                const uint32_t *q = taps[k];
+                b0 = to_u8(blend4(lut_at(lut, (q[0] << 2) & 0x3fc), lut_at(lut, (q[1] << 2) & 0x3fc),
+                                  lut_at(lut, (q[2] << 2) & 0x3fc), lut_at(lut, (q[3] << 2) & 0x3fc), plan[k]));
+                b1 = to_u8(blend4(lut_at(lut, (q[0] >> 6) & 0x3fc), lut_at(lut, (q[1] >> 6) & 0x3fc),
+                                  lut_at(lut, (q[2] >> 6) & 0x3fc), lut_at(lut, (q[3] >> 6) & 0x3fc), plan[k]));
+                b2 = to_u8(blend4(lut_at(lut, (q[0] >> 14) & 0x3fc), lut_at(lut, (q[1] >> 14) & 0x3fc),
+                                  lut_at(lut, (q[2] >> 14) & 0x3fc), lut_at(lut, (q[3] >> 14) & 0x3fc), plan[k]));
+            }
+            uint8_t *dst = out + ((size_t)Y * W + tx0) * 3;
+            uint8_t *stage = rows[ry] + (reinterpret_cast<uintptr_t>(dst) & 15) + 3 * threadIdx.x;
+            stage[0] = b0; stage[1] = b1; stage[2] = b2;
+            if (want_covered) covered[(size_t)Y * W + X] = valid ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    // 8 threads per row: aligned 128-bit stores of the staged bytes
+    const int ry = tid >> 3, Y = ty0 + ry;
+    if (Y >= y_begin && Y < y_end)
+        store_row_bytes(out + ((size_t)Y * W + tx0) * 3, rows[ry], 3 * ncols, tid & 7, 8);
 }
 
 // u8 x 3 -> {RGBX u32, alpha f32}: one aligned 64-bit word per source pixel
@@ -339,21 +541,58 @@ extern "C" int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_
     return check_launch(where);
 }
 
-extern "C" int p360_warp_gate_build(const p360_warp_job *jobs_dev, int n_jobs, int H, int W,
-                                    const p360_tile_maps *gate_host, void *stream) {
+static int seam_maps_ok(const p360::TileMaps &m, int n_jobs, int H, int W, const char *where) {
     using namespace p360;
-    const char *where = "p360_warp_gate_build";
-    P360_REQUIRE(jobs_dev && gate_host && n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0, where);
-    TileMaps m;
-    memcpy(&m, gate_host, sizeof(m));
-    P360_REQUIRE(m.cand && m.need && m.words == (n_jobs + 31) / 32 && m.row0 <= 0 && m.row0 > -TILE_Y, where);
+    P360_REQUIRE(m.present && m.cand && m.need && m.wneed && m.multi, where);
+    P360_REQUIRE(m.words == (n_jobs + 31) / 32 && m.row0 <= 0 && m.row0 > -TILE_Y, where);
     P360_REQUIRE(m.tiles_x == (int)cdiv(W, TILE_X) && m.tiles_y == (int)cdiv(H - m.row0, TILE_Y), where);
     P360_REQUIRE(m.reach_x >= 0 && m.reach_y >= 0, where);
+    return 0;
+}
+
+extern "C" int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, p360_band_patch *patches_dev,
+                                    int H, int W, int abs_row0, int mosaic_h,
+                                    const p360_tile_maps *maps_host, void *stream) {
+    using namespace p360;
+    const char *where = "p360_seam_plan_build";
+    P360_REQUIRE(jobs_dev && maps_host && n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0, where);
+    P360_REQUIRE(abs_row0 >= 0 && mosaic_h >= abs_row0 + H, where);
+    TileMaps m;
+    memcpy(&m, maps_host, sizeof(m));
+    if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
     cudaStream_t s = (cudaStream_t)stream;
     const long long tiles = (long long)m.tiles_x * m.tiles_y;
-    warp_candidates_kernel<<<cdiv(tiles, 128), 128, 0, s>>>(reinterpret_cast<const WarpJob *>(jobs_dev), n_jobs, H, W, m);
+    auto jobs = reinterpret_cast<const WarpJob *>(jobs_dev);
+    seam_candidates_kernel<<<cdiv(tiles, 128), 128, 0, s>>>(jobs, n_jobs, reinterpret_cast<BandPatch *>(patches_dev),
+                                                            H, W, abs_row0, mosaic_h, m);
     if (int e = check_launch(where)) return e;
-    tile_dilate_kernel<<<cdiv(tiles, 256), 256, 0, s>>>(m);
+    seam_cand_kernel<<<cdiv(tiles, 256), 256, 0, s>>>(jobs, n_jobs, W, m);
+    if (int e = check_launch(where)) return e;
+    seam_need_kernel<<<cdiv(tiles, 256), 256, 0, s>>>(m);
+    return check_launch(where);
+}
+
+extern "C" int p360_warp_direct(const p360_warp_job *jobs_dev, int n_jobs, int packed, uint64_t *owner_keys,
+                                uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
+                                int want_covered, const p360_tile_maps *maps_host, void *stream) {
+    using namespace p360;
+    const char *where = "p360_warp_direct";
+    P360_REQUIRE(jobs_dev && maps_host && owner_keys && covered && out_u8, where);
+    P360_REQUIRE(n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0 && y_begin >= 0 && y_end <= H, where);
+    TileMaps m;
+    memcpy(&m, maps_host, sizeof(m));
+    if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
+    // every tile of the window: zone tiles are cleared on all their rows, pixels only go to [y_begin, y_end)
+    dim3 grid(m.tiles_x, m.tiles_y), block(TILE_X, 4);
+    P360_REQUIRE(grid.y <= 65535, where);
+    auto jobs = reinterpret_cast<const WarpJob *>(jobs_dev);
+    auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
+    if (packed)
+        warp_direct_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(jobs, n_jobs, keys, covered, out_u8, m.row0,
+                                                                          y_begin, y_end, H, W, want_covered, m);
+    else
+        warp_direct_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(jobs, n_jobs, keys, covered, out_u8, m.row0,
+                                                                           y_begin, y_end, H, W, want_covered, m);
     return check_launch(where);
 }
 
@@ -367,7 +606,7 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
     memset(&gate, 0, sizeof(gate));
     if (gate_host != nullptr) {
         memcpy(&gate, gate_host, sizeof(gate));
-        P360_REQUIRE(gate.need && gate.tiles_x > 0 && gate.tiles_y > 0 && gate.words > 0 && owner_keys, where);
+        P360_REQUIRE(gate.wneed && gate.tiles_x > 0 && gate.tiles_y > 0 && gate.words > 0 && owner_keys, where);
     }
     P360_REQUIRE(owner_keys == nullptr || (covered != nullptr && W > 0), where);
     cudaStream_t s = (cudaStream_t)stream;

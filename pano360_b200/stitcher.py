@@ -217,7 +217,7 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     else:
         banded = out if _is_pinned_out(out, plan.shape) else None
         mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded,
-                                             gate=False if crop else None)
+                                             want_covered=crop)
         if banded is not None:
             comp.finish_download()
             mosaic = out
@@ -225,7 +225,11 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
             mosaic = _download(mosaic_dev, out)
     if crop:
         logging.debug("Cropping...")
-        mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))
+        if kind is None:
+            valid = _valid(patches, plan.shape)
+        else:                                  # union of valid pixels, kept by the composite
+            valid = comp.last_covered[:plan.shape[0]].cpu().numpy().astype(bool)
+        mosaic = crop_mosaic(mosaic, valid)
     del patches
     comp.release()          # everything has been waited for (the mosaic is on the host)
     return mosaic

@@ -27,7 +27,9 @@ def blur_halo(kind, n_levels):
     (``Compositor.window_halo``) plus the alignment slack of cropped tops."""
     if kind != "multiband" or n_levels < 2:
         return 0
-    return geo.coarse_band_plan(n_levels)[0] + 4 + 32 + 3
+    pad = geo.coarse_band_plan(n_levels)[0]
+    # (= Compositor.window_margin: windows are widened to the whole tiles the seam plan consults)
+    return max(pad + 4 + 32, 32 * -(-pad // 32) + 31) + 3
 
 
 def row_costs(plan, kind="multiband", n_levels=5):

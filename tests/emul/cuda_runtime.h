@@ -35,6 +35,7 @@
 #define __launch_bounds__(...)
 #define __constant__
 #define __shared__ static thread_local
+#define __align__(n) alignas(n)
 
 // ---- vector types ------------------------------------------------------------
 struct uint3 { unsigned x, y, z; };
@@ -45,6 +46,7 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -54,7 +54,7 @@ test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
-test_warp_gate_is_exact_and_conservative = gpu.test_warp_gate_is_exact_and_conservative
+test_seam_plan_is_conservative_and_cut_independent = gpu.test_seam_plan_is_conservative_and_cut_independent
 test_window_without_any_image = gpu.test_window_without_any_image
 test_blur_kernel_generic_taps = gpu.test_blur_kernel_generic_taps
 test_batched_blur_paths = gpu.test_batched_blur_paths
@@ -166,7 +166,7 @@ def test_random_rigs_against_the_oracle(st, comp, restore_globals):
         "fuzz_host", os.path.join(os.path.dirname(__file__), "..", "tools", "fuzz_host.py"))
     fuzz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fuzz)
-    saved = comp.seam_maps, comp.warp_gate
+    saved = comp.seam_maps, comp.direct
     try:
         for seed in range(900, 916):
             rng = np.random.default_rng(seed)
@@ -177,15 +177,16 @@ def test_random_rigs_against_the_oracle(st, comp, restore_globals):
                 if not case["equalize"]:
                     fuzz.run_blender_api(st, case)
     finally:
-        comp.seam_maps, comp.warp_gate = saved
+        comp.seam_maps, comp.direct = saved
 
 
-def test_warp_gate_candidates_at_full_scale(comp):
+def test_seam_plan_candidates_at_full_scale(comp):
     """K0 alone on the benchmark geometry at FULL size (one thread per tile, no pixels needed)
     against the NumPy statement of the same interval arithmetic (tools/gate_bounds.py), plus the
     case that once broke it: at the right end of the ring image 24's box ends at column 31640,
     inside the last tile column, although the image itself continues (it wraps) — it must not
-    out-bid the crop of image 35 that owns the columns beyond."""
+    out-bid the crop of image 35 that owns the columns beyond.  Also sizes what the plan buys:
+    the share of solo tiles (written straight to uint8) and of float-warp tiles per patch."""
     import importlib.util
     import os
 
@@ -205,20 +206,38 @@ def test_warp_gate_candidates_at_full_scale(comp):
     rays = torch.from_numpy(np.concatenate([ray_x, ray_z, ray_y]))
     base = rays.data_ptr()
     jobs = np.zeros(len(crops), dtype=_lib.WARP_JOB)
-    for k, (i, x0, y0, x1, y1, k_r) in enumerate(crops):
+    for k, (i, x0, y0, x1, y1, k_r, ty0, ty1) in enumerate(crops):
         h, w = regs[i].img.shape[:2]
         jobs[k]["ray_x"], jobs[k]["ray_z"], jobs[k]["ray_y"] = base, base + 8 * len(ray_x), base + 8 * (len(ray_x) + len(ray_z))
         jobs[k]["kr"], jobs[k]["h"], jobs[k]["w"] = k_r, h, w
         jobs[k]["pw"], jobs[k]["ph"], jobs[k]["x0"], jobs[k]["y0"] = x1 - x0, y1 - y0, x0, y0
-        jobs[k]["col0"], jobs[k]["row0"], jobs[k]["patch"] = x0, y0, k
-    gate, (bits, _) = comp._warp_gate(jobs, plan.shape, 0, pad)
-    tx, ty, words = int(gate["tiles_x"][0]), int(gate["tiles_y"][0]), int(gate["words"][0])
-    device = bits.numpy().view(np.uint32)[:tx * ty * words].reshape(ty, tx, words)
+        jobs[k]["col0"], jobs[k]["row0"], jobs[k]["patch"], jobs[k]["ty0"], jobs[k]["ty1"] = x0, y0, k, ty0, ty1
+    n = len(crops)
+    table = np.zeros(n, dtype=_lib.BAND_PATCH)
+    table["w4"] = table["h4"] = 1
+    maps, (bits, multi) = comp._tile_maps(table, 4, plan.shape[0], plan.shape[1], pad, 0, seam_plan=True)
+    dev_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy())
+    _lib.call("p360_seam_plan_build", dev_jobs.data_ptr(), n, None, plan.shape[0], plan.shape[1], 0, plan.shape[0],
+              maps.ctypes.data, None)
+    tx, ty, words = int(maps["tiles_x"][0]), int(maps["tiles_y"][0]), int(maps["words"][0])
+    planes = bits.numpy().view(np.uint32)[2 + 2 * int(maps["work_cap"][0]):].reshape(4, ty, tx, words)
+    unpack = lambda plane: np.stack([((plane[..., k >> 5] >> np.uint32(k & 31)) & 1).astype(bool) for k in range(n)])
+    got = unpack(planes[0])
     want = gb.candidates(regs, plan, crops=[c[:5] for c in crops])
-    got = np.stack([((device[..., k >> 5] >> np.uint32(k & 31)) & 1).astype(bool) for k in range(len(crops))])
     assert got.shape == want.shape
     assert np.mean(got != want) < 1e-4 and not np.any(want & ~got & (want.sum(0) == 1)[None])
     crop41 = [k for k, c in enumerate(crops) if c[0] == 35 and c[3] == plan.shape[1]][0]
     assert got[crop41, 198, 494]
     single = (got.sum(0) == 1).mean()
     assert single > 0.85, single            # the bound is tight: most tiles have one possible owner
+    cand, need, wneed = unpack(planes[1]), unpack(planes[2]), unpack(planes[3])
+    is_multi = multi.numpy().reshape(ty, tx).astype(bool)
+    assert np.array_equal(is_multi, cand.sum(0) > 1)
+    assert not np.any(need & ~wneed) and not np.any(cand[:, is_multi] & ~need[:, is_multi])
+    solo_share = 1.0 - is_multi.mean()
+    boxes = np.stack([np.zeros((ty, tx), bool)] * n)
+    for k, c in enumerate(crops):
+        boxes[k, c[2] // 32:-(-c[4] // 32), c[1] // 64:-(-c[3] // 64)] = True
+    float_share = (wneed & boxes).sum() / boxes.sum()
+    print(f"cfg4 seam plan: {solo_share:.3f} of the tiles solo, float warp on {float_share:.3f} of the patch tiles")
+    assert solo_share > 0.8 and float_share < 0.35

@@ -1,7 +1,7 @@
 """Randomised parity campaign on the HOST build of the kernels (tests/emul): random rigs
 (view count, image size incl. odd and tiny, focal length, yaw / pitch incl. rings that straddle
 the +-pi seam and steep pitches, roll), blenders, band counts, -e, projection, resolution cap,
-forced seam-band maps, gated warp, random row windows — each compared with the CPU oracle
+forced seam-band maps, seam plan / direct tiles, random row windows — each compared with the CPU oracle
 (none / linear bit-exact, multiband and -e within max|d| <= 2 and PSNR >= 45 dB) and, for windows,
 with the whole mosaic byte for byte.
 
@@ -67,7 +67,7 @@ def random_case(rng):
     return dict(regs=regs, blend=str(rng.choice(["none", "linear", "multiband", "multiband"])),
                 equalize=bool(rng.random() < 0.3) and not mixed, levels=int(rng.choice([1, 2, 3, 5, 5, 6, 8])),
                 cylindrical=bool(rng.random() < 0.25), cap=float(rng.choice([1e9, 1e9, 1400, 300])),
-                maps=[None, True, False][int(rng.integers(3))], gate=bool(rng.random() < 0.5), layout=str(layout))
+                maps=[None, True, False][int(rng.integers(3))], direct=bool(rng.random() < 0.7), layout=str(layout))
 
 
 def only_on_slivers(regs, case, levels, bad):
@@ -91,7 +91,7 @@ def run_case(st, comp, case):
     st.MAX_RESOLUTION = case["cap"]
     st.SphProj = geo.CylProj if case["cylindrical"] else geo.SphProj
     comp.seam_maps = case["maps"]
-    comp.warp_gate = case["gate"]
+    comp.direct = case["direct"]
     proj = st.SphProj
     try:
         want = rs.stitch(regs, blend, case["equalize"], levels, case["cap"],
@@ -169,7 +169,7 @@ def main():
             case = random_case(rng)
             tag = (f"seed {seed}: {len(case['regs'])} x {case['regs'][0].img.shape[1]}x{case['regs'][0].img.shape[0]} "
                    f"{case['layout']} {case['blend']} L{case['levels']} eq={case['equalize']} cyl={case['cylindrical']} "
-                   f"cap={case['cap']:g} maps={case['maps']} gate={case['gate']}")
+                   f"cap={case['cap']:g} maps={case['maps']} direct={case['direct']}")
             try:
                 whole = run_case(st, comp, case)
                 if whole is not None:

@@ -22,7 +22,7 @@ def main(comp=None):
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--h-rows", type=int, default=1, help="4: horizontal blur lists in 64-cell segments")
-    ap.add_argument("--gate", action="store_true", help="maps_on also gates the warp (p360_warp_gate_build)")
+    ap.add_argument("--direct", action="store_true", help="maps_on = the seam plan with direct tiles (p360_seam_plan_build)")
     args = ap.parse_args()
     t0 = time.time()
     import torch
@@ -36,13 +36,13 @@ def main(comp=None):
     plan = geo.plan_mosaic(regs, wl.blend == "multiband", 1e9)
     comp = comp or Compositor()
     comp.blur_h_rows = args.h_rows
-    gate = args.gate
+    direct = args.direct
     src = comp.upload(regs)
     out = {"workload": args.workload, "scale": args.scale, "mosaic": list(plan.shape), "setup_s": round(time.time() - t0, 1)}
     mosaics = {}
     for maps in (False, True):
         comp.seam_maps = maps
-        comp.warp_gate = maps and gate
+        comp.direct = maps and direct
         for _ in range(2 if args.steps else 0):
             comp.composite(regs, src, plan, wl.blend, wl.n_levels)
         torch.cuda.synchronize()
@@ -64,6 +64,8 @@ def main(comp=None):
         out["maps_on" if maps else "maps_off"] = {"ms_per_step": round(ms, 3), "kernels_ms": kernels}
         print(json.dumps(out), flush=True)
     out["identical"] = bool(torch.equal(mosaics[False], mosaics[True]))
+    diff = (mosaics[False].to(torch.int16) - mosaics[True].to(torch.int16)).abs()
+    out["max_abs_diff"], out["differing_px"] = int(diff.max()), int((diff > 0).sum())
     print(json.dumps(out), flush=True)
 
 
