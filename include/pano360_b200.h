@@ -92,10 +92,8 @@ int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const do
                     int h, int w, uint8_t *dst_rgbxa, void *stream);
 struct p360_tile_maps;
 struct p360_band_patch;
-/* gate_host (optional): a seam plan; blocks of a patch over tiles without its `wneed` bit are skipped. */
 int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
-                    uint64_t *owner_keys, uint8_t *covered, int W,
-                    const struct p360_tile_maps *gate_host, void *stream);
+                    uint64_t *owner_keys, uint8_t *covered, int W, void *stream);
 
 /* ---- K0 + K1d: the seam plan and the direct tiles (multiband, >= 2 bands) -----------------
  * Ownership (stitcher.py:196-204) is arg-max of alpha = hat_y(v) * hat_x(u): a function of the
@@ -116,19 +114,22 @@ int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
  * tile that lies with its reach inside the window exactly like the whole mosaic does.
  * jobs_dev = DEVICE copy of the job table (patch = position), at most 1024 jobs.
  *
- * p360_warp_direct then writes every non-multi tile of rows [y_begin, y_end) of the uint8 mosaic
- * straight from the source images (one block per tile, rows staged in shared memory and stored
- * as aligned 128-bit words), clears owner_keys / covered on the tiles with a `wneed` bit (neither
- * buffer needs initialising) and, if want_covered, records the valid mask of the tiles it writes
- * (stitcher.py:266-271).  p360_warp_batch with the same record as gate warps float RGBA only
- * where `wneed` asks for it, and p360_multiband_collapse writes only the multi tiles.
+ * p360_warp_tiles (jobs_host: the same table in HOST memory, at most 256 jobs: it is staged in
+ * constant memory) then runs one block per tile (K1t).  A non-multi tile of rows [y_begin, y_end)
+ * is written to the uint8 mosaic straight from the source images (rows staged in shared memory,
+ * stored as aligned 128-bit words).  In every tile with `wneed` bits those patches are warped
+ * to float RGBA + mask (job.out / job.invalid, tile by tile: pixels outside such tiles stay
+ * unwritten and are never read) and compete for the pixels in patch order in registers:
+ * owner_keys / covered are written once per pixel, without atomics, and need no initialising.
+ * If want_covered, covered also records the valid mask of the other tiles (stitcher.py:266-271).
+ * p360_multiband_collapse with the same record writes only the multi tiles.
  * packed: every job's src is in the c = 8 layout. */
 int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
                          int H, int W, int abs_row0, int mosaic_h,
                          const struct p360_tile_maps *maps_host, void *stream);
-int p360_warp_direct(const p360_warp_job *jobs_dev, int n_jobs, int packed, uint64_t *owner_keys,
-                     uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
-                     int want_covered, const struct p360_tile_maps *maps_host, void *stream);
+int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, int packed, uint64_t *owner_keys,
+                    uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
+                    int want_covered, const struct p360_tile_maps *maps_host, void *stream);
 
 /* ---- K2: owner map for externally supplied patches (stitcher.py:196-208) ---
  * p360_owner_update: the same competition for one already-warped patch (the

@@ -389,13 +389,13 @@ class Compositor:
                    for i, b, o in zip(image.tolist(), box.tolist(), offs[:-1].tolist())]
         return jobs, patches, (dev_rays, rgba_pool, inv_pool, int(offs[-1]))
 
-    def _launch_warp(self, src, crops, jobs, keys, covered, width, gate_ptr, per_px, pixels):
+    def _launch_warp(self, src, crops, jobs, keys, covered, width, per_px, pixels):
         """K1 over the job table: one launch, or — while uploads are still in flight — one per
         group of images as they arrive."""
         n = len(jobs)
         if src.ready is None:
             self._traced("K1_warp", per_px * pixels, "p360_warp_batch", jobs.ctypes.data, n,
-                         _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
+                         _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
             return
         main = torch.cuda.current_stream(self.device)
         group = max(1, -(-len(src.ready) // 8))
@@ -408,7 +408,7 @@ class Compositor:
             for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
                 main.wait_event(src.ready[i])
             _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
-                      _lib.ptr(keys), _lib.ptr(covered), width, gate_ptr, self.stream)
+                      _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
             a = b
 
     def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
@@ -425,7 +425,7 @@ class Compositor:
         else:
             keys, covered = owner_state
             width, per_px = keys.shape[1], 30
-        self._launch_warp(src, crops, jobs, keys, covered, width, None, per_px, keep[3])
+        self._launch_warp(src, crops, jobs, keys, covered, width, per_px, keep[3])
         self._keep["warp"] = keep[:3] + (jobs,)
         return patches
 
@@ -651,30 +651,25 @@ class Compositor:
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         if seam is not None:
-            # K0: plan the tiles; K1d: solo tiles straight to uint8 (+ clears the zone's keys);
-            # K1: float patches in the seam zone only
+            # K0: plan the tiles; K1t: one block per tile — solo tiles straight to uint8, float
+            # patches + owner keys in the seam zone only
             assert plan, "the seam plan needs at least two bands"
             jobs, crops, src = seam["jobs"], seam["crops"], seam["src"]
             maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin, seam_plan=True)
             dev_wjobs = self._table(jobs, "warp_jobs")
             self._traced("K0_seam_plan", 216 * n, "p360_seam_plan_build", _lib.ptr(dev_wjobs), n, _lib.ptr(dev_table),
                          h, w, row_origin, seam["mosaic_h"], maps.ctypes.data, self.stream)
-            keys = torch.empty((h, w), dtype=torch.int64, device=self.device)       # cleared where they are used
+            keys = torch.empty((h, w), dtype=torch.int64, device=self.device)       # written where they are read
             covered = torch.empty((h, w), dtype=torch.uint8, device=self.device)
-            if src.ready is not None:          # direct tiles read whichever image owns them: all uploads first
+            if src.ready is not None:          # a tile reads whichever images meet it: all uploads first
                 main = torch.cuda.current_stream(self.device)
                 for i in sorted({c[0] for c in crops}):
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
             packed = int(bool(np.all(jobs["c"] == 8)))
-            self._traced("K1d_warp_direct", 3 * w * (yb - ya), "p360_warp_direct", _lib.ptr(dev_wjobs), n, packed,
+            self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, n, packed,
                          _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
-            ready, src.ready = src.ready, None                   # (already waited for)
-            try:
-                self._launch_warp(src, crops, jobs, keys, covered, w, maps.ctypes.data, 30, seam["pixels"])
-            finally:
-                src.ready = ready
             self._keep["seam"] = (dev_wjobs,)
         else:
             keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
@@ -827,7 +822,7 @@ class Compositor:
                 on_band(holder["mosaic"][y0:y1], y0 + top, y1 + top)
         local = (ya - top, yb - top)
         use_plan = (self.direct if direct is None else direct) and kind == "multiband" and n_levels > 1 \
-            and 0 < len(crops) <= 1024                         # (the tile bitmaps hold 1024 patches)
+            and 0 < len(crops) <= 256                          # (the tile warp keeps its job table in constant memory)
         if use_plan:
             jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(0, top))
             self._keep["warp"] = keep[:3] + (jobs,)

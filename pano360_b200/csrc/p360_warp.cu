@@ -151,7 +151,9 @@ __device__ __forceinline__ void warp_commit(const WarpJob &s, int c, int r, cons
 }
 
 constexpr int WARP_JOBS_PER_LAUNCH = 128;
-__constant__ WarpJob c_warp_jobs[WARP_JOBS_PER_LAUNCH];   // block-uniform reads: no LSU traffic per pixel
+constexpr int TILE_JOBS_MAX = 256;                 // p360_warp_tiles: the whole job table sits in constant memory
+__constant__ WarpJob c_warp_jobs[TILE_JOBS_MAX];   // block-uniform reads: no LSU traffic per pixel, and the compiler
+                                                   // may re-read a field instead of holding it in a register
 
 // PACKED: every job's source is in the 8-byte {RGBX, alpha} format; OWNER: owner keys wanted.
 template <bool PACKED, bool OWNER>
@@ -191,20 +193,6 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
     const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
     if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
     warp_block<PACKED, OWNER>(job, lut, keys, covered, W);
-}
-
-// The same with a gate: gate.wneed = "float pixels wanted" bitmap of p360_seam_plan_build; blocks
-// of a patch over tiles where its bit is clear produce nothing anybody reads and are skipped.
-template <bool PACKED>
-__global__ void __launch_bounds__(WARP_BX *WARP_BY)
-warp_batch_gated_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W, TileMaps gate) {
-    __shared__ float lut[256];
-    const WarpJob &job = c_warp_jobs[blockIdx.z];
-    const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
-    if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
-    const int bx = job.x0 + (int)(blockIdx.x * WARP_BX), by = job.y0 + r0;
-    if (!tiles_test(gate, gate.wneed, job.patch, bx, by, bx + WARP_BX, by + WARP_BY * WARP_ROWS)) return;   // block-uniform
-    warp_block<PACKED, true>(job, lut, keys, covered, W);
 }
 
 // ---- K0: the seam plan — who can own a pixel of a tile?  (geometry only, before anything is
@@ -383,14 +371,18 @@ seam_need_kernel(TileMaps m) {
     }
 }
 
-// ---- K1d: direct tiles ------------------------------------------------------------------------
-// One block per 64 x 32 mosaic tile.  A solo tile (one candidate) is that patch's warped pixels
-// wherever it is valid, truncated to uint8 like the blender's last line (stitcher.py:240-241), and
-// zero elsewhere — exactly what the multiband sum telescopes to; the tile never exists as float
-// RGBA, owner keys or coarse levels.  Tiles inside the seam zone get their owner keys / covered
-// bytes cleared here (the float warp that follows competes into them); multi tiles are left to
-// the collapse.  Rows are staged in shared memory at the byte phase of their destination, so that
-// the mosaic is written with aligned 128-bit stores whatever W is.
+// ---- K1t: the tile warp --------------------------------------------------------------------
+// One block per 64 x 32 mosaic tile, driven by the seam plan.
+//  * A solo tile (one candidate) is that patch's warped pixels wherever it is valid, truncated to
+//    uint8 like the blender's last line (stitcher.py:240-241), and zero elsewhere — exactly what
+//    the multiband sum telescopes to.  Outside the seam zone such a tile never exists as float
+//    RGBA, owner keys or coarse levels: source pixels in, mosaic bytes out.
+//  * In the seam zone every patch with a `wneed` bit is warped to float RGBA + mask over the tile
+//    (what reduce and collapse read).  The block visits the patches in order, so the owner
+//    competition of stitcher.py:196-204 is a running maximum in registers — first maximum wins,
+//    like np.argmax — and keys / covered are written once, without atomics or clearing.
+// Rows of uint8 output are staged in shared memory at the byte phase of their destination, so
+// that the mosaic is written with aligned 128-bit stores whatever W is.
 constexpr int DT_PITCH = 3 * TILE_X + 16 + 16;          // 192 bytes of pixels + alignment phase (+ bank skew)
 
 template <bool PACKED>
@@ -418,97 +410,159 @@ __device__ __forceinline__ void store_row_bytes(uint8_t *dst, const uint8_t *row
     for (int i = lane; i < tail; i += lanes) dst[head + 16 * body + i] = src[head + 16 * body + i];
 }
 
-template <bool PACKED>
-__global__ void __launch_bounds__(256)
-warp_direct_kernel(const WarpJob *__restrict__ jobs, int n_jobs, unsigned long long *__restrict__ keys,
-                   uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
-                   int y_begin, int y_end, int H, int W, int want_covered, TileMaps m) {
-    __align__(16) __shared__ uint8_t rows[TILE_Y][DT_PITCH];
-    __align__(16) __shared__ WarpJob job;
-    __shared__ float lut[256];
-    __shared__ int who;
-    const int tid = threadIdx.y * TILE_X + threadIdx.x;
-    const int tx0 = blockIdx.x * TILE_X, ty0 = first_tile_row + blockIdx.y * TILE_Y;
-    const size_t tile = (size_t)((ty0 - m.row0) >> 5) * m.tiles_x + blockIdx.x;
-    if (tid == 0) {
-        int single = -1;
-        bool zone = false;
-        for (int w = 0; w < m.words; ++w) {
-            const uint32_t c = __ldg(m.cand + tile * m.words + w);
-            if (c && single < 0) single = 32 * w + __ffs(c) - 1;
-            zone |= __ldg(m.wneed + tile * m.words + w) != 0u;
-        }
-        // bit 30: seam zone, bit 29: multi; low bits: the candidate (0x1fffffff: none)
-        who = (single < 0 ? 0x1fffffff : single) | (zone ? 1 << 30 : 0) | (__ldg(m.multi + tile) ? 1 << 29 : 0);
-    }
-    __syncthreads();
-    const bool zone = who & (1 << 30), multi = who & (1 << 29);
-    const int cand = who & 0x1fffffff;
-    const int X = tx0 + threadIdx.x;
-    if (zone && X < W) {            // the float warp competes into these keys next
-        for (int sub = 0; sub < TILE_Y / 4; ++sub) {
-            const int Y = ty0 + threadIdx.y + 4 * sub;
-            if (Y < 0 || Y >= H) continue;
-            keys[(size_t)Y * W + X] = 0ull;
-            covered[(size_t)Y * W + X] = 0;
-        }
-    }
-    if (multi) return;                                   // block-uniform: the collapse writes this tile
-    const bool have = cand < n_jobs;
-    if (have) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(jobs + cand);
-        if (tid < (int)(sizeof(WarpJob) / 4)) reinterpret_cast<uint32_t *>(&job)[tid] = __ldg(src + tid);
-    }
-    __syncthreads();
-    if (have) lut[tid] = __ldg(job.lut + tid);
-    __syncthreads();
-    const int ncols = min(TILE_X, W - tx0);
+constexpr int TW_ROWS = TILE_Y / 4;     // rows per thread (block = 64 x 4 threads)
+
+// One patch over one tile.  FLOAT: write RGBA + mask to the patch and compete for the pixels;
+// BYTES: stage the truncated pixel for the mosaic.  Rows [y_lo, y_hi) of the window get bytes.
+template <bool PACKED, bool FLOAT, bool BYTES>
+__device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float *lut, int tx0, int ty0,
+                                                uint8_t (*rows)[DT_PITCH], const uint8_t *out, int W,
+                                                int y_lo, int y_hi, float (*best_a)[TILE_X],
+                                                int16_t (*best_p)[TILE_X], unsigned &valid_bits) {
+    const int X = tx0 + threadIdx.x, c = X - job.x0;
+    if ((unsigned)c >= (unsigned)job.pw) return;
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        // four rows per thread and pass: all coordinates, then all gathers, then LUT + blend
+    for (int half = 0; half < TW_ROWS / WARP_ROWS; ++half) {
+        // four rows per pass, branch-free up to the stores: all coordinates (rows clamped into the
+        // patch), then all gathers, then LUT + blend; only the commit looks at what is live
         TapPlan plan[WARP_ROWS];
-        uint32_t taps[WARP_ROWS][4];
-        bool live[WARP_ROWS];
+        RawTap taps[WARP_ROWS][4];
 #pragma unroll
         for (int k = 0; k < WARP_ROWS; ++k) {
-            const int Y = ty0 + 16 * half + threadIdx.y + 4 * k;
-            const int c = have ? X - job.x0 : -1, r = have ? Y - job.y0 : -1;
-            live[k] = have && Y >= y_begin && Y < y_end && X < W &&
-                      (unsigned)c < (unsigned)job.pw && (unsigned)r < (unsigned)job.ph;
-            if (live[k]) plan[k] = plan_taps(job, c, r);
+            const int r = ty0 + (int)threadIdx.y + 4 * (WARP_ROWS * half + k) - job.y0;
+            plan[k] = plan_taps(job, c, min(max(r, 0), job.ph - 1));
         }
 #pragma unroll
         for (int k = 0; k < WARP_ROWS; ++k) {
-            if (!live[k]) continue;
-            taps[k][0] = load_rgbx<PACKED>(job, plan[k].off00); taps[k][1] = load_rgbx<PACKED>(job, plan[k].off01);
-            taps[k][2] = load_rgbx<PACKED>(job, plan[k].off10); taps[k][3] = load_rgbx<PACKED>(job, plan[k].off11);
-        }
-#pragma unroll
-        for (int k = 0; k < WARP_ROWS; ++k) {
-            const int ry = 16 * half + threadIdx.y + 4 * k, Y = ty0 + ry;
-            if (Y < y_begin || Y >= y_end || X >= W) continue;
-            uint8_t b0 = 0, b1 = 0, b2 = 0;
-            const bool valid = live[k] && !plan[k].bad;
-            if (valid) {
-                const uint32_t *q = taps[k];
-                b0 = to_u8(blend4(lut_at(lut, (q[0] << 2) & 0x3fc), lut_at(lut, (q[1] << 2) & 0x3fc),
-                                  lut_at(lut, (q[2] << 2) & 0x3fc), lut_at(lut, (q[3] << 2) & 0x3fc), plan[k]));
-                b1 = to_u8(blend4(lut_at(lut, (q[0] >> 6) & 0x3fc), lut_at(lut, (q[1] >> 6) & 0x3fc),
-                                  lut_at(lut, (q[2] >> 6) & 0x3fc), lut_at(lut, (q[3] >> 6) & 0x3fc), plan[k]));
-                b2 = to_u8(blend4(lut_at(lut, (q[0] >> 14) & 0x3fc), lut_at(lut, (q[1] >> 14) & 0x3fc),
-                                  lut_at(lut, (q[2] >> 14) & 0x3fc), lut_at(lut, (q[3] >> 14) & 0x3fc), plan[k]));
+            if (FLOAT) {
+                taps[k][0] = load_tap<PACKED>(job, plan[k].off00); taps[k][1] = load_tap<PACKED>(job, plan[k].off01);
+                taps[k][2] = load_tap<PACKED>(job, plan[k].off10); taps[k][3] = load_tap<PACKED>(job, plan[k].off11);
+            } else {
+                taps[k][0].rgbx = load_rgbx<PACKED>(job, plan[k].off00); taps[k][1].rgbx = load_rgbx<PACKED>(job, plan[k].off01);
+                taps[k][2].rgbx = load_rgbx<PACKED>(job, plan[k].off10); taps[k][3].rgbx = load_rgbx<PACKED>(job, plan[k].off11);
             }
-            uint8_t *dst = out + ((size_t)Y * W + tx0) * 3;
-            uint8_t *stage = rows[ry] + (reinterpret_cast<uintptr_t>(dst) & 15) + 3 * threadIdx.x;
-            stage[0] = b0; stage[1] = b1; stage[2] = b2;
-            if (want_covered) covered[(size_t)Y * W + X] = valid ? 1 : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < WARP_ROWS; ++k) {
+            const int slot = WARP_ROWS * half + k;
+            const int ry = threadIdx.y + 4 * slot, Y = ty0 + ry, r = Y - job.y0;
+            const RawTap (&q)[4] = taps[k];
+            float4 o;
+            o.x = blend4(lut_at(lut, (q[0].rgbx << 2) & 0x3fc), lut_at(lut, (q[1].rgbx << 2) & 0x3fc),
+                         lut_at(lut, (q[2].rgbx << 2) & 0x3fc), lut_at(lut, (q[3].rgbx << 2) & 0x3fc), plan[k]);
+            o.y = blend4(lut_at(lut, (q[0].rgbx >> 6) & 0x3fc), lut_at(lut, (q[1].rgbx >> 6) & 0x3fc),
+                         lut_at(lut, (q[2].rgbx >> 6) & 0x3fc), lut_at(lut, (q[3].rgbx >> 6) & 0x3fc), plan[k]);
+            o.z = blend4(lut_at(lut, (q[0].rgbx >> 14) & 0x3fc), lut_at(lut, (q[1].rgbx >> 14) & 0x3fc),
+                         lut_at(lut, (q[2].rgbx >> 14) & 0x3fc), lut_at(lut, (q[3].rgbx >> 14) & 0x3fc), plan[k]);
+            const bool bad = plan[k].bad;
+            if ((unsigned)r >= (unsigned)job.ph) continue;            // the tile row lies outside the patch
+            if (FLOAT) {
+                o.w = bad ? 0.0f : blend4(q[0].alpha, q[1].alpha, q[2].alpha, q[3].alpha, plan[k]);   // stitcher.py:317
+                const size_t idx = (size_t)r * job.pw + c;
+                st_stream(job.out + idx, o);
+                job.invalid[idx] = bad ? 1 : 0;
+                if (o.w > best_a[ry][threadIdx.x]) {                  // first maximum wins (patches come in order)
+                    best_a[ry][threadIdx.x] = o.w;
+                    best_p[ry][threadIdx.x] = (int16_t)job.patch;
+                }
+            }
+            if (!bad) valid_bits |= 1u << slot;
+            if (BYTES && !bad && Y >= y_lo && Y < y_hi) {
+                const uint8_t *dst = out + ((size_t)Y * W + tx0) * 3;
+                uint8_t *stage = rows[ry] + (reinterpret_cast<uintptr_t>(dst) & 15) + 3 * threadIdx.x;
+                stage[0] = to_u8(o.x); stage[1] = to_u8(o.y); stage[2] = to_u8(o.z);
+            }
         }
     }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256, 3)
+warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
+                  uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end, int H, int W,
+                  int want_covered, TileMaps m) {
+    __align__(16) __shared__ uint8_t rows[TILE_Y][DT_PITCH];
+    __shared__ float lut[256];
+    __shared__ float best_a[TILE_Y][TILE_X];             // running owner of every pixel: each thread only
+    __shared__ int16_t best_p[TILE_Y][TILE_X];           // ever touches its own eight slots
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int tx0 = blockIdx.x * TILE_X, ty0 = m.row0 + (int)blockIdx.y * TILE_Y;
+    const size_t tile = (size_t)blockIdx.y * m.tiles_x + blockIdx.x;
+    const bool multi = __ldg(m.multi + tile) != 0;
+    const uint32_t *cand = m.cand + tile * m.words, *wneed = m.wneed + tile * m.words;
+    bool zone = false;
+    int solo = -1;                                       // the candidate of a non-multi tile
+    for (int w = 0; w < m.words; ++w) {
+        zone |= __ldg(wneed + w) != 0u;
+        const uint32_t c = __ldg(cand + w);
+        if (c && solo < 0) solo = 32 * w + __ffs(c) - 1;
+    }
+    if (multi) solo = -1;
+    const bool bytes = !multi && ty0 < y_end && ty0 + TILE_Y > y_begin;      // this block writes mosaic bytes
+    if (!zone && !bytes) return;                         // (block-uniform)
+    if (bytes) {                                         // zeros wherever the candidate has no valid pixel
+        for (int i = tid; i < TILE_Y * DT_PITCH / 16; i += 256)
+            reinterpret_cast<uint4 *>(&rows[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    unsigned valid_bits = 0u;
+    if (zone) {
+#pragma unroll
+        for (int k = 0; k < TW_ROWS; ++k) {
+            best_a[threadIdx.y + 4 * k][threadIdx.x] = 0.0f;
+            best_p[threadIdx.y + 4 * k][threadIdx.x] = -1;
+        }
+    }
+    const float *lut_of = nullptr;
+    // the patches wanted as float here (ascending = patch order), then the solo candidate if it
+    // was not among them
+    bool solo_done = false;
+    for (int w = 0; w <= m.words; ++w) {
+        uint32_t bits;
+        if (w < m.words) bits = zone ? __ldg(wneed + w) : 0u;
+        else bits = (solo >= 0 && !solo_done && bytes) ? 1u : 0u;
+        while (bits) {
+            int id;
+            bool as_float;
+            if (w < m.words) { id = 32 * w + __ffs(bits) - 1; as_float = true; } else { id = solo; as_float = false; }
+            bits &= bits - 1;
+            if (id >= n_jobs) break;
+            const WarpJob &job = c_warp_jobs[id];
+            if (job.lut != lut_of) {                     // (block-uniform) all images without gains share one table
+                __syncthreads();
+                lut[tid] = __ldg(job.lut + tid);
+                lut_of = job.lut;
+                __syncthreads();
+            }
+            const bool to_bytes = bytes && id == solo;
+            if (as_float && to_bytes)
+                warp_tile_patch<PACKED, true, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+            else if (as_float)
+                warp_tile_patch<PACKED, true, false>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+            else
+                warp_tile_patch<PACKED, false, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+            solo_done |= id == solo;
+        }
+    }
+    const int X = tx0 + threadIdx.x;
+    if (X < W && (zone || want_covered)) {
+#pragma unroll
+        for (int k = 0; k < TW_ROWS; ++k) {
+            const int Y = ty0 + threadIdx.y + 4 * k;
+            if (Y < 0 || Y >= H) continue;
+            const size_t mi = (size_t)Y * W + X;
+            if (zone) {
+                const int p = best_p[threadIdx.y + 4 * k][threadIdx.x];
+                keys[mi] = p < 0 ? 0ull : owner_key(best_a[threadIdx.y + 4 * k][threadIdx.x], p);
+            }
+            covered[mi] = (valid_bits >> k) & 1u;
+        }
+    }
+    if (!bytes) return;
     __syncthreads();
     // 8 threads per row: aligned 128-bit stores of the staged bytes
     const int ry = tid >> 3, Y = ty0 + ry;
     if (Y >= y_begin && Y < y_end)
-        store_row_bytes(out + ((size_t)Y * W + tx0) * 3, rows[ry], 3 * ncols, tid & 7, 8);
+        store_row_bytes(out + ((size_t)Y * W + tx0) * 3, rows[ry], 3 * min(TILE_X, W - tx0), tid & 7, 8);
 }
 
 // u8 x 3 -> {RGBX u32, alpha f32}: one aligned 64-bit word per source pixel
@@ -572,42 +626,36 @@ extern "C" int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, p
     return check_launch(where);
 }
 
-extern "C" int p360_warp_direct(const p360_warp_job *jobs_dev, int n_jobs, int packed, uint64_t *owner_keys,
-                                uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
-                                int want_covered, const p360_tile_maps *maps_host, void *stream) {
+extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, int packed, uint64_t *owner_keys,
+                               uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
+                               int want_covered, const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
-    const char *where = "p360_warp_direct";
-    P360_REQUIRE(jobs_dev && maps_host && owner_keys && covered && out_u8, where);
-    P360_REQUIRE(n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0 && y_begin >= 0 && y_end <= H, where);
+    const char *where = "p360_warp_tiles";
+    P360_REQUIRE(jobs_host && maps_host && owner_keys && covered && out_u8, where);
+    P360_REQUIRE(n_jobs > 0 && n_jobs <= TILE_JOBS_MAX && H > 0 && W > 0 && y_begin >= 0 && y_end <= H, where);
     TileMaps m;
     memcpy(&m, maps_host, sizeof(m));
     if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
-    // every tile of the window: zone tiles are cleared on all their rows, pixels only go to [y_begin, y_end)
     dim3 grid(m.tiles_x, m.tiles_y), block(TILE_X, 4);
     P360_REQUIRE(grid.y <= 65535, where);
-    auto jobs = reinterpret_cast<const WarpJob *>(jobs_dev);
+    cudaStream_t s = (cudaStream_t)stream;
+    // stream-ordered: waits for the previous launch that still reads the table
+    P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host, sizeof(WarpJob) * n_jobs, 0, cudaMemcpyHostToDevice, s), where);
     auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
     if (packed)
-        warp_direct_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(jobs, n_jobs, keys, covered, out_u8, m.row0,
-                                                                          y_begin, y_end, H, W, want_covered, m);
+        warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8,
+                                                                         y_begin, y_end, H, W, want_covered, m);
     else
-        warp_direct_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(jobs, n_jobs, keys, covered, out_u8, m.row0,
-                                                                           y_begin, y_end, H, W, want_covered, m);
+        warp_tiles_kernel<false><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8,
+                                                                          y_begin, y_end, H, W, want_covered, m);
     return check_launch(where);
 }
 
 extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
-                               uint64_t *owner_keys, uint8_t *covered, int W,
-                               const p360_tile_maps *gate_host, void *stream) {
+                               uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_batch";
     P360_REQUIRE(jobs_host && n_jobs >= 0, where);
-    TileMaps gate;
-    memset(&gate, 0, sizeof(gate));
-    if (gate_host != nullptr) {
-        memcpy(&gate, gate_host, sizeof(gate));
-        P360_REQUIRE(gate.wneed && gate.tiles_x > 0 && gate.tiles_y > 0 && gate.words > 0 && owner_keys, where);
-    }
     P360_REQUIRE(owner_keys == nullptr || (covered != nullptr && W > 0), where);
     cudaStream_t s = (cudaStream_t)stream;
     for (int first = 0; first < n_jobs; first += WARP_JOBS_PER_LAUNCH) {
@@ -633,9 +681,7 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
         dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
         auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
-        if (gate_host != nullptr && packed) warp_batch_gated_kernel<true><<<grid, block, 0, s>>>(keys, covered, W, gate);
-        else if (gate_host != nullptr) warp_batch_gated_kernel<false><<<grid, block, 0, s>>>(keys, covered, W, gate);
-        else if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
+        if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
         else if (packed) warp_batch_kernel<true, false><<<grid, block, 0, s>>>(keys, covered, W);
         else if (keys) warp_batch_kernel<false, true><<<grid, block, 0, s>>>(keys, covered, W);
         else warp_batch_kernel<false, false><<<grid, block, 0, s>>>(keys, covered, W);
