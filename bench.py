@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink views (debug only; invalid as a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg1/cfg2/cfg3/cfg5 runs after cfg4")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
@@ -61,17 +62,19 @@ def parse_args():
 # CPU arm: the reference's own NumPy/OpenCV path on a bounded sample
 # ----------------------------------------------------------------------------
 def cpu_sample(wl):
-    """A sub-panorama of the workload small enough for ~10-25 s of CPU work:
-    adjacent views of the same ring at full resolution, same blender."""
+    """A sub-panorama of the workload small enough for the CPU arm's budget: neighbouring views
+    at full resolution, same blender.  cfg4: 2 yaw columns x 2 pitch rows (vertical and
+    horizontal seams and a four-image corner; ~1 min per run on 8 cores — the whole workload is
+    ~20 min and needs ~85 GiB); P/M of the sample is reported next to the workload's."""
     from pano360_b200 import synth  # noqa: F401
     if wl.name == "cfg4":
-        pick = [17, 18]          # two neighbouring views of the pitch-0 row
+        pick = [5, 6, 17, 18]
     elif wl.name == "cfg3":
-        pick = [2, 3]
+        pick = [2, 3, 8, 9]
     else:
         pick = list(range(wl.n_views))
     sample = replace(wl, yaws=tuple(wl.yaws[i] for i in pick), pitches=tuple(wl.pitches[i] for i in pick))
-    what = (f"{len(pick)} adjacent views of {wl.name} ({wl.width}x{wl.height}, views {pick}), "
+    what = (f"{len(pick)} views of {wl.name} ({wl.width}x{wl.height}, views {pick}), "
             f"{wl.blend}" + (f" {wl.n_levels} bands" if wl.blend == "multiband" else "")
             + (" + gains" if wl.equalize else ""))
     return sample, what
@@ -113,8 +116,15 @@ def time_cpu(wl, steps, warmup, budget_s):
         if time.perf_counter() - t_begin > budget_s:
             break
     sec = float(np.mean(times))
+    from pano360_b200 import geometry as geo
+    ratio = []
+    for w in (sample, wl):          # P/M: patch-box pixels per mosaic pixel, the reference's own boxes
+        cams = synth.make_views(w, only=set())
+        pl = geo.plan_mosaic(cams, w.blend == "multiband", w.max_resolution)
+        ratio.append(sum((x1 - x0) * (y1 - y0) for x0, y0, x1, y1 in pl.boxes) / (pl.shape[0] * pl.shape[1]))
     return {"value": mpix / sec, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": kind,
-            "sample": f"{what}; mosaic {mpix:.1f} Mpix in {sec:.2f} s/step, {len(times)} timed steps "
+            "sample": f"{what}; mosaic {mpix:.1f} Mpix in {sec:.2f} s/step, {len(times)} timed steps, {done_warm} warm-up; "
+                      f"P/M of the sample {ratio[0]:.2f} vs {ratio[1]:.2f} for the workload "
                       f"(OpenCV pool {cv2.getNumThreads()} threads of {os.cpu_count()} cores, NumPy single-threaded)"}, \
         sec, len(times), done_warm
 
@@ -229,7 +239,8 @@ class ClockSampler:
 
 
 def model_bytes(wl, plan, n_src_bytes):
-    """Algorithmic bytes of one step, stage-materialised model of SURVEY.md §8(d)."""
+    """Algorithmic bytes of one step, stage-materialised model of SURVEY.md §8(d), on the
+    reference's own patch boxes."""
     m = plan.shape[0] * plan.shape[1]
     p = sum((x1 - x0) * (y1 - y0) for x0, y0, x1, y1 in plan.boxes)
     if wl.blend == "multiband":
@@ -240,7 +251,37 @@ def model_bytes(wl, plan, n_src_bytes):
     return n_src_bytes + 17 * p + 17 * p + 3 * m, p, m
 
 
-def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8):
+def mosaic_checksum(mosaic):
+    """Order-sensitive checksum of a device uint8 mosaic (outside every timed region): the sum of
+    the bytes and a position-weighted sum, row chunk by row chunk.  Equal checksums at N = 1, 2,
+    4, 8 say the strips reassemble the single-GPU mosaic."""
+    import torch
+    flat = mosaic.reshape(-1)
+    total, weighted = 0, 0
+    chunk = 1 << 26
+    for start in range(0, flat.numel(), chunk):
+        part = flat[start:start + chunk].to(torch.int64)
+        idx = torch.arange(start, start + part.numel(), device=part.device, dtype=torch.int64)
+        total += int(part.sum())
+        weighted = (weighted + int((part * (idx % 65521 + 1)).sum())) % (1 << 61)
+    return f"{total:x}-{weighted:x}"
+
+
+def algorithmic_bytes(trace_name, wl, crop_px, src_bytes, m_px, h2d_px=0):
+    """SURVEY.md §8(d) bytes of the stage(s) a traced kernel stands for, on the patch pixels the
+    launch really covers (crop_px: after the seam split), None for implementation-only kernels."""
+    lv = wl.n_levels
+    table = {
+        "K1t_warp_tiles": src_bytes + 17 * crop_px + 4 * crop_px + m_px,      # K1 + K2 fused: 3S + 17P + (4P + M)
+        "K1_warp": src_bytes + 17 * crop_px + (4 * crop_px + m_px if wl.blend == "multiband" else 0),
+        "K3a_pyramid_reduce": None, "K3_gauss_blur": 32 * crop_px * (lv - 1),
+        "K4_multiband_collapse": 64 * crop_px * lv + m_px * (40 * lv + 16),
+        "K6_linear_collapse": 48 * crop_px + 19 * m_px, "K7_paste_collapse": 17 * crop_px + 3 * m_px,
+    }
+    return table.get(trace_name)
+
+
+def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8, steps=None):
     """cfg5: independent panoramas, pano_id % N -> GPU, no communication
     (replicas only).  One step = the whole batch of 64."""
     import torch
@@ -254,7 +295,7 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8):
             t.numpy()[...] = reg.img
             reg.img, reg._pin = t.numpy(), t
         plan = geo.plan_mosaic(regs, True, wl.max_resolution)
-        scenes.append((regs, plan, comp.upload(regs),
+        scenes.append((regs, plan, comp.upload(regs, pack=False),
                        torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True)))
     mine = list(range(rank, n_panos, world))
     stitcher.MAX_RESOLUTION = wl.max_resolution
@@ -266,8 +307,8 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8):
 
     def device_step():
         for pano in mine:
-            regs, plan, src, _ = scenes[pano % n_scenes]
-            comp.composite(regs, src, plan, wl.blend, wl.n_levels)
+            regs, plan, raw, _ = scenes[pano % n_scenes]
+            comp.composite(regs, comp.pack_sources(raw), plan, wl.blend, wl.n_levels)
 
     def e2e_step():
         for pano in mine:
@@ -293,18 +334,19 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8):
             launched = int(n.item())
         return dev_ms / steps, host_ms / steps, launched
 
+    steps = args.steps if steps is None else steps
     for _ in range(args.warmup):
         device_step()
     with ClockSampler(comp.device.index or 0) as clocks:
-        ms, _, launches = timed(device_step, args.steps)
+        ms, _, launches = timed(device_step, steps)
     e2e_step()
-    _, e2e_ms, _ = timed(e2e_step, args.steps)
+    _, e2e_ms, _ = timed(e2e_step, steps)
     mpix = sum(np.prod(scenes[p % n_scenes][1].shape) for p in range(n_panos)) / 1e6
     if rank == 0:
         src_bytes = sum(int(np.prod(r.img.shape)) for p in mine for r in scenes[p % n_scenes][0])
         out_bytes = sum(int(np.prod(scenes[p % n_scenes][1].shape)) * 3 for p in mine)
-        print(json.dumps({
-            "metric": METRIC, "value": mpix / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        return {
+            "metric": METRIC, "value": mpix / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": DESCRIPTIONS["cfg5"], "panoramas": n_panos, "distinct_scenes": n_scenes,
@@ -314,15 +356,263 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8):
             "clocks": clocks.summary(),
             "e2e": {"value": mpix / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": src_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms, "api": "pano360_b200.stitcher.stitch"},
-            "gpu_launches": launches, "roofline": None}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            "gpu_launches": launches, "roofline": None}
+    return None
+
+
+class Bench:
+    """One workload on this rank's GPU: device-timed leg, end-to-end legs, roofline."""
+
+    def __init__(self, args, wl, comp, world, rank):
+        import torch
+        from pano360_b200 import geometry as geo, strips, synth
+        self.args, self.wl, self.comp, self.world, self.rank = args, wl, comp, world, rank
+        self.torch, self.strips = torch, strips
+        kind, levels = wl.blend, wl.n_levels
+        cameras = synth.make_views(wl, only=set())          # cameras only: nothing rendered yet
+        self.plan = plan = geo.plan_mosaic(cameras, kind == "multiband", wl.max_resolution)
+        self.parts = strips.partition_rows(plan, world, kind, levels)
+        self.halo = strips.blur_halo(kind, levels)
+        rows = self.parts[rank]
+        need = set(strips.images_for_rows(plan, rows, self.halo)) if rows[1] > rows[0] else set()
+        if wl.equalize:
+            need = set(range(len(cameras)))
+        self.need = need
+        self.regions = regions = synth.make_views(wl, only=need)   # each rank renders only the views its strip needs
+        # pinned host copies of the inputs (the e2e leg reads these every step), pageable ones for
+        # what main() / a PKL user hands to stitch()
+        self.pageable = []
+        for i, reg in enumerate(regions):
+            self.pageable.append(reg.img if i in need else None)
+            if i not in need:
+                continue
+            t = torch.empty(reg.img.shape, dtype=torch.uint8, pin_memory=True)
+            t.numpy()[...] = reg.img
+            reg._pin, reg.img = t, t.numpy()                 # numpy view of pinned memory
+        self.raw = comp.upload(regions, need=need, pack=False)     # u8 x 3 as uploaded, resident in HBM
+        self.src_bytes_all = sum(int(np.prod(r.img.shape)) for r in regions)
+        self.h2d_bytes = sum(int(np.prod(regions[i].img.shape)) for i in need)
+        self.out_pinned = torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def device_step(self):
+        """value leg: the uploaded u8 x 3 images are resident in HBM; everything stitch() does
+        with them is inside (RGBX packing, gains, warp, blend, gather of the strips)."""
+        comp, wl = self.comp, self.wl
+        src = comp.pack_sources(self.raw)
+        if wl.equalize:
+            from pano360_b200.stitcher import find_gains
+            overlaps, sizes = self.strips.all_pair_statistics(comp, self.regions, src)
+            comp.set_gains(src, find_gains(overlaps, sizes))
+        return self.strips.composite_gather(comp, self.regions, src, self.plan, wl.blend, wl.n_levels, self.parts)
+
+    def e2e_step(self, pageable=False):
+        """e2e leg: public API, host buffers in, host mosaic out."""
+        wl = self.wl
+        regions = self.regions
+        if pageable:
+            from pano360_b200.camera import Image
+            regions = [Image(img if img is not None else r.img, r.rot, r.intr) for r, img in zip(self.regions, self.pageable)]
+        if self.world == 1:
+            from pano360_b200 import stitcher
+            stitcher.MAX_RESOLUTION = wl.max_resolution
+            return stitcher.stitch(regions, blender=stitcher.BLENDERS[wl.blend], equalize=wl.equalize,
+                                   n_levels=wl.n_levels, out=None if pageable else self.out_pinned.numpy())
+        return self.strips.stitch_strips(self.comp, regions, wl.blend, wl.n_levels, wl.equalize, wl.max_resolution,
+                                         out=None if self.out_pinned is None or pageable else self.out_pinned.numpy())
+
+    def timed(self, step_fn, n_steps, trace=False):
+        import torch.distributed as dist
+        from pano360_b200 import _lib
+        torch, comp = self.torch, self.comp
+        self.barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launch_count
+        comp.trace = [] if trace else None
+        t_host = time.perf_counter()
+        start.record(torch.cuda.current_stream())
+        for _ in range(n_steps):
+            result = step_fn()
+        end.record(torch.cuda.current_stream())
+        enqueue_s = time.perf_counter() - t_host          # host time to issue the steps (no sync)
+        self.barrier()
+        host_s = time.perf_counter() - t_host
+        ms = start.elapsed_time(end)
+        launched = _lib.launch_count - launches0
+        trace_out, comp.trace = comp.trace, None
+        if self.world > 1:
+            t = torch.tensor([ms, host_s * 1e3], dtype=torch.float64, device=comp.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, host_ms = t.tolist()
+            host_s = host_ms / 1e3
+            n = torch.tensor([launched], dtype=torch.int64, device=comp.device)
+            dist.all_reduce(n, op=dist.ReduceOp.SUM)
+            launched = int(n.item())
+        return {"ms": ms, "host_s": host_s, "launches": launched, "trace": trace_out, "result": result,
+                "enqueue_ms": enqueue_s / n_steps * 1e3}
+
+    def run(self, steps, warmup, local_gpu, full=True):
+        """-> the result record (rank 0) or None.  ``full``: also the roofline / per-kernel tables,
+        the pageable e2e leg and the block statistics (the main workload)."""
+        import torch.distributed as dist
+        torch, comp, wl, plan, world, rank = self.torch, self.comp, self.wl, self.plan, self.world, self.rank
+        for _ in range(warmup):
+            self.device_step()
+        with ClockSampler(local_gpu) as clocks:
+            dev = self.timed(self.device_step, steps, trace=True)
+        clock_summary = clocks.summary()
+        checksum = mosaic_checksum(dev["result"]) if rank == 0 and dev["result"] is not None else None
+        stats = self.block_stats() if full and world == 1 else None
+        for _ in range(min(warmup, 2)):
+            self.e2e_step()
+        e2e = self.timed(self.e2e_step, steps)
+        e2e_page = None
+        if full and world == 1:
+            self.e2e_step(pageable=True)
+            e2e_page = self.timed(lambda: self.e2e_step(pageable=True), max(1, min(steps, 3)))
+
+        mpix = plan.shape[0] * plan.shape[1] / 1e6
+        ms_per_step = max(dev["ms"], 1e-9) / steps
+        e2e_ms = e2e["host_s"] / steps * 1e3
+        crop_px = self.crop_pixels()
+        # ---- per-kernel table + roofline of the dominant kernel, from CUDA events in the timed steps
+        per_kernel = {}
+        for name, _, ev0, ev1 in dev["trace"] or []:
+            agg = per_kernel.setdefault(name, [0.0, 0])
+            agg[0] += ev0.elapsed_time(ev1)
+            agg[1] += 1
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        roofline, shares = None, {}
+        m_px = plan.shape[0] * plan.shape[1]
+        if per_kernel:
+            traced_ms = sum(v[0] for v in per_kernel.values())
+            for k, v in sorted(per_kernel.items()):
+                nbytes = algorithmic_bytes(k, wl, crop_px, self.src_bytes_all, m_px)
+                shares[k] = {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps,
+                             "share_of_traced": v[0] / max(traced_ms, 1e-9),
+                             "algorithmic_GBps": None if nbytes is None else nbytes * steps / max(v[0], 1e-9) / 1e6}
+            top = max(per_kernel, key=lambda k: per_kernel[k][0])
+            t_ms, count = per_kernel[top]
+            nbytes = algorithmic_bytes(top, wl, crop_px, self.src_bytes_all, m_px) or 0
+            per_launch = nbytes * steps / count
+            t_ms = max(t_ms, 1e-9)
+            achieved = nbytes * steps / t_ms / 1e6                     # GB/s
+            traffic = None
+            try:           # ncu-measured DRAM bytes per launch of this kernel (1 GPU, same workload)
+                table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                if world == 1 and self.args.scale == 1.0:
+                    traffic = table.get(wl.name, {}).get(top)
+            except OSError:
+                pass
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                        "launch_ms": t_ms / count, "algorithmic_bytes_per_launch": per_launch,
+                        "bytes_model": "SURVEY 8(d): 3S + 17P [K1] + 4P + M [K2] for the fused tile warp, P = patch pixels "
+                                       "after the seam split (%.1f Mpix), S = %.1f Mpix, M = %.1f Mpix"
+                                       % (crop_px / 1e6, self.src_bytes_all / 3e6, m_px / 1e6),
+                        "share_of_step": t_ms / max(dev["ms"], 1e-9)}
+            if "K1p_pack_rgbx" in per_kernel and top.startswith("K1"):     # the same bytes over warp + RGBX packing
+                both = t_ms + per_kernel["K1p_pack_rgbx"][0]
+                roofline["frac_with_pack"] = nbytes * steps / both / 1e6 / peak
+        my_kernel_ms = sum(v[0] for v in per_kernel.values()) / steps if per_kernel else 0.0
+        per_rank = [my_kernel_ms]
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=comp.device)
+            t[rank] = my_kernel_ms
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank = [round(v, 3) for v in t.tolist()]
+        total_bytes, p_px, _ = model_bytes(wl, plan, self.src_bytes_all)
+        if rank != 0:
+            return None
+        line = {
+            "metric": METRIC, "value": mpix / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": DESCRIPTIONS[wl.name] + (f" (DEBUG scale 1/{self.args.scale})" if self.args.scale != 1 else ""),
+                       "views": wl.n_views, "view_size": [wl.width, wl.height], "blend": wl.blend,
+                       "n_levels": wl.n_levels if wl.blend == "multiband" else None, "equalize": wl.equalize,
+                       "mosaic": list(plan.shape), "mosaic_mpix": mpix, "patch_mpix_reference_boxes": p_px / 1e6,
+                       "patch_mpix_after_seam_split": crop_px / 1e6,
+                       "strips": [list(p) for p in self.parts], "halo_rows": self.halo,
+                       "timed_region": "sources resident in HBM as uploaded (u8 x 3); RGBX packing, gains, warp, blend and "
+                                       "the gather of the strips are all inside",
+                       "l2": "no flush: each step streams >> 126 MB (model bytes %.1f GB) so nothing survives in L2 between steps"
+                             % (total_bytes / 1e9)},
+            "clocks": clock_summary,
+            "e2e": {"value": mpix / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": self.h2d_bytes,
+                    "d2h_bytes_per_step": int(np.prod(plan.shape)) * 3, "ms_per_step": e2e_ms,
+                    "api": "pano360_b200.stitcher.stitch" if world == 1 else "pano360_b200.strips.stitch_strips",
+                    "host_buffers": "pinned"},
+            "gpu_launches": dev["launches"],
+            "mosaic_checksum": checksum,
+            "roofline": roofline,
+            "kernels": shares,
+            "per_rank_kernel_ms": per_rank,
+            "host_ms_per_step": dev["host_s"] / steps * 1e3,
+            "host_enqueue_ms_per_step": dev["enqueue_ms"],
+        }
+        if full:
+            line["pipeline"] = {"model_bytes_per_step": total_bytes, "GBps": total_bytes / (ms_per_step / 1e3) / 1e9,
+                                "note": "whole-step SURVEY 8(d) model bytes / time: the pipeline decimates and fuses, so "
+                                        "this exceeds the HBM peak and is not a roofline"}
+        if e2e_page is not None:
+            n = max(1, min(steps, 3))
+            line["e2e_pageable"] = {"value": mpix / (e2e_page["host_s"] / n), "unit": UNIT,
+                                    "ms_per_step": e2e_page["host_s"] / n * 1e3,
+                                    "note": "same call with plain (pageable) NumPy inputs and a returned array, as main() makes it"}
+        if stats is not None:
+            line["blocks_run"] = stats
+        return line
+
+    def crop_pixels(self):
+        """Patch pixels this rank's composite covers (after the seam split; its row window only)."""
+        comp, wl = self.comp, self.wl
+        rows = self.parts[self.rank]
+        if rows[1] <= rows[0]:
+            return 0
+        reach = comp.blur_reach(wl.blend, wl.n_levels)
+        if self.world == 1:
+            crops, _ = comp.plan_crops(self.regions, self.plan, split_dilate=2 * reach)
+        else:
+            wa, wb = comp.window_rows(rows, wl.blend, wl.n_levels, self.plan.shape[0])
+            crops, _ = comp.plan_crops(self.regions, self.plan, rows=(wa, wb), row_align=4 if reach else 1,
+                                       split_dilate=2 * reach)
+        return int(sum((c[3] - c[1]) * (c[4] - c[2]) for c in crops))
+
+    def block_stats(self):
+        """Blocks the list kernels really ran in the last composite and the bytes they moved
+        (reduce: 32 x 32 px of RGBA + keys in, d2 + d4 out; blur: staged cells in, cells out)."""
+        keep = self.comp._keep.get("bands")
+        if not keep or keep[3] is None:
+            return None
+        self.torch.cuda.synchronize()
+        bits = keep[4][0]
+        n_red, n_h, n_v = [int(v) for v in bits[1:4].tolist()]
+        h_rows = int(keep[3]["h_rows"][0])
+        seg, rows_h = (64, 16) if h_rows == 4 else (256, 4)
+        ks = 25                                   # widest coarse tap set (level L-2 on the f = 4 grid)
+        red_b = n_red * (1024 * 24 + 256 * 16 + 64 * 16)
+        h_b = n_h * ((seg + ks - 1) * rows_h * 16 + seg * rows_h * 16)
+        v_b = n_v * (32 * (64 + ks - 1) * 16 + 32 * 64 * 16)
+        return {"reduce_blocks": n_red, "blur_h_blocks": n_h, "blur_v_blocks": n_v,
+                "reduce_bytes": red_b, "blur_bytes": h_b + v_b}
 
 
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from pano360_b200 import _lib, geometry as geo, strips, synth
+    from pano360_b200 import synth
     from pano360_b200.compositor import Compositor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,176 +627,36 @@ def run_gpu_arm(args):
 
     wl = synth.workload(args.workload, scale=args.scale)
     if wl.name == "cfg5":
-        return run_batch_of_panoramas(args, wl, comp, world, rank)
-    kind, levels = wl.blend, wl.n_levels
-    cameras = synth.make_views(wl, only=set())          # cameras only: nothing rendered yet
-    plan = geo.plan_mosaic(cameras, kind == "multiband", wl.max_resolution)
-    parts = strips.partition_rows(plan, world, kind, levels)
-    halo = strips.blur_halo(kind, levels)
-    rows = parts[rank]
-    need = set(strips.images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
-    if wl.equalize:
-        need = set(range(len(cameras)))
-    regions = synth.make_views(wl, only=need)           # each rank renders only the views its strip needs
-
-    # pinned host copies of the inputs (the e2e leg reads these every step)
-    pinned = []
-    for i, reg in enumerate(regions):
-        if i not in need:
-            pinned.append(None)
-            continue
-        t = torch.empty(reg.img.shape, dtype=torch.uint8, pin_memory=True)
-        t.numpy()[...] = reg.img
-        reg.img = t.numpy()                      # numpy view of pinned memory
-        pinned.append(t)
-    src = comp.upload(regions, need=need)
-    src_bytes_all = sum(int(np.prod(r.img.shape)) for r in regions)
-    h2d_bytes = sum(int(np.prod(regions[i].img.shape)) for i in need)
-    out_pinned = torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def device_step():
-        """value leg: sources resident in HBM."""
-        if wl.equalize:
-            overlaps, sizes = strips.all_pair_statistics(comp, regions, src)
-            from pano360_b200.stitcher import find_gains
-            comp.set_gains(src, find_gains(overlaps, sizes))
-        return strips.composite_gather(comp, regions, src, plan, kind, levels, parts)
-
-    def e2e_step():
-        """e2e leg: public API, host buffers in, host mosaic out."""
-        if world == 1:
-            from pano360_b200 import stitcher
-            stitcher.MAX_RESOLUTION = wl.max_resolution
-            return stitcher.stitch(regions, blender=stitcher.BLENDERS[kind], equalize=wl.equalize,
-                                   n_levels=levels, out=out_pinned.numpy())
-        return strips.stitch_strips(comp, regions, kind, levels, wl.equalize, wl.max_resolution,
-                                    out=None if out_pinned is None else out_pinned.numpy())
-
-    def timed(step_fn, n_steps, trace=False):
-        barrier()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _lib.launch_count
-        comp.trace = [] if trace else None
-        t_host = time.perf_counter()
-        start.record(torch.cuda.current_stream())
-        for _ in range(n_steps):
-            result = step_fn()
-        end.record(torch.cuda.current_stream())
-        enqueue_s = time.perf_counter() - t_host          # host time to issue the steps (no sync)
-        barrier()
-        host_s = time.perf_counter() - t_host
-        ms = start.elapsed_time(end)
-        launched = _lib.launch_count - launches0
-        trace_out, comp.trace = comp.trace, None
-        if world > 1:
-            t = torch.tensor([ms, host_s * 1e3], dtype=torch.float64, device=comp.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, host_ms = t.tolist()
-            host_s = host_ms / 1e3
-            n = torch.tensor([launched], dtype=torch.int64, device=comp.device)
-            dist.all_reduce(n, op=dist.ReduceOp.SUM)
-            launched = int(n.item())
-        timed.enqueue_ms = enqueue_s / n_steps * 1e3
-        return ms, host_s, launched, trace_out, result
-
-    for _ in range(args.warmup):
-        device_step()
-    with ClockSampler(local) as clocks:
-        ms, host_s, launches, trace, mosaic = timed(device_step, args.steps, trace=True)
-    clock_summary = clocks.summary()
-    enqueue_ms = timed.enqueue_ms
-    # e2e: host wall clock (includes the blocking D2H), max over ranks
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    _, e2e_host_s, _, _, _ = timed(e2e_step, args.steps)
-
-    mpix = plan.shape[0] * plan.shape[1] / 1e6
-    ms_per_step = ms / args.steps
-    value = mpix / (ms_per_step / 1e3)
-    e2e_value = mpix / (e2e_host_s / args.steps)
-
-    # ---- roofline of the dominant kernel, from CUDA events in the timed region
-    per_kernel = {}
-    for name, nbytes, ev0, ev1 in trace or []:
-        agg = per_kernel.setdefault(name, [0.0, 0, 0])
-        agg[0] += ev0.elapsed_time(ev1)
-        agg[1] += nbytes
-        agg[2] += 1
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    roofline, shares = None, {}
-    if per_kernel:
-        traced_ms = sum(v[0] for v in per_kernel.values())
-        shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
-                      "share_of_traced": v[0] / traced_ms, "GBps": v[1] / v[0] / 1e6}
-                  for k, v in sorted(per_kernel.items())}
-        top = max(per_kernel, key=lambda k: per_kernel[k][0])
-        t_ms, nbytes, count = per_kernel[top]
-        achieved = nbytes / t_ms / 1e6                     # GB/s
-        traffic = None
-        try:           # ncu-measured DRAM bytes per launch of this kernel (1 GPU, same workload)
-            table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if world == 1 and args.scale == 1.0:
-                traffic = table.get(wl.name, {}).get(top)
-        except OSError:
-            pass
-        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                    "launch_ms": t_ms / count, "algorithmic_bytes_per_launch": nbytes / count,
-                    "share_of_step": t_ms / ms}
-    # per-rank load (strip balance): traced kernel time of every rank, gathered on rank 0
-    my_kernel_ms = sum(v[0] for v in per_kernel.values()) / args.steps if per_kernel else 0.0
-    per_rank = [my_kernel_ms]
-    if world > 1:
-        t = torch.zeros(world, dtype=torch.float64, device=comp.device)
-        t[rank] = my_kernel_ms
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        per_rank = [round(v, 3) for v in t.tolist()]
-    total_bytes, p_px, m_px = model_bytes(wl, plan, src_bytes_all)
-    pipeline = {"model_bytes_per_step": total_bytes, "GBps": total_bytes / (ms_per_step / 1e3) / 1e9,
-                "frac_of_hbm_peak": total_bytes / (ms_per_step / 1e3) / 1e9 / peak}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DESCRIPTIONS[wl.name] + (f" (DEBUG scale 1/{args.scale})" if args.scale != 1 else ""),
-                   "views": wl.n_views, "view_size": [wl.width, wl.height], "blend": kind,
-                   "n_levels": levels if kind == "multiband" else None, "equalize": wl.equalize,
-                   "mosaic": list(plan.shape), "mosaic_mpix": mpix, "patch_mpix": p_px / 1e6,
-                   "strips": [list(p) for p in parts], "halo_rows": halo,
-                   "l2": "no flush: each step streams >> 126 MB (model bytes %.1f GB) so nothing survives in L2 between steps"
-                         % (total_bytes / 1e9)},
-        "clocks": clock_summary,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": int(np.prod(plan.shape)) * 3, "ms_per_step": e2e_host_s / args.steps * 1e3,
-                "api": "pano360_b200.stitcher.stitch" if world == 1 else "pano360_b200.strips.stitch_strips"},
-        "gpu_launches": launches,
-        "roofline": roofline,
-        "pipeline": pipeline,
-        "kernels": shares,
-        "per_rank_kernel_ms": per_rank,
-        "host_ms_per_step": host_s / args.steps * 1e3,
-        "host_enqueue_ms_per_step": enqueue_ms,
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        base, _, _, _ = time_cpu(wl, 1, 1, args.cpu_budget_s / 4)
-        line["cpu_baseline"] = base
-    print(json.dumps(line), flush=True)
+        line = run_batch_of_panoramas(args, wl, comp, world, rank)
+    else:
+        bench = Bench(args, wl, comp, world, rank)
+        line = bench.run(args.steps, args.warmup, local)
+        bench = None
+        comp.release()
+        torch.cuda.empty_cache()
+    # the other BASELINE configs, short runs, so that they are in the driver's record too
+    others = {}
+    if args.workload == "cfg4" and args.scale == 1.0 and not args.no_other_configs:
+        for name in ("cfg1", "cfg2", "cfg3"):
+            if world > 1:
+                break                      # single-GPU configurations
+            sub = Bench(args, synth.workload(name), comp, 1, 0).run(max(3, args.steps), 3, local, full=False)
+            others[name] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
+                                                "mosaic_checksum", "host_enqueue_ms_per_step")}
+            others[name]["config"] = sub["config"]["workload"]
+            comp.release()
+            torch.cuda.empty_cache()
+        sub = run_batch_of_panoramas(args, synth.workload("cfg5"), comp, world, rank, steps=max(2, min(args.steps, 3)))
+        if sub is not None:
+            others["cfg5"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "n_gpus")}
+            others["cfg5"]["config"] = sub["config"]["workload"] + "; replicas: pano_id % n_gpus"
+    if rank == 0 and line is not None:
+        if others:
+            line["other_configs"] = others
+        if world == 1 and not args.no_cpu_baseline and wl.name != "cfg5":
+            base, _, _, _ = time_cpu(wl, 1, 0, args.cpu_budget_s / 4)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -46,10 +46,9 @@ int  p360_device_info(int device, int32_t out_host[4]);
  * One launch warps every patch of a composite (up to 128 per launch; the job
  * records are staged in constant memory): `jobs_host` is a HOST array whose
  * pointer members are device pointers.
- *   src         u8, h x w x c bytes per pixel: c = 3 or 4 (as uploaded; a 4th
- *               channel is ignored) or c = 8 ({RGBX u32, alpha f32} per pixel,
- *               p360_pack_rgbxa: alpha = float32(hat_y * hat_x) evaluated once
- *               per source pixel, not once per tap)
+ *   src         u8, h x w x c bytes per pixel: c = 3 (as uploaded) or c = 4 (RGBX:
+ *               p360_pack_rgbx or a 4-channel upload, the 4th byte is ignored);
+ *               alpha = float32(hat_y * hat_x) is evaluated at the four taps
  *   lut         256 float32: value of a u8 sample (u8/255, optionally
  *               gain-scaled and clipped, stitcher.py:65-66)
  *   hat_y/hat_x float64 tables of `_hat(h)` / `_hat(w)` (stitcher.py:251-254)
@@ -88,8 +87,8 @@ typedef struct p360_warp_job {
                                   /* be cropped to a row window; the seam plan must not depend on it) */
 } p360_warp_job;
 
-int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
-                    int h, int w, uint8_t *dst_rgbxa, void *stream);
+/* u8 x 3 -> u8 x 4 (RGBX): the source layout in which a bilinear tap is one aligned 32-bit load. */
+int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream);
 struct p360_tile_maps;
 struct p360_band_patch;
 int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
@@ -123,11 +122,11 @@ int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
  * owner_keys / covered are written once per pixel, without atomics, and need no initialising.
  * If want_covered, covered also records the valid mask of the other tiles (stitcher.py:266-271).
  * p360_multiband_collapse with the same record writes only the multi tiles.
- * packed: every job's src is in the c = 8 layout. */
+ */
 int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
                          int H, int W, int abs_row0, int mosaic_h,
                          const struct p360_tile_maps *maps_host, void *stream);
-int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, int packed, uint64_t *owner_keys,
+int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint64_t *owner_keys,
                     uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
                     int want_covered, const struct p360_tile_maps *maps_host, void *stream);
 
@@ -230,8 +229,10 @@ typedef struct p360_tile_maps {
     uint32_t *present, *cand, *need;          /* DEVICE [tiles_y][tiles_x][words]       */
     uint8_t *multi;                           /* DEVICE [tiles_y][tiles_x]              */
     uint32_t *work;                           /* DEVICE scratch, 2 * work_cap uint32: the list  */
-    int32_t *work_count;                      /* of blocks a reduce / blur pass has to run (+ its */
-                                              /* length); work_cap >= blocks of the largest grid */
+    int32_t *work_count;                      /* of blocks a reduce / blur pass has to run; work_count: */
+                                              /* 4 int32 — [0] its length (live), [1..3] blocks run by   */
+                                              /* the last reduce / horizontal / vertical blur pass;      */
+                                              /* work_cap >= blocks of the largest grid                  */
     uint32_t *wneed;                          /* seam plan only (else NULL): where float pixels and  */
                                               /* owner keys are wanted, see p360_seam_plan_build     */
     int32_t tiles_x, tiles_y, words;

@@ -24,10 +24,10 @@ SIGNATURES = {
     "p360_version": [],
     "p360_last_error": [C.c_char_p, _i],
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
-    "p360_pack_rgbxa": [_vp, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "p360_pack_rgbx": [_vp, _i, _i, _vp, _vp],
     "p360_warp_batch": [_vp, _i, _vp, _vp, _i, _vp],
     "p360_seam_plan_build": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
-    "p360_warp_tiles": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_warp_tiles": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "p360_owner_decode": [_vp, _vp, _i64, _vp],
     "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
@@ -74,7 +74,7 @@ _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
-_LAUNCHES = {"p360_pack_rgbxa": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
+_LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
              "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,
              "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,

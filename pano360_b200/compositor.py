@@ -206,15 +206,23 @@ class Compositor:
         return rc
 
     # -- sources --------------------------------------------------------------
-    def pack_pixels(self, dev_img, hats):
-        """u8 x 3 -> {RGBX u32, alpha f32} on the device: one aligned 64-bit
-        word per pixel holds everything a bilinear tap of the warp needs."""
+    def pack_pixels(self, dev_img):
+        """u8 x 3 -> u8 x 4 (RGBX) on the device: a bilinear tap of the warp is then one aligned
+        32-bit load.  4-channel images are used as they are."""
         h, w, c = dev_img.shape
-        hat_y, hat_x = hats
-        packed = torch.empty((h, w, 8), dtype=torch.uint8, device=self.device)
-        _lib.call("p360_pack_rgbxa", _lib.ptr(dev_img), c, _lib.ptr(hat_y), _lib.ptr(hat_x), h, w,
-                  _lib.ptr(packed), self.stream)
+        if c == 4:
+            return dev_img
+        packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
+        self._traced("K1p_pack_rgbx", 7 * h * w, "p360_pack_rgbx", _lib.ptr(dev_img), h, w, _lib.ptr(packed), self.stream)
         return packed
+
+    def pack_sources(self, raw):
+        """A ``DeviceSources`` whose images are in the warp's RGBX layout, from one holding the
+        images as uploaded (``upload(pack=False)``): the device-side part of ``_add_weights``
+        (stitcher.py:257-263) that is executed once per image and stitch."""
+        src = DeviceSources([None if p is None else self.pack_pixels(p) for p in raw.pixels], raw.luts, raw.hats,
+                            raw.shapes, raw.ready)
+        return src
 
     def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
@@ -247,8 +255,8 @@ class Compositor:
                         side.wait_stream(main)               # hat tables were copied on the main stream
                 with torch.cuda.stream(side):
                     dev_img = host.to(self.device, non_blocking=host.is_pinned())
-                    # pack=False keeps the uploaded u8 x 3 layout (the warp then evaluates alpha per tap)
-                    src.pixels[i] = self.pack_pixels(dev_img, src.hats[(h, w)]) if pack else dev_img
+                    # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
+                    src.pixels[i] = self.pack_pixels(dev_img) if pack else dev_img
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
@@ -500,12 +508,14 @@ class Compositor:
                   -(-2 * w4 // 256) * -(-2 * h4 // 4) * n * n_blurs,      # horizontal blur blocks (256 x 4 cells)
                   -(-2 * w4 // 64) * -(-2 * h4 // 16) * n * n_blurs,      # ... in 64 x 16 blocks
                   -(-2 * w4 // 32) * -(-2 * h4 // 64) * n * n_blurs)      # vertical blur blocks
-        bits = torch.empty(2 + 2 * cap + 4 * cells * words, dtype=torch.int32, device=self.device)
+        bits = torch.empty(4 + 2 * cap + 4 * cells * words, dtype=torch.int32, device=self.device)
         multi = torch.empty(cells, dtype=torch.uint8, device=self.device)
         maps = np.zeros(1, dtype=_lib.TILE_MAPS)
         base = bits.data_ptr()
-        maps["work_count"], maps["work"], maps["work_cap"] = base, base + 8, cap      # work: 8-byte items
-        base += 8 + 8 * cap
+        # work_count: [0] the live counter, [1..3] blocks run by reduce / horizontal / vertical blur (kept
+        # for the bench's "bytes of the blocks actually run"); work: 8-byte items
+        maps["work_count"], maps["work"], maps["work_cap"] = base, base + 16, cap
+        base += 16 + 8 * cap
         maps["present"], maps["cand"], maps["need"] = base, base + 4 * cells * words, base + 8 * cells * words
         if seam_plan:
             maps["wneed"] = base + 12 * cells * words
@@ -666,8 +676,7 @@ class Compositor:
                 for i in sorted({c[0] for c in crops}):
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
-            packed = int(bool(np.all(jobs["c"] == 8)))
-            self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, n, packed,
+            self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, n,
                          _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
             self._keep["seam"] = (dev_wjobs,)

@@ -174,6 +174,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_list_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     const int n = min(*maps.work_count, maps.work_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) maps.work_count[2] = n;      // (statistics for the bench)
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         const BlurJob &job = jobs[item.x];
@@ -244,6 +245,7 @@ blur_v_scan_kernel(const BlurJob *__restrict__ jobs, int n_jobs, int gx, int gy,
 __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_list_kernel(const BlurJob *__restrict__ jobs, TileMaps maps) {
     const int n = min(*maps.work_count, maps.work_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) maps.work_count[3] = n;      // (statistics for the bench)
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         const BlurJob &job = jobs[item.x];

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256)
 pyramid_reduce_list_kernel(const BandPatch *__restrict__ patches,
                            const unsigned long long *__restrict__ keys, int W, TileMaps maps) {
     const int n = min(*maps.work_count, maps.work_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) maps.work_count[1] = n;      // (statistics for the bench)
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         reduce_block(patches[item.x], (int)(item.y & 0xffffu), (int)(item.y >> 16), keys, W);

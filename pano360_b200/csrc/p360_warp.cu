@@ -55,13 +55,10 @@ struct TapPlan {            // phase 1: where to sample and with which weights
     float w00, w01, w10, w11;             // bilinear weights, products of 1/32 fractions (exact)
     bool bad;
 };
+struct TapAlpha { float a00, a01, a10, a11; };   // alpha of the four taps: float32(hat_y * hat_x), stitcher.py:261
 
-struct RawTap {             // phase 2: what a tap returns before the LUT
-    uint32_t rgbx;
-    float alpha;
-};
-
-__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r) {
+template <bool ALPHA>
+__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r, TapAlpha &alpha) {
     // p = K R (rx, ry, rz) in float64, k = 0, 1, 2 in order, then cast to
     // float32 (stitcher.py:303-306)
     const double rx = __ldg(s.ray_x + s.col0 + c), rz = __ldg(s.ray_z + s.col0 + c);
@@ -87,27 +84,22 @@ __device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r) {
     const float ax = (float)(sx & 31) * 0.03125f, ay = (float)(sy & 31) * 0.03125f;
     t.w00 = __fmul_rn(1.0f - ay, 1.0f - ax); t.w01 = __fmul_rn(1.0f - ay, ax);
     t.w10 = __fmul_rn(ay, 1.0f - ax); t.w11 = __fmul_rn(ay, ax);
+    if (ALPHA) {            // the weight image of _add_weights, evaluated at the taps (float64 product, then cast)
+        const double hy0 = __ldg(s.hat_y + y0), hy1 = __ldg(s.hat_y + y1);
+        const double hx0 = __ldg(s.hat_x + x0), hx1 = __ldg(s.hat_x + x1);
+        alpha.a00 = (float)(hy0 * hx0); alpha.a01 = (float)(hy0 * hx1);
+        alpha.a10 = (float)(hy1 * hx0); alpha.a11 = (float)(hy1 * hx1);
+    }
     return t;
 }
 
-template <bool PACKED>
-__device__ __forceinline__ RawTap load_tap(const WarpJob &s, int off) {
-    RawTap t;
-    if (PACKED) {                                     // {RGBX u32, alpha f32} per pixel (p360_pack_rgbxa)
-        const uint2 u = __ldg(reinterpret_cast<const uint2 *>(s.src) + off);
-        t.rgbx = u.x;
-        t.alpha = __uint_as_float(u.y);
-        return t;
-    }
-    if (s.c == 4) {
-        t.rgbx = __ldg(reinterpret_cast<const uint32_t *>(s.src) + off);
-    } else {
-        const uint8_t *p = s.src + (size_t)off * 3;
-        t.rgbx = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-    }
-    const int y = off / s.w, x = off - y * s.w;       // alpha not pre-packed: float32(hat_y * hat_x), stitcher.py:261
-    t.alpha = (float)(__ldg(s.hat_y + y) * __ldg(s.hat_x + x));
-    return t;
+// One tap: the three u8 samples of a source pixel in the low 24 bits.  RGBX: the source is the
+// 4-byte-per-pixel layout of p360_pack_rgbx (or a 4-channel upload): one aligned 32-bit load.
+template <bool RGBX>
+__device__ __forceinline__ uint32_t load_tap(const WarpJob &s, int off) {
+    if (RGBX) return __ldg(reinterpret_cast<const uint32_t *>(s.src) + off);
+    const uint8_t *p = s.src + (size_t)off * 3;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
 }
 
 // ((s00*w00 + s01*w01) + s10*w10) + s11*w11, separately rounded products and
@@ -121,15 +113,20 @@ __device__ __forceinline__ float blend4(float a, float b, float c, float d, cons
 }
 
 // phase 3: LUT (u8 -> float exactly as the reference's float image holds it) + bilinear blend
-__device__ __forceinline__ float4 finish_pixel(const float *lut, const TapPlan &t, const RawTap (&q)[4]) {
-    float4 o;
-    o.x = blend4(lut_at(lut, (q[0].rgbx << 2) & 0x3fc), lut_at(lut, (q[1].rgbx << 2) & 0x3fc),
-                 lut_at(lut, (q[2].rgbx << 2) & 0x3fc), lut_at(lut, (q[3].rgbx << 2) & 0x3fc), t);
-    o.y = blend4(lut_at(lut, (q[0].rgbx >> 6) & 0x3fc), lut_at(lut, (q[1].rgbx >> 6) & 0x3fc),
-                 lut_at(lut, (q[2].rgbx >> 6) & 0x3fc), lut_at(lut, (q[3].rgbx >> 6) & 0x3fc), t);
-    o.z = blend4(lut_at(lut, (q[0].rgbx >> 14) & 0x3fc), lut_at(lut, (q[1].rgbx >> 14) & 0x3fc),
-                 lut_at(lut, (q[2].rgbx >> 14) & 0x3fc), lut_at(lut, (q[3].rgbx >> 14) & 0x3fc), t);
-    o.w = blend4(q[0].alpha, q[1].alpha, q[2].alpha, q[3].alpha, t);
+__device__ __forceinline__ float3 finish_rgb(const float *lut, const TapPlan &t, const uint32_t (&q)[4]) {
+    float3 o;
+    o.x = blend4(lut_at(lut, (q[0] << 2) & 0x3fc), lut_at(lut, (q[1] << 2) & 0x3fc),
+                 lut_at(lut, (q[2] << 2) & 0x3fc), lut_at(lut, (q[3] << 2) & 0x3fc), t);
+    o.y = blend4(lut_at(lut, (q[0] >> 6) & 0x3fc), lut_at(lut, (q[1] >> 6) & 0x3fc),
+                 lut_at(lut, (q[2] >> 6) & 0x3fc), lut_at(lut, (q[3] >> 6) & 0x3fc), t);
+    o.z = blend4(lut_at(lut, (q[0] >> 14) & 0x3fc), lut_at(lut, (q[1] >> 14) & 0x3fc),
+                 lut_at(lut, (q[2] >> 14) & 0x3fc), lut_at(lut, (q[3] >> 14) & 0x3fc), t);
+    return o;
+}
+__device__ __forceinline__ float4 finish_pixel(const float *lut, const TapPlan &t, const TapAlpha &a,
+                                               const uint32_t (&q)[4]) {
+    const float3 c = finish_rgb(lut, t, q);
+    float4 o = make_float4(c.x, c.y, c.z, blend4(a.a00, a.a01, a.a10, a.a11, t));
     if (t.bad) o.w = 0.0f;                                       // stitcher.py:317
     return o;
 }
@@ -155,8 +152,8 @@ constexpr int TILE_JOBS_MAX = 256;                 // p360_warp_tiles: the whole
 __constant__ WarpJob c_warp_jobs[TILE_JOBS_MAX];   // block-uniform reads: no LSU traffic per pixel, and the compiler
                                                    // may re-read a field instead of holding it in a register
 
-// PACKED: every job's source is in the 8-byte {RGBX, alpha} format; OWNER: owner keys wanted.
-template <bool PACKED, bool OWNER>
+// RGBX: every job's source has 4 bytes per pixel; OWNER: owner keys wanted.
+template <bool RGBX, bool OWNER>
 __device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsigned long long *__restrict__ keys,
                                            uint8_t *__restrict__ covered, int W) {
     const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
@@ -168,31 +165,32 @@ __device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsig
     // coordinates of every row first, then all gathers back to back, then LUT + blend,
     // then the stores and the owner competition
     TapPlan plan[WARP_ROWS];
-    RawTap taps[WARP_ROWS][4];
+    TapAlpha alpha[WARP_ROWS];
+    uint32_t taps[WARP_ROWS][4];
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k)
-        plan[k] = plan_taps(job, c, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1));
+        plan[k] = plan_taps<true>(job, c, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1), alpha[k]);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
-        taps[k][0] = load_tap<PACKED>(job, plan[k].off00); taps[k][1] = load_tap<PACKED>(job, plan[k].off01);
-        taps[k][2] = load_tap<PACKED>(job, plan[k].off10); taps[k][3] = load_tap<PACKED>(job, plan[k].off11);
+        taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
+        taps[k][2] = load_tap<RGBX>(job, plan[k].off10); taps[k][3] = load_tap<RGBX>(job, plan[k].off11);
     }
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
         const int r = r0 + threadIdx.y + k * WARP_BY;
         if (r < job.ph)
-            warp_commit<OWNER>(job, c, r, finish_pixel(lut, plan[k], taps[k]), plan[k].bad, keys, covered, W);
+            warp_commit<OWNER>(job, c, r, finish_pixel(lut, plan[k], alpha[k], taps[k]), plan[k].bad, keys, covered, W);
     }
 }
 
-template <bool PACKED, bool OWNER>
+template <bool RGBX, bool OWNER>
 __global__ void __launch_bounds__(WARP_BX *WARP_BY)
 warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ covered, int W) {
     __shared__ float lut[256];
     const WarpJob &job = c_warp_jobs[blockIdx.z];
     const int r0 = blockIdx.y * (WARP_BY * WARP_ROWS);
     if ((int)(blockIdx.x * WARP_BX) >= job.pw || r0 >= job.ph) return;   // block-uniform
-    warp_block<PACKED, OWNER>(job, lut, keys, covered, W);
+    warp_block<RGBX, OWNER>(job, lut, keys, covered, W);
 }
 
 // ---- K0: the seam plan — who can own a pixel of a tile?  (geometry only, before anything is
@@ -385,14 +383,6 @@ seam_need_kernel(TileMaps m) {
 // that the mosaic is written with aligned 128-bit stores whatever W is.
 constexpr int DT_PITCH = 3 * TILE_X + 16 + 16;          // 192 bytes of pixels + alignment phase (+ bank skew)
 
-template <bool PACKED>
-__device__ __forceinline__ uint32_t load_rgbx(const WarpJob &s, int off) {
-    if (PACKED) return __ldg(reinterpret_cast<const uint32_t *>(s.src) + 2 * (size_t)off);
-    if (s.c == 4) return __ldg(reinterpret_cast<const uint32_t *>(s.src) + off);
-    const uint8_t *p = s.src + (size_t)off * 3;
-    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-}
-
 __device__ __forceinline__ uint8_t to_u8(float v) {      // (255 * clip(v, 0, 1)).astype(uint8)
     return (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(v, 0.f), 1.f)));
 }
@@ -414,7 +404,7 @@ constexpr int TW_ROWS = TILE_Y / 4;     // rows per thread (block = 64 x 4 threa
 
 // One patch over one tile.  FLOAT: write RGBA + mask to the patch and compete for the pixels;
 // BYTES: stage the truncated pixel for the mosaic.  Rows [y_lo, y_hi) of the window get bytes.
-template <bool PACKED, bool FLOAT, bool BYTES>
+template <bool RGBX, bool FLOAT, bool BYTES>
 __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float *lut, int tx0, int ty0,
                                                 uint8_t (*rows)[DT_PITCH], const uint8_t *out, int W,
                                                 int y_lo, int y_hi, float (*best_a)[TILE_X],
@@ -426,38 +416,28 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
         // four rows per pass, branch-free up to the stores: all coordinates (rows clamped into the
         // patch), then all gathers, then LUT + blend; only the commit looks at what is live
         TapPlan plan[WARP_ROWS];
-        RawTap taps[WARP_ROWS][4];
+        TapAlpha alpha[WARP_ROWS];
+        uint32_t taps[WARP_ROWS][4];
 #pragma unroll
         for (int k = 0; k < WARP_ROWS; ++k) {
             const int r = ty0 + (int)threadIdx.y + 4 * (WARP_ROWS * half + k) - job.y0;
-            plan[k] = plan_taps(job, c, min(max(r, 0), job.ph - 1));
+            plan[k] = plan_taps<FLOAT>(job, c, min(max(r, 0), job.ph - 1), alpha[k]);
         }
 #pragma unroll
         for (int k = 0; k < WARP_ROWS; ++k) {
-            if (FLOAT) {
-                taps[k][0] = load_tap<PACKED>(job, plan[k].off00); taps[k][1] = load_tap<PACKED>(job, plan[k].off01);
-                taps[k][2] = load_tap<PACKED>(job, plan[k].off10); taps[k][3] = load_tap<PACKED>(job, plan[k].off11);
-            } else {
-                taps[k][0].rgbx = load_rgbx<PACKED>(job, plan[k].off00); taps[k][1].rgbx = load_rgbx<PACKED>(job, plan[k].off01);
-                taps[k][2].rgbx = load_rgbx<PACKED>(job, plan[k].off10); taps[k][3].rgbx = load_rgbx<PACKED>(job, plan[k].off11);
-            }
+            taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
+            taps[k][2] = load_tap<RGBX>(job, plan[k].off10); taps[k][3] = load_tap<RGBX>(job, plan[k].off11);
         }
 #pragma unroll
         for (int k = 0; k < WARP_ROWS; ++k) {
             const int slot = WARP_ROWS * half + k;
             const int ry = threadIdx.y + 4 * slot, Y = ty0 + ry, r = Y - job.y0;
-            const RawTap (&q)[4] = taps[k];
-            float4 o;
-            o.x = blend4(lut_at(lut, (q[0].rgbx << 2) & 0x3fc), lut_at(lut, (q[1].rgbx << 2) & 0x3fc),
-                         lut_at(lut, (q[2].rgbx << 2) & 0x3fc), lut_at(lut, (q[3].rgbx << 2) & 0x3fc), plan[k]);
-            o.y = blend4(lut_at(lut, (q[0].rgbx >> 6) & 0x3fc), lut_at(lut, (q[1].rgbx >> 6) & 0x3fc),
-                         lut_at(lut, (q[2].rgbx >> 6) & 0x3fc), lut_at(lut, (q[3].rgbx >> 6) & 0x3fc), plan[k]);
-            o.z = blend4(lut_at(lut, (q[0].rgbx >> 14) & 0x3fc), lut_at(lut, (q[1].rgbx >> 14) & 0x3fc),
-                         lut_at(lut, (q[2].rgbx >> 14) & 0x3fc), lut_at(lut, (q[3].rgbx >> 14) & 0x3fc), plan[k]);
+            const float3 rgb = finish_rgb(lut, plan[k], taps[k]);
+            float4 o = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
             const bool bad = plan[k].bad;
             if ((unsigned)r >= (unsigned)job.ph) continue;            // the tile row lies outside the patch
             if (FLOAT) {
-                o.w = bad ? 0.0f : blend4(q[0].alpha, q[1].alpha, q[2].alpha, q[3].alpha, plan[k]);   // stitcher.py:317
+                if (!bad) o.w = blend4(alpha[k].a00, alpha[k].a01, alpha[k].a10, alpha[k].a11, plan[k]);   // stitcher.py:317
                 const size_t idx = (size_t)r * job.pw + c;
                 st_stream(job.out + idx, o);
                 job.invalid[idx] = bad ? 1 : 0;
@@ -476,7 +456,7 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
     }
 }
 
-template <bool PACKED>
+template <bool RGBX>
 __global__ void __launch_bounds__(256, 3)
 warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
                   uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end, int H, int W,
@@ -535,11 +515,11 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
             }
             const bool to_bytes = bytes && id == solo;
             if (as_float && to_bytes)
-                warp_tile_patch<PACKED, true, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+                warp_tile_patch<RGBX, true, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
             else if (as_float)
-                warp_tile_patch<PACKED, true, false>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+                warp_tile_patch<RGBX, true, false>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
             else
-                warp_tile_patch<PACKED, false, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+                warp_tile_patch<RGBX, false, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
             solo_done |= id == solo;
         }
     }
@@ -565,33 +545,39 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
         store_row_bytes(out + ((size_t)Y * W + tx0) * 3, rows[ry], 3 * min(TILE_X, W - tx0), tid & 7, 8);
 }
 
-// u8 x 3 -> {RGBX u32, alpha f32}: one aligned 64-bit word per source pixel
-// holding everything a bilinear tap needs; alpha = float32(hat_y * hat_x) is
-// evaluated once per source pixel here instead of once per tap in the warp
-// (stitcher.py:257-263).
+// u8 x 3 -> u8 x 4 (RGBX): one aligned 32-bit word per source pixel, so that a bilinear tap of the
+// warp is a single load.  Four pixels per thread: three 32-bit loads, one 128-bit store.
 __global__ void __launch_bounds__(256)
-pack_rgbxa_kernel(const uint8_t *__restrict__ src, int sc, const double *__restrict__ hat_y,
-                  const double *__restrict__ hat_x, int h, int w, uint2 *__restrict__ dst) {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const uint8_t *p = src + ((size_t)y * w + x) * sc;
-    uint2 o;
-    o.x = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-    o.y = __float_as_uint((float)(__ldg(hat_y + y) * __ldg(hat_x + x)));
-    dst[(size_t)y * w + x] = o;
+pack_rgbx_kernel(const uint8_t *__restrict__ src, long long n_px, uint32_t *__restrict__ dst) {
+    const long long g = (long long)blockIdx.x * 256 + threadIdx.x;     // group of 4 pixels
+    const long long first = 4 * g;
+    if (first >= n_px) return;
+    if (first + 4 <= n_px) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(src) + 3 * g;
+        const uint32_t a = __ldg(in), b = __ldg(in + 1), c = __ldg(in + 2);
+        uint4 o;
+        o.x = a & 0xffffffu;
+        o.y = (a >> 24) | ((b & 0xffffu) << 8);
+        o.z = (b >> 16) | ((c & 0xffu) << 16);
+        o.w = c >> 8;
+        *reinterpret_cast<uint4 *>(dst + first) = o;
+        return;
+    }
+    for (long long i = first; i < n_px; ++i) {
+        const uint8_t *p = src + 3 * i;
+        dst[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
 }
 
 }  // namespace p360
 
-extern "C" int p360_pack_rgbxa(const uint8_t *src, int src_c, const double *hat_y, const double *hat_x,
-                               int h, int w, uint8_t *dst_rgbxa, void *stream) {
+extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream) {
     using namespace p360;
-    const char *where = "p360_pack_rgbxa";
-    P360_REQUIRE(src && hat_y && hat_x && dst_rgbxa && h > 0 && w > 0 && h <= 65535, where);
-    P360_REQUIRE(src_c == 3 || src_c == 4, where);
-    P360_REQUIRE((reinterpret_cast<uintptr_t>(dst_rgbxa) & 7) == 0, where);
-    pack_rgbxa_kernel<<<dim3(cdiv(w, 256), h), 256, 0, (cudaStream_t)stream>>>(
-        src, src_c, hat_y, hat_x, h, w, reinterpret_cast<uint2 *>(dst_rgbxa));
+    const char *where = "p360_pack_rgbx";
+    P360_REQUIRE(src_rgb && dst_rgbx && h > 0 && w > 0, where);
+    P360_REQUIRE((reinterpret_cast<uintptr_t>(src_rgb) & 3) == 0 && aligned16(dst_rgbx), where);
+    const long long n = (long long)h * w;
+    pack_rgbx_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src_rgb, n, reinterpret_cast<uint32_t *>(dst_rgbx));
     return check_launch(where);
 }
 
@@ -626,7 +612,7 @@ extern "C" int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, p
     return check_launch(where);
 }
 
-extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, int packed, uint64_t *owner_keys,
+extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint64_t *owner_keys,
                                uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
                                int want_covered, const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
@@ -641,8 +627,17 @@ extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, int p
     cudaStream_t s = (cudaStream_t)stream;
     // stream-ordered: waits for the previous launch that still reads the table
     P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host, sizeof(WarpJob) * n_jobs, 0, cudaMemcpyHostToDevice, s), where);
+    bool rgbx = true;
+    for (int k = 0; k < n_jobs; ++k) {
+        const p360_warp_job &j = jobs_host[k];
+        P360_REQUIRE(j.src && j.lut && j.hat_y && j.hat_x && j.ray_x && j.ray_z && j.ray_y && j.out && j.invalid, where);
+        P360_REQUIRE(j.h > 0 && j.w > 0 && j.h <= 32767 && j.w <= 32767 && j.pw > 0 && j.ph > 0 && aligned16(j.out), where);
+        P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0), where);
+        P360_REQUIRE(j.x0 >= 0 && j.y0 >= 0 && j.x0 + j.pw <= W && j.y0 + j.ph <= H && j.patch == k, where);
+        rgbx = rgbx && j.c == 4;
+    }
     auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
-    if (packed)
+    if (rgbx)
         warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8,
                                                                          y_begin, y_end, H, W, want_covered, m);
     else
@@ -661,16 +656,15 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
     for (int first = 0; first < n_jobs; first += WARP_JOBS_PER_LAUNCH) {
         const int count = n_jobs - first < WARP_JOBS_PER_LAUNCH ? n_jobs - first : WARP_JOBS_PER_LAUNCH;
         int max_pw = 0, max_ph = 0;
-        bool packed = true;
+        bool rgbx = true;
         for (int k = first; k < first + count; ++k) {
             const p360_warp_job &j = jobs_host[k];
             P360_REQUIRE(j.src && j.lut && j.hat_y && j.hat_x && j.ray_x && j.ray_z && j.ray_y && j.out && j.invalid, where);
             P360_REQUIRE(j.h > 0 && j.w > 0 && j.h <= 32767 && j.w <= 32767 && j.pw >= 0 && j.ph >= 0, where);
-            P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0) ||
-                         (j.c == 8 && (reinterpret_cast<uintptr_t>(j.src) & 7) == 0), where);
+            P360_REQUIRE(j.c == 3 || (j.c == 4 && (reinterpret_cast<uintptr_t>(j.src) & 3) == 0), where);
             P360_REQUIRE(aligned16(j.out), where);
             P360_REQUIRE(owner_keys == nullptr || (j.x0 >= 0 && j.y0 >= 0 && j.x0 + j.pw <= W), where);
-            packed = packed && j.c == 8;
+            rgbx = rgbx && j.c == 4;
             max_pw = j.pw > max_pw ? j.pw : max_pw;
             max_ph = j.ph > max_ph ? j.ph : max_ph;
         }
@@ -681,8 +675,8 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
         dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
         auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
-        if (packed && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
-        else if (packed) warp_batch_kernel<true, false><<<grid, block, 0, s>>>(keys, covered, W);
+        if (rgbx && keys) warp_batch_kernel<true, true><<<grid, block, 0, s>>>(keys, covered, W);
+        else if (rgbx) warp_batch_kernel<true, false><<<grid, block, 0, s>>>(keys, covered, W);
         else if (keys) warp_batch_kernel<false, true><<<grid, block, 0, s>>>(keys, covered, W);
         else warp_batch_kernel<false, false><<<grid, block, 0, s>>>(keys, covered, W);
         if (int e = check_launch(where)) return e;

@@ -44,6 +44,7 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float2 { float x, y; };
+struct float3 { float x, y, z; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };

@@ -382,7 +382,7 @@ def _plan_planes(comp):
     """(present, cand, need, wneed) bitmaps [tiles, words] and multi [tiles] of the last composite."""
     maps, (bits, multi) = comp._keep["bands"][3], comp._keep["bands"][4]
     tiles, words = int(maps["tiles_x"][0]) * int(maps["tiles_y"][0]), int(maps["words"][0])
-    raw = bits.cpu().numpy().view(np.uint32)[2 + 2 * int(maps["work_cap"][0]):]
+    raw = bits.cpu().numpy().view(np.uint32)[4 + 2 * int(maps["work_cap"][0]):]
     return raw[:4 * tiles * words].reshape(4, tiles, words), multi.cpu().numpy().astype(bool), maps
 
 

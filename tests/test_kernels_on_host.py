@@ -220,7 +220,7 @@ def test_seam_plan_candidates_at_full_scale(comp):
     _lib.call("p360_seam_plan_build", dev_jobs.data_ptr(), n, None, plan.shape[0], plan.shape[1], 0, plan.shape[0],
               maps.ctypes.data, None)
     tx, ty, words = int(maps["tiles_x"][0]), int(maps["tiles_y"][0]), int(maps["words"][0])
-    planes = bits.numpy().view(np.uint32)[2 + 2 * int(maps["work_cap"][0]):].reshape(4, ty, tx, words)
+    planes = bits.numpy().view(np.uint32)[4 + 2 * int(maps["work_cap"][0]):].reshape(4, ty, tx, words)
     unpack = lambda plane: np.stack([((plane[..., k >> 5] >> np.uint32(k & 31)) & 1).astype(bool) for k in range(n)])
     got = unpack(planes[0])
     want = gb.candidates(regs, plan, crops=[c[:5] for c in crops])
