@@ -41,7 +41,7 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS
+    cmd = [nvcc()] + NVCC_FLAGS + os.environ.get("P360_NVCC_DEFS", "").split()      # (-D... for A/B builds)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     # One builder at a time (N ranks of a torchrun may all find the library stale), and the

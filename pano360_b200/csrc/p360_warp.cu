@@ -57,15 +57,20 @@ struct TapPlan {            // phase 1: where to sample and with which weights
 };
 struct TapAlpha { float a00, a01, a10, a11; };   // alpha of the four taps: float32(hat_y * hat_x), stitcher.py:261
 
+// What a thread needs of its mosaic column for every row it visits: the z component of the ray and
+// the first products of p = K R (rx, ry, rz) — float64, k = 0, 1, 2 in order (stitcher.py:303-306).
+struct ColumnTerms { double rz, x0, x1, x2; };
+__device__ __forceinline__ ColumnTerms column_terms(const WarpJob &s, int c) {
+    const double rx = __ldg(s.ray_x + s.col0 + c);
+    return ColumnTerms{__ldg(s.ray_z + s.col0 + c), s.kr[0] * rx, s.kr[3] * rx, s.kr[6] * rx};
+}
+
 template <bool ALPHA>
-__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, int c, int r, TapAlpha &alpha) {
-    // p = K R (rx, ry, rz) in float64, k = 0, 1, 2 in order, then cast to
-    // float32 (stitcher.py:303-306)
-    const double rx = __ldg(s.ray_x + s.col0 + c), rz = __ldg(s.ray_z + s.col0 + c);
+__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, const ColumnTerms &col, int r, TapAlpha &alpha) {
     const double ry = __ldg(s.ray_y + s.row0 + r);
-    const float px = (float)fma(s.kr[2], rz, fma(s.kr[1], ry, s.kr[0] * rx));
-    const float py = (float)fma(s.kr[5], rz, fma(s.kr[4], ry, s.kr[3] * rx));
-    const float pz = (float)fma(s.kr[8], rz, fma(s.kr[7], ry, s.kr[6] * rx));
+    const float px = (float)fma(s.kr[2], col.rz, fma(s.kr[1], ry, col.x0));     // then cast to float32 (stitcher.py:306)
+    const float py = (float)fma(s.kr[5], col.rz, fma(s.kr[4], ry, col.x1));
+    const float pz = (float)fma(s.kr[8], col.rz, fma(s.kr[7], ry, col.x2));
     TapPlan t;
     t.bad = pz < 0.0f;                                           // stitcher.py:308
     const float x = __fadd_rn(__fdiv_rn(px, pz), s.half_w);      // stitcher.py:310
@@ -167,9 +172,10 @@ __device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsig
     TapPlan plan[WARP_ROWS];
     TapAlpha alpha[WARP_ROWS];
     uint32_t taps[WARP_ROWS][4];
+    const ColumnTerms col = column_terms(job, c);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k)
-        plan[k] = plan_taps<true>(job, c, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1), alpha[k]);
+        plan[k] = plan_taps<true>(job, col, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1), alpha[k]);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
         taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
@@ -402,41 +408,47 @@ __device__ __forceinline__ void store_row_bytes(uint8_t *dst, const uint8_t *row
 
 constexpr int TW_ROWS = TILE_Y / 4;     // rows per thread (block = 64 x 4 threads)
 
+// A warped pixel lies in [0, 1] (a convex combination of table values in [0, 1], the weights are
+// exact and sum to one, rounding is monotonic): the blender's clip (stitcher.py:240) is a no-op.
+__device__ __forceinline__ uint8_t to_u8_unit(float v) { return (uint8_t)__float2int_rz(__fmul_rn(255.0f, v)); }
+
 // One patch over one tile.  FLOAT: write RGBA + mask to the patch and compete for the pixels;
-// BYTES: stage the truncated pixel for the mosaic.  Rows [y_lo, y_hi) of the window get bytes.
-template <bool RGBX, bool FLOAT, bool BYTES>
-__device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float *lut, int tx0, int ty0,
+// to_bytes (block-uniform): stage the truncated pixel for the mosaic (rows [y_lo, y_hi) of the window).
+template <bool RGBX, bool FLOAT>
+__device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float *lut, int tx0, int ty0, bool to_bytes,
                                                 uint8_t (*rows)[DT_PITCH], const uint8_t *out, int W,
                                                 int y_lo, int y_hi, float (*best_a)[TILE_X],
                                                 int16_t (*best_p)[TILE_X], unsigned &valid_bits) {
     const int X = tx0 + threadIdx.x, c = X - job.x0;
     if ((unsigned)c >= (unsigned)job.pw) return;
+    const ColumnTerms col = column_terms(job, c);
+    constexpr int RP = FLOAT ? 2 : 4;       // rows per pass (the float path carries alpha and more addresses)
 #pragma unroll 1
-    for (int half = 0; half < TW_ROWS / WARP_ROWS; ++half) {
-        // four rows per pass, branch-free up to the stores: all coordinates (rows clamped into the
+    for (int half = 0; half < TW_ROWS / RP; ++half) {
+        // RP rows per pass, branch-free up to the stores: all coordinates (rows clamped into the
         // patch), then all gathers, then LUT + blend; only the commit looks at what is live
-        TapPlan plan[WARP_ROWS];
-        TapAlpha alpha[WARP_ROWS];
-        uint32_t taps[WARP_ROWS][4];
+        TapPlan plan[RP];
+        TapAlpha alpha[RP];
+        uint32_t taps[RP][4];
 #pragma unroll
-        for (int k = 0; k < WARP_ROWS; ++k) {
-            const int r = ty0 + (int)threadIdx.y + 4 * (WARP_ROWS * half + k) - job.y0;
-            plan[k] = plan_taps<FLOAT>(job, c, min(max(r, 0), job.ph - 1), alpha[k]);
+        for (int k = 0; k < RP; ++k) {
+            const int r = ty0 + (int)threadIdx.y + 4 * (RP * half + k) - job.y0;
+            plan[k] = plan_taps<FLOAT>(job, col, min(max(r, 0), job.ph - 1), alpha[k]);
         }
 #pragma unroll
-        for (int k = 0; k < WARP_ROWS; ++k) {
+        for (int k = 0; k < RP; ++k) {
             taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
             taps[k][2] = load_tap<RGBX>(job, plan[k].off10); taps[k][3] = load_tap<RGBX>(job, plan[k].off11);
         }
 #pragma unroll
-        for (int k = 0; k < WARP_ROWS; ++k) {
-            const int slot = WARP_ROWS * half + k;
+        for (int k = 0; k < RP; ++k) {
+            const int slot = RP * half + k;
             const int ry = threadIdx.y + 4 * slot, Y = ty0 + ry, r = Y - job.y0;
             const float3 rgb = finish_rgb(lut, plan[k], taps[k]);
-            float4 o = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
             const bool bad = plan[k].bad;
             if ((unsigned)r >= (unsigned)job.ph) continue;            // the tile row lies outside the patch
             if (FLOAT) {
+                float4 o = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
                 if (!bad) o.w = blend4(alpha[k].a00, alpha[k].a01, alpha[k].a10, alpha[k].a11, plan[k]);   // stitcher.py:317
                 const size_t idx = (size_t)r * job.pw + c;
                 st_stream(job.out + idx, o);
@@ -447,17 +459,20 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
                 }
             }
             if (!bad) valid_bits |= 1u << slot;
-            if (BYTES && !bad && Y >= y_lo && Y < y_hi) {
+            if (to_bytes && !bad && Y >= y_lo && Y < y_hi) {
                 const uint8_t *dst = out + ((size_t)Y * W + tx0) * 3;
                 uint8_t *stage = rows[ry] + (reinterpret_cast<uintptr_t>(dst) & 15) + 3 * threadIdx.x;
-                stage[0] = to_u8(o.x); stage[1] = to_u8(o.y); stage[2] = to_u8(o.z);
+                stage[0] = to_u8_unit(rgb.x); stage[1] = to_u8_unit(rgb.y); stage[2] = to_u8_unit(rgb.z);
             }
         }
     }
 }
 
+#ifndef P360_TILE_BLOCKS
+#define P360_TILE_BLOCKS 4      // resident blocks per SM the tile warp is compiled for (64 registers; B200, cfg4: 3.92 -> 3.69 ms vs 3)
+#endif
 template <bool RGBX>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, P360_TILE_BLOCKS)
 warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
                   uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end, int H, int W,
                   int want_covered, TileMaps m) {
@@ -513,13 +528,12 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
                 lut_of = job.lut;
                 __syncthreads();
             }
-            const bool to_bytes = bytes && id == solo;
-            if (as_float && to_bytes)
-                warp_tile_patch<RGBX, true, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
-            else if (as_float)
-                warp_tile_patch<RGBX, true, false>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+            if (as_float)
+                warp_tile_patch<RGBX, true>(job, lut, tx0, ty0, bytes && id == solo, rows, out, W, y_begin, y_end,
+                                            best_a, best_p, valid_bits);
             else
-                warp_tile_patch<RGBX, false, true>(job, lut, tx0, ty0, rows, out, W, y_begin, y_end, best_a, best_p, valid_bits);
+                warp_tile_patch<RGBX, false>(job, lut, tx0, ty0, true, rows, out, W, y_begin, y_end,
+                                             best_a, best_p, valid_bits);
             solo_done |= id == solo;
         }
     }
