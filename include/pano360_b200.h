@@ -282,6 +282,15 @@ int p360_pair_overlap_stats(const p360_pair_job *jobs, int n_pairs, int h, int w
 int p360_cover_update(const uint8_t *invalid, int pw, int ph, int x0, int y0,
                       uint8_t *covered, int W, void *stream);
 
+/* ---- crop stage: largest all-valid rectangle (stitcher.py:340-369, crop_mosaic) ------------
+ * covered: H x W u8 union of valid pixels (stitcher.py:266-271).  rect_dev receives
+ * {y0, y1, x0, x1} (int32, device): the crop is mosaic[y0:y1, x0:x1]; all zero if nothing is
+ * valid.  Same scan order and tie rules as the reference (first strictly larger area in
+ * (row, column) order; column 0 never extends to the right, its :359 loop stops at j = 1).
+ * scratch: p360_crop_scratch_bytes(H, W) bytes, 16-byte aligned. */
+int64_t p360_crop_scratch_bytes(int H, int W);
+int p360_crop_rect(const uint8_t *covered, int H, int W, void *scratch, int32_t *rect_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -334,7 +334,59 @@ def equalize(regions, rgba, backend="cv2"):
 
 
 # --------------------------------------------------------------------------
-# whole path (stitcher.py:274-327, crop excluded)
+# crop (stitcher.py:266-271, :340-369)
+# --------------------------------------------------------------------------
+def valid_mask(patches, shape):
+    """Area of validity (stitcher.py:266-271)."""
+    valid = np.zeros(shape, dtype=bool)
+    for _, invalid, irange in patches:
+        valid[irange] |= ~invalid
+    return valid
+
+
+def _crop_rect(valid):
+    """The scan of stitcher.py:346-367, statement by statement (jitted with Numba when it is
+    installed, like the reference's try_jit at :330-337): rows [y0, y1) x columns [x0, x1)."""
+    height, width = valid.shape
+    heights = np.zeros(width, dtype=np.int32)
+    lefts = np.zeros(width, dtype=np.int32)
+    rights = np.zeros(width, dtype=np.int32)
+    area = 0
+    ll = rr = hh = last = 0
+    for i in range(height):
+        for j in range(width):
+            heights[j] = (heights[j] + 1) if valid[i, j] else 0
+        for j in range(width):
+            lefts[j] = j
+            while lefts[j] > 0 and heights[j] <= heights[lefts[j] - 1]:
+                lefts[j] = lefts[lefts[j] - 1]
+        for j in range(width - 1, 0, -1):          # (rights[0] is never written: it stays 0)
+            rights[j] = j
+            while rights[j] < width - 1 and heights[j] <= heights[rights[j] + 1]:
+                rights[j] = rights[rights[j] + 1]
+        for j in range(width):
+            new_area = (rights[j] - lefts[j] + 1) * heights[j]
+            if new_area > area:
+                area = new_area
+                ll, rr, hh, last = lefts[j], rights[j], heights[j], i
+    if area == 0:
+        return 0, 0, 0, 0
+    return last - hh + 1, last + 1, ll, rr + 1
+
+
+try:
+    import numba as _numba
+    _crop_rect = _numba.njit(cache=False)(_crop_rect)
+except ImportError:                                  # pure Python then: small masks only
+    pass
+
+
+def crop_rect(valid):
+    return tuple(int(v) for v in _crop_rect(np.ascontiguousarray(valid, dtype=np.bool_)))
+
+
+# --------------------------------------------------------------------------
+# whole path (stitcher.py:274-327)
 # --------------------------------------------------------------------------
 def build_patches(regions, blend="none", equalize_gains=False, max_resolution=1400,
                   proj="spherical", backend="cv2", window=None, halo=0):
@@ -368,15 +420,21 @@ def build_patches(regions, blend="none", equalize_gains=False, max_resolution=14
 
 
 def stitch(regions, blend="none", equalize_gains=False, n_levels=5, max_resolution=1400,
-           proj="spherical", backend="cv2", owner_mode="auto", stages=None):
+           proj="spherical", backend="cv2", owner_mode="auto", stages=None, crop=False):
     """uint8 H x W x 3 mosaic; inputs are not modified."""
     patches, pl = build_patches(regions, blend, equalize_gains, max_resolution, proj, backend)
     if stages is not None:
         stages["plan"] = pl
         stages["patches"] = [(w.copy(), m.copy(), s) for w, m, s in patches]
+    valid = valid_mask(patches, pl.shape) if crop else None      # (multiband overwrites nothing of the masks)
     if blend == "multiband":
-        return multiband(patches, pl.shape, n_levels, backend, owner_mode, stages)
-    return BLENDERS[blend](patches, pl.shape)
+        mosaic = multiband(patches, pl.shape, n_levels, backend, owner_mode, stages)
+    else:
+        mosaic = BLENDERS[blend](patches, pl.shape)
+    if crop:                                                     # stitcher.py:322-325
+        y0, y1, x0, x1 = crop_rect(valid)
+        mosaic = mosaic[y0:y1, x0:x1]
+    return mosaic
 
 
 def stitch_window(regions, window, blend="multiband", equalize_gains=False, n_levels=5,

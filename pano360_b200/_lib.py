@@ -43,6 +43,8 @@ SIGNATURES = {
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_crop_scratch_bytes": [_i, _i],
+    "p360_crop_rect": [_vp, _i, _i, _vp, _vp, _vp],
 }
 MAX_LEVELS = 8
 
@@ -70,7 +72,7 @@ assert TILE_MAPS.itemsize == 88
 OWN_OFFSET = BAND_PATCH.fields["own"][1]
 
 # entry points whose int return is a value, not a status
-_VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks"}
+_VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks", "p360_crop_scratch_bytes"}
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
@@ -79,7 +81,7 @@ _LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_batch": 1, "p360_owner_update": 1, 
              "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,
              "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
-             "p360_pair_overlap_stats": 2, "p360_cover_update": 1}
+             "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_crop_rect": 3}
 
 
 def load():
@@ -99,7 +101,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = _i
+        fn.restype = _i64 if name == "p360_crop_scratch_bytes" else _i
     _lib = lib
     return lib
 

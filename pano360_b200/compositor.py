@@ -754,6 +754,17 @@ class Compositor:
                       self.stream)
         return covered
 
+    def crop_rect(self, covered):
+        """Largest all-valid rectangle of a device ``covered`` mask (stitcher.py:340-369):
+        (y0, y1, x0, x1), the crop being mosaic[y0:y1, x0:x1]."""
+        h, w = covered.shape
+        covered = covered.contiguous()
+        scratch = torch.empty(int(_lib.call("p360_crop_scratch_bytes", h, w)), dtype=torch.uint8, device=self.device)
+        rect = torch.empty(4, dtype=torch.int32, device=self.device)
+        self._traced("K9_crop_rect", 5 * h * w, "p360_crop_rect", _lib.ptr(covered), h, w, _lib.ptr(scratch), _lib.ptr(rect),
+                     self.stream)
+        return tuple(int(v) for v in rect.cpu().tolist())
+
     def blend(self, kind, patches, shape, n_levels=5, out_host=None, rows=None, on_band=None):
         if kind == "none":
             return self.blend_none(patches, shape, out_host, rows, on_band)

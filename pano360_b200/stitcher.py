@@ -214,68 +214,42 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     if kind is None:                       # foreign blender: the reference's one-box-per-image NumPy triples
         patches = comp.warp(regions, src, plan, proj)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
+    elif crop:
+        # the union of valid pixels stays in HBM, the rectangle is found there (K9) and only the
+        # cropped mosaic crosses PCIe
+        logging.debug("Cropping...")
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, want_covered=True)
+        y0, y1, x0, x1 = comp.crop_rect(comp.last_covered[:plan.shape[0]])
+        mosaic = mosaic_dev[y0:y1, x0:x1].contiguous().cpu().numpy()
     else:
         banded = out if _is_pinned_out(out, plan.shape) else None
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded,
-                                             want_covered=crop)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded)
         if banded is not None:
             comp.finish_download()
             mosaic = out
         else:
             mosaic = _download(mosaic_dev, out)
-    if crop:
+    if crop and kind is None:
         logging.debug("Cropping...")
-        if kind is None:
-            valid = _valid(patches, plan.shape)
-        else:                                  # union of valid pixels, kept by the composite
-            valid = comp.last_covered[:plan.shape[0]].cpu().numpy().astype(bool)
-        mosaic = crop_mosaic(mosaic, valid)
+        mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))
     del patches
     comp.release()          # everything has been waited for (the mosaic is on the host)
     return mosaic
 
 
 # ---------------------------------------------------------------------------
-# crop (stitcher.py:340-369) — host, after the blend
+# crop (stitcher.py:340-369) — K9 on the device
 # ---------------------------------------------------------------------------
-def _nearest_lower(heights):
-    """For every column the extent [left, right] over which it is the minimum
-    (ties extend), by monotonic stack."""
-    n = len(heights)
-    left, right = np.empty(n, np.int64), np.empty(n, np.int64)
-    stack = []
-    for j in range(n):
-        while stack and heights[stack[-1]] >= heights[j]:
-            stack.pop()
-        left[j] = stack[-1] + 1 if stack else 0
-        stack.append(j)
-    stack = []
-    for j in range(n - 1, -1, -1):
-        while stack and heights[stack[-1]] >= heights[j]:
-            stack.pop()
-        right[j] = stack[-1] - 1 if stack else n - 1
-        stack.append(j)
-    return left, right
-
-
 def crop_mosaic(mosaic, valid):
-    """Largest all-valid axis-aligned rectangle (histogram method,
-    stitcher.py:340-369).  Mirrors the reference's scan order and strict '>'
-    update so ties resolve identically, including its quirk that column 0
-    never extends to the right (its loop at :359 stops at j = 1)."""
-    height, width = valid.shape
-    heights = np.zeros(width, np.int64)
-    best = (0, 0, 0, 0, 0)         # area, left, right, height, last row
-    for i in range(height):
-        heights = np.where(valid[i], heights + 1, 0)
-        left, right = _nearest_lower(heights)
-        right[0] = 0
-        areas = (right - left + 1) * heights
-        j = int(np.argmax(areas))
-        if areas[j] > best[0]:
-            best = (int(areas[j]), int(left[j]), int(right[j]), int(heights[j]), i)
-    _, ll, rr, hh, last = best
-    return mosaic[last - hh + 1:last + 1, ll:rr + 1, :]
+    """Remove the black borders: the largest all-valid axis-aligned rectangle (histogram method,
+    stitcher.py:340-369), found on the device (p360_crop_rect) with the reference's scan order
+    and strict '>' update, so ties resolve identically — including its quirk that column 0
+    never extends to the right (its loop at :359 stops at j = 1).  Returns a view of ``mosaic``."""
+    import torch
+    comp = _compositor()
+    covered = torch.from_numpy(np.ascontiguousarray(valid, dtype=np.uint8)).to(comp.device)
+    y0, y1, x0, x1 = comp.crop_rect(covered)
+    return mosaic[y0:y1, x0:x1, :]
 
 
 # ---------------------------------------------------------------------------

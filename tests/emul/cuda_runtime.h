@@ -63,6 +63,8 @@ typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
 enum { cudaMemcpyHostToDevice = 1 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 227 * 1024; return cudaSuccess; }
 struct cudaDeviceProp { int multiProcessorCount, major, minor, l2CacheSize; };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }

@@ -59,7 +59,7 @@ def _load_library():
     for name, argtypes in _lib.SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
+        fn.restype = ctypes.c_int64 if name == "p360_crop_scratch_bytes" else ctypes.c_int
     return lib
 
 

@@ -233,9 +233,11 @@ def test_full_size_cfg3_windows_and_properties(st, comp, restore_globals):
     got = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
     h, w = got.shape[:2]
     assert (h, w) == geo.plan_mosaic(regs, True, 1e9).shape
-    for win in [(h // 2 - 100, h // 2 + 28, w // 2 - 150, w // 2 + 106),      # centre: 4 images meet
-                (0, 96, 2000, 2256),                                            # top mosaic edge
-                (h // 3, h // 3 + 96, 40, 296)]:                                # left edge of the first image
+    wins = [(h // 2 - 100, h // 2 + 28, w // 2 - 150, w // 2 + 106),      # centre: 4 images meet
+            (0, 96, 2000, 2256),                                            # top mosaic edge
+            (h // 3, h // 3 + 96, 40, 296)]                                 # left edge of the first image
+    wins += _seam_windows(comp, regs, wl, got.shape, 16)
+    for win in wins:
         want = rs.stitch_window(regs, win, "multiband", False, wl.n_levels, 1e9)
         assert_mosaic_close(got[win[0]:win[1], win[2]:win[3]], want, what=f"cfg3 window {win}")
     again = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
@@ -281,9 +283,8 @@ def test_cli_with_reference_style_caches(st, tmp_path, monkeypatch, restore_glob
         assert np.array_equal(cv2.imread(str(out)), mosaic)
         want = rs.stitch(regs, blend, "-e" in extra, 5, 1400)
         if "-c" in extra:
-            assert mosaic.shape[0] <= want.shape[0] and mosaic.shape[1] <= want.shape[1] and mosaic.min() >= 0
-        else:
-            assert_mosaic_close(mosaic, want, what=blend)
+            want = rs.stitch(regs, blend, False, 5, 1400, crop=True)
+        assert_mosaic_close(mosaic, want, what=blend)
 
 
 def test_many_small_views(st, restore_globals):
@@ -301,7 +302,73 @@ def test_many_small_views(st, restore_globals):
         assert_mosaic_close(got, rs.stitch(regs, blend, False, 5, 1e9), what=blend)
 
 
-def test_full_size_cfg4_windows(st, restore_globals):
+def _seam_windows(comp, regs, wl, shape, count, size=(96, 192)):
+    """Windows of the mosaic centred on owner seams — where the multiband blend actually blends:
+    read from the plan of a composite (multi tiles), spread over the mosaic (vertical seams,
+    seams between pitch rows, four-image corners), plus the cut edges of seam-straddling boxes."""
+    h, w = shape[:2]
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    comp.composite(regs, comp.upload(regs), plan, "multiband", wl.n_levels)
+    planes, multi, maps = _plan_planes(comp)
+    tx, ty = int(maps["tiles_x"][0]), int(maps["tiles_y"][0])
+    multi = multi.reshape(ty, tx)
+    ncand = np.zeros((ty, tx), int)
+    for word in range(planes.shape[2]):
+        bits = planes[1, :, word].reshape(ty, tx)
+        for b in range(32):
+            ncand += (bits >> np.uint32(b)) & 1
+    rng = np.random.default_rng(5)
+    wins = []
+    corners = np.argwhere(ncand >= 3)                    # three or more patches may carry weight
+    seams = np.argwhere(multi)
+    picks = [corners[i] for i in rng.choice(len(corners), min(count // 3, len(corners)), replace=False)] if len(corners) else []
+    picks += [seams[i] for i in rng.choice(len(seams), count - len(picks), replace=False)]
+    for tyi, txi in picks:
+        y0 = int(np.clip(32 * tyi + 16 - size[0] // 2, 0, h - size[0]))
+        x0 = int(np.clip(64 * txi + 32 - size[1] // 2, 0, w - size[1]))
+        wins.append((y0, y0 + size[0], x0, x0 + size[1]))
+    reach = comp.blur_reach("multiband", wl.n_levels)
+    crops, _ = comp.plan_crops(regs, plan, split_dilate=2 * reach)
+    for c in crops:                                      # artificial edges of split (seam-straddling) boxes
+        box = plan.boxes[c[0]]
+        for x_edge in (c[1], c[3]):
+            if x_edge not in (box[0], box[2]) and len(wins) < count + 4:
+                yc = (c[2] + c[4]) // 2
+                x0 = int(np.clip(x_edge - size[1] // 2, 0, w - size[1]))
+                wins.append((yc - size[0] // 2, yc + size[0] // 2, x0, x0 + size[1]))
+    return wins
+
+
+def test_full_size_cfg2_linear_gains_and_crop(st, restore_globals):
+    """BASELINE config 2 at its stated size: 8 x 1920x1080, linear blend + exposure gains (-e),
+    whole mosaic against the oracle; and the same panorama cropped (-c) without gains, where
+    linear blending is bit-exact."""
+    wl = synth.workload("cfg2")
+    regs = synth.make_views(wl)
+    st.MAX_RESOLUTION = wl.max_resolution
+    got = st.stitch(regs, blender=st.linear_blend, equalize=True)
+    want = rs.stitch(regs, "linear", True, 5, wl.max_resolution)
+    assert got.shape[0] > 1100 and got.shape[1] > 6000
+    assert_mosaic_close(got, want, max_abs=1, what="cfg2 linear -e")      # (gains: float64 sums in another order)
+    assert np.mean(got != want) < 1e-3
+    got = st.stitch(regs, blender=st.linear_blend, crop=True)
+    want = rs.stitch(regs, "linear", False, 5, wl.max_resolution, crop=True)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_full_size_cfg5_panorama(st, restore_globals):
+    """One panorama of BASELINE config 5 at its stated size (6 x 1920x1080, multiband 5 bands):
+    the whole mosaic against the oracle."""
+    wl = synth.workload("cfg5")
+    regs = synth.make_views(wl)
+    st.MAX_RESOLUTION = wl.max_resolution
+    got = st.stitch(regs, blender=st.multiband_blend)
+    want = rs.stitch(regs, "multiband", False, 5, wl.max_resolution)
+    worst, differing = assert_mosaic_close(got, want, what="cfg5 panorama")
+    assert differing / got.size < 0.02, (worst, differing / got.size)
+
+
+def test_full_size_cfg4_windows(st, comp, restore_globals):
     """The benchmark workload itself — BASELINE config 4, 36 x 4000x3000 views on a
     full ring, 8819 x 31654 mosaic, which the reference cannot hold in RAM (~85 GiB):
     windows of the GPU mosaic against the oracle's exact window mode, at the +-pi seam
@@ -313,10 +380,12 @@ def test_full_size_cfg4_windows(st, restore_globals):
     got = st.stitch(regs, blender=st.multiband_blend, n_levels=wl.n_levels)
     h, w = got.shape[:2]
     assert (h, w) == geo.plan_mosaic(regs, True, 1e9).shape and h > 8000 and w > 30000
-    for win in [(h // 2 - 64, h // 2 + 64, 0, 256),                      # left end of the ring (theta = -pi)
-                (h // 2 - 64, h // 2 + 64, w - 256, w),                  # right end (theta = +pi)
-                (h // 3 - 48, h // 3 + 48, w // 2 - 128, w // 2 + 128),  # interior seam crossing
-                (h - 96, h, w // 4, w // 4 + 256)]:                      # bottom edge
+    wins = [(h // 2 - 64, h // 2 + 64, 0, 256),                      # left end of the ring (theta = -pi)
+            (h // 2 - 64, h // 2 + 64, w - 256, w),                  # right end (theta = +pi)
+            (h // 3 - 48, h // 3 + 48, w // 2 - 128, w // 2 + 128),  # interior seam crossing
+            (h - 96, h, w // 4, w // 4 + 256)]                       # bottom edge
+    wins += _seam_windows(comp, regs, wl, got.shape, 16)             # vertical seams, seams between pitch rows, corners, cut edges
+    for win in wins:
         want = rs.stitch_window(regs, win, "multiband", False, wl.n_levels, 1e9)
         assert_mosaic_close(got[win[0]:win[1], win[2]:win[3]], want, what=f"cfg4 window {win}")
     assert (got.sum(axis=2) > 0).mean() > 0.9
@@ -331,7 +400,41 @@ def test_edge_cases(st, restore_globals):
         one = st.stitch(regs[:1], blender=st.BLENDERS[blend])
         assert_mosaic_close(one, rs.stitch(regs[:1], blend), what=blend + "/single")
     cropped = st.stitch(regs, blender=st.linear_blend, crop=True)
-    assert cropped.ndim == 3 and cropped.shape[0] > 0 and (cropped.sum(axis=2) > 0).mean() > 0.95
+    assert np.array_equal(cropped, rs.stitch(regs, "linear", crop=True))
+
+
+def test_crop_rectangle_matches_the_reference_scan(st, comp):
+    """K9 (p360_crop_rect) against the oracle's statement-by-statement restatement of the
+    reference's scan (stitcher.py:346-367; pinned against the live crop_mosaic in
+    test_oracle_vs_reference.py): random masks, rows wider than one and than 32 chunks of the min
+    hierarchy, the column-0 quirk, ties, nothing valid, everything valid."""
+    import torch
+    rng = np.random.default_rng(21)
+    cases = [(rng.random((h, w)) > p) for h, w, p in
+             [(40, 60, 0.05), (33, 1100, 0.01), (9, 2500, 0.003), (70, 31, 0.2), (1, 64, 0.1), (50, 1, 0.1)]]
+    cases += [np.zeros((7, 40), bool), np.ones((12, 77), bool)]
+    tie = np.zeros((20, 90), bool)
+    tie[2:8, 3:13] = tie[10:16, 40:50] = tie[2:8, 60:70] = True        # three equal rectangles: the first in scan order
+    col0 = np.ones((6, 50), bool)
+    col0[:, 1] = False                                                 # column 0 can only ever be 1 wide
+    cases += [tie, col0]
+    for k, valid in enumerate(cases):
+        want = rs.crop_rect(valid)
+        got = comp.crop_rect(torch.from_numpy(valid.astype(np.uint8)).to(comp.device))
+        assert got == want, (k, valid.shape, got, want)
+    mosaic = rng.integers(0, 255, cases[0].shape + (3,), dtype=np.uint8)
+    y0, y1, x0, x1 = rs.crop_rect(cases[0])
+    assert np.array_equal(st.crop_mosaic(mosaic, cases[0]), mosaic[y0:y1, x0:x1])
+
+
+@pytest.mark.parametrize("blend", ["none", "linear", "multiband"])
+def test_cropped_stitch_matches_oracle(st, blend):
+    """stitch(..., crop=True) (-c): same rectangle and same pixels as the oracle's cropped mosaic."""
+    regs = synth.make_views(synth.workload("cfg1", scale=4.0), noise=10.0)
+    want = rs.stitch(regs, blend, False, 5, 1400, crop=True)
+    got = st.stitch(regs, blender=st.BLENDERS[blend], crop=True)
+    assert got.shape == want.shape and want.shape[0] > 20
+    assert_mosaic_close(got, want, what=f"{blend}/crop")
 
 
 def test_row_window_equals_full_mosaic(st, comp, restore_globals):

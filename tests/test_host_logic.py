@@ -93,40 +93,6 @@ def test_find_gains_recovers_gains():
     np.testing.assert_allclose(invert3x3(m) @ m, np.eye(3), atol=1e-12)
 
 
-def test_crop_mosaic_matches_reference_algorithm():
-    from pano360_b200 import stitcher
-    rng = np.random.default_rng(5)
-
-    def reference_crop(valid):          # literal transcription used only as a checker
-        height, width = valid.shape
-        heights = np.zeros(width, np.int32); lefts = np.zeros(width, np.int32); rights = np.zeros(width, np.int32)
-        area = 0
-        for i in range(height):
-            for j in range(width):
-                heights[j] = heights[j] + 1 if valid[i, j] else 0
-            for j in range(width):
-                lefts[j] = j
-                while lefts[j] > 0 and heights[j] <= heights[lefts[j] - 1]:
-                    lefts[j] = lefts[lefts[j] - 1]
-            for j in range(width - 1, 0, -1):
-                rights[j] = j
-                while rights[j] < width - 1 and heights[j] <= heights[rights[j] + 1]:
-                    rights[j] = rights[rights[j] + 1]
-            for j in range(width):
-                new_area = max(area, (rights[j] - lefts[j] + 1) * heights[j])
-                if new_area > area:
-                    area = new_area
-                    ll, rr, hh, last = lefts[j], rights[j], heights[j], i
-        return last - hh + 1, last + 1, ll, rr + 1
-    for trial in range(6):
-        valid = rng.random((40, 60)) > (0.05 + 0.05 * trial)
-        valid[5:30, 8:50] |= rng.random((25, 42)) > 0.02
-        mosaic = np.arange(40 * 60 * 3, dtype=np.int64).reshape(40, 60, 3)
-        y0, y1, x0, x1 = reference_crop(valid)
-        got = stitcher.crop_mosaic(mosaic, valid)
-        assert np.array_equal(got, mosaic[y0:y1, x0:x1]), trial
-
-
 def test_camera_record_and_pickle_roundtrip(tmp_path):
     reg = camera.Image(np.zeros((4, 6, 3), np.uint8), camera.rotation_to_mat([0.1, -0.2, 0.05]),
                        camera.intrinsics(500.0))

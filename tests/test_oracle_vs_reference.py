@@ -33,6 +33,27 @@ def test_two_row_layout():
     assert np.array_equal(rs.stitch(regs, "multiband", False, 6, 1e9), ref)
 
 
+@pytest.mark.parametrize("blend", ["none", "multiband"])
+def test_crop_is_the_references(views, blend):
+    """-c: the oracle's crop (valid mask + largest-rectangle scan) gives the reference's cropped mosaic."""
+    ref = rh.ref_stitch(views, blend, n_levels=5, max_resolution=1400, crop=True)
+    got = rs.stitch(views, blend, False, 5, 1400, crop=True)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_crop_scan_against_the_references_on_random_masks():
+    st, _ = rh.load()
+    rng = np.random.default_rng(12)
+    for trial in range(8):
+        h, w = int(rng.integers(3, 70)), int(rng.integers(3, 1200))
+        valid = rng.random((h, w)) > 0.02 * (trial + 1)
+        valid[:, 0] |= trial % 2 == 0                     # exercise the column-0 quirk
+        mosaic = rng.integers(0, 255, (h, w, 3), dtype=np.uint8)
+        want = st.crop_mosaic(mosaic, valid)
+        y0, y1, x0, x1 = rs.crop_rect(valid)
+        assert np.array_equal(mosaic[y0:y1, x0:x1], want), trial
+
+
 def test_reference_unit_tests_still_pass():
     """The reference's own 8 unit tests (pano_tests.py) through the harness:
     regression for the untouched host code we lean on."""
