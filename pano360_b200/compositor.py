@@ -135,6 +135,7 @@ class Compositor:
         self._down = None
         self._download = None
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
+        self.timeline = None   # list of (label, event) across the upload / compute / download streams when enabled
         # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
         # blur reach.  Bit-identical output either way; None = on for mosaics large enough for the
         # extra launches to pay (B200, cfg4: 15.9 -> 13.2 ms), P360_SEAM_MAPS=0/1 forces it.
@@ -174,6 +175,13 @@ class Compositor:
             self._pinned[pinned_key] = (stage, busy)
             return dev
         return host.to(self.device)
+
+    def _mark(self, label, stream=None):
+        """Timeline mark (tools/e2e_probe.py): a timing event on ``stream`` (default: the compute stream)."""
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+            self.timeline.append((label, ev))
 
     def copy_stream(self):
         """Side stream of the uploads (and of the NVLink pushes of strips.py)."""
@@ -238,6 +246,7 @@ class Compositor:
         lut0 = None
         main = torch.cuda.current_stream(self.device)
         side = self.copy_stream() if overlap else main
+        self._mark("upload begins")
         if overlap:
             src.ready = [None] * n
             side.wait_stream(main)
@@ -260,6 +269,7 @@ class Compositor:
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
+                    self._mark(f"image {i} uploaded + packed", side)
             if gains is None:
                 lut0 = self._to_device(geo.sample_lut(None)) if lut0 is None else lut0
                 src.luts[i] = lut0
@@ -609,6 +619,8 @@ class Compositor:
                 side.wait_event(done)
                 with torch.cuda.stream(side):       # buffer row y is mosaic row y + row_origin
                     host[y0 + row_origin:y1 + row_origin].copy_(mosaic[y0:y1], non_blocking=True)
+                self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} collapsed")
+                self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} downloaded", side)
         if host is not None:
             self._download = torch.cuda.Event()
             self._download.record(side)
@@ -825,6 +837,7 @@ class Compositor:
         (``strip_rows`` = that part of the device result).  ``want_covered``: keep the union of
         valid pixels of the rows produced in ``last_covered`` (crop stage, stitcher.py:266-271)."""
         reach = self.blur_reach(kind, n_levels)
+        self._mark(f"composite {rows} begins")
         if rows is None:
             ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
             crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
