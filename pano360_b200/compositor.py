@@ -44,6 +44,25 @@ from . import _lib, geometry as geo
 SEAM_MAPS_MIN_PIXELS = 1 << 24
 
 
+_copy_pool = None
+
+
+def parallel_copy(dst, src, workers=8):
+    """dst[...] = src for two large host arrays of equal shape, split by rows over a few threads
+    (NumPy releases the GIL while it copies): the staging of pageable buffers runs at several
+    times the rate of a single memcpy."""
+    global _copy_pool
+    n = dst.shape[0]
+    if dst.nbytes < (4 << 20) or n < 2 * workers:
+        np.copyto(dst, src)
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(max(2, min(workers, os.cpu_count() or 2)))
+    cuts = [n * k // workers for k in range(workers + 1)]
+    list(_copy_pool.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(cuts, cuts[1:])))
+
+
 def band_edges(ya, yb, bands):
     """[ya, yb) cut into ``bands`` row ranges with integer arithmetic only, so
     that every rank derives identical cuts whatever its local row origin."""
@@ -134,6 +153,11 @@ class Compositor:
         self._copy = None      # side streams for uploads / downloads that overlap the kernels
         self._down = None
         self._download = None
+        self._bands_down = []  # (y0, y1, event) of the banded download in flight
+        self._ring = []        # pinned staging slots for pageable inputs: [tensor, busy event]
+        self._ring_at = 0
+        self._out_stage = None  # pinned staging for a pageable output
+        self.stage_min_bytes = 1 << 20   # pageable images from this size on go through the pinned ring
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
         self.timeline = None   # list of (label, event) across the upload / compute / download streams when enabled
         # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
@@ -262,8 +286,14 @@ class Compositor:
                     src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
                     if overlap:
                         side.wait_stream(main)               # hat tables were copied on the main stream
+                if not host.is_pinned() and host.numel() >= self.stage_min_bytes:
+                    host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
                 with torch.cuda.stream(side):
                     dev_img = host.to(self.device, non_blocking=host.is_pinned())
+                    if getattr(host, "_p360_slot", None) is not None:
+                        busy = torch.cuda.Event()
+                        busy.record(side)
+                        host._p360_slot[1] = busy
                     # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
                     src.pixels[i] = self.pack_pixels(dev_img) if pack else dev_img
                     if overlap:
@@ -276,6 +306,30 @@ class Compositor:
             else:
                 src.luts[i] = self._to_device(geo.sample_lut(gains[i]))
         return src
+
+    def _stage_pageable(self, host, side, slots=3):
+        """Copy a pageable host image into the next slot of a small ring of pinned buffers (a few
+        threads share the memcpy) so that its upload is an asynchronous DMA: the copy of image
+        k + 1 into its slot overlaps the DMA of image k."""
+        if len(self._ring) < slots:
+            self._ring.append([torch.empty(0, dtype=torch.uint8, pin_memory=True), None])
+        slot = self._ring[self._ring_at % len(self._ring)]
+        self._ring_at += 1
+        if slot[1] is not None:
+            slot[1].synchronize()                    # the DMA out of this slot has finished
+        if slot[0].numel() < host.numel():
+            slot[0] = torch.empty(host.numel(), dtype=torch.uint8, pin_memory=True)
+        view = slot[0][:host.numel()].view(host.shape)
+        parallel_copy(view.numpy(), host.numpy())
+        view._p360_slot = slot
+        return view
+
+    def host_stage(self, shape):
+        """Pinned staging buffer for a mosaic that goes to pageable host memory (kept, grow-only)."""
+        n = int(np.prod(shape))
+        if self._out_stage is None or self._out_stage.numel() < n:
+            self._out_stage = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        return self._out_stage[:n].view(tuple(shape)).numpy()
 
     def set_gains(self, src, gains):
         src.luts = [self._to_device(geo.sample_lut(g)) for g in gains]
@@ -619,6 +673,9 @@ class Compositor:
                 side.wait_event(done)
                 with torch.cuda.stream(side):       # buffer row y is mosaic row y + row_origin
                     host[y0 + row_origin:y1 + row_origin].copy_(mosaic[y0:y1], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(side)
+                self._bands_down.append((y0 + row_origin, y1 + row_origin, landed))
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} collapsed")
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} downloaded", side)
         if host is not None:
@@ -641,8 +698,15 @@ class Compositor:
         for key in ("warp", "bands", "collapse", "streamed", "seam"):
             self._keep.pop(key, None)
 
-    def finish_download(self):
-        """Block until a banded download started by ``_collapse`` has landed."""
+    def finish_download(self, copy_to=None, staged=None):
+        """Block until a banded download started by ``_collapse`` has landed.  ``copy_to`` (a
+        pageable host array) receives the rows from the pinned staging buffer ``staged`` band by
+        band as they land, while the later bands are still crossing PCIe."""
+        if copy_to is not None:
+            for y0, y1, landed in self._bands_down:
+                landed.synchronize()
+                parallel_copy(copy_to[y0:y1], staged[y0:y1])
+        self._bands_down = []
         if self._download is not None:
             self._download.synchronize()
             self._download = None

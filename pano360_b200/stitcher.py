@@ -38,8 +38,9 @@ from .geometry import CylProj, SphProj  # noqa: F401  (module globals, looked up
 MAX_RESOLUTION = 1400
 
 # Row windows of the streamed end-to-end pipeline (Compositor.composite_streamed); 0 = off.
-# Opt-in until it has been timed on the B200: P360_STREAM_WINDOWS=3.
-STREAM_WINDOWS = int(os.environ.get("P360_STREAM_WINDOWS", "0"))
+# B200, cfg4 (36 x 4000x3000 -> 8819 x 31654): 46.9 ms without, 40.2 ms with 3 windows (4 and 6: the
+# same — the tail is the part of the mosaic that needs the last images, profiles/r02_e2e_probe.log).
+STREAM_WINDOWS = int(os.environ.get("P360_STREAM_WINDOWS", "3"))
 STREAM_MIN_PIXELS = 1 << 24
 
 _compositors = {}
@@ -194,23 +195,33 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     levels = 5
     if kind == "multiband":
         levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
-    plan = None
-    if STREAM_WINDOWS and kind is not None and not equalize and not crop and out is not None:
-        plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
-                               max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
-        if _is_pinned_out(out, plan.shape) and plan.shape[0] * plan.shape[1] >= STREAM_MIN_PIXELS:
-            # both PCIe directions at once: row windows are composited and downloaded while the
-            # images of the windows below are still being uploaded
-            comp.composite_streamed(regions, plan, kind, levels, proj, out, windows=STREAM_WINDOWS)
-            comp.finish_download()
-            comp.release()
-            return out
+    plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
+                           max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
+    # where the mosaic lands: the caller's array if it is pinned, else a pinned staging buffer
+    # from which the rows are copied (by a few threads) into the caller's / a fresh array as
+    # they arrive
+    if out is not None and (out.shape != plan.shape + (3,) or out.dtype != np.uint8 or not out.flags.c_contiguous):
+        raise ValueError(f"out must be a C-contiguous uint8 array of shape {plan.shape + (3,)}")
+    direct_out = _is_pinned_out(out, plan.shape)
+    big = plan.shape[0] * plan.shape[1] >= STREAM_MIN_PIXELS
+
+    def landing():
+        if direct_out:
+            return out, None
+        result = out if out is not None else np.empty(plan.shape + (3,), np.uint8)
+        return comp.host_stage(plan.shape + (3,)), result
+
+    if STREAM_WINDOWS and kind is not None and not equalize and not crop and big:
+        # both PCIe directions at once: row windows are composited and downloaded while the
+        # images of the windows below are still being uploaded
+        stage, result = landing()
+        comp.composite_streamed(regions, plan, kind, levels, proj, stage, windows=STREAM_WINDOWS)
+        comp.finish_download(result, stage)
+        comp.release()
+        return out if direct_out else result
     src = comp.upload(regions, overlap=not equalize)       # warp starts while late images still upload
     if equalize:
         comp.set_gains(src, equalize_gains(regions, src))
-    if plan is None:
-        plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
-                               max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
     if kind is None:                       # foreign blender: the reference's one-box-per-image NumPy triples
         patches = comp.warp(regions, src, plan, proj)
         mosaic = blender([p.to_numpy() for p in patches], plan.shape)
@@ -221,14 +232,14 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, want_covered=True)
         y0, y1, x0, x1 = comp.crop_rect(comp.last_covered[:plan.shape[0]])
         mosaic = mosaic_dev[y0:y1, x0:x1].contiguous().cpu().numpy()
+    elif direct_out or big:
+        stage, result = landing()
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=stage)
+        comp.finish_download(result, stage)
+        mosaic = out if direct_out else result
     else:
-        banded = out if _is_pinned_out(out, plan.shape) else None
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=banded)
-        if banded is not None:
-            comp.finish_download()
-            mosaic = out
-        else:
-            mosaic = _download(mosaic_dev, out)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj)
+        mosaic = _download(mosaic_dev, out)
     if crop and kind is None:
         logging.debug("Cropping...")
         mosaic = crop_mosaic(mosaic, _valid(patches, plan.shape))

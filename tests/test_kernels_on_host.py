@@ -86,6 +86,29 @@ def test_streamed_windows_pipeline(st, monkeypatch, restore_globals):
     assert all(a[1] == b[0] and a[2] <= b[2] for a, b in zip(wins, wins[1:])) and len(wins) >= 2
 
 
+def test_pageable_buffers_are_staged(st, comp, monkeypatch, restore_globals):
+    """Pageable inputs go through the ring of pinned slots (threaded memcpy + asynchronous DMA),
+    a pageable / absent ``out`` through the pinned staging buffer, band by band — streamed and
+    not: the bytes of the plain stitch."""
+    regs = gpu.synth.make_views(gpu.synth.workload("cfg3", scale=8.0), noise=10.0)
+    st.MAX_RESOLUTION = 10 ** 9
+    monkeypatch.setattr(st, "STREAM_WINDOWS", 0)
+    want = st.stitch(regs, blender=st.multiband_blend)
+    monkeypatch.setattr(st, "_is_pinned_out", lambda out, shape: False)
+    monkeypatch.setattr(st, "STREAM_MIN_PIXELS", 0)
+    comp = st._compositor()
+    comp.stage_min_bytes = 0
+    for windows in (0, 3):
+        monkeypatch.setattr(st, "STREAM_WINDOWS", windows)
+        got = st.stitch(regs, blender=st.multiband_blend)
+        assert gpu.np.array_equal(got, want), windows
+        mine = gpu.np.full(want.shape, 9, gpu.np.uint8)
+        assert st.stitch(regs, blender=st.multiband_blend, out=mine) is mine and gpu.np.array_equal(mine, want)
+    assert len(comp._ring) == 3 and comp._out_stage is not None
+    with pytest.raises(ValueError):
+        st.stitch(regs, blender=st.multiband_blend, out=gpu.np.zeros((3, 3, 3), gpu.np.uint8))
+
+
 def test_smoke_entry_point(comp, capsys):
     """__graft_entry__.smoke() — what the driver runs first on the GPU box — end to end."""
     import __graft_entry__
