@@ -252,19 +252,12 @@ def model_bytes(wl, plan, n_src_bytes):
 
 
 def mosaic_checksum(mosaic):
-    """Order-sensitive checksum of a device uint8 mosaic (outside every timed region): the sum of
-    the bytes and a position-weighted sum, row chunk by row chunk.  Equal checksums at N = 1, 2,
-    4, 8 say the strips reassemble the single-GPU mosaic."""
-    import torch
-    flat = mosaic.reshape(-1)
-    total, weighted = 0, 0
-    chunk = 1 << 26
-    for start in range(0, flat.numel(), chunk):
-        part = flat[start:start + chunk].to(torch.int64)
-        idx = torch.arange(start, start + part.numel(), device=part.device, dtype=torch.int64)
-        total += int(part.sum())
-        weighted = (weighted + int((part * (idx % 65521 + 1)).sum())) % (1 << 61)
-    return f"{total:x}-{weighted:x}"
+    """CRC-32 of a mosaic (device tensor or host array), outside every timed region.  Equal values
+    at N = 1, 2, 4, 8 — and for the device-timed and the end-to-end legs — say that the strips
+    reassemble the single-GPU mosaic byte for byte."""
+    import zlib
+    host = mosaic.cpu().numpy() if hasattr(mosaic, "cpu") else np.ascontiguousarray(mosaic)
+    return f"{zlib.crc32(host.reshape(-1).data):08x}"
 
 
 def algorithmic_bytes(trace_name, wl, crop_px, src_bytes, m_px, h2d_px=0):
@@ -423,8 +416,8 @@ class Bench:
             stitcher.MAX_RESOLUTION = wl.max_resolution
             return stitcher.stitch(regions, blender=stitcher.BLENDERS[wl.blend], equalize=wl.equalize,
                                    n_levels=wl.n_levels, out=None if pageable else self.out_pinned.numpy())
-        return self.strips.stitch_strips(self.comp, regions, wl.blend, wl.n_levels, wl.equalize, wl.max_resolution,
-                                         out=None if self.out_pinned is None or pageable else self.out_pinned.numpy())
+        # (N ranks: rank 0 gets a view of the host buffer the ranks share — every rank downloads its own strip)
+        return self.strips.stitch_strips(self.comp, regions, wl.blend, wl.n_levels, wl.equalize, wl.max_resolution)
 
     def timed(self, step_fn, n_steps, trace=False):
         import torch.distributed as dist
@@ -471,6 +464,7 @@ class Bench:
         for _ in range(min(warmup, 2)):
             self.e2e_step()
         e2e = self.timed(self.e2e_step, steps)
+        e2e_crc = mosaic_checksum(e2e["result"]) if rank == 0 and e2e["result"] is not None else None
         e2e_page = None
         if full and world == 1:
             self.e2e_step(pageable=True)
@@ -553,7 +547,7 @@ class Bench:
             "e2e": {"value": mpix / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": self.h2d_bytes,
                     "d2h_bytes_per_step": int(np.prod(plan.shape)) * 3, "ms_per_step": e2e_ms,
                     "api": "pano360_b200.stitcher.stitch" if world == 1 else "pano360_b200.strips.stitch_strips",
-                    "host_buffers": "pinned"},
+                    "host_buffers": "pinned", "mosaic_checksum": e2e_crc},
             "gpu_launches": dev["launches"],
             "mosaic_checksum": checksum,
             "roofline": roofline,

@@ -47,7 +47,7 @@ SEAM_MAPS_MIN_PIXELS = 1 << 24
 _copy_pool = None
 
 
-def parallel_copy(dst, src, workers=8):
+def parallel_copy(dst, src, workers=16):
     """dst[...] = src for two large host arrays of equal shape, split by rows over a few threads
     (NumPy releases the GIL while it copies): the staging of pageable buffers runs at several
     times the rate of a single memcpy."""

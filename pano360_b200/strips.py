@@ -267,12 +267,79 @@ def all_pair_statistics(comp, regions, src, group=None):
     return both[0], both[1]
 
 
+class SharedHostMosaic:
+    """One mosaic-sized buffer in host shared memory, mapped by every rank of the node, with each
+    rank's own rows registered as page-locked: every rank downloads its strip over its own PCIe
+    link, band by band while it is still computing, instead of funnelling the mosaic through
+    rank 0's link.  (Re)allocation is collective; the mapping is kept and grown as needed."""
+
+    _cache = {}
+
+    def __init__(self, group):
+        self.group, self.capacity, self.map, self.registered = group, 0, None, None
+
+    @classmethod
+    def get(cls, group):
+        key = id(group)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group)
+        return cls._cache[key]
+
+    def ensure(self, nbytes):
+        if nbytes <= self.capacity:
+            return
+        import os
+        rank = dist.get_rank(self.group)
+        self.release()
+        cap = (int(nbytes * 1.25) + (1 << 21) - 1) >> 21 << 21
+        name = [f"/dev/shm/p360_mosaic_{os.getpid()}_{cap}" if rank == 0 else None]
+        if rank == 0:
+            with open(name[0], "wb") as fid:
+                fid.truncate(cap)
+        dist.broadcast_object_list(name, src=0, group=self.group)
+        self.map = np.memmap(name[0], dtype=np.uint8, mode="r+", shape=(cap,))
+        dist.barrier(self.group)                     # everybody has mapped it: the name can go
+        if rank == 0:
+            os.unlink(name[0])
+        self.capacity = cap
+
+    def rows(self, h, w):
+        return self.map[:h * w * 3].reshape(h, w, 3)
+
+    def register(self, lo, hi):
+        """Page-lock bytes [lo, hi) of the mapping (rounded out to pages) for asynchronous DMA."""
+        page = 4096
+        lo, hi = lo // page * page, min(-(-hi // page) * page, self.capacity)
+        if self.registered is not None and self.registered[0] <= lo and hi <= self.registered[1]:
+            return
+        self.unregister()
+        rt = torch.cuda.cudart()
+        err = rt.cudaHostRegister(self.map.ctypes.data + lo, hi - lo, 0)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {err}")
+        self.registered = (lo, hi)
+
+    def unregister(self):
+        if self.registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self.map.ctypes.data + self.registered[0])
+            self.registered = None
+
+    def release(self):
+        self.unregister()
+        self.map, self.capacity = None, 0
+
+
 def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolution=1400,
                   proj=geo.SphProj, group=None, to_host=True, out=None):
     """Collective: every rank calls this with the same ``regions``; rank 0
     gets the full mosaic (NumPy uint8 if ``to_host`` else a device tensor),
-    other ranks get None.  Each rank uploads only the images its strip needs.
-    """
+    other ranks get None.  Each rank uploads only the images its strip needs
+    (the warp starts while the last ones are still crossing PCIe) and — with
+    ``to_host`` — downloads its own strip into a host buffer shared by the
+    ranks, so that N PCIe links carry the mosaic.  The array rank 0 gets back
+    is ``out`` if given, else a view of that shared buffer (valid until the
+    next call)."""
+    from .compositor import parallel_copy
     from .stitcher import find_gains
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -283,16 +350,34 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     need = set(images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
     if equalize:
         need = set(range(len(regions)))          # pair statistics touch every image
-    src = comp.upload(regions, need=need)
+    src = comp.upload(regions, need=need, overlap=not equalize)
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
         comp.set_gains(src, find_gains(overlaps, sizes))
-    mosaic = composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj, group)
-    if rank != 0 or mosaic is None:
-        return None
-    if not to_host:
-        return mosaic
-    from .stitcher import _download
-    host = _download(mosaic, out)
+    if not to_host or world == 1:
+        mosaic = composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj, group)
+        if rank != 0 or mosaic is None:
+            return None
+        if not to_host:
+            return mosaic
+        from .stitcher import _download
+        host = _download(mosaic, out)
+        comp.release()
+        return host
+    h, w = plan.shape
+    shared = SharedHostMosaic.get(group)
+    shared.ensure(h * w * 3)                     # collective on first use / growth
+    host = shared.rows(h, w)
+    if rows[1] > rows[0]:
+        if comp.device.type == "cuda":
+            shared.register(rows[0] * w * 3, rows[1] * w * 3)
+        comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, out_host=host, bands=4)
+        comp.finish_download()
     comp.release()
+    dist.barrier(group)                          # every strip has landed
+    if rank != 0:
+        return None
+    if out is not None:
+        parallel_copy(out, host)
+        return out
     return host
