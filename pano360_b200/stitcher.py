@@ -195,8 +195,8 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
     levels = 5
     if kind == "multiband":
         levels = n_levels if n_levels is not None else (blender.__defaults__ or (5,))[0]
-    plan = geo.plan_mosaic(regions, pad=(kind == "multiband"),
-                           max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
+    plan = geo.plan_mosaic_cached(regions, pad=(kind == "multiband"),
+                                  max_resolution=globals()["MAX_RESOLUTION"], proj=proj)
     # where the mosaic lands: the caller's array if it is pinned, else a pinned staging buffer
     # from which the rows are copied (by a few threads) into the caller's / a fresh array as
     # they arrive

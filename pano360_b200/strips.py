@@ -341,16 +341,29 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     next call)."""
     from .compositor import parallel_copy
     from .stitcher import find_gains
+    import time
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    plan = geo.plan_mosaic(regions, kind == "multiband", max_resolution, proj)
-    parts = partition_rows(plan, world, kind, n_levels)
+    phases = [("begin", time.perf_counter())] if comp.phases is not None else None
+
+    def phase(label):
+        if phases is not None:
+            phases.append((label, time.perf_counter()))
+    plan = geo.plan_mosaic_cached(regions, kind == "multiband", max_resolution, proj)
+    cut_key = (world, kind, n_levels)
+    if getattr(plan, "_parts", None) is None:
+        plan._parts = {}
+    if cut_key not in plan._parts:
+        plan._parts[cut_key] = partition_rows(plan, world, kind, n_levels)
+    parts = plan._parts[cut_key]
     halo = blur_halo(kind, n_levels)
     rows = parts[rank]
     need = set(images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
     if equalize:
         need = set(range(len(regions)))          # pair statistics touch every image
+    phase("planned")
     src = comp.upload(regions, need=need, overlap=not equalize)
+    phase("uploads queued")
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
         comp.set_gains(src, find_gains(overlaps, sizes))
@@ -372,9 +385,14 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
         if comp.device.type == "cuda":
             shared.register(rows[0] * w * 3, rows[1] * w * 3)
         comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, out_host=host, bands=4)
+        phase("kernels queued")
         comp.finish_download()
+        phase("strip landed")
     comp.release()
     dist.barrier(group)                          # every strip has landed
+    phase("barrier")
+    if phases is not None:
+        comp.phases.append([(label, round((t - phases[0][1]) * 1e3, 3)) for label, t in phases[1:]])
     if rank != 0:
         return None
     if out is not None:
