@@ -360,32 +360,62 @@ class Bench:
         import torch
         from pano360_b200 import geometry as geo, strips, synth
         self.args, self.wl, self.comp, self.world, self.rank = args, wl, comp, world, rank
-        self.torch, self.strips = torch, strips
+        self.torch, self.strips, self.synth = torch, strips, synth
         kind, levels = wl.blend, wl.n_levels
-        cameras = synth.make_views(wl, only=set())          # cameras only: nothing rendered yet
-        self.plan = plan = geo.plan_mosaic(cameras, kind == "multiband", wl.max_resolution)
-        self.parts = strips.partition_rows(plan, world, kind, levels)
+        self.regions = synth.make_views(wl, only=set())     # cameras only: nothing rendered yet
+        self.rendered, self.pageable = set(), [None] * wl.n_views
+        self.plan = plan = geo.plan_mosaic_cached(self.regions, kind == "multiband", wl.max_resolution)
         self.halo = strips.blur_halo(kind, levels)
-        rows = self.parts[rank]
-        need = set(strips.images_for_rows(plan, rows, self.halo)) if rows[1] > rows[0] else set()
+        self.tuned = None
+        if world > 1:
+            # measured-feedback strip cuts (untimed): the model's cuts first, then moved by the
+            # device time every rank measures for its own strip
+            def step(parts):
+                self.place(parts)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                for k in range(2):                        # (the second run is the measurement)
+                    torch.cuda.synchronize()
+                    ev[0].record(torch.cuda.current_stream())
+                    if parts[rank][1] > parts[rank][0]:
+                        comp.composite(self.regions, comp.pack_sources(self.raw), plan, kind, levels, rows=parts[rank])
+                    ev[1].record(torch.cuda.current_stream())
+                    torch.cuda.synchronize()
+                return ev[0].elapsed_time(ev[1])
+            first = strips.partition_rows(plan, world, kind, levels)
+            self.tuned = {"model_cuts": [list(p) for p in first]}
+            self.place(strips.tune_partition(comp, self.regions, plan, kind, levels, step))
+        else:
+            self.place(strips.strip_cuts(plan, 1, kind, levels))
+        self.src_bytes_all = sum(int(np.prod(r.img.shape)) for r in self.regions)
+        self.out_pinned = torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True) if rank == 0 and world == 1 else None
+
+    def place(self, parts):
+        """Adopt row cuts: render the views this rank's strip needs (those not rendered yet), keep
+        pinned host copies (the e2e leg reads these every step) and pageable ones (what main() / a
+        PKL user hands to stitch()), and make the rows the strip reads resident in HBM as uploaded."""
+        torch, comp, wl, plan, rank = self.torch, self.comp, self.wl, self.plan, self.rank
+        self.parts = parts
+        rows = parts[rank]
+        need = set(self.strips.images_for_rows(plan, rows, self.halo)) if rows[1] > rows[0] else set()
         if wl.equalize:
-            need = set(range(len(cameras)))
+            need = set(range(wl.n_views))
+        missing = need - self.rendered
+        if missing:
+            fresh = self.synth.make_views(wl, only=missing)
+            for i in missing:
+                self.pageable[i] = fresh[i].img
+                t = torch.empty(fresh[i].img.shape, dtype=torch.uint8, pin_memory=True)
+                t.numpy()[...] = fresh[i].img
+                self.regions[i]._pin, self.regions[i].img = t, t.numpy()     # numpy view of pinned memory
+            self.rendered |= missing
         self.need = need
-        self.regions = regions = synth.make_views(wl, only=need)   # each rank renders only the views its strip needs
-        # pinned host copies of the inputs (the e2e leg reads these every step), pageable ones for
-        # what main() / a PKL user hands to stitch()
-        self.pageable = []
-        for i, reg in enumerate(regions):
-            self.pageable.append(reg.img if i in need else None)
-            if i not in need:
-                continue
-            t = torch.empty(reg.img.shape, dtype=torch.uint8, pin_memory=True)
-            t.numpy()[...] = reg.img
-            reg._pin, reg.img = t, t.numpy()                 # numpy view of pinned memory
-        self.raw = comp.upload(regions, need=need, pack=False)     # u8 x 3 as uploaded, resident in HBM
-        self.src_bytes_all = sum(int(np.prod(r.img.shape)) for r in regions)
-        self.h2d_bytes = sum(int(np.prod(regions[i].img.shape)) for i in need)
-        self.out_pinned = torch.empty(plan.shape + (3,), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        self.rows_of = None
+        if self.world > 1 and not wl.equalize and rows[1] > rows[0]:
+            self.rows_of = comp.source_rows(self.regions, plan, wl.blend, wl.n_levels, rows=rows)
+        self.raw = comp.upload(self.regions, need=need, pack=False, rows_of=self.rows_of)   # u8 x 3 as uploaded, resident in HBM
+        width3 = {i: int(np.prod(self.regions[i].img.shape[1:])) for i in need}
+        self.h2d_bytes = sum((self.rows_of[i][1] - self.rows_of[i][0] if self.rows_of and i in self.rows_of
+                              else self.regions[i].img.shape[0]) * width3[i] for i in need)
 
     def barrier(self):
         if self.world > 1:
@@ -545,7 +575,7 @@ class Bench:
                        "n_levels": wl.n_levels if wl.blend == "multiband" else None, "equalize": wl.equalize,
                        "mosaic": list(plan.shape), "mosaic_mpix": mpix, "patch_mpix_reference_boxes": p_px / 1e6,
                        "patch_mpix_after_seam_split": crop_px / 1e6,
-                       "strips": [list(p) for p in self.parts], "halo_rows": self.halo,
+                       "strips": [list(p) for p in self.parts], "strip_cuts": self.tuned or "model", "halo_rows": self.halo,
                        "timed_region": "sources resident in HBM as uploaded (u8 x 3); RGBX packing, gains, warp, blend and "
                                        "the gather of the strips are all inside",
                        "l2": "no flush: each step streams >> 126 MB (model bytes %.1f GB) so nothing survives in L2 between steps"

@@ -139,6 +139,7 @@ class DeviceSources:
     hats: dict = field(default_factory=dict)   # (h, w) -> (hat_y, hat_x) f64 tensors
     shapes: list = field(default_factory=list)
     ready: list = None                 # per image CUDA event (uploads issued on the copy stream)
+    rows: list = None                  # per image (r0, r1): only these rows are resident / packed (None: all)
 
 
 class Compositor:
@@ -239,34 +240,42 @@ class Compositor:
         return rc
 
     # -- sources --------------------------------------------------------------
-    def pack_pixels(self, dev_img):
+    def pack_pixels(self, dev_img, rows=None):
         """u8 x 3 -> u8 x 4 (RGBX) on the device: a bilinear tap of the warp is then one aligned
-        32-bit load.  4-channel images are used as they are."""
+        32-bit load.  4-channel images are used as they are.  ``rows = (r0, r1)``: only those rows
+        hold data (and only they are converted)."""
         h, w, c = dev_img.shape
         if c == 4:
             return dev_img
         packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
-        self._traced("K1p_pack_rgbx", 7 * h * w, "p360_pack_rgbx", _lib.ptr(dev_img), h, w, _lib.ptr(packed), self.stream)
+        r0, r1 = (0, h) if rows is None else rows
+        r0 = r0 // 4 * 4                                   # keeps source and destination addresses aligned
+        if r1 > r0:
+            self._traced("K1p_pack_rgbx", 7 * (r1 - r0) * w, "p360_pack_rgbx", dev_img.data_ptr() + 3 * w * r0, r1 - r0, w,
+                         packed.data_ptr() + 4 * w * r0, self.stream)
         return packed
 
     def pack_sources(self, raw):
         """A ``DeviceSources`` whose images are in the warp's RGBX layout, from one holding the
         images as uploaded (``upload(pack=False)``): the device-side part of ``_add_weights``
         (stitcher.py:257-263) that is executed once per image and stitch."""
-        src = DeviceSources([None if p is None else self.pack_pixels(p) for p in raw.pixels], raw.luts, raw.hats,
-                            raw.shapes, raw.ready)
-        return src
+        rows = raw.rows or [None] * len(raw.pixels)
+        return DeviceSources([None if p is None else self.pack_pixels(p, r) for p, r in zip(raw.pixels, rows)],
+                             raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
 
-    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None):
+    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
         ``overlap`` the copies (and the RGBX packing) run on a side stream and
         every image gets a ``ready`` event, so the warp of the first images
         starts while the last ones are still crossing PCIe.  ``order`` (a
-        permutation of the indices) is the order in which the copies are issued."""
+        permutation of the indices) is the order in which the copies are issued.  ``rows_of``
+        ({image: (r0, r1)}, ``source_rows``) uploads only the rows a composite will read."""
         n = len(regions)
         src = DeviceSources([None] * n, [None] * n)
+        if rows_of is not None:
+            src.rows = [rows_of.get(i) for i in range(n)]
         src.shapes = [reg.img.shape[:2] for reg in regions]
         lut0 = None
         main = torch.cuda.current_stream(self.device)
@@ -283,6 +292,10 @@ class Compositor:
                 if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
                 host = torch.from_numpy(np.ascontiguousarray(img))
+                part = None if rows_of is None else rows_of.get(i)
+                if part is not None:
+                    part = (part[0] // 4 * 4, part[1])        # (4-row granularity: aligned addresses for the packing)
+                    host = host[part[0]:part[1]]
                 if (h, w) not in src.hats:
                     src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
                     if overlap:
@@ -290,13 +303,17 @@ class Compositor:
                 if not host.is_pinned() and host.numel() >= self.stage_min_bytes:
                     host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
                 with torch.cuda.stream(side):
-                    dev_img = host.to(self.device, non_blocking=host.is_pinned())
+                    if part is None:
+                        dev_img = host.to(self.device, non_blocking=host.is_pinned())
+                    else:                                    # rows outside `part` stay unwritten: nobody reads them
+                        dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+                        dev_img[part[0]:part[1]].copy_(host, non_blocking=host.is_pinned())
                     if getattr(host, "_p360_slot", None) is not None:
                         busy = torch.cuda.Event()
                         busy.record(side)
                         host._p360_slot[1] = busy
                     # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
-                    src.pixels[i] = self.pack_pixels(dev_img) if pack else dev_img
+                    src.pixels[i] = self.pack_pixels(dev_img, part) if pack else dev_img
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
@@ -404,6 +421,30 @@ class Compositor:
         if plan._crops is not None:
             plan._crops[key] = crops
         return crops, plan.rays(proj)
+
+    def source_rows(self, regions, plan, kind, n_levels=5, proj=geo.SphProj, rows=None):
+        """{image: (r0, r1)}: the source rows ``composite(..., rows=rows)`` can touch — for
+        ``upload(rows_of=...)``.  Images the composite does not meet are absent."""
+        reach = self.blur_reach(kind, n_levels)
+        if rows is None:
+            crops, _ = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
+        else:
+            wa, wb = self.window_rows(rows, kind, n_levels, plan.shape[0])
+            crops, _ = self.plan_crops(regions, plan, proj, rows=(wa, wb), row_align=4 if reach else 1,
+                                       split_dilate=2 * reach)
+        key = ("rows", len(regions), proj, rows, kind, n_levels)
+        cached = plan._crops.get(key) if plan._crops is not None else None
+        if cached is not None:
+            return cached
+        needed = {}
+        for c in crops:
+            r0, r1 = geo.source_rows_needed(regions[c[0]], c[1:5], plan, proj)
+            if r1 > r0:
+                old = needed.get(c[0])
+                needed[c[0]] = (r0, r1) if old is None else (min(r0, old[0]), max(r1, old[1]))
+        if plan._crops is not None:
+            plan._crops[key] = needed
+        return needed
 
     def new_owner_state(self, shape):
         """(owner keys u64, covered u8) for a mosaic (or strip) of ``shape``."""

@@ -210,6 +210,51 @@ def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     return runs
 
 
+def source_rows_needed(region, crop, plan, proj=SphProj, tile=(64, 32)):
+    """Rows [r0, r1) of ``region.img`` that the warp can touch when it produces the mosaic box
+    ``crop = (x0, y0, x1, y1)`` — so that only those rows need to be uploaded and packed (a strip
+    of a multi-GPU composite reads a fraction of every image it meets).
+
+    Conservative by construction: interval arithmetic per 64 x 32 tile of the box (ray tables ->
+    K R ray -> source row, the arithmetic of the seam plan), widened by the bilinear taps and the
+    1/32-px rounding; source rows beyond the image fold back by BORDER_REFLECT (cv2.remap at
+    stitcher.py:315-316).  Anything uncertain — a tile not wholly in front of the camera, more
+    than one reflection period — means the whole image."""
+    x0, y0, x1, y1 = crop
+    h = region.img.shape[0]
+    if x1 <= x0 or y1 <= y0:
+        return 0, 0
+    ray_x, ray_z, ray_y = plan.rays(proj)
+    kr = np.asarray(region.proj(), dtype=np.float64)
+
+    def per_tile(values, a, b, size):
+        starts = np.arange(0, b - a, size)
+        return np.minimum.reduceat(values[a:b], starts), np.maximum.reduceat(values[a:b], starts)
+
+    def scaled(k, lo, hi):
+        return np.minimum(k * lo, k * hi), np.maximum(k * lo, k * hi)
+
+    bx, bz, by = per_tile(ray_x, x0, x1, tile[0]), per_tile(ray_z, x0, x1, tile[0]), per_tile(ray_y, y0, y1, tile[1])
+
+    def component(row):
+        ax, az, ay = scaled(kr[row, 0], *bx), scaled(kr[row, 2], *bz), scaled(kr[row, 1], *by)
+        return (ax[0] + az[0])[None, :] + ay[0][:, None], (ax[1] + az[1])[None, :] + ay[1][:, None]
+
+    (py_lo, py_hi), (pz_lo, pz_hi) = component(1), component(2)
+    if not np.all(pz_lo > 1e-9):
+        return 0, h
+    quotients = np.stack([py_lo / pz_lo, py_lo / pz_hi, py_hi / pz_lo, py_hi / pz_hi])
+    v_min, v_max = float(quotients.min()) + h / 2.0 - 2.0, float(quotients.max()) + h / 2.0 + 2.0
+    if not (np.isfinite(v_min) and np.isfinite(v_max)) or v_min < -(h - 1) or v_max > 2 * (h - 1):
+        return 0, h
+    r0, r1 = int(np.floor(v_min)), int(np.floor(v_max)) + 2
+    if v_min < 0:                                   # rows above the image fold back onto rows 0 .. -v
+        r0, r1 = 0, max(r1, int(np.ceil(-v_min)) + 2)
+    if v_max > h - 1:                               # rows below fold back onto rows 2h - 1 - v .. h - 1
+        r0, r1 = min(r0, int(np.floor(2 * h - 1 - v_max)) - 2), h
+    return max(r0, 0), min(r1, h)
+
+
 def inverse_map_tables(region, box, plan, proj=SphProj):
     """Separable float64 tables for one patch: ``p = K R proj2hom(theta, phi)``
     splits into a per-column part and a per-row part (stitcher.py:300-306).

@@ -97,6 +97,62 @@ def partition_rows(plan, n_parts, kind="multiband", n_levels=5):
     return best
 
 
+def rebalance(parts, times, height, align=32, damping=0.75):
+    """New row cuts from the measured device time of every strip (same cuts -> same bytes, so the
+    partition is free to follow the measurement): the cost per row is taken as constant within
+    each old strip, the new cuts sit at equal shares of the total, moved ``damping`` of the way
+    and rounded to whole 32-row tiles (a cut inside a tile makes two ranks plan and warp it)."""
+    n = len(parts)
+    if n < 2 or min(times) <= 0:
+        return list(parts)
+    edges = [p[0] for p in parts] + [parts[-1][1]]
+    cum = np.concatenate([[0.0], np.cumsum(times)])
+    new = [0]
+    for k in range(1, n):
+        target = cum[-1] * k / n
+        r = min(int(np.searchsorted(cum, target, side="right")) - 1, n - 1)
+        span = edges[r + 1] - edges[r]
+        y = edges[r] + (target - cum[r]) / max(times[r], 1e-12) * span
+        y = edges[k] + damping * (y - edges[k])
+        y = int(round(y / align)) * align
+        new.append(min(max(y, new[-1] + align), height - align * (n - k)))
+    new.append(height)
+    return [(new[i], new[i + 1]) for i in range(n)]
+
+
+def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds=3):
+    """Measured-feedback strip cuts (collective): ``step(parts)`` runs one composite of this
+    rank's strip for the given cuts (uploading what it needs; untimed by the caller) and returns
+    the device time in ms; the cuts are moved ``rounds`` times and remembered in the plan, where
+    ``stitch_strips`` and ``composite_gather`` callers find them.  Returns the final cuts."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    parts = partition_rows(plan, world, kind, n_levels)
+    if world > 1:
+        for _ in range(rounds):
+            mine = torch.zeros(world, dtype=torch.float64, device=comp.device)
+            mine[rank] = step(parts)
+            dist.all_reduce(mine, group=group)
+            times = mine.cpu().tolist()
+            if max(times) <= 1.04 * (sum(times) / world):
+                break
+            parts = rebalance(parts, times, plan.shape[0])
+    if getattr(plan, "_parts", None) is None:
+        plan._parts = {}
+    plan._parts[(world, kind, n_levels)] = parts
+    return parts
+
+
+def strip_cuts(plan, world, kind, n_levels):
+    """The row cuts in force for this plan: tuned ones if ``tune_partition`` ran, else the model's."""
+    if getattr(plan, "_parts", None) is None:
+        plan._parts = {}
+    key = (world, kind, n_levels)
+    if key not in plan._parts:
+        plan._parts[key] = partition_rows(plan, world, kind, n_levels)
+    return plan._parts[key]
+
+
 def images_for_rows(plan, rows, halo):
     """Indices of images whose box intersects rows [ya - halo, yb + halo)."""
     ya, yb = rows[0] - halo, rows[1] + halo
@@ -143,7 +199,7 @@ class PeerMosaic:
 
     def __init__(self, device, group):
         self.device, self.group = device, group
-        self.capacity, self.handle, self.local = 0, None, None
+        self.capacity, self.handle, self.local, self.flip = 0, None, None, 0
 
     @classmethod
     def get(cls, device, group):
@@ -158,12 +214,15 @@ class PeerMosaic:
             return
         import torch.distributed._symmetric_memory as symm
         cap = (int(nbytes * 1.25) + (1 << 21) - 1) >> 21 << 21
-        self.local = symm.empty(cap, dtype=torch.uint8, device=self.device)
+        # two mosaics: a step writes the one the previous step did not, so rank 0 may still be
+        # reading the last result while the next one arrives — one barrier per step, not two
+        self.local = symm.empty(2 * cap, dtype=torch.uint8, device=self.device)
         self.handle = symm.rendezvous(self.local, self.group if self.group is not None else dist.group.WORLD)
         self.capacity = cap
 
     def rows_of_rank0(self, h, w):
-        return self.handle.get_buffer(0, (h, w, 3), torch.uint8)
+        self.flip ^= 1
+        return self.handle.get_buffer(0, (h, w, 3), torch.uint8, storage_offset=self.flip * self.capacity)
 
     def barrier(self):
         self.handle.barrier(channel=0)
@@ -179,7 +238,7 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
     soon as it is done, while the next band is being computed.  Preferred
     transport: peer-mapped destination (``PeerMosaic``, copy-engine DMA); if
     symmetric memory cannot be set up, grouped NCCL send/recv.  Returns the
-    device mosaic on rank 0 (valid until the next call), None elsewhere."""
+    device mosaic on rank 0 (valid until the call after the next), None elsewhere."""
     global _peer_ok
     from .compositor import band_edges
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -199,8 +258,7 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
             _peer_ok, peer = False, None
     if peer is not None:
         main, side = torch.cuda.current_stream(comp.device), comp.copy_stream()
-        dst = peer.rows_of_rank0(h, w)
-        peer.barrier()                                # rank 0 is done with the previous mosaic
+        dst = peer.rows_of_rank0(h, w)                # (the buffer the previous step did not write)
         if rows[1] > rows[0]:
             if rank == 0:
                 strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
@@ -350,19 +408,16 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
         if phases is not None:
             phases.append((label, time.perf_counter()))
     plan = geo.plan_mosaic_cached(regions, kind == "multiband", max_resolution, proj)
-    cut_key = (world, kind, n_levels)
-    if getattr(plan, "_parts", None) is None:
-        plan._parts = {}
-    if cut_key not in plan._parts:
-        plan._parts[cut_key] = partition_rows(plan, world, kind, n_levels)
-    parts = plan._parts[cut_key]
+    parts = strip_cuts(plan, world, kind, n_levels)
     halo = blur_halo(kind, n_levels)
     rows = parts[rank]
     need = set(images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
     if equalize:
         need = set(range(len(regions)))          # pair statistics touch every image
+    # a strip reads only some rows of every image it meets: upload (and pack) just those
+    rows_of = None if equalize or rows[1] <= rows[0] else comp.source_rows(regions, plan, kind, n_levels, proj, rows)
     phase("planned")
-    src = comp.upload(regions, need=need, overlap=not equalize)
+    src = comp.upload(regions, need=need, overlap=not equalize, rows_of=rows_of)
     phase("uploads queued")
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)

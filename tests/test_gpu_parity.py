@@ -558,6 +558,32 @@ def test_row_windows_cut_anywhere(comp):
         assert np.array_equal(strip, full[ya:yb]), (ya, yb)
 
 
+def test_partial_row_uploads_are_sufficient(comp):
+    """A row window reads only some rows of the images it meets (geometry.source_rows_needed,
+    interval arithmetic): uploading and packing just those must not change a byte — every other
+    source row stays uninitialised on the device."""
+    regs = synth.make_views(synth.workload("cfg4", scale=8.0), noise=5.0)
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    h = plan.shape[0]
+    full = comp.composite(regs, comp.upload(regs), plan, "multiband", 5)[0].cpu().numpy()
+    saved = 0.0
+    for rows in [(0, h // 8), (3 * h // 8, h // 2), (h // 2 - 20, h // 2 + 40), (7 * h // 8, h)]:
+        rows_of = comp.source_rows(regs, plan, "multiband", 5, rows=rows)
+        assert rows_of and all(0 <= a < b <= regs[i].img.shape[0] for i, (a, b) in rows_of.items())
+        saved += 1.0 - sum(b - a for a, b in rows_of.values()) / (len(rows_of) * regs[0].img.shape[0])
+        src = comp.upload(regs, need=set(rows_of), rows_of=rows_of)
+        strip = comp.composite(regs, src, plan, "multiband", 5, rows=rows)[0].cpu().numpy()
+        assert np.array_equal(strip, full[rows[0]:rows[1]]), rows
+    assert saved / 4 > 0.3                      # (the strips really skip a good part of every image)
+    for kind in ("linear", "none"):
+        plan = geo.plan_mosaic(regs, False, 1e9)
+        want = comp.composite(regs, comp.upload(regs), plan, kind)[0].cpu().numpy()
+        rows = (h // 3, h // 2)
+        rows_of = comp.source_rows(regs, plan, kind, rows=rows)
+        got = comp.composite(regs, comp.upload(regs, need=set(rows_of), rows_of=rows_of), plan, kind, rows=rows)[0]
+        assert np.array_equal(got.cpu().numpy(), want[rows[0]:rows[1]]), kind
+
+
 def test_unpacked_source_layout_is_equivalent(comp, tiny4):
     """K1 accepts the uploaded u8 x 3 pixels directly (alpha evaluated per tap
     from the hat tables) or the packed {RGBX, alpha} words: identical patches."""

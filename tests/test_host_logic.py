@@ -131,7 +131,7 @@ def test_c_abi_exports_every_declared_symbol():
     """The shared library loads and exports exactly what include/*.h declares
     (no compute calls here: there is no GPU)."""
     header = open(os.path.join(ROOT, "include", "pano360_b200.h")).read()
-    declared = set(re.findall(r"^\s*int\s+(p360_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t)\s+(p360_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     if not os.path.exists(_lib.LIB_PATH):
         from pano360_b200 import build

@@ -54,6 +54,7 @@ test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
+test_partial_row_uploads_are_sufficient = gpu.test_partial_row_uploads_are_sufficient
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
 test_seam_plan_is_conservative_and_cut_independent = gpu.test_seam_plan_is_conservative_and_cut_independent
