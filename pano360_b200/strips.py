@@ -120,23 +120,35 @@ def rebalance(parts, times, height, align=32, damping=0.75):
     return [(new[i], new[i + 1]) for i in range(n)]
 
 
-def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds=3):
-    """Measured-feedback strip cuts (collective): ``step(parts)`` runs one composite of this
+def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds=4, log=None):
+    """Measured-feedback strip cuts (collective): ``step(parts)`` runs the composite of this
     rank's strip for the given cuts (uploading what it needs; untimed by the caller) and returns
-    the device time in ms; the cuts are moved ``rounds`` times and remembered in the plan, where
-    ``stitch_strips`` and ``composite_gather`` callers find them.  Returns the final cuts."""
+    its device time in ms; the cuts are moved up to ``rounds`` times and the best partition seen
+    (smallest time of the slowest rank — the model's cuts included) is remembered in the plan,
+    where ``stitch_strips`` / ``strip_cuts`` find it.  Returns the cuts."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     parts = partition_rows(plan, world, kind, n_levels)
+    best = None
     if world > 1:
-        for _ in range(rounds):
+        damping = 0.6
+        for it in range(rounds + 1):
             mine = torch.zeros(world, dtype=torch.float64, device=comp.device)
             mine[rank] = step(parts)
             dist.all_reduce(mine, group=group)
             times = mine.cpu().tolist()
-            if max(times) <= 1.04 * (sum(times) / world):
+            if log is not None:
+                log.append({"cuts": [list(p) for p in parts], "ms": [round(t, 3) for t in times]})
+            if best is None or max(times) < max(best[1]):
+                best = (parts, times)
+            else:
+                damping *= 0.5                       # overshot: a smaller step from the best cuts so far
+            if it == rounds or min(best[1]) <= 0 or max(best[1]) <= 1.04 * (sum(best[1]) / world):
                 break
-            parts = rebalance(parts, times, plan.shape[0])
+            parts = rebalance(best[0], best[1], plan.shape[0], damping=damping)
+            if parts == best[0]:
+                break
+        parts = best[0]
     if getattr(plan, "_parts", None) is None:
         plan._parts = {}
     plan._parts[(world, kind, n_levels)] = parts
