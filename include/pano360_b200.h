@@ -91,7 +91,10 @@ typedef struct p360_warp_job {
 int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream);
 struct p360_tile_maps;
 struct p360_band_patch;
-int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
+/* jobs_dev (optional): a DEVICE copy of the same table — the constant-memory staging then is a
+ * device-to-device copy and the call never synchronises the stream (a copy from pageable host
+ * memory does). */
+int p360_warp_batch(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs,
                     uint64_t *owner_keys, uint8_t *covered, int W, void *stream);
 
 /* ---- K0 + K1d: the seam plan and the direct tiles (multiband, >= 2 bands) -----------------
@@ -126,7 +129,7 @@ int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
 int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
                          int H, int W, int abs_row0, int mosaic_h,
                          const struct p360_tile_maps *maps_host, void *stream);
-int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint64_t *owner_keys,
+int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
                     uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
                     int want_covered, const struct p360_tile_maps *maps_host, void *stream);
 
@@ -281,6 +284,20 @@ int p360_pair_overlap_stats(const p360_pair_job *jobs, int n_pairs, int h, int w
 /* ---- valid-area mask for the crop stage (stitcher.py:266-271) -------------*/
 int p360_cover_update(const uint8_t *invalid, int pw, int ph, int x0, int y0,
                       uint8_t *covered, int W, void *stream);
+
+/* ---- the reference's multiband loop nest at full resolution (stitcher.py:186-241) ---------
+ * Stage by stage, as SURVEY.md §8(b) lists them: the owner mask into alpha (:207-208), one
+ * p360_gauss_blur per patch and level (:226), band x weight accumulated per level into a mosaic-
+ * sized {sum r*w, sum g*w, sum b*w, sum w} float4 image (:224-232; cur_rgba == NULL: the last
+ * level), then per-level normalisation, sum, clip, uint8 (:236-241) over acc_rgbw =
+ * [n_levels][H][W] float4.  FP32-issue-bound; used as the device-side ground truth of the
+ * coarse-grid pipeline and for images too small for it (pano360_b200/compositor.py). */
+int p360_owner_to_alpha(float *rgba, int pw, int ph, int x0, int y0, int idx,
+                        const uint64_t *owner_keys, int W, void *stream);
+int p360_band_accumulate(const float *prev_rgba, const float *cur_rgba, int pw, int ph, int x0, int y0,
+                         float *acc_rgbw, int W, void *stream);
+int p360_exact_collapse(const float *acc_rgbw, int n_levels, const uint8_t *covered, uint8_t *out_u8,
+                        int H, int W, void *stream);
 
 /* ---- crop stage: largest all-valid rectangle (stitcher.py:340-369, crop_mosaic) ------------
  * covered: H x W u8 union of valid pixels (stitcher.py:266-271).  rect_dev receives

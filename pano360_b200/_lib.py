@@ -25,9 +25,9 @@ SIGNATURES = {
     "p360_last_error": [C.c_char_p, _i],
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
     "p360_pack_rgbx": [_vp, _i, _i, _vp, _vp],
-    "p360_warp_batch": [_vp, _i, _vp, _vp, _i, _vp],
+    "p360_warp_batch": [_vp, _vp, _i, _vp, _vp, _i, _vp],
     "p360_seam_plan_build": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
-    "p360_warp_tiles": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_warp_tiles": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "p360_owner_decode": [_vp, _vp, _i64, _vp],
     "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
@@ -43,6 +43,9 @@ SIGNATURES = {
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_owner_to_alpha": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_band_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "p360_exact_collapse": [_vp, _i, _vp, _vp, _i, _i, _vp],
     "p360_crop_scratch_bytes": [_i, _i],
     "p360_crop_rect": [_vp, _i, _i, _vp, _vp, _vp],
 }
@@ -81,7 +84,8 @@ _LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_batch": 1, "p360_owner_update": 1, 
              "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,
              "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
-             "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_crop_rect": 3}
+             "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_crop_rect": 3,
+             "p360_owner_to_alpha": 1, "p360_band_accumulate": 1, "p360_exact_collapse": 1}
 
 
 def load():

@@ -42,6 +42,8 @@ from . import _lib, geometry as geo
 # 15.9 -> 13.2 ms); the five extra launches and the persistent grids are not free, so the 1-8 Mpix
 # panoramas of cfg1 / cfg5 (0.2-0.5 ms per composite) keep the dense path until they are measured.
 SEAM_MAPS_MIN_PIXELS = 1 << 24
+# Rigs with an image side below this many pixels are blended at full resolution (see needs_exact).
+EXACT_BELOW = 64
 
 
 _copy_pool = None
@@ -145,10 +147,18 @@ class DeviceSources:
 class Compositor:
     """Runs warp / gain / blend stages on one GPU."""
 
+    # What fresh coarse-pool memory holds, and whether it is refilled before every composite: the
+    # batched blurs may stage cells no kernel of the composite wrote (skipped neighbours), which
+    # is harmless exactly as long as those hold finite values.  Zeroed once in production; the
+    # host build of the kernels (tests/emul) poisons with 1e30 every time.
+    pool_fill = 0.0
+    repoison = False
+
     def __init__(self, device=None):
         self.device = _require_cuda(device)
         _lib.load()
         self._pinned = {}
+        self._pools = {}
         self._taps_key = None
         self._keep = {}
         self._copy = None      # side streams for uploads / downloads that overlap the kernels
@@ -507,8 +517,11 @@ class Compositor:
         """K1 over the job table: one launch, or — while uploads are still in flight — one per
         group of images as they arrive."""
         n = len(jobs)
+        dev_jobs = self._table(jobs, "warp_jobs")        # (constant memory is staged from this copy: no stream sync)
+        base = dev_jobs.data_ptr()
+        self._keep["warp_jobs"] = dev_jobs
         if src.ready is None:
-            self._traced("K1_warp", per_px * pixels, "p360_warp_batch", jobs.ctypes.data, n,
+            self._traced("K1_warp", per_px * pixels, "p360_warp_batch", jobs.ctypes.data, base, n,
                          _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
             return
         main = torch.cuda.current_stream(self.device)
@@ -521,8 +534,8 @@ class Compositor:
                 b += 1
             for i in sorted({c[0] for c in crops[a:b]}):        # uploads may be issued in any order
                 main.wait_event(src.ready[i])
-            _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize, b - a,
-                      _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
+            _lib.call("p360_warp_batch", jobs.ctypes.data + a * _lib.WARP_JOB.itemsize,
+                      base + a * _lib.WARP_JOB.itemsize, b - a, _lib.ptr(keys), _lib.ptr(covered), width, self.stream)
             a = b
 
     def warp_crops(self, src, crops, tables, origin=(0, 0), owner_state=None):
@@ -639,8 +652,8 @@ class Compositor:
         cells = table["w4"].astype(np.int64) * table["h4"]                # f = 4 cells per patch
         first = np.concatenate([[0], np.cumsum(cells)]).astype(np.uint64)
         total = int(first[-1])
-        pool2 = torch.empty(3 * 4 * total * 4, dtype=torch.float32, device=self.device)
-        pool4 = torch.empty((1 + 2 * (n_blurs - 1)) * total * 4, dtype=torch.float32, device=self.device)
+        pool2 = self._coarse_pool("pool2", 3 * 4 * total * 4)
+        pool4 = self._coarse_pool("pool4", (1 + 2 * (n_blurs - 1)) * total * 4)
         base2, base4 = np.uint64(pool2.data_ptr()), np.uint64(pool4.data_ptr())
         plane2, plane4 = np.uint64(16 * 4 * total), np.uint64(16 * total)      # bytes per plane
         at2, at4 = np.uint64(64) * first[:-1], np.uint64(16) * first[:-1]      # byte offset of each patch
@@ -652,6 +665,19 @@ class Compositor:
         for lvl, (_, _, out) in enumerate(levels):
             table["low"][:, lvl] = out
         return {"pool2": pool2, "pool4": pool4, "levels": levels, "cells": total, "first": first}
+
+    def _coarse_pool(self, name, numel):
+        """Grow-only float32 buffer for the coarse levels, filled once with finite values and from
+        then on only ever written by the reduce / blur kernels (see ``pool_fill``)."""
+        pool = self._pools.get(name)
+        if pool is None or pool.numel() < numel:
+            self._pools.pop(name, None)
+            pool = torch.empty(int(numel * 1.1) + 1024, dtype=torch.float32, device=self.device)
+            pool.fill_(self.pool_fill)
+            self._pools[name] = pool
+        elif self.repoison:
+            pool.fill_(self.pool_fill)
+        return pool[:numel]
 
     def _blur_jobs(self, table, layout, dev_table, pad):
         """One p360_blur_job per (level, patch): level 0 on the f = 2 grid, the others on f = 4."""
@@ -737,7 +763,7 @@ class Compositor:
         pool, coarse levels, job tables); the memory goes back to torch's caching
         allocator.  Call only after the work that uses them has been waited for."""
         self.last_covered = None
-        for key in ("warp", "bands", "collapse", "streamed", "seam"):
+        for key in ("warp", "warp_jobs", "bands", "collapse", "streamed", "seam", "exact"):
             self._keep.pop(key, None)
 
     def finish_download(self, copy_to=None, staged=None):
@@ -794,7 +820,7 @@ class Compositor:
                 for i in sorted({c[0] for c in crops}):
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
-            self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, n,
+            self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, _lib.ptr(dev_wjobs), n,
                          _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
             self._keep["seam"] = (dev_wjobs,)
@@ -833,6 +859,46 @@ class Compositor:
         self.last_covered = covered
         if stages is not None:
             stages.update(keys=keys, covered=covered, lows=lows, maps=maps)
+        return mosaic
+
+    def blend_multiband_exact(self, patches, shape, n_levels=5, owner_state=None, mosaic=None):
+        """stitcher.py:186-241 stage by stage at full resolution: every patch blurred with the
+        reference's own 33-97-tap Gaussians at every level, bands accumulated per level in
+        mosaic-sized float images.  Two orders of magnitude slower than ``blend_multiband`` and
+        agreeing with the reference to float rounding: the device-side ground truth of the
+        coarse-grid pipeline, and the path for images too small for the coarse grids.  The alpha
+        channel of the patches is overwritten with the owner mask, like the reference's."""
+        h, w = shape
+        if not 1 <= n_levels <= _lib.MAX_LEVELS:
+            raise ValueError(f"n_levels must be in 1..{_lib.MAX_LEVELS}")
+        if mosaic is None:
+            mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
+        if not patches:
+            return mosaic.zero_()
+        keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
+        acc = torch.zeros((n_levels, h, w, 4), dtype=torch.float32, device=self.device)
+        level_bytes = 16 * h * w
+        biggest = max((p.box[2] - p.box[0]) * (p.box[3] - p.box[1]) for p in patches)
+        work = torch.empty((3, biggest * 4), dtype=torch.float32, device=self.device)     # two blur outputs + scratch
+        taps = [geo.gaussian_taps(geo.band_sigma(lvl)) for lvl in range(n_levels - 1)]
+        for k, p in enumerate(patches):
+            pw, ph, x0, y0 = self._args(p)
+            if pw == 0 or ph == 0:
+                continue
+            _lib.call("p360_owner_to_alpha", p.rgba_ptr, pw, ph, x0, y0, k, _lib.ptr(keys), w, self.stream)
+            prev = p.rgba_ptr
+            for lvl in range(n_levels - 1):
+                cur = work[lvl & 1].data_ptr()
+                t = taps[lvl]
+                _lib.call("p360_gauss_blur", p.rgba_ptr, cur, work[2].data_ptr(), pw, ph,
+                          t.ctypes.data_as(C.POINTER(C.c_float)), len(t), self.stream)
+                _lib.call("p360_band_accumulate", prev, cur, pw, ph, x0, y0, acc.data_ptr() + lvl * level_bytes, w, self.stream)
+                prev = cur
+            _lib.call("p360_band_accumulate", prev, None, pw, ph, x0, y0,
+                      acc.data_ptr() + (n_levels - 1) * level_bytes, w, self.stream)
+        _lib.call("p360_exact_collapse", _lib.ptr(acc), n_levels, _lib.ptr(covered), _lib.ptr(mosaic), h, w, self.stream)
+        self._keep["exact"] = (acc, work, keys, covered)
+        self.last_covered = covered
         return mosaic
 
     def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
@@ -931,8 +997,14 @@ class Compositor:
             wb = max(wb, 32 * ((yb - 1) // 32 + reach_y + 1))
         return max(0, wa), min(height, wb)
 
+    def needs_exact(self, regions):
+        """Images smaller than a few blur radii: the owner masks can be slivers a pixel or two wide,
+        which the f = 2 / f = 4 grids cannot resolve (deviations of up to 4 grey levels were seen on
+        20-30 px wide views) — such rigs are blended at full resolution (``blend_multiband_exact``)."""
+        return min(min(r.img.shape[:2]) for r in regions) < EXACT_BELOW
+
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8, direct=None, want_covered=False):
+                  on_band=None, bands=8, direct=None, want_covered=False, exact=False):
         """warp + blend for the whole mosaic or for a row window [ya, yb)
         (the returned strip has exactly yb - ya rows and is bit-identical to
         those rows of the full composite; only those rows are collapsed).
@@ -960,6 +1032,13 @@ class Compositor:
             def band_cb(y0, y1):
                 on_band(holder["mosaic"][y0:y1], y0 + top, y1 + top)
         local = (ya - top, yb - top)
+        if exact and kind == "multiband" and n_levels > 1:      # (stitch() asks for it when needs_exact())
+            # full-resolution loop nest on the whole window, then hand the rows on like a collapse
+            state = self.new_owner_state(shape)
+            patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+            holder["mosaic"] = self.blend_multiband_exact(patches, shape, n_levels, owner_state=state)
+            self._collapse("exact", 0, None, (), holder["mosaic"], out_host, local, band_cb, bands, top)
+            return holder["mosaic"][local[0]:local[1]], patches
         use_plan = (self.direct if direct is None else direct) and kind == "multiband" and n_levels > 1 \
             and 0 < len(crops) <= 256                          # (the tile warp keeps its job table in constant memory)
         if use_plan:
@@ -1007,7 +1086,7 @@ class Compositor:
         cuts.append(height)
         return order, [(a, b, int(last[b - 1]) + 1) for a, b in zip(cuts, cuts[1:]) if b > a]
 
-    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=3, bands=4):
+    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=3, bands=4, exact=False):
         """Upload + composite + download with both PCIe directions busy: the images are uploaded
         top edge first, and as soon as the images a row window of the mosaic depends on have
         arrived that window is composited (exactly the bytes of the whole composite, see
@@ -1018,7 +1097,7 @@ class Compositor:
         strips = []
         for ya, yb, _ in wins:
             strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, rows=(ya, yb), out_host=out_host,
-                                      bands=bands)
+                                      bands=bands, exact=exact)
             strips.append(strip)          # the download stream still reads it: keep it allocated
         self._keep["streamed"] = (strips, src)
         return src

@@ -10,6 +10,7 @@
 // traffic is (R + ksize - 1) / R loads per output instead of ksize, and the
 // inner loop is pure packed FFMA2 (fma.rn.f32x2, two RGBA halves per tap).
 #include "p360_common.cuh"
+#include "p360_tma.cuh"
 
 namespace p360 {
 
@@ -44,18 +45,11 @@ __device__ __forceinline__ void convolve_r(float2 (&lo)[R], float2 (&hi)[R], con
     }
 }
 
-// The batched kernels skip blocks nobody reads, so a block that does run may stage cells that
-// were never written (stale memory).  Those cells only ever meet zero taps or outputs that are
-// themselves unread — unless they hold NaN / Inf, where 0 * x != 0.  FINITE clamps what is
-// staged to +-1e30 (fmaxf / fminf drop NaN); written data lies in [0, 1] and is unaffected.
-template <bool FINITE>
-__device__ __forceinline__ float4 staged(float4 v) {
-    if (FINITE) {
-        v.x = fminf(fmaxf(v.x, -1e30f), 1e30f); v.y = fminf(fmaxf(v.y, -1e30f), 1e30f);
-        v.z = fminf(fmaxf(v.z, -1e30f), 1e30f); v.w = fminf(fmaxf(v.w, -1e30f), 1e30f);
-    }
-    return v;
-}
+// The batched kernels skip blocks nobody reads, so a block that does run may stage cells that no
+// kernel of this composite wrote.  Those cells only ever meet zero taps or outputs that are
+// themselves unread, which is harmless as long as they hold FINITE values (0 * NaN != 0): the
+// caller keeps the coarse pools in buffers that were zeroed once and are only ever written by
+// these kernels (Compositor._coarse_pool).
 
 // ---- horizontal ------------------------------------------------------------
 constexpr int H_WARPS = 4;             // rows per block (one warp per row)
@@ -65,7 +59,7 @@ __host__ __device__ __forceinline__ int h_phys(int q) { return q + (q >> 3); }  
 // ROWS rows per warp, H_SEG / ROWS outputs on each (ROWS = 1: one 256-wide segment per warp;
 // ROWS = 4: four 64-wide ones, for the block lists of the seam-band maps, where a 1024-pixel
 // segment across a 200-pixel seam band is mostly wasted work).  pitch = h_phys(segment + ksize - 1) + 1.
-template <bool FINITE, int ROWS>
+template <int ROWS>
 __device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float4 *__restrict__ out,
                                             int pw, int ph, int pitch, const Taps &t, int block) {
     constexpr int LPR = 32 / ROWS, SEG = H_SEG / ROWS;   // lanes, outputs per row
@@ -82,7 +76,7 @@ __device__ __forceinline__ void blur_h_body(const float4 *__restrict__ in, float
     const float4 *src = in + (size_t)(live ? row : 0) * pw;
     const int nq = SEG + t.ksize - 1;
     if (live)
-        for (int q = lr; q < nq; q += LPR) tile[h_phys(q)] = staged<FINITE>(__ldg(src + reflect_101(xb - r + q, pw)));
+        for (int q = lr; q < nq; q += LPR) tile[h_phys(q)] = __ldg(src + reflect_101(xb - r + q, pw));
     __syncwarp();
     float2 lo[R], hi[R];
 #pragma unroll
@@ -136,7 +130,7 @@ __constant__ Taps c_taps[P360_MAX_LEVELS];     // tap sets of the batched blurs 
 
 __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, int pitch, Taps t) {
-    blur_h_body<false, 1>(in, out, pw, ph, pitch, t, blockIdx.x);
+    blur_h_body<1>(in, out, pw, ph, pitch, t, blockIdx.x);
 }
 
 // block `b` of a job's horizontal grid (H_SEG / ROWS cells x H_WARPS * ROWS rows): exists and is
@@ -154,7 +148,7 @@ __global__ void __launch_bounds__(32 * H_WARPS)
 blur_h_batch_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     const BlurJob &job = jobs[blockIdx.y];
     if (!h_block_needed<1>(job, maps, blockIdx.x)) return;                            // block-uniform
-    blur_h_body<true, 1>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
+    blur_h_body<1>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], blockIdx.x);
 }
 
 // With seam-band maps: the needed blocks of the dense grids are compacted into a work list by
@@ -178,7 +172,7 @@ blur_h_list_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         const BlurJob &job = jobs[item.x];
-        blur_h_body<true, ROWS>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], (int)item.y);
+        blur_h_body<ROWS>(job.in, job.tmp, job.w, job.h, pitch, c_taps[job.slot], (int)item.y);
         __syncwarp();                   // the warp's tiles are restaged by the next item
     }
 }
@@ -187,19 +181,35 @@ blur_h_list_kernel(const BlurJob *__restrict__ jobs, int pitch, TileMaps maps) {
 constexpr int V_WARPS = 8;
 constexpr int V_ROWS = V_WARPS * R;    // output rows per block, 32 columns wide
 
-template <bool FINITE>
+// One 32-column x V_ROWS-row tile.  Interior tiles (32 whole columns, no reflection above or
+// below) are staged by the TMA engine: one 512-byte bulk copy per row, issued by the lanes of warp
+// 0, completing on `bar` (phase parity in `phase`); edge tiles are staged by the threads with the
+// reflection applied.  `bar` is initialised by the caller; every thread of the block calls this.
 __device__ __forceinline__ void blur_v_body(const float4 *__restrict__ in, float4 *__restrict__ out,
-                                            int pw, int ph, const Taps &t, int bxi, int byi) {
+                                            int pw, int ph, const Taps &t, int bxi, int byi,
+                                            uint64_t *bar, uint32_t &phase) {
     extern __shared__ float4 smem[];   // [V_ROWS + ksize - 1][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = bxi * 32 + lane;
     const int yb = byi * V_ROWS;
     const int r = t.ksize >> 1;
     const int nq = V_ROWS + t.ksize - 1;
-    const int xs = min(x, pw - 1);
-    for (int q = warp; q < nq; q += V_WARPS)
-        smem[q * 32 + lane] = staged<FINITE>(__ldg(in + (size_t)reflect_101(yb - r + q, ph) * pw + xs));
-    __syncthreads();
+    const bool interior = kHaveTma && bxi * 32 + 32 <= pw && yb - r >= 0 && yb - r + nq <= ph;   // block-uniform
+    if (interior) {
+        if (warp == 0) {
+            fence_async_smem();        // the tile's previous readers / writers are behind a block barrier
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)nq * 512u);
+            const float4 *src = in + (size_t)(yb - r) * pw + bxi * 32;
+            for (int q = lane; q < nq; q += 32) bulk_g2s(smem + q * 32, src + (size_t)q * pw, 512u, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    } else {
+        const int xs = min(x, pw - 1);
+        for (int q = warp; q < nq; q += V_WARPS)
+            smem[q * 32 + lane] = __ldg(in + (size_t)reflect_101(yb - r + q, ph) * pw + xs);
+        __syncthreads();
+    }
     float2 lo[R], hi[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) lo[i] = hi[i] = make_float2(0.f, 0.f);
@@ -215,9 +225,21 @@ __device__ __forceinline__ void blur_v_body(const float4 *__restrict__ in, float
     }
 }
 
+// the block's mbarrier for the bulk copies: one arrival (the thread that announces the bytes)
+__device__ __forceinline__ void v_barrier_init(uint64_t *bar) {
+    if (kHaveTma && threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_async_smem();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, int pw, int ph, Taps t) {
-    blur_v_body<false>(in, out, pw, ph, t, blockIdx.x, blockIdx.y);
+    __shared__ uint64_t bar;
+    uint32_t phase = 0u;
+    v_barrier_init(&bar);
+    blur_v_body(in, out, pw, ph, t, blockIdx.x, blockIdx.y, &bar, phase);
 }
 
 __device__ __forceinline__ bool v_block_needed(const BlurJob &job, const TileMaps &maps, int bxi, int byi) {
@@ -227,9 +249,12 @@ __device__ __forceinline__ bool v_block_needed(const BlurJob &job, const TileMap
 
 __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_batch_kernel(const BlurJob *__restrict__ jobs, TileMaps maps) {
+    __shared__ uint64_t bar;
     const BlurJob &job = jobs[blockIdx.z];
     if (!v_block_needed(job, maps, blockIdx.x, blockIdx.y)) return;                   // block-uniform
-    blur_v_body<true>(job.tmp, job.out, job.w, job.h, c_taps[job.slot], blockIdx.x, blockIdx.y);
+    uint32_t phase = 0u;
+    v_barrier_init(&bar);
+    blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot], blockIdx.x, blockIdx.y, &bar, phase);
 }
 
 __global__ void __launch_bounds__(256)
@@ -244,13 +269,16 @@ blur_v_scan_kernel(const BlurJob *__restrict__ jobs, int n_jobs, int gx, int gy,
 
 __global__ void __launch_bounds__(32 * V_WARPS)
 blur_v_list_kernel(const BlurJob *__restrict__ jobs, TileMaps maps) {
+    __shared__ uint64_t bar;
     const int n = min(*maps.work_count, maps.work_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) maps.work_count[3] = n;      // (statistics for the bench)
+    uint32_t phase = 0u;
+    v_barrier_init(&bar);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint2 item = maps.work[i];
         const BlurJob &job = jobs[item.x];
-        blur_v_body<true>(job.tmp, job.out, job.w, job.h, c_taps[job.slot], (int)(item.y & 0xffffu),
-                          (int)(item.y >> 16));
+        blur_v_body(job.tmp, job.out, job.w, job.h, c_taps[job.slot], (int)(item.y & 0xffffu),
+                    (int)(item.y >> 16), &bar, phase);
         __syncthreads();                // the staged tile is replaced by the next item
     }
 }

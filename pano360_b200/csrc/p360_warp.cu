@@ -626,7 +626,7 @@ extern "C" int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, p
     return check_launch(where);
 }
 
-extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint64_t *owner_keys,
+extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
                                uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
                                int want_covered, const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
@@ -639,8 +639,13 @@ extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint6
     dim3 grid(m.tiles_x, m.tiles_y), block(TILE_X, 4);
     P360_REQUIRE(grid.y <= 65535, where);
     cudaStream_t s = (cudaStream_t)stream;
-    // stream-ordered: waits for the previous launch that still reads the table
-    P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host, sizeof(WarpJob) * n_jobs, 0, cudaMemcpyHostToDevice, s), where);
+    // Stream-ordered: waits for the previous launch that still reads the table.  From the DEVICE copy
+    // of the table if there is one: a copy from pageable host memory makes the runtime synchronise
+    // the stream first, which would put the host in lockstep with the GPU.
+    if (jobs_dev != nullptr)
+        P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_dev, sizeof(WarpJob) * n_jobs, 0, cudaMemcpyDeviceToDevice, s), where);
+    else
+        P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host, sizeof(WarpJob) * n_jobs, 0, cudaMemcpyHostToDevice, s), where);
     bool rgbx = true;
     for (int k = 0; k < n_jobs; ++k) {
         const p360_warp_job &j = jobs_host[k];
@@ -660,7 +665,7 @@ extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, int n_jobs, uint6
     return check_launch(where);
 }
 
-extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
+extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs,
                                uint64_t *owner_keys, uint8_t *covered, int W, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_batch";
@@ -683,9 +688,13 @@ extern "C" int p360_warp_batch(const p360_warp_job *jobs_host, int n_jobs,
             max_ph = j.ph > max_ph ? j.ph : max_ph;
         }
         if (max_pw == 0 || max_ph == 0) continue;
-        // stream-ordered: waits for the previous launch that still reads the table
-        P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host + first, sizeof(WarpJob) * count, 0,
-                                          cudaMemcpyHostToDevice, s), where);
+        // stream-ordered: waits for the previous launch that still reads the table (see p360_warp_tiles)
+        if (jobs_dev != nullptr)
+            P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_dev + first, sizeof(WarpJob) * count, 0,
+                                              cudaMemcpyDeviceToDevice, s), where);
+        else
+            P360_CUDA(cudaMemcpyToSymbolAsync(c_warp_jobs, jobs_host + first, sizeof(WarpJob) * count, 0,
+                                              cudaMemcpyHostToDevice, s), where);
         dim3 block(WARP_BX, WARP_BY), grid(cdiv(max_pw, WARP_BX), cdiv(max_ph, WARP_BY * WARP_ROWS), count);
         P360_REQUIRE(grid.y <= 65535, where);
         auto keys = reinterpret_cast<unsigned long long *>(owner_keys);

@@ -116,7 +116,11 @@ def multiband_blend(patches, shape, n_levels=5):
     reference, the alpha channel of the patches is overwritten with the
     owner mask."""
     comp = _compositor()
-    return comp.blend_multiband(_device_patches(comp, patches), tuple(shape), n_levels).cpu().numpy()
+    dev = _device_patches(comp, patches)
+    from .compositor import EXACT_BELOW
+    if n_levels > 1 and dev and min(min(p.shape) for p in dev) < EXACT_BELOW:     # (see Compositor.needs_exact)
+        return comp.blend_multiband_exact(dev, tuple(shape), n_levels).cpu().numpy()
+    return comp.blend_multiband(dev, tuple(shape), n_levels).cpu().numpy()
 
 
 BLENDERS = {
@@ -204,6 +208,8 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         raise ValueError(f"out must be a C-contiguous uint8 array of shape {plan.shape + (3,)}")
     direct_out = _is_pinned_out(out, plan.shape)
     big = plan.shape[0] * plan.shape[1] >= STREAM_MIN_PIXELS
+    # views a few blur radii small: owner masks can be slivers the coarse grids cannot resolve
+    exact = kind == "multiband" and levels > 1 and comp.needs_exact(regions)
 
     def landing():
         if direct_out:
@@ -215,7 +221,7 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         # both PCIe directions at once: row windows are composited and downloaded while the
         # images of the windows below are still being uploaded
         stage, result = landing()
-        comp.composite_streamed(regions, plan, kind, levels, proj, stage, windows=STREAM_WINDOWS)
+        comp.composite_streamed(regions, plan, kind, levels, proj, stage, windows=STREAM_WINDOWS, exact=exact)
         comp.finish_download(result, stage)
         comp.release()
         return out if direct_out else result
@@ -229,16 +235,16 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         # the union of valid pixels stays in HBM, the rectangle is found there (K9) and only the
         # cropped mosaic crosses PCIe
         logging.debug("Cropping...")
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, want_covered=True)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, want_covered=True, exact=exact)
         y0, y1, x0, x1 = comp.crop_rect(comp.last_covered[:plan.shape[0]])
         mosaic = mosaic_dev[y0:y1, x0:x1].contiguous().cpu().numpy()
     elif direct_out or big:
         stage, result = landing()
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=stage)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, out_host=stage, exact=exact)
         comp.finish_download(result, stage)
         mosaic = out if direct_out else result
     else:
-        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj)
+        mosaic_dev, patches = comp.composite(regions, src, plan, kind, levels, proj, exact=exact)
         mosaic = _download(mosaic_dev, out)
     if crop and kind is None:
         logging.debug("Cropping...")

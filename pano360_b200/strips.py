@@ -451,7 +451,8 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     if rows[1] > rows[0]:
         if comp.device.type == "cuda":
             shared.register(rows[0] * w * 3, rows[1] * w * 3)
-        comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, out_host=host, bands=4)
+        comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, out_host=host, bands=4,
+                       exact=kind == "multiband" and n_levels > 1 and comp.needs_exact(regions))
         phase("kernels queued")
         comp.finish_download()
         phase("strip landed")

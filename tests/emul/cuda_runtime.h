@@ -35,6 +35,7 @@
 #define __launch_bounds__(...)
 #define __constant__
 #define __shared__ static thread_local
+#define P360_EMUL_BUILD 1
 #define __align__(n) alignas(n)
 
 // ---- vector types ------------------------------------------------------------
@@ -61,7 +62,7 @@ inline thread_local dim3 blockDim, gridDim;
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
-enum { cudaMemcpyHostToDevice = 1 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 227 * 1024; return cudaSuccess; }
@@ -139,6 +140,7 @@ inline void yield() {
     Block &b = block();
     swapcontext(&b.ctx[b.current], &b.scheduler);
 }
+inline void no_tma() { fprintf(stderr, "p360_emul: TMA path reached in the host build\n"); abort(); }
 inline int linear_tid() { return (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x; }
 inline unsigned popc(unsigned v) { return (unsigned)__builtin_popcount(v); }
 

@@ -98,6 +98,10 @@ def install(monkeypatch):
         return t
 
     monkeypatch.setattr(torch, "empty", poisoned_empty)
+    # the coarse pools are persistent and zeroed once in production; here every composite starts
+    # from a large finite poison, so that a read of a cell nobody wrote shows wherever it matters
+    monkeypatch.setattr(compositor.Compositor, "pool_fill", 1e30)
+    monkeypatch.setattr(compositor.Compositor, "repoison", True)
     monkeypatch.setattr(stitcher, "_is_pinned_out", lambda out, shape: (
         out is not None and out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == tuple(shape) + (3,)))
     monkeypatch.setattr(stitcher, "_compositors", {})

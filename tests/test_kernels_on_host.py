@@ -56,6 +56,8 @@ test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_partial_row_uploads_are_sufficient = gpu.test_partial_row_uploads_are_sufficient
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
+test_full_resolution_path_is_the_reference_to_rounding = gpu.test_full_resolution_path_is_the_reference_to_rounding
+test_tiny_views_with_sliver_owners = gpu.test_tiny_views_with_sliver_owners
 test_seam_band_maps_are_exact = gpu.test_seam_band_maps_are_exact
 test_seam_plan_is_conservative_and_cut_independent = gpu.test_seam_plan_is_conservative_and_cut_independent
 test_window_without_any_image = gpu.test_window_without_any_image
