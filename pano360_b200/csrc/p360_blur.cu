@@ -293,7 +293,7 @@ inline void fill_taps(Taps &t, const float *taps_host, int ksize) {
 // is per device; one process may drive several GPUs)
 struct SmemLimit {
     size_t bytes[64];
-    SmemLimit() { for (size_t &b : bytes) b = 48 * 1024; }
+    SmemLimit() { for (size_t &b : bytes) b = 48 * 1024 - 256; }      // (static shared memory counts too: barriers)
 };
 template <class K>
 int ensure_smem(K kernel, size_t bytes, SmemLimit &limit, const char *where) {
