@@ -107,6 +107,30 @@ __device__ __forceinline__ uint32_t load_tap(const WarpJob &s, int off) {
     return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
 }
 
+// The two taps of one source row.  RGBX: two aligned 32-bit loads.  Packed u8 x 3 (as uploaded):
+// the usual case — the second tap is the next pixel — reads the six bytes through three aligned
+// 32-bit words and two funnel shifts; anything else (reflection at the border, the last pixels of
+// the image) takes byte loads.  `n_px` = pixels in the image.
+template <bool RGBX>
+__device__ __forceinline__ void load_row_taps(const WarpJob &s, int off_a, int off_b, uint32_t &qa, uint32_t &qb) {
+    if (RGBX) {
+        qa = __ldg(reinterpret_cast<const uint32_t *>(s.src) + off_a);
+        qb = __ldg(reinterpret_cast<const uint32_t *>(s.src) + off_b);
+        return;
+    }
+    if (off_b == off_a + 1 && off_a + 4 <= s.h * s.w) {
+        const unsigned b0 = 3u * (unsigned)off_a;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(s.src) + (b0 >> 2);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        const unsigned sh = (b0 & 3u) * 8u;
+        qa = __funnelshift_r(w0, w1, sh) & 0xffffffu;
+        qb = (sh ? __funnelshift_r(w1, w2, sh - 8u) : __funnelshift_r(w0, w1, 24u)) & 0xffffffu;
+        return;
+    }
+    qa = load_tap<false>(s, off_a);
+    qb = load_tap<false>(s, off_b);
+}
+
 // ((s00*w00 + s01*w01) + s10*w10) + s11*w11, separately rounded products and
 // sums: the exact evaluation order of OpenCV's remapBilinear float path.
 __device__ __forceinline__ float blend4(float a, float b, float c, float d, const TapPlan &t) {
@@ -178,8 +202,8 @@ __device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsig
         plan[k] = plan_taps<true>(job, col, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1), alpha[k]);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
-        taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
-        taps[k][2] = load_tap<RGBX>(job, plan[k].off10); taps[k][3] = load_tap<RGBX>(job, plan[k].off11);
+        load_row_taps<RGBX>(job, plan[k].off00, plan[k].off01, taps[k][0], taps[k][1]);
+        load_row_taps<RGBX>(job, plan[k].off10, plan[k].off11, taps[k][2], taps[k][3]);
     }
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
@@ -437,8 +461,8 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
         }
 #pragma unroll
         for (int k = 0; k < RP; ++k) {
-            taps[k][0] = load_tap<RGBX>(job, plan[k].off00); taps[k][1] = load_tap<RGBX>(job, plan[k].off01);
-            taps[k][2] = load_tap<RGBX>(job, plan[k].off10); taps[k][3] = load_tap<RGBX>(job, plan[k].off11);
+            load_row_taps<RGBX>(job, plan[k].off00, plan[k].off01, taps[k][0], taps[k][1]);
+            load_row_taps<RGBX>(job, plan[k].off10, plan[k].off11, taps[k][2], taps[k][3]);
         }
 #pragma unroll
         for (int k = 0; k < RP; ++k) {

@@ -210,49 +210,77 @@ def active_column_runs(index, box, plan, dilate=0, margin=4, align=4):
     return runs
 
 
-def source_rows_needed(region, crop, plan, proj=SphProj, tile=(64, 32)):
-    """Rows [r0, r1) of ``region.img`` that the warp can touch when it produces the mosaic box
-    ``crop = (x0, y0, x1, y1)`` — so that only those rows need to be uploaded and packed (a strip
-    of a multi-GPU composite reads a fraction of every image it meets).
+def source_rect_needed(region, crop, plan, proj=SphProj, tile=(64, 32), tile_mask=None, tile_origin=(0, 0)):
+    """Rows [r0, r1) and columns [c0, c1) of ``region.img`` that the warp can touch when it
+    produces the mosaic box ``crop = (x0, y0, x1, y1)`` — so that only that rectangle needs to be
+    uploaded and packed (a strip of a multi-GPU composite reads a fraction of every image it
+    meets; with the seam plan an image is only read where it owns pixels or takes part in a seam).
+    Returns (r0, r1, c0, c1); all zero if nothing is read.
 
     Conservative by construction: interval arithmetic per 64 x 32 tile of the box (ray tables ->
-    K R ray -> source row, the arithmetic of the seam plan), widened by the bilinear taps and the
-    1/32-px rounding; source rows beyond the image fold back by BORDER_REFLECT (cv2.remap at
+    K R ray -> source position, the arithmetic of the seam plan), widened by the bilinear taps and
+    the 1/32-px rounding; positions beyond the image fold back by BORDER_REFLECT (cv2.remap at
     stitcher.py:315-316).  Anything uncertain — a tile not wholly in front of the camera, more
-    than one reflection period — means the whole image."""
+    than one reflection period — means the whole image.  ``tile_mask`` (bool [tiles_y, tiles_x] of a
+    grid of ``tile``-sized cells whose cell (0, 0) starts at mosaic position ``tile_origin`` =
+    (x, y)) restricts the box to the cells that are set."""
     x0, y0, x1, y1 = crop
-    h = region.img.shape[0]
+    h, w = region.img.shape[:2]
     if x1 <= x0 or y1 <= y0:
-        return 0, 0
+        return 0, 0, 0, 0
     ray_x, ray_z, ray_y = plan.rays(proj)
     kr = np.asarray(region.proj(), dtype=np.float64)
+    ox, oy = tile_origin
+    # cell boundaries of the tile grid inside the box
+    xs = np.unique(np.concatenate([[x0], np.arange(ox + (-(-(x0 - ox) // tile[0])) * tile[0], x1, tile[0]), [x1]]))
+    ys = np.unique(np.concatenate([[y0], np.arange(oy + (-(-(y0 - oy) // tile[1])) * tile[1], y1, tile[1]), [y1]]))
+    xs, ys = xs[(xs >= x0) & (xs <= x1)], ys[(ys >= y0) & (ys <= y1)]
 
-    def per_tile(values, a, b, size):
-        starts = np.arange(0, b - a, size)
-        return np.minimum.reduceat(values[a:b], starts), np.maximum.reduceat(values[a:b], starts)
+    def per_cell(values, edges):
+        starts = edges[:-1]
+        return np.minimum.reduceat(values[edges[0]:edges[-1]], starts - edges[0]), \
+            np.maximum.reduceat(values[edges[0]:edges[-1]], starts - edges[0])
 
     def scaled(k, lo, hi):
         return np.minimum(k * lo, k * hi), np.maximum(k * lo, k * hi)
 
-    bx, bz, by = per_tile(ray_x, x0, x1, tile[0]), per_tile(ray_z, x0, x1, tile[0]), per_tile(ray_y, y0, y1, tile[1])
+    bx, bz, by = per_cell(ray_x, xs), per_cell(ray_z, xs), per_cell(ray_y, ys)
 
     def component(row):
         ax, az, ay = scaled(kr[row, 0], *bx), scaled(kr[row, 2], *bz), scaled(kr[row, 1], *by)
         return (ax[0] + az[0])[None, :] + ay[0][:, None], (ax[1] + az[1])[None, :] + ay[1][:, None]
 
-    (py_lo, py_hi), (pz_lo, pz_hi) = component(1), component(2)
-    if not np.all(pz_lo > 1e-9):
-        return 0, h
-    quotients = np.stack([py_lo / pz_lo, py_lo / pz_hi, py_hi / pz_lo, py_hi / pz_hi])
-    v_min, v_max = float(quotients.min()) + h / 2.0 - 2.0, float(quotients.max()) + h / 2.0 + 2.0
-    if not (np.isfinite(v_min) and np.isfinite(v_max)) or v_min < -(h - 1) or v_max > 2 * (h - 1):
-        return 0, h
-    r0, r1 = int(np.floor(v_min)), int(np.floor(v_max)) + 2
-    if v_min < 0:                                   # rows above the image fold back onto rows 0 .. -v
-        r0, r1 = 0, max(r1, int(np.ceil(-v_min)) + 2)
-    if v_max > h - 1:                               # rows below fold back onto rows 2h - 1 - v .. h - 1
-        r0, r1 = min(r0, int(np.floor(2 * h - 1 - v_max)) - 2), h
-    return max(r0, 0), min(r1, h)
+    keep = np.ones((len(ys) - 1, len(xs) - 1), bool)
+    if tile_mask is not None:
+        ty = np.clip((ys[:-1] - oy) // tile[1], 0, tile_mask.shape[0] - 1)
+        tx = np.clip((xs[:-1] - ox) // tile[0], 0, tile_mask.shape[1] - 1)
+        keep = tile_mask[np.ix_(ty, tx)]
+        if not keep.any():
+            return 0, 0, 0, 0
+    (px_lo, px_hi), (py_lo, py_hi), (pz_lo, pz_hi) = component(0), component(1), component(2)
+    if not np.all(pz_lo[keep] > 1e-9):
+        return 0, h, 0, w
+
+    def extent(lo, hi, size):
+        q = np.stack([lo[keep] / pz_lo[keep], lo[keep] / pz_hi[keep], hi[keep] / pz_lo[keep], hi[keep] / pz_hi[keep]])
+        v_min, v_max = float(q.min()) + size / 2.0 - 2.0, float(q.max()) + size / 2.0 + 2.0
+        if not (np.isfinite(v_min) and np.isfinite(v_max)) or v_min < -(size - 1) or v_max > 2 * (size - 1):
+            return 0, size
+        a, b = int(np.floor(v_min)), int(np.floor(v_max)) + 2
+        if v_min < 0:                                   # positions before the image fold back onto 0 .. -v
+            a, b = 0, max(b, int(np.ceil(-v_min)) + 2)
+        if v_max > size - 1:                            # positions behind it fold back onto 2 size - 1 - v .. size - 1
+            a, b = min(a, int(np.floor(2 * size - 1 - v_max)) - 2), size
+        return max(a, 0), min(b, size)
+
+    r0, r1 = extent(py_lo, py_hi, h)
+    c0, c1 = extent(px_lo, px_hi, w)
+    return r0, r1, c0, c1
+
+
+def source_rows_needed(region, crop, plan, proj=SphProj, tile=(64, 32)):
+    """Rows [r0, r1) of ``source_rect_needed``."""
+    return source_rect_needed(region, crop, plan, proj, tile)[:2]
 
 
 def inverse_map_tables(region, box, plan, proj=SphProj):

@@ -352,6 +352,7 @@ inline int __float2int_rd(float v) { return p360_emul_sat_int(floor((double)v));
 inline int __double2int_rn(double v) { return p360_emul_sat_int(nearbyint(v)); }
 inline unsigned __float_as_uint(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
 inline float __uint_as_float(unsigned u) { float v; memcpy(&v, &u, 4); return v; }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)(v >> (s & 31)); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 

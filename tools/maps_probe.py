@@ -22,6 +22,7 @@ def main(comp=None):
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--h-rows", type=int, default=1, help="4: horizontal blur lists in 64-cell segments")
+    ap.add_argument("--no-pack", action="store_true", help="sources stay u8 x 3 as uploaded (no RGBX packing)")
     ap.add_argument("--direct", action="store_true", help="maps_on = the seam plan with direct tiles (p360_seam_plan_build)")
     args = ap.parse_args()
     t0 = time.time()
@@ -37,7 +38,7 @@ def main(comp=None):
     comp = comp or Compositor()
     comp.blur_h_rows = args.h_rows
     direct = args.direct
-    src = comp.upload(regs)
+    src = comp.upload(regs, pack=not args.no_pack)
     out = {"workload": args.workload, "scale": args.scale, "mosaic": list(plan.shape), "setup_s": round(time.time() - t0, 1)}
     mosaics = {}
     for maps in (False, True):
