@@ -534,7 +534,13 @@ class Bench:
                 nbytes = algorithmic_bytes(k, wl, crop_px, self.src_bytes_all, m_px)
                 shares[k] = {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps,
                              "share_of_traced": v[0] / max(traced_ms, 1e-9),
-                             "algorithmic_GBps": None if nbytes is None else nbytes * steps / max(v[0], 1e-9) / 1e6}
+                             # SURVEY 8(d) stage-materialised bytes / time: the pipeline decimates and fuses, so for
+                             # the blur and collapse stages this exceeds the HBM peak and is no roofline
+                             "model_GBps": None if nbytes is None else nbytes * steps / max(v[0], 1e-9) / 1e6}
+            if stats is not None:          # bytes of the blocks the list kernels really ran
+                for k, key in (("K3a_pyramid_reduce", "reduce_bytes"), ("K3_gauss_blur", "blur_bytes")):
+                    if k in shares:
+                        shares[k]["run_GBps"] = stats[key] / (shares[k]["ms_per_step"] / 1e3) / 1e9
             top = max(per_kernel, key=lambda k: per_kernel[k][0])
             t_ms, count = per_kernel[top]
             nbytes = algorithmic_bytes(top, wl, crop_px, self.src_bytes_all, m_px) or 0
