@@ -671,7 +671,7 @@ def run_gpu_arm(args):
         bench = Bench(args, wl, comp, world, rank)
         line = bench.run(args.steps, args.warmup, local)
         bench = None
-        comp.release()
+        comp.release(everything=True)
         torch.cuda.empty_cache()
     # the other BASELINE configs, short runs, so that they are in the driver's record too
     others = {}
@@ -683,7 +683,7 @@ def run_gpu_arm(args):
             others[name] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
                                                 "mosaic_checksum", "host_enqueue_ms_per_step")}
             others[name]["config"] = sub["config"]["workload"]
-            comp.release()
+            comp.release(everything=True)
             torch.cuda.empty_cache()
         sub = run_batch_of_panoramas(args, synth.workload("cfg5"), comp, world, rank, steps=max(2, min(args.steps, 3)))
         if sub is not None:

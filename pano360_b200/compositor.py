@@ -159,6 +159,10 @@ class Compositor:
         _lib.load()
         self._pinned = {}
         self._pools = {}
+        self._consts = {}
+        self._packed = {}      # raw image addresses -> the buffers their RGBX copies go to
+        self._images = {}      # (slot, shape) -> device buffers of uploaded images (upload(reuse=True))
+        self._prepared = {}    # what a composite of one geometry over one set of buffers needs, kept ready
         self._taps_key = None
         self._keep = {}
         self._copy = None      # side streams for uploads / downloads that overlap the kernels
@@ -250,14 +254,14 @@ class Compositor:
         return rc
 
     # -- sources --------------------------------------------------------------
-    def pack_pixels(self, dev_img, rows=None):
+    def pack_pixels(self, dev_img, rows=None, out=None):
         """u8 x 3 -> u8 x 4 (RGBX) on the device: a bilinear tap of the warp is then one aligned
         32-bit load.  4-channel images are used as they are.  ``rows = (r0, r1)``: only those rows
         hold data (and only they are converted)."""
         h, w, c = dev_img.shape
         if c == 4:
             return dev_img
-        packed = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
+        packed = out if out is not None else torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
         r0, r1 = (0, h) if rows is None else rows
         r0 = r0 // 4 * 4                                   # keeps source and destination addresses aligned
         if r1 > r0:
@@ -270,10 +274,22 @@ class Compositor:
         images as uploaded (``upload(pack=False)``): the device-side part of ``_add_weights``
         (stitcher.py:257-263) that is executed once per image and stitch."""
         rows = raw.rows or [None] * len(raw.pixels)
-        return DeviceSources([None if p is None else self.pack_pixels(p, r) for p, r in zip(raw.pixels, rows)],
-                             raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
+        # the packed copies of one set of resident images always land in the same buffers: stable
+        # addresses let ``composite`` reuse everything it prepared for them
+        key = tuple(0 if p is None else p.data_ptr() for p in raw.pixels)
+        outs = self._packed.get(key)
+        if outs is None:
+            if len(self._packed) >= 8:
+                self._packed.pop(next(iter(self._packed)))
+            outs = self._packed[key] = [None] * len(raw.pixels)
+        pixels = []
+        for i, (p, r) in enumerate(zip(raw.pixels, rows)):
+            if p is not None and p.shape[2] != 4 and (outs[i] is None or outs[i].shape[:2] != p.shape[:2]):
+                outs[i] = torch.empty(p.shape[:2] + (4,), dtype=torch.uint8, device=self.device)
+            pixels.append(None if p is None else self.pack_pixels(p, r, out=outs[i]))
+        return DeviceSources(pixels, raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
 
-    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None):
+    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None, reuse=False):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
@@ -281,7 +297,10 @@ class Compositor:
         every image gets a ``ready`` event, so the warp of the first images
         starts while the last ones are still crossing PCIe.  ``order`` (a
         permutation of the indices) is the order in which the copies are issued.  ``rows_of``
-        ({image: (r0, r1)}, ``source_rows``) uploads only the rows a composite will read."""
+        ({image: (r0, r1)}, ``source_rows``) uploads only the rows a composite will read.
+        ``reuse``: the images go to device buffers kept from the previous such call (same slot,
+        same shape) — for callers that drop the result before they upload again (``stitch``):
+        stable addresses let ``composite`` reuse what it prepared."""
         n = len(regions)
         src = DeviceSources([None] * n, [None] * n)
         if rows_of is not None:
@@ -307,13 +326,22 @@ class Compositor:
                     part = (part[0] // 4 * 4, part[1])        # (4-row granularity: aligned addresses for the packing)
                     host = host[part[0]:part[1]]
                 if (h, w) not in src.hats:
-                    src.hats[(h, w)] = (self._to_device(geo.hat(h)), self._to_device(geo.hat(w)))
-                    if overlap:
+                    fresh = ("hat", h) not in self._consts or ("hat", w) not in self._consts
+                    src.hats[(h, w)] = (self._constant(("hat", h), lambda: geo.hat(h)),
+                                        self._constant(("hat", w), lambda: geo.hat(w)))
+                    if overlap and fresh:
                         side.wait_stream(main)               # hat tables were copied on the main stream
                 if not host.is_pinned() and host.numel() >= self.stage_min_bytes:
                     host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
                 with torch.cuda.stream(side):
-                    if part is None:
+                    if reuse:
+                        slot = (n, i, tuple(img.shape))
+                        dev_img = self._images.get(slot)
+                        if dev_img is None:
+                            dev_img = self._images[slot] = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+                        target = dev_img if part is None else dev_img[part[0]:part[1]]
+                        target.copy_(host, non_blocking=host.is_pinned())
+                    elif part is None:
                         dev_img = host.to(self.device, non_blocking=host.is_pinned())
                     else:                                    # rows outside `part` stay unwritten: nobody reads them
                         dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
@@ -323,17 +351,30 @@ class Compositor:
                         busy.record(side)
                         host._p360_slot[1] = busy
                     # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
-                    src.pixels[i] = self.pack_pixels(dev_img, part) if pack else dev_img
+                    out = None
+                    if pack and reuse and img.shape[2] != 4:
+                        slot = (n, i, tuple(img.shape), "rgbx")
+                        out = self._images.get(slot)
+                        if out is None:
+                            out = self._images[slot] = torch.empty(img.shape[:2] + (4,), dtype=torch.uint8, device=self.device)
+                    src.pixels[i] = self.pack_pixels(dev_img, part, out=out) if pack else dev_img
                     if overlap:
                         src.ready[i] = torch.cuda.Event()
                         src.ready[i].record(side)
                     self._mark(f"image {i} uploaded + packed", side)
             if gains is None:
-                lut0 = self._to_device(geo.sample_lut(None)) if lut0 is None else lut0
+                lut0 = self._constant("lut0", lambda: geo.sample_lut(None)) if lut0 is None else lut0
                 src.luts[i] = lut0
             else:
                 src.luts[i] = self._to_device(geo.sample_lut(gains[i]))
         return src
+
+    def _constant(self, key, make):
+        """Small per-device tables that never change (the u8 -> float LUT without gains, the hat
+        tables of an image size): uploaded once, same address ever after."""
+        if key not in self._consts:
+            self._consts[key] = self._to_device(make())
+        return self._consts[key]
 
     def _stage_pageable(self, host, side, slots=3):
         """Copy a pageable host image into the next slot of a small ring of pinned buffers (a few
@@ -378,7 +419,7 @@ class Compositor:
             todo = [t for k, t in enumerate(todo) if k in pairs]
         if not todo:
             return overlaps, sizes, todo
-        lut0 = self._to_device(geo.sample_lut(None))
+        lut0 = self._constant("lut0", lambda: geo.sample_lut(None))
         hat_y, hat_x = src.hats[(h, w)]
         nblocks = _lib.call("p360_pair_stats_blocks", h, w)
         jobs = np.zeros(len(todo), dtype=_lib.PAIR_JOB)
@@ -758,11 +799,18 @@ class Compositor:
         self._collapse("blank", 0, None, (), mosaic, out_host, rows, on_band, bands, row_origin)
         return mosaic
 
-    def release(self):
-        """Drop the references that keep the last composite's pools alive (patch
-        pool, coarse levels, job tables); the memory goes back to torch's caching
-        allocator.  Call only after the work that uses them has been waited for."""
+    def release(self, everything=False):
+        """Drop the references that keep the last composite's transient buffers alive; the memory
+        goes back to torch's caching allocator.  Call only after the work that uses them has been
+        waited for.  What is kept for the next composite of the same rig (prepared job tables and
+        patch pools, the coarse pools, image buffers of ``upload(reuse=True)``) goes too with
+        ``everything``."""
         self.last_covered = None
+        if everything:
+            self._prepared.clear()
+            self._pools.clear()
+            self._images.clear()
+            self._packed.clear()
         for key in ("warp", "warp_jobs", "bands", "collapse", "streamed", "seam", "exact"):
             self._keep.pop(key, None)
 
@@ -796,25 +844,36 @@ class Compositor:
         if not patches:      # nothing lands here: still produce (and download / hand on) every band
             return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
         pad, plan = geo.coarse_band_plan(n_levels)
-        table = self._band_table(patches, pad, coarse=True)
         n = len(patches)
         lows, maps = [], None
-        layout = self._coarse_layout(table, len(plan)) if plan else None
         if plan:
             self._set_taps(n_levels, plan)
-        dev_table = self._table(table, "band_table")
-        pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         if seam is not None:
             # K0: plan the tiles; K1t: one block per tile — solo tiles straight to uint8, float
-            # patches + owner keys in the seam zone only
+            # patches + owner keys in the seam zone only.  Everything that depends on the geometry
+            # and on the buffer addresses alone is prepared once (``seam["prepared"]``).
             assert plan, "the seam plan needs at least two bands"
-            jobs, crops, src = seam["jobs"], seam["crops"], seam["src"]
-            maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin, seam_plan=True)
-            dev_wjobs = self._table(jobs, "warp_jobs")
+            prep = seam["prepared"]
+            jobs, crops, src = prep["jobs"], seam["crops"], seam["src"]
+            if "table" not in prep:
+                table = self._band_table(patches, pad, coarse=True)
+                layout = self._coarse_layout(table, len(plan))
+                pristine = self._to_device(table.view(np.uint8).reshape(-1))
+                dev_table = torch.empty_like(pristine)
+                maps, maps_keep = self._tile_maps(table, len(plan), h, w, pad, row_origin, seam_plan=True)
+                blur_jobs = self._blur_jobs(table, layout, dev_table, pad)
+                prep.update(table=table, layout=layout, pristine=pristine, dev_table=dev_table, maps=maps,
+                            maps_keep=maps_keep, dev_wjobs=self._to_device(jobs.view(np.uint8).reshape(-1)),
+                            blur_jobs=blur_jobs, dev_blur_jobs=self._to_device(blur_jobs.view(np.uint8).reshape(-1)),
+                            keys=torch.empty((h, w), dtype=torch.int64, device=self.device),     # written where they are read
+                            covered=torch.empty((h, w), dtype=torch.uint8, device=self.device),
+                            pix=int((table["pw"].astype(np.int64) * table["ph"]).sum()),
+                            pools=(layout["pool2"].data_ptr(), layout["pool4"].data_ptr()))
+            table, layout, dev_table, maps, maps_keep = (prep[k] for k in ("table", "layout", "dev_table", "maps", "maps_keep"))
+            dev_wjobs, keys, covered, pix = prep["dev_wjobs"], prep["keys"], prep["covered"], prep["pix"]
+            dev_table.copy_(prep["pristine"])                     # (K0 grows the `own` boxes in it)
             self._traced("K0_seam_plan", 216 * n, "p360_seam_plan_build", _lib.ptr(dev_wjobs), n, _lib.ptr(dev_table),
                          h, w, row_origin, seam["mosaic_h"], maps.ctypes.data, self.stream)
-            keys = torch.empty((h, w), dtype=torch.int64, device=self.device)       # written where they are read
-            covered = torch.empty((h, w), dtype=torch.uint8, device=self.device)
             if src.ready is not None:          # a tile reads whichever images meet it: all uploads first
                 main = torch.cuda.current_stream(self.device)
                 for i in sorted({c[0] for c in crops}):
@@ -823,9 +882,13 @@ class Compositor:
             self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, _lib.ptr(dev_wjobs), n,
                          _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
-            self._keep["seam"] = (dev_wjobs,)
+            self._keep["seam"] = (prep,)
         else:
             keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
+            table = self._band_table(patches, pad, coarse=True)
+            layout = self._coarse_layout(table, len(plan)) if plan else None
+            dev_table = self._table(table, "band_table")
+            pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         if plan:
             # where can a patch carry weight at all: seam-band bitmaps, or the box around its owned pixels
             if seam is None:
@@ -840,8 +903,11 @@ class Compositor:
                     self._traced("K2b_owned_boxes", 8 * h * w, "p360_owned_boxes", _lib.ptr(keys), _lib.ptr(dev_table),
                                  n, h, w, self.stream)
             maps_ptr = None if maps is None else maps.ctypes.data
-            jobs = self._blur_jobs(table, layout, dev_table, pad)
-            dev_jobs = self._table(jobs, "blur_jobs")
+            if seam is not None:
+                jobs, dev_jobs = seam["prepared"]["blur_jobs"], seam["prepared"]["dev_blur_jobs"]
+            else:
+                jobs = self._blur_jobs(table, layout, dev_table, pad)
+                dev_jobs = self._table(jobs, "blur_jobs")
             self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
                          int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, maps_ptr, self.stream)
             coarse_px = int((4 + len(plan) - 1) * layout["cells"])
@@ -1042,9 +1108,25 @@ class Compositor:
         use_plan = (self.direct if direct is None else direct) and kind == "multiband" and n_levels > 1 \
             and 0 < len(crops) <= 256                          # (the tile warp keeps its job table in constant memory)
         if use_plan:
-            jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(0, top))
-            self._keep["warp"] = keep[:3] + (jobs,)
-            seam = {"jobs": jobs, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": keep[3],
+            # job tables, pools, tile-map storage: prepared once per (geometry, window, source
+            # buffers) and reused as long as the addresses they name are the ones in use
+            needed = sorted({c[0] for c in crops})
+            key = (id(plan), rows, n_levels, proj, shape, tuple(src.pixels[i].data_ptr() for i in needed),
+                   tuple(src.luts[i].data_ptr() for i in needed))
+            prep = self._prepared.get(key)
+            if prep is not None and "pools" in prep and prep["pools"] != tuple(
+                    self._pools[k].data_ptr() if k in self._pools else 0 for k in ("pool2", "pool4")):
+                prep = None                                    # (the coarse pools were re-allocated since)
+            if prep is None:
+                jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(0, top))
+                prep = {"jobs": jobs, "patches": patches, "keep": keep, "plan": plan}
+                self._prepared.pop(key, None)
+                while len(self._prepared) >= 6:
+                    self._prepared.pop(next(iter(self._prepared)))
+                self._prepared[key] = prep
+            patches = prep["patches"]
+            self._keep["warp"] = prep["keep"][:3] + (prep["jobs"],)
+            seam = {"prepared": prep, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": prep["keep"][3],
                     "want_covered": want_covered}
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels, out_host=out_host,
                                      rows=local, on_band=band_cb, bands=bands, row_origin=top, seam=seam)
@@ -1093,7 +1175,7 @@ class Compositor:
         ``composite``) and downloaded, while the uploads for the windows below continue on their
         own stream.  ``out_host``: pinned uint8 H x W x 3.  Call ``finish_download`` afterwards."""
         order, wins = self.streamed_windows(plan, kind, n_levels, windows)
-        src = self.upload(regions, overlap=True, order=order)
+        src = self.upload(regions, overlap=True, order=order, reuse=True)
         strips = []
         for ya, yb, _ in wins:
             strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, rows=(ya, yb), out_host=out_host,

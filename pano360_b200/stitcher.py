@@ -225,7 +225,7 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         comp.finish_download(result, stage)
         comp.release()
         return out if direct_out else result
-    src = comp.upload(regions, overlap=not equalize)       # warp starts while late images still upload
+    src = comp.upload(regions, overlap=not equalize, reuse=True)       # warp starts while late images still upload
     if equalize:
         comp.set_gains(src, equalize_gains(regions, src))
     if kind is None:                       # foreign blender: the reference's one-box-per-image NumPy triples

@@ -429,7 +429,7 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     # a strip reads only some rows of every image it meets: upload (and pack) just those
     rows_of = None if equalize or rows[1] <= rows[0] else comp.source_rows(regions, plan, kind, n_levels, proj, rows)
     phase("planned")
-    src = comp.upload(regions, need=need, overlap=not equalize, rows_of=rows_of)
+    src = comp.upload(regions, need=need, overlap=not equalize, rows_of=rows_of, reuse=True)
     phase("uploads queued")
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
