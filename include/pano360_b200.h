@@ -83,12 +83,22 @@ typedef struct p360_warp_job {
     float half_w, half_h;         /* float32(w / 2.0), float32(h / 2.0)                   */
     float max_x, max_y;           /* float32(w - 1), float32(h - 1)                       */
     float inv_2w, inv_2h;         /* 1 / (2 w), 1 / (2 h)                                 */
-    int32_t ty0, ty1;             /* rows of the image's TRUE box in window coordinates (y0 / ph may */
-                                  /* be cropped to a row window; the seam plan must not depend on it) */
+    int32_t ty0, ty1;             /* rows / columns of the image's TRUE box (of this column run, for a */
+    int32_t tx0, tx1;             /* seam-split image) in window coordinates: x0 / y0 / pw / ph may be   */
+                                  /* cropped to a window; the seam plan must not depend on the cut       */
 } p360_warp_job;
 
-/* u8 x 3 -> u8 x 4 (RGBX): the source layout in which a bilinear tap is one aligned 32-bit load. */
+/* u8 x 3 -> u8 x 4 (RGBX): the source layout in which a bilinear tap is one aligned 32-bit load.
+ * _rect: only pixels [c0, c1) of rows [r0, r1) of the h x w image (c0 % 4 == 0) — what was uploaded
+ * of an image when only part of it is read (p360_source_rects). */
 int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream);
+int p360_pack_rgbx_rect(const uint8_t *src_rgb, int h, int w, int r0, int r1, int c0, int c1,
+                        uint8_t *dst_rgbx, void *stream);
+/* Rectangle copy (cudaMemcpy2DAsync, direction inferred): `rows` runs of width_bytes bytes, pitches
+ * in bytes; device, peer-device and page-locked host addresses alike.  Uploads of image
+ * sub-rectangles, downloads / NVLink pushes of mosaic column windows. */
+int p360_copy_rect(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
+                   int64_t width_bytes, int64_t rows, void *stream);
 struct p360_tile_maps;
 struct p360_band_patch;
 /* jobs_dev (optional): a DEVICE copy of the same table — the constant-memory staging then is a
@@ -125,13 +135,26 @@ int p360_warp_batch(const p360_warp_job *jobs_host, const p360_warp_job *jobs_de
  * owner_keys / covered are written once per pixel, without atomics, and need no initialising.
  * If want_covered, covered also records the valid mask of the other tiles (stitcher.py:266-271).
  * p360_multiband_collapse with the same record writes only the multi tiles.
+ * Mosaic bytes are produced for rows [y_begin, y_end) x columns [x_begin, x_end) of the buffer
+ * (x_begin % 64 == 0; x_end % 64 == 0 or x_end == W): a window of the mosaic, computed in a buffer
+ * that also holds the halo the blurs need.  The buffer's column 0 must sit on a multiple of 64 of
+ * the whole mosaic and its width must be a multiple of 64 unless it ends at the mosaic's right
+ * edge, so that its tiles are tiles of the whole mosaic.
+ *
+ * p360_source_rects (K0s): after the plan, per patch the rectangle {u0, v0, u1, v1} (source pixels,
+ * half-open; rects_dev: 4 int32 per job, initialised to {INT_MAX, INT_MAX, INT_MIN, INT_MIN}) that
+ * covers every tap p360_warp_tiles can load for it — the same interval arithmetic, over the tiles
+ * where the patch is wanted as float or is the solo candidate, BORDER_REFLECT folded in.  Pixels
+ * outside are never read: only that rectangle of the image has to be uploaded.
  */
 int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
                          int H, int W, int abs_row0, int mosaic_h,
                          const struct p360_tile_maps *maps_host, void *stream);
 int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
-                    uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
-                    int want_covered, const struct p360_tile_maps *maps_host, void *stream);
+                    uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                    int H, int W, int want_covered, const struct p360_tile_maps *maps_host, void *stream);
+int p360_source_rects(const p360_warp_job *jobs_dev, int n_jobs, int H, int W, int abs_row0, int mosaic_h,
+                      const struct p360_tile_maps *maps_host, int32_t *rects_dev, void *stream);
 
 /* ---- K2: owner map for externally supplied patches (stitcher.py:196-208) ---
  * p360_owner_update: the same competition for one already-warped patch (the
@@ -186,7 +209,8 @@ int p360_gauss_blur_batch(const p360_blur_job *jobs, int n_jobs, int max_w, int 
  *   p360_paste_collapse        stitcher.py:160-168 in the same gather form
  * Nothing mosaic-sized is accumulated in HBM.  `patches` is a DEVICE array.
  * The collapse kernels produce rows [y_begin, y_end) of the output buffer (0 and
- * H for the whole mosaic) so that callers can overlap the download or the NVLink
+ * H for the whole mosaic; the multiband one also takes columns [x_begin, x_end),
+ * x_begin % 64 == 0) so that callers can overlap the download or the NVLink
  * send of finished row bands with the computation of the next ones.  row_origin
  * is the absolute mosaic row of buffer row 0 (0 unless the buffer is a strip):
  * work tiles are anchored at absolute rows, which makes the result independent
@@ -254,8 +278,8 @@ int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int
                               const p360_tile_maps *maps_host, void *stream);
 int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                             const uint64_t *owner_keys, const uint8_t *covered,
-                            uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
-                            const p360_tile_maps *maps_host, void *stream);
+                            uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                            int row_origin, int W, const p360_tile_maps *maps_host, void *stream);
 int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
                          int y_begin, int y_end, int row_origin, int W, void *stream);
 int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,

@@ -25,9 +25,12 @@ SIGNATURES = {
     "p360_last_error": [C.c_char_p, _i],
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
     "p360_pack_rgbx": [_vp, _i, _i, _vp, _vp],
+    "p360_pack_rgbx_rect": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_copy_rect": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
+    "p360_source_rects": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "p360_warp_batch": [_vp, _vp, _i, _vp, _vp, _i, _vp],
     "p360_seam_plan_build": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
-    "p360_warp_tiles": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_warp_tiles": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "p360_owner_decode": [_vp, _vp, _i64, _vp],
     "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
@@ -37,7 +40,7 @@ SIGNATURES = {
     "p360_tile_maps_build": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
     "p360_pyramid_reduce_batch": [_vp, _i, _i, _i, _vp, _i, _vp, _vp],
-    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "p360_pair_stats_blocks": [_i, _i],
@@ -58,7 +61,7 @@ WARP_JOB = np.dtype([("src", "u8"), ("lut", "u8"), ("hat_y", "u8"), ("hat_x", "u
                      ("h", "i4"), ("w", "i4"), ("c", "i4"), ("pw", "i4"), ("ph", "i4"), ("x0", "i4"),
                      ("y0", "i4"), ("col0", "i4"), ("row0", "i4"), ("patch", "i4"), ("half_w", "f4"),
                      ("half_h", "f4"), ("max_x", "f4"), ("max_y", "f4"), ("inv_2w", "f4"), ("inv_2h", "f4"),
-                     ("ty0", "i4"), ("ty1", "i4")])
+                     ("ty0", "i4"), ("ty1", "i4"), ("tx0", "i4"), ("tx1", "i4")])
 BLUR_JOB = np.dtype([("in", "u8"), ("out", "u8"), ("tmp", "u8"), ("w", "i4"), ("h", "i4"), ("slot", "i4"),
                      ("shift", "i4"), ("patch", "u8"), ("pad", "i4"), ("grow", "i4")])
 BAND_PATCH = np.dtype([("rgba", "u8"), ("invalid", "u8"), ("d2", "u8"), ("d4", "u8"),
@@ -70,7 +73,7 @@ TILE_MAPS = np.dtype([("present", "u8"), ("cand", "u8"), ("need", "u8"), ("multi
                       ("reach_x", "i4"), ("reach_y", "i4"), ("work_cap", "i4"), ("h_rows", "i4")])
 PAIR_JOB = np.dtype([("src_i", "u8"), ("src_j", "u8"), ("inv", "f8", (9,))])
 assert PAIR_JOB.itemsize == 88
-assert WARP_JOB.itemsize == 216 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
+assert WARP_JOB.itemsize == 224 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
 assert TILE_MAPS.itemsize == 88
 OWN_OFFSET = BAND_PATCH.fields["own"][1]
 
@@ -79,7 +82,7 @@ _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks", "p360_crop_scratch_by
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
-_LAUNCHES = {"p360_pack_rgbx": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
+_LAUNCHES = {"p360_pack_rgbx": 1, "p360_pack_rgbx_rect": 1, "p360_source_rects": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
              "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,
              "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,

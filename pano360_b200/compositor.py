@@ -163,6 +163,7 @@ class Compositor:
         self._packed = {}      # raw image addresses -> the buffers their RGBX copies go to
         self._images = {}      # (slot, shape) -> device buffers of uploaded images (upload(reuse=True))
         self._prepared = {}    # what a composite of one geometry over one set of buffers needs, kept ready
+        self.prepared_max = 6  # ... for at most this many (geometry, window) combinations
         self._taps_key = None
         self._keep = {}
         self._copy = None      # side streams for uploads / downloads that overlap the kernels
@@ -442,18 +443,20 @@ class Compositor:
         return overlaps, sizes, todo
 
     # -- K1: warp -------------------------------------------------------------
-    def plan_crops(self, regions, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None):
-        """Host side of the warp: which (row-cropped, column-split) boxes get
-        warped.  ``rows=(ya, yb)`` crops boxes to those mosaic rows; a cropped
-        top edge is moved up to a multiple of ``row_align`` rows below the
-        box's true top so that coarse grids anchored at the crop coincide with
+    def plan_crops(self, regions, plan, proj=geo.SphProj, rows=None, row_align=1, split_dilate=None, cols=None,
+                   col_align=1):
+        """Host side of the warp: which (window-cropped, column-split) boxes get
+        warped.  ``rows=(ya, yb)`` / ``cols=(xa, xb)`` crop boxes to those mosaic rows / columns; a
+        cropped top (left) edge is moved up (left) to a multiple of ``row_align`` (``col_align``)
+        pixels from the box's true edge so that coarse grids anchored at the crop coincide with
         those anchored at the true box.  With ``split_dilate`` (columns) the
         all-invalid middle of seam-straddling boxes is dropped
         (``geometry.active_column_runs``): such an image yields two crops with
         the same image index.
-        Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R, true y0, true y1)], tables =
-        the per-mosaic-column / per-row ray tables of the projection."""
-        key = (len(regions), proj, rows, row_align, split_dilate)        # (a plan belongs to one rig geometry)
+        Returns (crops, tables): crops = [(image, x0, y0, x1, y1, K*R, true y0, true y1, true x0,
+        true x1)] (the true columns are those of the run), tables = the per-mosaic-column /
+        per-row ray tables of the projection."""
+        key = (len(regions), proj, rows, row_align, split_dilate, cols, col_align)   # (a plan belongs to one rig geometry)
         cached = plan._crops.get(key) if plan._crops is not None else None
         if cached is not None:                       # same regions, same plan, same window as last time
             return cached, plan.rays(proj)
@@ -467,8 +470,12 @@ class Compositor:
             runs = [(x0, x1)] if split_dilate is None else \
                 geo.active_column_runs(i, box, plan, dilate=split_dilate)
             k_r = np.ascontiguousarray(reg.proj(), dtype=np.float64).ravel()
-            for cx0, cx1 in runs:
-                crops.append((i, cx0, ya, cx1, yb, k_r, y0, y1))
+            for rx0, rx1 in runs:
+                cx0, cx1 = (rx0, rx1) if cols is None else (max(rx0, cols[0]), min(rx1, cols[1]))
+                if cx0 >= cx1:
+                    continue
+                cx0 = rx0 + (cx0 - rx0) // col_align * col_align
+                crops.append((i, cx0, ya, cx1, yb, k_r, y0, y1, rx0, rx1))
         if plan._crops is not None:
             plan._crops[key] = crops
         return crops, plan.rays(proj)
@@ -503,9 +510,11 @@ class Compositor:
         return (torch.zeros((h, w), dtype=torch.int64, device=self.device),
                 torch.zeros((h, w), dtype=torch.uint8, device=self.device))
 
-    def _warp_jobs(self, src, crops, tables, origin=(0, 0)):
+    def _warp_jobs(self, src, crops, tables, origin=(0, 0), pools=True, shapes=None):
         """Host side of K1: the job table (one p360_warp_job per crop), the patch pools and the
-        patches.  Returns (jobs, patches, keep) — ``keep`` holds what the launches reference."""
+        patches.  Returns (jobs, patches, keep) — ``keep`` holds what the launches reference.
+        ``pools=False`` (with ``src=None`` and the image ``shapes``): the geometry of the jobs only,
+        for the seam plan (no patch memory, no source addresses)."""
         ray_x, ray_z, ray_y = tables
         cached = self._keep.get("rays")
         if cached is not None and cached[0] is ray_x:          # same plan as last time: tables already on the device
@@ -519,15 +528,24 @@ class Compositor:
         n = len(crops)
         sizes = np.array([(c[3] - c[1]) * (c[4] - c[2]) for c in crops], dtype=np.int64)
         offs = np.concatenate([[0], np.cumsum(sizes)])
-        rgba_pool = torch.empty(int(offs[-1]) * 4, dtype=torch.float32, device=self.device)
-        inv_pool = torch.empty(int(offs[-1]), dtype=torch.uint8, device=self.device)
-        rgba_base, inv_base = rgba_pool.data_ptr(), inv_pool.data_ptr()
+        if pools:
+            rgba_pool = torch.empty(int(offs[-1]) * 4, dtype=torch.float32, device=self.device)
+            inv_pool = torch.empty(int(offs[-1]), dtype=torch.uint8, device=self.device)
+            rgba_base, inv_base = rgba_pool.data_ptr(), inv_pool.data_ptr()
+        else:
+            rgba_pool = inv_pool = None
+            rgba_base = inv_base = 0
         # the job table column by column (per-image constants looked up once per image, not per crop)
         image = np.array([c[0] for c in crops], dtype=np.int64)
         box = np.array([c[1:5] for c in crops], dtype=np.int64).reshape(n, 4)          # x0, ya, x1, yb
         true_rows = np.array([c[6:8] for c in crops], dtype=np.int64).reshape(n, 2)
+        true_cols = np.array([c[8:10] for c in crops], dtype=np.int64).reshape(n, 2)
         per_image = {}
         for i in set(image.tolist()):
+            if src is None:
+                h, w = shapes[i]
+                per_image[i] = (0, 0, 0, 0, h, w, 4)
+                continue
             h, w = src.shapes[i]
             hat_y, hat_x = src.hats[(h, w)]
             pix = src.pixels[i]
@@ -544,11 +562,14 @@ class Compositor:
         jobs["pw"], jobs["ph"] = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
         jobs["x0"], jobs["y0"], jobs["col0"], jobs["row0"] = box[:, 0] - ox, box[:, 1] - oy, box[:, 0], box[:, 1]
         jobs["ty0"], jobs["ty1"] = true_rows[:, 0] - oy, true_rows[:, 1] - oy
+        jobs["tx0"], jobs["tx1"] = true_cols[:, 0] - ox, true_cols[:, 1] - ox
         jobs["patch"] = np.arange(n)
         jobs["half_w"], jobs["half_h"] = (ws / 2).astype(np.float32), (hs / 2).astype(np.float32)
         jobs["max_x"], jobs["max_y"] = (ws - 1).astype(np.float32), (hs - 1).astype(np.float32)
         jobs["inv_2w"] = np.float32(1.0) / (2 * ws).astype(np.float32)
         jobs["inv_2h"] = np.float32(1.0) / (2 * hs).astype(np.float32)
+        if not pools:
+            return jobs, None, (dev_rays, None, None, int(offs[-1]))
         pools, bases = (rgba_pool, inv_pool), (rgba_base, inv_base)
         patches = [DevicePatch(box=(b[0] - ox, b[1] - oy, b[2] - ox, b[3] - oy), index=i, pools=pools, offset=o, bases=bases)
                    for i, b, o in zip(image.tolist(), box.tolist(), offs[:-1].tolist())]
@@ -754,25 +775,30 @@ class Compositor:
         self._taps_key = n_levels
 
     def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8,
-                  row_origin=0, tail=()):
+                  row_origin=0, tail=(), cols=None, col_origin=0):
         """Launch a collapse kernel over rows ``rows`` (default: all) of the
         mosaic buffer.  With ``out_host`` (pinned host array) or ``on_band``
         (callback(y0, y1), e.g. an NVLink send) the rows are produced band by
         band so that the transfer of each finished band overlaps the
-        computation of the next."""
+        computation of the next.  ``cols = (xa, xb)`` (buffer columns, xa a multiple of 64): only
+        those columns are wanted — the multiband collapse produces just them, and just they are
+        downloaded (buffer column x is mosaic column x + ``col_origin``)."""
         h, w = mosaic.shape[:2]
         ya, yb = (0, h) if rows is None else rows
+        xa, xb = (0, w) if cols is None else cols
+        xargs = (xa, xb) if fn == "p360_multiband_collapse" else ()
         if out_host is None and on_band is None:
             if fn is not None:
-                self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, row_origin, w, *tail, self.stream)
+                self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, *xargs, row_origin, w, *tail, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
+        whole_rows = host is not None and xa == 0 and xb == w and col_origin == 0 and host.shape[1] == w
         main, side = torch.cuda.current_stream(self.device), self.download_stream()
         for y0, y1 in band_edges(ya, yb, bands):
             if y1 <= y0:
                 continue
             if fn is not None:             # (None: the rows are already final, e.g. a blank window)
-                self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1,
+                self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1, *xargs,
                              row_origin, w, *tail, self.stream)
             if on_band is not None:
                 on_band(y0, y1)
@@ -781,22 +807,29 @@ class Compositor:
                 done.record(main)
                 side.wait_event(done)
                 with torch.cuda.stream(side):       # buffer row y is mosaic row y + row_origin
-                    host[y0 + row_origin:y1 + row_origin].copy_(mosaic[y0:y1], non_blocking=True)
+                    if whole_rows:
+                        host[y0 + row_origin:y1 + row_origin].copy_(mosaic[y0:y1], non_blocking=True)
+                    else:                           # a column window: a rectangle of the host mosaic
+                        pitch = 3 * host.shape[1]
+                        _lib.call("p360_copy_rect", host.data_ptr() + (y0 + row_origin) * pitch + 3 * (xa + col_origin),
+                                  pitch, mosaic.data_ptr() + 3 * (y0 * w + xa), 3 * w, 3 * (xb - xa), y1 - y0,
+                                  side.cuda_stream)
                 landed = torch.cuda.Event()
                 landed.record(side)
-                self._bands_down.append((y0 + row_origin, y1 + row_origin, landed))
+                self._bands_down.append((y0 + row_origin, y1 + row_origin, landed, xa + col_origin, xb + col_origin))
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} collapsed")
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} downloaded", side)
         if host is not None:
             self._download = torch.cuda.Event()
             self._download.record(side)
 
-    def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin):
-        """A mosaic (or row window) no image touches: zeros — through the same banded path as a
+    def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin, cols=None, col_origin=0):
+        """A mosaic (or window) no image touches: zeros — through the same banded path as a
         collapse, so that ``out_host`` receives its rows and ``on_band`` fires for every band
         (a strip that falls into a gap between images must still send its bands)."""
         mosaic.zero_()
-        self._collapse("blank", 0, None, (), mosaic, out_host, rows, on_band, bands, row_origin)
+        self._collapse("blank", 0, None, (), mosaic, out_host, rows, on_band, bands, row_origin, cols=cols,
+                       col_origin=col_origin)
         return mosaic
 
     def release(self, everything=False):
@@ -819,16 +852,17 @@ class Compositor:
         pageable host array) receives the rows from the pinned staging buffer ``staged`` band by
         band as they land, while the later bands are still crossing PCIe."""
         if copy_to is not None:
-            for y0, y1, landed in self._bands_down:
+            for y0, y1, landed, x0, x1 in self._bands_down:
                 landed.synchronize()
-                parallel_copy(copy_to[y0:y1], staged[y0:y1])
+                parallel_copy(copy_to[y0:y1, x0:x1], staged[y0:y1, x0:x1])
         self._bands_down = []
         if self._download is not None:
             self._download.synchronize()
             self._download = None
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
-                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None, seam=None):
+                        rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None, seam=None,
+                        cols=None, col_origin=0):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM.
@@ -842,7 +876,7 @@ class Compositor:
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:      # nothing lands here: still produce (and download / hand on) every band
-            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
+            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin, cols, col_origin)
         pad, plan = geo.coarse_band_plan(n_levels)
         n = len(patches)
         lows, maps = [], None
@@ -879,8 +913,9 @@ class Compositor:
                 for i in sorted({c[0] for c in crops}):
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
+            xa, xb = (0, w) if cols is None else cols
             self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, _lib.ptr(dev_wjobs), n,
-                         _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, h, w,
+                         _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, xa, xb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
             self._keep["seam"] = (prep,)
         else:
@@ -920,7 +955,8 @@ class Compositor:
                 lows = self._level_views(table, layout)
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
-                       rows, on_band, bands, row_origin, tail=(None if maps is None else maps.ctypes.data,))
+                       rows, on_band, bands, row_origin, tail=(None if maps is None else maps.ctypes.data,),
+                       cols=cols, col_origin=col_origin)
         self._keep["collapse"] = (dev_table, keys, covered)
         self.last_covered = covered
         if stages is not None:
@@ -968,31 +1004,31 @@ class Compositor:
         return mosaic
 
     def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
-                   bands=8, row_origin=0):
+                   bands=8, row_origin=0, cols=None, col_origin=0):
         h, w = shape
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
         if not patches:
-            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin)
+            return self._blank(mosaic, out_host, rows, on_band, bands, row_origin, cols, col_origin)
         table = self._band_table(patches)
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host,
-                       rows, on_band, bands, row_origin)
+                       rows, on_band, bands, row_origin, cols=cols, col_origin=col_origin)
         self._keep["collapse"] = (dev_table,)
         return mosaic
 
     def blend_none(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
-                   row_origin=0):
+                   row_origin=0, cols=None, col_origin=0):
         """stitcher.py:160-168 (last valid writer wins), gather form."""
         return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands, row_origin)
+                               on_band, mosaic, bands, row_origin, cols, col_origin)
 
     def blend_linear(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
-                     row_origin=0):
+                     row_origin=0, cols=None, col_origin=0):
         """stitcher.py:171-183, gather form."""
         return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands, row_origin)
+                               on_band, mosaic, bands, row_origin, cols, col_origin)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""
@@ -1069,59 +1105,113 @@ class Compositor:
         20-30 px wide views) — such rigs are blended at full resolution (``blend_multiband_exact``)."""
         return min(min(r.img.shape[:2]) for r in regions) < EXACT_BELOW
 
-    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8, direct=None, want_covered=False, exact=False):
-        """warp + blend for the whole mosaic or for a row window [ya, yb)
-        (the returned strip has exactly yb - ya rows and is bit-identical to
-        those rows of the full composite; only those rows are collapsed).
-        ``out_host`` (pinned uint8 H x W x 3: the WHOLE mosaic, also in window
-        mode) receives the rows produced through a banded download that overlaps
-        the collapse; call ``finish_download`` before reading it.  ``on_band(strip_rows, y0, y1)``
-        is called after the collapse of mosaic rows [y0, y1) has been launched
-        (``strip_rows`` = that part of the device result).  ``want_covered``: keep the union of
-        valid pixels of the rows produced in ``last_covered`` (crop stage, stitcher.py:266-271)."""
+    def window_cols(self, cols, kind, n_levels, width):
+        """Columns [ca, cb) a column window [xa, xb) has to warp: the blur reach plus one 64-column
+        collapse tile on both sides, widened to the whole tiles the seam plan consults (the
+        column counterpart of ``window_rows``)."""
+        xa, xb = cols
         reach = self.blur_reach(kind, n_levels)
-        self._mark(f"composite {rows} begins")
-        if rows is None:
-            ya, yb, wa, wb = 0, plan.shape[0], 0, plan.shape[0]
+        if not reach:
+            return xa, xb
+        halo = reach + 64
+        reach_x = -(-geo.coarse_band_plan(n_levels)[0] // 64)
+        ca = min(xa - halo, 64 * (xa // 64 - reach_x))
+        cb = max(xb + halo, 64 * ((xb - 1) // 64 + reach_x + 1))
+        return max(0, ca), min(width, cb)
+
+    def col_margin(self, kind, n_levels):
+        """Upper bound of the columns beyond [xa, xb) a column window may ask for (halo, tile
+        rounding of the buffer, alignment of cropped left edges): which images it depends on."""
+        reach = self.blur_reach(kind, n_levels)
+        if not reach:
+            return 0
+        return max(reach + 64, 64 * -(-geo.coarse_band_plan(n_levels)[0] // 64) + 63) + 64 + 3
+
+    def _window_geometry(self, regions, plan, kind, n_levels, proj, rows, cols):
+        """What a window [ya, yb) x [xa, xb) of the mosaic is computed from: the crops of the images
+        (window + halo), the buffer that holds them — rows [top, top + shape[0]), columns [left,
+        left + shape[1]) of the mosaic, whole 64-column tiles of it — and the window in buffer
+        coordinates (``local`` rows, ``local_cols`` or None for all columns)."""
+        reach = self.blur_reach(kind, n_levels)
+        height, width = plan.shape
+        if cols is not None:
+            xa, xb = cols
+            if not (0 <= xa < xb <= width and xa % 64 == 0 and (xb % 64 == 0 or xb == width)):
+                raise ValueError(f"column window {cols} must lie on 64-column tile edges of the {width}-column mosaic")
+        if rows is None and cols is None:
+            ya, yb, wa, wb = 0, height, 0, height
             crops, tables = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
         else:
-            ya, yb = rows
-            wa, wb = self.window_rows(rows, kind, n_levels, plan.shape[0])
-            crops, tables = self.plan_crops(regions, plan, proj, rows=(wa, wb),
-                                            row_align=4 if reach else 1, split_dilate=2 * reach)
+            ya, yb = (0, height) if rows is None else rows
+            wa, wb = (0, height) if rows is None else self.window_rows(rows, kind, n_levels, height)
+            span = None if cols is None else self.window_cols(cols, kind, n_levels, width)
+            crops, tables = self.plan_crops(regions, plan, proj, rows=None if rows is None else (wa, wb),
+                                            row_align=4 if reach else 1, split_dilate=2 * reach,
+                                            cols=span, col_align=4 if reach else 1)
         top = min([c[2] for c in crops] + [wa])                # aligned crops may start above wa
-        shape = (wb - top, plan.shape[1])
+        if cols is None:
+            left, right, local_cols = 0, width, None
+        else:
+            # the buffer spans whole tiles of the mosaic: its tiles are tiles of the whole mosaic
+            left = min([c[1] for c in crops] + [span[0]]) // 64 * 64
+            right = min(width, -(-span[1] // 64) * 64)
+            local_cols = (xa - left, xb - left)
+        return crops, tables, top, left, (wb - top, right - left), (ya - top, yb - top), local_cols
+
+    def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
+                  on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None):
+        """warp + blend for the whole mosaic or for a window of it: rows [ya, yb) and / or columns
+        [xa, xb) (xa a multiple of 64; xb too unless it is the mosaic width).  The returned strip
+        has exactly (yb - ya) x (xb - xa) pixels and is bit-identical to that part of the full
+        composite; only that part is collapsed.
+        ``out_host`` (pinned uint8 H x W x 3: the WHOLE mosaic, also in window
+        mode) receives the pixels produced through a banded download that overlaps
+        the collapse; call ``finish_download`` before reading it.  ``on_band(strip_part, y0, y1)``
+        is called after the collapse of mosaic rows [y0, y1) has been launched
+        (``strip_part`` = that part of the device result, columns [xa, xb) only).  ``want_covered``:
+        keep the union of valid pixels of the rows produced in ``last_covered`` (crop stage,
+        stitcher.py:266-271)."""
+        self._mark(f"composite {rows} {cols} begins")
+        if cols is not None and want_covered:
+            raise ValueError("want_covered needs every column of the mosaic")
+        crops, tables, top, left, shape, local, local_cols = self._window_geometry(regions, plan, kind, n_levels, proj,
+                                                                                   rows, cols)
         holder = {}
         band_cb = None
         if on_band is not None:
             def band_cb(y0, y1):
-                on_band(holder["mosaic"][y0:y1], y0 + top, y1 + top)
-        local = (ya - top, yb - top)
+                part = holder["mosaic"][y0:y1] if local_cols is None else holder["mosaic"][y0:y1, local_cols[0]:local_cols[1]]
+                on_band(part, y0 + top, y1 + top)
+
+        def result(strip):
+            strip = strip[local[0]:local[1]]
+            return strip if local_cols is None else strip[:, local_cols[0]:local_cols[1]]
+        window = dict(rows=local, on_band=band_cb, bands=bands, row_origin=top, cols=local_cols, col_origin=left)
         if exact and kind == "multiband" and n_levels > 1:      # (stitch() asks for it when needs_exact())
             # full-resolution loop nest on the whole window, then hand the rows on like a collapse
             state = self.new_owner_state(shape)
-            patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+            patches = self.warp_crops(src, crops, tables, origin=(left, top), owner_state=state)
             holder["mosaic"] = self.blend_multiband_exact(patches, shape, n_levels, owner_state=state)
-            self._collapse("exact", 0, None, (), holder["mosaic"], out_host, local, band_cb, bands, top)
-            return holder["mosaic"][local[0]:local[1]], patches
+            self._collapse("exact", 0, None, (), holder["mosaic"], out_host, local, band_cb, bands, top,
+                           cols=local_cols, col_origin=left)
+            return result(holder["mosaic"]), patches
         use_plan = (self.direct if direct is None else direct) and kind == "multiband" and n_levels > 1 \
             and 0 < len(crops) <= 256                          # (the tile warp keeps its job table in constant memory)
         if use_plan:
             # job tables, pools, tile-map storage: prepared once per (geometry, window, source
             # buffers) and reused as long as the addresses they name are the ones in use
             needed = sorted({c[0] for c in crops})
-            key = (id(plan), rows, n_levels, proj, shape, tuple(src.pixels[i].data_ptr() for i in needed),
+            key = (id(plan), rows, cols, n_levels, proj, shape, tuple(src.pixels[i].data_ptr() for i in needed),
                    tuple(src.luts[i].data_ptr() for i in needed))
             prep = self._prepared.get(key)
             if prep is not None and "pools" in prep and prep["pools"] != tuple(
                     self._pools[k].data_ptr() if k in self._pools else 0 for k in ("pool2", "pool4")):
                 prep = None                                    # (the coarse pools were re-allocated since)
             if prep is None:
-                jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(0, top))
+                jobs, patches, keep = self._warp_jobs(src, crops, tables, origin=(left, top))
                 prep = {"jobs": jobs, "patches": patches, "keep": keep, "plan": plan}
                 self._prepared.pop(key, None)
-                while len(self._prepared) >= 6:
+                while len(self._prepared) >= self.prepared_max:
                     self._prepared.pop(next(iter(self._prepared)))
                 self._prepared[key] = prep
             patches = prep["patches"]
@@ -1129,21 +1219,19 @@ class Compositor:
             seam = {"prepared": prep, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": prep["keep"][3],
                     "want_covered": want_covered}
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels, out_host=out_host,
-                                     rows=local, on_band=band_cb, bands=bands, row_origin=top, seam=seam)
-            return strip[local[0]:local[1]], patches
+                                     seam=seam, **window)
+            return result(strip), patches
         state = self.new_owner_state(shape) if kind == "multiband" else None
-        patches = self.warp_crops(src, crops, tables, origin=(0, top), owner_state=state)
+        patches = self.warp_crops(src, crops, tables, origin=(left, top), owner_state=state)
         if kind == "multiband":
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels,
-                                     owner_state=state, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands, row_origin=top)
+                                     owner_state=state, out_host=out_host, **window)
         else:
             strip = self._blend_into(holder, self.blend_none if kind == "none" else self.blend_linear,
-                                     patches, shape, out_host=out_host, rows=local, on_band=band_cb,
-                                     bands=bands, row_origin=top)
+                                     patches, shape, out_host=out_host, **window)
             if want_covered:
                 self.last_covered = self.covered_mask(patches, shape)
-        return strip[local[0]:local[1]], patches
+        return result(strip), patches
 
     def streamed_windows(self, plan, kind, n_levels, windows=3):
         """Plan of ``composite_streamed``: the order in which to upload the images (top edge

@@ -373,18 +373,19 @@ __global__ void __launch_bounds__(256, (L <= 5) ? 4 : 3)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
                           const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
-                          int y_begin, int H, int W, TileMaps maps) {
+                          int y_begin, int H, int first_tile_col, int x_end, int W, TileMaps maps) {
     // Tiles are anchored at absolute mosaic rows (first_tile_row may be < y_begin, even < 0):
     // whether a tile takes the single-contributor shortcut must not depend on how the
     // mosaic was cut into strips or row bands.
     __shared__ int16_t list[MAX_TILE_PATCHES];
-    const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
+    const int tile_col = first_tile_col + (int)blockIdx.x;          // (columns [64 * first_tile_col, x_end) are produced)
+    const int tx0 = tile_col * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
     int n_hit;
     bool pure = false;      // every valid pixel of the tile belongs to list[0]: the owner keys are not needed
     if (maps.cand != nullptr) {
         // a single candidate: every valid pixel of the tile is its own (p360_tile_maps_build), no
         // coarse level is read and none was computed here — nothing to cull either
-        const size_t tile = (size_t)((ty0 - maps.row0) >> 5) * maps.tiles_x + blockIdx.x;
+        const size_t tile = (size_t)((ty0 - maps.row0) >> 5) * maps.tiles_x + tile_col;
         const bool blended = __ldg(maps.multi + tile) != 0;
         if (maps.wneed != nullptr && !blended) return;   // seam plan: p360_warp_direct wrote this tile (block-uniform)
         n_hit = tile_list_from_maps(patches, n_patches, maps, tile, tx0, ty0, list);
@@ -408,7 +409,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         }
     }
     const int X = tx0 + threadIdx.x;
-    if (X >= W) return;
+    if (X >= x_end) return;
     for (int sub = 0; sub < ROWS_PER_THREAD; ++sub) {
         const int Y = ty0 + threadIdx.y + 4 * sub;
         if (Y >= H) break;
@@ -547,12 +548,12 @@ inline int first_tile(int y_begin, int row_origin) {     // absolute-row-aligned
 
 template <int L>
 int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
-                    const uint8_t *covered, uint8_t *out, int y0, int y1, int row_origin, int W,
+                    const uint8_t *covered, uint8_t *out, int y0, int y1, int x0, int x1, int row_origin, int W,
                     const TileMaps &maps, cudaStream_t s) {
     const int first = first_tile(y0, row_origin);
-    dim3 grid(cdiv(W, CT_X), cdiv(y1 - first, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1, W,
-                                                        maps);
+    dim3 grid(cdiv(x1 - x0, CT_X), cdiv(y1 - first, CT_Y)), block(CT_X, 4);
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1,
+                                                        x0 / CT_X, x1, W, maps);
     return check_launch("p360_multiband_collapse");
 }
 
@@ -644,8 +645,8 @@ extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_p
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                                        const uint64_t *owner_keys, const uint8_t *covered,
-                                       uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W,
-                                       const p360_tile_maps *maps_host, void *stream) {
+                                       uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                                       int row_origin, int W, const p360_tile_maps *maps_host, void *stream) {
     const char *where = "p360_multiband_collapse";
     P360_REQUIRE(maps_ok(maps_host), where);
     const TileMaps maps = device_maps(maps_host);
@@ -659,20 +660,21 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
     P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && W > 0, where);
     P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
-    if (y_end == y_begin) return 0;
+    P360_REQUIRE(x_begin >= 0 && x_begin <= x_end && x_end <= W && x_begin % CT_X == 0, where);
+    if (y_end == y_begin || x_end == x_begin) return 0;
     const int H = y_end;
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
-        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, row_origin, W, maps, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
     }
 }
 

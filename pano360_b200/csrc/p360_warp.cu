@@ -27,8 +27,9 @@ struct WarpJob {                 // == p360_warp_job
     float half_w, half_h;        // float32(w / 2), float32(h / 2)          (stitcher.py:310)
     float max_x, max_y;          // float32(w - 1), float32(h - 1)          (stitcher.py:311-312)
     float inv_2w, inv_2h;        // 1 / (2w), 1 / (2h): reflection period reciprocals
-    int ty0, ty1;                // rows of the image's TRUE box in window coordinates (a row window crops
-                                 // y0 / ph; the seam plan must not depend on where the window was cut)
+    int ty0, ty1;                // rows / columns of the image's TRUE box (for a seam-split image: of this column
+    int tx0, tx1;                // run) in window coordinates: a window crops x0 / y0 / pw / ph, and the seam plan
+                                 // must not depend on where the window was cut
 };
 static_assert(sizeof(WarpJob) == sizeof(p360_warp_job), "ABI struct mismatch");
 
@@ -314,16 +315,16 @@ seam_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, BandPatch *
     double best_min = 0.0;
     for (int k = 0; k < n_jobs; ++k) {
         const WarpJob &j = jobs[k];
-        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
+        if (j.tx0 >= xb || j.tx1 <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
         // a patch only dominates a tile it covers completely: beyond its box it has no pixels,
         // however large alpha would be there (boxes end where the reference's ranges end)
-        if (j.x0 > xa || j.x0 + j.pw < xb || j.ty0 > ya || j.ty1 < yb) continue;
+        if (j.tx0 > xa || j.tx1 < xb || j.ty0 > ya || j.ty1 < yb) continue;
         double a_min, a_max;
         if (alpha_range(j, rx, ry, rz, a_min, a_max)) best_min = fmax(best_min, a_min);
     }
     for (int k = 0; k < n_jobs; ++k) {
         const WarpJob &j = jobs[k];
-        if (j.x0 >= xb || j.x0 + j.pw <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
+        if (j.tx0 >= xb || j.tx1 <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
         double a_min, a_max;
         if (alpha_range(j, rx, ry, rz, a_min, a_max) && a_max >= best_min) {
             m.present[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
@@ -360,7 +361,7 @@ seam_cand_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int W, TileMaps m
             const int k = 32 * w + b;
             if (k >= n_jobs) break;
             const WarpJob &j = jobs[k];
-            if (j.x0 < xb && j.x0 + j.pw > xa && j.ty0 < ta + TILE_Y && j.ty1 > ta) keep |= 1u << b;
+            if (j.tx0 < xb && j.tx1 > xa && j.ty0 < ta + TILE_Y && j.ty1 > ta) keep |= 1u << b;
         }
         m.cand[(size_t)t * m.words + w] = keep;
         count += __popc(keep);
@@ -498,8 +499,8 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
 template <bool RGBX>
 __global__ void __launch_bounds__(256, P360_TILE_BLOCKS)
 warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
-                  uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end, int H, int W,
-                  int want_covered, TileMaps m) {
+                  uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end,
+                  int x_begin, int x_end, int H, int W, int want_covered, TileMaps m) {
     __align__(16) __shared__ uint8_t rows[TILE_Y][DT_PITCH];
     __shared__ float lut[256];
     __shared__ float best_a[TILE_Y][TILE_X];             // running owner of every pixel: each thread only
@@ -517,7 +518,8 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
         if (c && solo < 0) solo = 32 * w + __ffs(c) - 1;
     }
     if (multi) solo = -1;
-    const bool bytes = !multi && ty0 < y_end && ty0 + TILE_Y > y_begin;      // this block writes mosaic bytes
+    // this block writes mosaic bytes (x_begin / x_end sit on tile edges)
+    const bool bytes = !multi && ty0 < y_end && ty0 + TILE_Y > y_begin && tx0 >= x_begin && tx0 < x_end;
     if (!zone && !bytes) return;                         // (block-uniform)
     if (bytes) {                                         // zeros wherever the candidate has no valid pixel
         for (int i = tid; i < TILE_Y * DT_PITCH / 16; i += 256)
@@ -607,6 +609,113 @@ pack_rgbx_kernel(const uint8_t *__restrict__ src, long long n_px, uint32_t *__re
     }
 }
 
+
+// The same for the pixels [c0, c1) of rows [r0, r1) of an h x w image (c0 % 4 == 0): what a column
+// window of the compositor uploads of an image.  grid.y = row.
+__global__ void __launch_bounds__(256)
+pack_rgbx_rect_kernel(const uint8_t *__restrict__ src, int w, int r0, int c0, int c1, uint32_t *__restrict__ dst) {
+    const int row = r0 + (int)blockIdx.y;
+    const int first = c0 + 4 * ((int)blockIdx.x * 256 + (int)threadIdx.x);
+    if (first >= c1) return;
+    const size_t px = (size_t)row * w + first;                 // pixel index in the image
+    if (first + 4 <= c1 && ((3 * px) & 3) == 0) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(src + 3 * px);
+        const uint32_t a = __ldg(in), b = __ldg(in + 1), c = __ldg(in + 2);
+        uint4 o;
+        o.x = a & 0xffffffu;
+        o.y = (a >> 24) | ((b & 0xffffu) << 8);
+        o.z = (b >> 16) | ((c & 0xffu) << 16);
+        o.w = c >> 8;
+        if (((px & 3) == 0)) { *reinterpret_cast<uint4 *>(dst + px) = o; return; }
+        dst[px] = o.x; dst[px + 1] = o.y; dst[px + 2] = o.z; dst[px + 3] = o.w;
+        return;
+    }
+    for (int i = first; i < min(first + 4, c1); ++i) {
+        const uint8_t *q = src + 3 * ((size_t)row * w + i);
+        dst[(size_t)row * w + i] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+    }
+}
+
+// ---- K0s: which source pixels does the plan read? ---------------------------------------------
+// For every patch, the box (source pixels) around everything its tiles can sample: the tiles
+// where it is warped to float (`wneed`) and the solo tiles it writes directly, each pushed through
+// the same interval arithmetic as the alpha bounds (ray tables -> K R ray -> source position),
+// grown by the bilinear footprint and the fixed-point slack.  Uploading just that rectangle of
+// every image is exact: nothing else is ever loaded.  rects[4 * patch] = {u0, v0, u1, v1}
+// (half-open, clipped to the image; initialise to {MAX, MAX, MIN, MIN}); positions beyond the image
+// fold back by BORDER_REFLECT; a patch partly behind the camera on a tile takes the whole image.
+// One thread per tile.
+// taps of positions in [a, b] along an axis of n pixels: floor(p) and floor(p) + 1, indices outside
+// the image folded back by BORDER_REFLECT (p < 0 -> -p - 1, p >= n -> 2n - 1 - p).  [lo, hi) covers them.
+__device__ __forceinline__ void axis_taps(double a, double b, int n, int &lo, int &hi) {
+    if (!(a > -(double)n && b < 2.0 * n - 2.0)) { lo = 0; hi = n; return; }     // farther than one period (or NaN)
+    lo = a < 0.0 ? 0 : (int)floor(a);
+    hi = b > n - 2.0 ? n : (int)floor(b) + 2;
+    if (a < 0.0) hi = max(hi, min(n, (int)ceil(-a) + 1));
+    if (b > n - 2.0) lo = min(lo, max(0, 2 * n - 3 - (int)floor(b)));
+}
+
+__device__ __forceinline__ bool source_range(const WarpJob &j, Interval rx, Interval ry, Interval rz, int *box) {
+    Interval p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const Interval x = scaled(j.kr[3 * k], rx), y = scaled(j.kr[3 * k + 1], ry), z = scaled(j.kr[3 * k + 2], rz);
+        p[k] = Interval{x.lo + y.lo + z.lo, x.hi + y.hi + z.hi};
+    }
+    if (p[2].lo <= 1e-9) return false;                     // (partly) behind the camera: anything may be sampled
+    const double u0 = fmin(fmin(p[0].lo / p[2].lo, p[0].lo / p[2].hi), fmin(p[0].hi / p[2].lo, p[0].hi / p[2].hi));
+    const double u1 = fmax(fmax(p[0].lo / p[2].lo, p[0].lo / p[2].hi), fmax(p[0].hi / p[2].lo, p[0].hi / p[2].hi));
+    const double v0 = fmin(fmin(p[1].lo / p[2].lo, p[1].lo / p[2].hi), fmin(p[1].hi / p[2].lo, p[1].hi / p[2].hi));
+    const double v1 = fmax(fmax(p[1].lo / p[2].lo, p[1].lo / p[2].hi), fmax(p[1].hi / p[2].lo, p[1].hi / p[2].hi));
+    const double slack = 1.0 / 32 + 1e-3 + 1e-6 * (fabs(u0) + fabs(u1) + fabs(v0) + fabs(v1));   // fixed point + float32 quotient
+    axis_taps(u0 + 0.5 * j.w - slack, u1 + 0.5 * j.w + slack, j.w, box[0], box[2]);
+    axis_taps(v0 + 0.5 * j.h - slack, v1 + 0.5 * j.h + slack, j.h, box[1], box[3]);
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+source_rects_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int W, int abs_row0, int mosaic_h,
+                    TileMaps m, int *__restrict__ rects) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= m.tiles_x * m.tiles_y) return;
+    const int tx = t % m.tiles_x, ty = t / m.tiles_x;
+    const int xa = tx * TILE_X, xb = min(xa + TILE_X, W);
+    const int ta = m.row0 + ty * TILE_Y;
+    const int ya = max(ta, 0), yb = min(ta + TILE_Y, H);   // only pixels of the buffer are ever warped
+    if (yb <= ya) return;
+    const bool multi = m.multi[t] != 0;
+    const WarpJob &j0 = jobs[0];
+    const int dc = j0.col0 - j0.x0, dr = j0.row0 - j0.y0;
+    Interval rx{0.0, 0.0}, ry{0.0, 0.0}, rz{0.0, 0.0};
+    bool have = false;
+    bool solo_seen = false;
+    for (int w = 0; w < m.words; ++w) {
+        uint32_t bits = __ldg(m.wneed + (size_t)t * m.words + w);
+        if (!multi && !solo_seen) {                        // the solo candidate: the first cand bit
+            const uint32_t c = __ldg(m.cand + (size_t)t * m.words + w);
+            if (c) { bits |= c & (0u - c); solo_seen = true; }
+        }
+        while (bits) {
+            const int k = 32 * w + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (k >= n_jobs) break;
+            const WarpJob &j = jobs[k];
+            // the pixels of the tile the (cropped) patch covers
+            const int px0 = max(xa, j.x0), px1 = min(xb, j.x0 + j.pw), py0 = max(ya, j.y0), py1 = min(yb, j.y0 + j.ph);
+            if (px1 <= px0 || py1 <= py0) continue;
+            if (!have) {
+                rx = table_range(j0.ray_x, xa + dc, xb + dc); rz = table_range(j0.ray_z, xa + dc, xb + dc);
+                ry = table_range(j0.ray_y, ya + dr, yb + dr);
+                have = true;
+            }
+            int box[4];
+            if (!source_range(j, rx, ry, rz, box)) { box[0] = 0; box[1] = 0; box[2] = j.w; box[3] = j.h; }
+            atomicMin(rects + 4 * k, box[0]); atomicMin(rects + 4 * k + 1, box[1]);
+            atomicMax(rects + 4 * k + 2, box[2]); atomicMax(rects + 4 * k + 3, box[3]);
+        }
+    }
+}
+
 }  // namespace p360
 
 extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream) {
@@ -616,6 +725,19 @@ extern "C" int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst
     P360_REQUIRE((reinterpret_cast<uintptr_t>(src_rgb) & 3) == 0 && aligned16(dst_rgbx), where);
     const long long n = (long long)h * w;
     pack_rgbx_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src_rgb, n, reinterpret_cast<uint32_t *>(dst_rgbx));
+    return check_launch(where);
+}
+
+extern "C" int p360_pack_rgbx_rect(const uint8_t *src_rgb, int h, int w, int r0, int r1, int c0, int c1,
+                                   uint8_t *dst_rgbx, void *stream) {
+    using namespace p360;
+    const char *where = "p360_pack_rgbx_rect";
+    P360_REQUIRE(src_rgb && dst_rgbx && h > 0 && w > 0, where);
+    P360_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= h && 0 <= c0 && c0 <= c1 && c1 <= w && c0 % 4 == 0 && r1 - r0 <= 65535, where);
+    P360_REQUIRE((reinterpret_cast<uintptr_t>(src_rgb) & 3) == 0 && aligned16(dst_rgbx), where);
+    if (r1 == r0 || c1 == c0) return 0;
+    dim3 grid(cdiv((c1 - c0 + 3) / 4, 256), r1 - r0);
+    pack_rgbx_rect_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_rgb, w, r0, c0, c1, reinterpret_cast<uint32_t *>(dst_rgbx));
     return check_launch(where);
 }
 
@@ -650,13 +772,29 @@ extern "C" int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, p
     return check_launch(where);
 }
 
+extern "C" int p360_source_rects(const p360_warp_job *jobs_dev, int n_jobs, int H, int W, int abs_row0, int mosaic_h,
+                                 const p360_tile_maps *maps_host, int32_t *rects_dev, void *stream) {
+    using namespace p360;
+    const char *where = "p360_source_rects";
+    P360_REQUIRE(jobs_dev && maps_host && rects_dev && n_jobs > 0 && n_jobs <= 1024 && H > 0 && W > 0, where);
+    TileMaps m;
+    memcpy(&m, maps_host, sizeof(m));
+    if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
+    const long long tiles = (long long)m.tiles_x * m.tiles_y;
+    source_rects_kernel<<<cdiv(tiles, 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const WarpJob *>(jobs_dev), n_jobs, H, W, abs_row0, mosaic_h, m, rects_dev);
+    return check_launch(where);
+}
+
 extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
-                               uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int H, int W,
-                               int want_covered, const p360_tile_maps *maps_host, void *stream) {
+                               uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                               int H, int W, int want_covered, const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_tiles";
     P360_REQUIRE(jobs_host && maps_host && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_jobs > 0 && n_jobs <= TILE_JOBS_MAX && H > 0 && W > 0 && y_begin >= 0 && y_end <= H, where);
+    P360_REQUIRE(x_begin >= 0 && x_begin <= x_end && x_end <= W && x_begin % TILE_X == 0 &&
+                 (x_end % TILE_X == 0 || x_end == W), where);
     TileMaps m;
     memcpy(&m, maps_host, sizeof(m));
     if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
@@ -681,11 +819,11 @@ extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_j
     }
     auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
     if (rgbx)
-        warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8,
-                                                                         y_begin, y_end, H, W, want_covered, m);
+        warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, y_begin, y_end, x_begin, x_end,
+                                                       H, W, want_covered, m);
     else
-        warp_tiles_kernel<false><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8,
-                                                                          y_begin, y_end, H, W, want_covered, m);
+        warp_tiles_kernel<false><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, y_begin, y_end, x_begin, x_end,
+                                                        H, W, want_covered, m);
     return check_launch(where);
 }
 

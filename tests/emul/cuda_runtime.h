@@ -62,7 +62,7 @@ inline thread_local dim3 blockDim, gridDim;
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
-enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 227 * 1024; return cudaSuccess; }
@@ -75,6 +75,11 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 }
 inline cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int value, size_t n, cudaStream_t) { memset(p, value, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                                     int, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+    return cudaSuccess;
+}
 template <class K>
 inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 template <class T>

@@ -618,6 +618,46 @@ def test_row_windows_cut_anywhere(comp):
         assert np.array_equal(strip, full[ya:yb]), (ya, yb)
 
 
+def test_column_windows_equal_full_mosaic(comp):
+    """Windows in both directions — the building block of the streamed end-to-end pipeline and of
+    the column strips of the multi-GPU path: any rows x columns window whose column edges sit on
+    64-column tile edges, computed on its own (halo included), is the same bytes as that part of
+    the full composite.  The three-row ring of the benchmark layout at 1/8 scale (seam-straddling
+    images split into two column runs, horizontal and vertical seams), all three blenders, the
+    seam plan and the dense path, with the banded rectangle download."""
+    import torch
+    regs = synth.make_views(synth.workload("cfg4", scale=8.0), noise=5.0)
+    rng = np.random.default_rng(5)
+    saved = comp.direct
+    try:
+        for kind, direct in (("multiband", True), ("multiband", False), ("linear", True), ("none", True)):
+            comp.direct = direct
+            plan = geo.plan_mosaic(regs, kind == "multiband", 1e9)
+            src = comp.upload(regs)
+            full = comp.composite(regs, src, plan, kind, 5)[0].cpu().numpy()
+            h, w = plan.shape
+            tiles = -(-w // 64)
+            cuts = [(0, 64), (64 * (tiles - 1), w), (64 * (tiles // 3), 64 * (2 * tiles // 3)), (0, w)]
+            cuts += [tuple(int(64 * t) for t in sorted(rng.choice(tiles, 2, replace=False))) for _ in range(2)]
+            for k, (xa, xb) in enumerate(cuts if kind == "multiband" else cuts[:3]):
+                rows = None if k % 2 == 0 else tuple(int(v) for v in sorted(rng.choice(h, 2, replace=False)))
+                ya, yb = (0, h) if rows is None else rows
+                host = torch.full((h, w, 3), 9, dtype=torch.uint8)
+                if comp.device.type == "cuda":
+                    host = host.pin_memory()
+                part, _ = comp.composite(regs, src, plan, kind, 5, rows=rows, cols=(xa, xb), out_host=host.numpy(), bands=3)
+                comp.finish_download()
+                assert part.shape[:2] == (yb - ya, xb - xa)
+                assert np.array_equal(part.cpu().numpy(), full[ya:yb, xa:xb]), (kind, direct, rows, (xa, xb))
+                got = host.numpy()
+                assert np.array_equal(got[ya:yb, xa:xb], full[ya:yb, xa:xb]), (kind, direct, rows, (xa, xb))
+                outside = np.ones((h, w), bool)
+                outside[ya:yb, xa:xb] = False
+                assert bool((got[outside] == 9).all())          # nothing else of the host mosaic was touched
+    finally:
+        comp.direct = saved
+
+
 def test_partial_row_uploads_are_sufficient(comp):
     """A row window reads only some rows of the images it meets (geometry.source_rows_needed,
     interval arithmetic): uploading and packing just those must not change a byte — every other

@@ -52,6 +52,7 @@ test_crop_rectangle_matches_the_reference_scan = gpu.test_crop_rectangle_matches
 test_cropped_stitch_matches_oracle = gpu.test_cropped_stitch_matches_oracle
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
+test_column_windows_equal_full_mosaic = gpu.test_column_windows_equal_full_mosaic
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_partial_row_uploads_are_sufficient = gpu.test_partial_row_uploads_are_sufficient
@@ -234,12 +235,13 @@ def test_seam_plan_candidates_at_full_scale(comp):
     rays = torch.from_numpy(np.concatenate([ray_x, ray_z, ray_y]))
     base = rays.data_ptr()
     jobs = np.zeros(len(crops), dtype=_lib.WARP_JOB)
-    for k, (i, x0, y0, x1, y1, k_r, ty0, ty1) in enumerate(crops):
+    for k, (i, x0, y0, x1, y1, k_r, ty0, ty1, tx0, tx1) in enumerate(crops):
         h, w = regs[i].img.shape[:2]
         jobs[k]["ray_x"], jobs[k]["ray_z"], jobs[k]["ray_y"] = base, base + 8 * len(ray_x), base + 8 * (len(ray_x) + len(ray_z))
         jobs[k]["kr"], jobs[k]["h"], jobs[k]["w"] = k_r, h, w
         jobs[k]["pw"], jobs[k]["ph"], jobs[k]["x0"], jobs[k]["y0"] = x1 - x0, y1 - y0, x0, y0
         jobs[k]["col0"], jobs[k]["row0"], jobs[k]["patch"], jobs[k]["ty0"], jobs[k]["ty1"] = x0, y0, k, ty0, ty1
+        jobs[k]["tx0"], jobs[k]["tx1"] = tx0, tx1
     n = len(crops)
     table = np.zeros(n, dtype=_lib.BAND_PATCH)
     table["w4"] = table["h4"] = 1
