@@ -497,6 +497,11 @@ class Bench:
             self.e2e_step()
         e2e = self.timed(self.e2e_step, steps)
         e2e_crc = mosaic_checksum(e2e["result"]) if rank == 0 and e2e["result"] is not None else None
+        self.h2d_bytes = int(comp.last_upload_bytes)       # what the last e2e step's uploads really copied ...
+        if world > 1:                                      # ... summed over the ranks
+            t = torch.tensor([self.h2d_bytes], dtype=torch.int64, device=comp.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            self.h2d_bytes = int(t.item())
         phases = None
         if world > 1:                      # one more call, host-side phase times of rank 0
             comp.phases = []

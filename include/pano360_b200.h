@@ -142,10 +142,12 @@ int p360_warp_batch(const p360_warp_job *jobs_host, const p360_warp_job *jobs_de
  * edge, so that its tiles are tiles of the whole mosaic.
  *
  * p360_source_rects (K0s): after the plan, per patch the rectangle {u0, v0, u1, v1} (source pixels,
- * half-open; rects_dev: 4 int32 per job, initialised to {INT_MAX, INT_MAX, INT_MIN, INT_MIN}) that
- * covers every tap p360_warp_tiles can load for it — the same interval arithmetic, over the tiles
- * where the patch is wanted as float or is the solo candidate, BORDER_REFLECT folded in.  Pixels
- * outside are never read: only that rectangle of the image has to be uploaded.
+ * half-open) that covers every tap p360_warp_tiles can load for it — the same interval arithmetic,
+ * over the tiles where the patch is wanted as float or is the solo candidate, BORDER_REFLECT folded
+ * in — followed by {x0, y0, x1, y1}: the box (buffer pixels) around those tiles.  rects_dev: 8 int32
+ * per job, initialised to {INT_MAX, INT_MAX, INT_MIN, INT_MIN} twice.  Pixels outside the first
+ * rectangle are never read: only it has to be uploaded; a window of the mosaic that does not meet
+ * the second one does not need the image at all.
  */
 int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_band_patch *patches_dev,
                          int H, int W, int abs_row0, int mosaic_h,

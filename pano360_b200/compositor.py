@@ -141,7 +141,8 @@ class DeviceSources:
     hats: dict = field(default_factory=dict)   # (h, w) -> (hat_y, hat_x) f64 tensors
     shapes: list = field(default_factory=list)
     ready: list = None                 # per image CUDA event (uploads issued on the copy stream)
-    rows: list = None                  # per image (r0, r1): only these rows are resident / packed (None: all)
+    rows: list = None                  # per image (r0, r1) or (r0, r1, c0, c1): only that part is resident / packed (None: all)
+    bytes_up: int = 0                  # image bytes that crossed PCIe for this set
 
 
 class Compositor:
@@ -190,7 +191,10 @@ class Compositor:
         # (p360_warp_direct) — and the seam zone, the only place where float patches, owner keys and
         # coarse levels exist.  P360_DIRECT=0: every patch warped to float, maps from the owner keys.
         self.direct = os.environ.get("P360_DIRECT", "1") == "1"
+        # upload only the rectangle of every image the seam plan can sample (``source_rects``); P360_SOURCE_RECTS=0: whole images
+        self.partial_uploads = os.environ.get("P360_SOURCE_RECTS", "1") == "1"
         self.last_covered = None
+        self.last_upload_bytes = 0     # image bytes the last ``upload`` sent over PCIe
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -257,13 +261,20 @@ class Compositor:
     # -- sources --------------------------------------------------------------
     def pack_pixels(self, dev_img, rows=None, out=None):
         """u8 x 3 -> u8 x 4 (RGBX) on the device: a bilinear tap of the warp is then one aligned
-        32-bit load.  4-channel images are used as they are.  ``rows = (r0, r1)``: only those rows
-        hold data (and only they are converted)."""
+        32-bit load.  4-channel images are used as they are.  ``rows = (r0, r1)`` or ``(r0, r1, c0,
+        c1)``: only those rows (that rectangle) hold data, and only they are converted."""
         h, w, c = dev_img.shape
         if c == 4:
             return dev_img
         packed = out if out is not None else torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
-        r0, r1 = (0, h) if rows is None else rows
+        r0, r1 = (0, h) if rows is None else rows[:2]
+        c0, c1 = (0, w) if rows is None or len(rows) < 4 else rows[2:]
+        if (c0, c1) != (0, w):
+            c0 = c0 // 4 * 4
+            if r1 > r0 and c1 > c0:
+                self._traced("K1p_pack_rgbx", 7 * (r1 - r0) * (c1 - c0), "p360_pack_rgbx_rect", dev_img.data_ptr(), h, w,
+                             r0, r1, c0, c1, packed.data_ptr(), self.stream)
+            return packed
         r0 = r0 // 4 * 4                                   # keeps source and destination addresses aligned
         if r1 > r0:
             self._traced("K1p_pack_rgbx", 7 * (r1 - r0) * w, "p360_pack_rgbx", dev_img.data_ptr() + 3 * w * r0, r1 - r0, w,
@@ -290,7 +301,8 @@ class Compositor:
             pixels.append(None if p is None else self.pack_pixels(p, r, out=outs[i]))
         return DeviceSources(pixels, raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
 
-    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None, reuse=False):
+    def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None, reuse=False,
+               rects_of=None):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
@@ -298,15 +310,20 @@ class Compositor:
         every image gets a ``ready`` event, so the warp of the first images
         starts while the last ones are still crossing PCIe.  ``order`` (a
         permutation of the indices) is the order in which the copies are issued.  ``rows_of``
-        ({image: (r0, r1)}, ``source_rows``) uploads only the rows a composite will read.
+        ({image: (r0, r1)}, ``source_rows``) uploads only the rows a composite will read;
+        ``rects_of`` ({image: (r0, r1, c0, c1)}, ``source_rects``) only that rectangle.  ``bytes_up``
+        of the result counts what crossed PCIe.
         ``reuse``: the images go to device buffers kept from the previous such call (same slot,
         same shape) — for callers that drop the result before they upload again (``stitch``):
         stable addresses let ``composite`` reuse what it prepared."""
         n = len(regions)
         src = DeviceSources([None] * n, [None] * n)
+        if rects_of is not None:
+            rows_of = rects_of
         if rows_of is not None:
             src.rows = [rows_of.get(i) for i in range(n)]
         src.shapes = [reg.img.shape[:2] for reg in regions]
+        src.bytes_up = 0
         lut0 = None
         main = torch.cuda.current_stream(self.device)
         side = self.copy_stream() if overlap else main
@@ -323,25 +340,41 @@ class Compositor:
                     raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
                 host = torch.from_numpy(np.ascontiguousarray(img))
                 part = None if rows_of is None else rows_of.get(i)
-                if part is not None:
+                rect = False
+                if part is not None and len(part) == 4 and (part[2] > 0 or part[3] < w):
+                    part = (part[0], part[1], part[2] // 4 * 4, part[3])     # (the packing converts 4 pixels per thread)
+                    rect = True
+                    whole = host
+                    host = host[part[0]:part[1], part[2]:part[3]]          # a strided view
+                elif part is not None:
                     part = (part[0] // 4 * 4, part[1])        # (4-row granularity: aligned addresses for the packing)
                     host = host[part[0]:part[1]]
+                src.bytes_up += host.numel()
                 if (h, w) not in src.hats:
                     fresh = ("hat", h) not in self._consts or ("hat", w) not in self._consts
                     src.hats[(h, w)] = (self._constant(("hat", h), lambda: geo.hat(h)),
                                         self._constant(("hat", w), lambda: geo.hat(w)))
                     if overlap and fresh:
                         side.wait_stream(main)               # hat tables were copied on the main stream
-                if not host.is_pinned() and host.numel() >= self.stage_min_bytes:
+                pinned = (whole if rect else host).is_pinned()
+                if not pinned and (host.numel() >= self.stage_min_bytes or rect):
                     host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
                 with torch.cuda.stream(side):
-                    if reuse:
+                    if reuse or rect:
                         slot = (n, i, tuple(img.shape))
-                        dev_img = self._images.get(slot)
+                        dev_img = self._images.get(slot) if reuse else None
                         if dev_img is None:
-                            dev_img = self._images[slot] = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
-                        target = dev_img if part is None else dev_img[part[0]:part[1]]
-                        target.copy_(host, non_blocking=host.is_pinned())
+                            dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+                            if reuse:
+                                self._images[slot] = dev_img
+                        if rect:           # the rectangle lands at its place in the full-size device image
+                            r0, r1, c0, c1 = part
+                            ch = img.shape[2]
+                            _lib.call("p360_copy_rect", dev_img.data_ptr() + ch * (r0 * w + c0), ch * w, host.data_ptr(),
+                                      host.stride(0), ch * (c1 - c0), r1 - r0, side.cuda_stream)
+                        else:
+                            target = dev_img if part is None else dev_img[part[0]:part[1]]
+                            target.copy_(host, non_blocking=host.is_pinned())
                     elif part is None:
                         dev_img = host.to(self.device, non_blocking=host.is_pinned())
                     else:                                    # rows outside `part` stay unwritten: nobody reads them
@@ -368,6 +401,7 @@ class Compositor:
                 src.luts[i] = lut0
             else:
                 src.luts[i] = self._to_device(geo.sample_lut(gains[i]))
+        self.last_upload_bytes = src.bytes_up
         return src
 
     def _constant(self, key, make):
@@ -503,6 +537,61 @@ class Compositor:
         if plan._crops is not None:
             plan._crops[key] = needed
         return needed
+
+    def source_rects(self, regions, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, cols=None):
+        """{image: (r0, r1, c0, c1)}: the rectangle of every image that ``composite`` (of the whole
+        mosaic, or of the given window) can sample — for ``upload(rects_of=...)``.  From the seam
+        plan itself (K0 + K0s, before any pixel exists on the device): an image is only read where it
+        is the single candidate of a tile or takes part in a seam.  The rectangles of the whole
+        mosaic also cover every window of it (a window's plan is a subset of the whole plan).
+        None when the composite would not go through the seam plan (other blenders, the dense
+        warp, the full-resolution path): then everything may be read."""
+        if not (self.direct and self.partial_uploads and kind == "multiband" and n_levels > 1) or self.needs_exact(regions):
+            return None
+        key = ("rects", len(regions), proj, rows, cols, kind, n_levels)
+        if plan._crops is not None and key in plan._crops:
+            return plan._crops[key]
+        crops, tables, top, left, shape, _, _ = self._window_geometry(regions, plan, kind, n_levels, proj, rows, cols)
+        rects = None
+        if 0 < len(crops) <= 256:
+            shapes = {c[0]: regions[c[0]].img.shape[:2] for c in crops}
+            jobs, _, keep = self._warp_jobs(None, crops, tables, origin=(left, top), pools=False, shapes=shapes)
+            n = len(jobs)
+            pad, bands = geo.coarse_band_plan(n_levels)
+            table = np.zeros(n, dtype=_lib.BAND_PATCH)
+            table["w4"], table["h4"] = (jobs["pw"] + 2 * pad + 3) // 4, (jobs["ph"] + 2 * pad + 3) // 4
+            maps, maps_keep = self._tile_maps(table, len(bands), shape[0], shape[1], pad, top, seam_plan=True)
+            dev_jobs = self._to_device(jobs.view(np.uint8).reshape(-1))
+            big, small = np.iinfo(np.int32).max, np.iinfo(np.int32).min
+            dev_rects = torch.tensor([[big, big, small, small] * 2] * n, dtype=torch.int32, device=self.device)
+            _lib.call("p360_seam_plan_build", _lib.ptr(dev_jobs), n, None, shape[0], shape[1], top, plan.shape[0],
+                      maps.ctypes.data, self.stream)
+            _lib.call("p360_source_rects", _lib.ptr(dev_jobs), n, shape[0], shape[1], top, plan.shape[0],
+                      maps.ctypes.data, _lib.ptr(dev_rects), self.stream)
+            found = dev_rects.cpu().numpy()
+            del maps_keep, keep
+            rects, used = {}, {}
+            for c, (u0, v0, u1, v1, x0, y0, x1, y1) in zip(crops, found.tolist()):
+                h, w = shapes[c[0]]
+                if u1 <= u0 or v1 <= v0:
+                    u0, v0, u1, v1 = 0, 0, min(4, w), min(4, h)       # never sampled: a token corner keeps the tables uniform
+                else:
+                    used.setdefault(c[0], []).append((x0 + left, y0 + top, x1 + left, y1 + top))
+                old = rects.get(c[0])
+                rects[c[0]] = (v0, v1, u0, u1) if old is None else (min(v0, old[0]), max(v1, old[1]), min(u0, old[2]), max(u1, old[3]))
+            if plan._crops is not None:
+                plan._crops[("used",) + key[1:]] = used
+        if plan._crops is not None:
+            plan._crops[key] = rects
+        return rects
+
+    def used_boxes(self, regions, plan, kind, n_levels=5, proj=geo.SphProj):
+        """{image: [(x0, y0, x1, y1), ...]}: per column run of every image, the box (mosaic pixels)
+        around the tiles it is read for (from ``source_rects``): a window of the mosaic whose
+        buffer does not meet any of them does not need the image.  None without the seam plan."""
+        if self.source_rects(regions, plan, kind, n_levels, proj) is None:
+            return None
+        return plan._crops.get(("used", len(regions), proj, None, None, kind, n_levels))
 
     def new_owner_state(self, shape):
         """(owner keys u64, covered u8) for a mosaic (or strip) of ``shape``."""
@@ -1233,40 +1322,67 @@ class Compositor:
                 self.last_covered = self.covered_mask(patches, shape)
         return result(strip), patches
 
-    def streamed_windows(self, plan, kind, n_levels, windows=3):
-        """Plan of ``composite_streamed``: the order in which to upload the images (top edge
-        first) and row windows [ya, yb) of the mosaic with the number of uploads each one has
-        to wait for — window k needs nothing beyond the first ``count_k`` images."""
+    def streamed_windows(self, plan, kind, n_levels, windows=8, used=None):
+        """Plan of ``composite_streamed``: the order in which to upload the images (left edge
+        first; an image that straddles the +-pi seam counts with its left column run) and column
+        windows [xa, xb) of the mosaic, on 64-column tile edges, with the number of uploads each
+        one has to wait for — a window needs nothing beyond the first ``count`` images — sorted by
+        that number: the order in which they can be composited."""
         n = len(plan.boxes)
-        height = plan.shape[0]
-        halo = self.window_margin(kind, n_levels)
-        order = sorted(range(n), key=lambda i: (plan.boxes[i][1], i))
+        width = plan.shape[1]
+        margin = self.col_margin(kind, n_levels)
+        reach = self.blur_reach(kind, n_levels)
+        runs = {i: geo.active_column_runs(i, box, plan, dilate=2 * reach)
+                for i, box in enumerate(plan.boxes) if box[2] > box[0] and box[3] > box[1]}
+        if used is not None:        # (``used_boxes``) where the seam plan reads each image: tighter than its box
+            runs = {i: sorted((b[0], b[2]) for b in boxes) for i, boxes in used.items() if boxes}
+        order = sorted(range(n), key=lambda i: (runs[i][0][0] if i in runs else 0, plan.boxes[i][1], i))
         rank = {i: r for r, i in enumerate(order)}
-        last = np.zeros(height, dtype=np.int64)           # per mosaic row: rank of the last upload it needs
-        for i, (x0, y0, x1, y1) in enumerate(plan.boxes):
-            if x1 > x0 and y1 > y0:
-                a, b = max(0, y0 - halo), min(height, y1 + halo)
+        last = np.zeros(width, dtype=np.int64)            # per mosaic column: rank of the last upload it needs
+        for i, parts in runs.items():
+            for a, b in parts:
+                a, b = max(0, a - margin), min(width, b + margin)
                 last[a:b] = np.maximum(last[a:b], rank[i])
-        last = np.maximum.accumulate(last)                # windows are prefixes of the upload order
-        cuts = [0]
-        for k in range(1, windows):
-            y = int(np.searchsorted(last, -(-k * n // windows) - 1, side="right"))   # rows done with k/windows of the images
-            if y > cuts[-1] and y < height:
-                cuts.append(y)
-        cuts.append(height)
-        return order, [(a, b, int(last[b - 1]) + 1) for a, b in zip(cuts, cuts[1:]) if b > a]
+        # per 64-column tile column: how many uploads (in that order) it waits for
+        tiles = -(-width // 64)
+        need = np.array([int(last[64 * t:64 * (t + 1)].max()) + 1 for t in range(tiles)])
+        # consecutive tile columns at the same stage (k-th `windows`-th of the uploads) form a window;
+        # windows run in the order their images arrive — not necessarily left to right: the right
+        # end of a 360-degree mosaic belongs to the images that straddle the seam, which come first
+        stage = -(-need * windows // max(n, 1))
+        wins, a = [], 0
+        for t in range(1, tiles + 1):
+            if t == tiles or stage[t] != stage[a]:
+                wins.append((64 * a, min(64 * t, width), int(need[a:t].max())))
+                a = t
+        # a window pays a halo on both sides: slivers join the neighbour that delays them least
+        while len(wins) > 1:
+            k = min(range(len(wins)), key=lambda i: wins[i][1] - wins[i][0])
+            if wins[k][1] - wins[k][0] >= 512:
+                break
+            near = [j for j in (k - 1, k + 1) if 0 <= j < len(wins)]
+            j = min(near, key=lambda i: max(wins[i][2], wins[k][2]))
+            lo, hi = min(j, k), max(j, k)
+            wins[lo:hi + 1] = [(wins[lo][0], wins[hi][1], max(wins[lo][2], wins[hi][2]))]
+        wins.sort(key=lambda w: (w[2], w[0]))
+        return order, wins
 
-    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=3, bands=4, exact=False):
+    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=8, bands=2, exact=False):
         """Upload + composite + download with both PCIe directions busy: the images are uploaded
-        top edge first, and as soon as the images a row window of the mosaic depends on have
-        arrived that window is composited (exactly the bytes of the whole composite, see
-        ``composite``) and downloaded, while the uploads for the windows below continue on their
-        own stream.  ``out_host``: pinned uint8 H x W x 3.  Call ``finish_download`` afterwards."""
-        order, wins = self.streamed_windows(plan, kind, n_levels, windows)
-        src = self.upload(regions, overlap=True, order=order, reuse=True)
+        left edge first — of each only the rectangle the seam plan can sample (``source_rects``) —
+        and as soon as the images a column window of the mosaic depends on have arrived that
+        window is composited (exactly the bytes of the whole composite, see ``composite``) and
+        downloaded, while the uploads for the windows to its right continue on their own stream.
+        ``out_host``: pinned uint8 H x W x 3.  Call ``finish_download`` afterwards."""
+        rects = None if exact else self.source_rects(regions, plan, kind, n_levels, proj)
+        order, wins = self.streamed_windows(plan, kind, n_levels, windows,
+                                            used=None if rects is None else self.used_boxes(regions, plan, kind, n_levels, proj))
+        self.prepared_max = max(self.prepared_max, len(wins) + 2)
+        src = self.upload(regions, overlap=True, order=order, reuse=True, rects_of=rects,
+                          need=None if rects is None else set(rects))
         strips = []
-        for ya, yb, _ in wins:
-            strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, rows=(ya, yb), out_host=out_host,
+        for xa, xb, _ in wins:
+            strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, cols=(xa, xb), out_host=out_host,
                                       bands=bands, exact=exact)
             strips.append(strip)          # the download stream still reads it: keep it allocated
         self._keep["streamed"] = (strips, src)

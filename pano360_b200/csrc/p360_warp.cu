@@ -641,8 +641,9 @@ pack_rgbx_rect_kernel(const uint8_t *__restrict__ src, int w, int r0, int c0, in
 // where it is warped to float (`wneed`) and the solo tiles it writes directly, each pushed through
 // the same interval arithmetic as the alpha bounds (ray tables -> K R ray -> source position),
 // grown by the bilinear footprint and the fixed-point slack.  Uploading just that rectangle of
-// every image is exact: nothing else is ever loaded.  rects[4 * patch] = {u0, v0, u1, v1}
-// (half-open, clipped to the image; initialise to {MAX, MAX, MIN, MIN}); positions beyond the image
+// every image is exact: nothing else is ever loaded.  rects[8 * patch] = {u0, v0, u1, v1} (source
+// pixels) and {x0, y0, x1, y1} (the buffer pixels of the tiles the patch is read for): half-open,
+// clipped to the image / the patch; initialise to {MAX, MAX, MIN, MIN} twice; positions beyond the image
 // fold back by BORDER_REFLECT; a patch partly behind the camera on a tile takes the whole image.
 // One thread per tile.
 // taps of positions in [a, b] along an axis of n pixels: floor(p) and floor(p) + 1, indices outside
@@ -710,8 +711,10 @@ source_rects_kernel(const WarpJob *__restrict__ jobs, int n_jobs, int H, int W, 
             }
             int box[4];
             if (!source_range(j, rx, ry, rz, box)) { box[0] = 0; box[1] = 0; box[2] = j.w; box[3] = j.h; }
-            atomicMin(rects + 4 * k, box[0]); atomicMin(rects + 4 * k + 1, box[1]);
-            atomicMax(rects + 4 * k + 2, box[2]); atomicMax(rects + 4 * k + 3, box[3]);
+            atomicMin(rects + 8 * k, box[0]); atomicMin(rects + 8 * k + 1, box[1]);
+            atomicMax(rects + 8 * k + 2, box[2]); atomicMax(rects + 8 * k + 3, box[3]);
+            atomicMin(rects + 8 * k + 4, px0); atomicMin(rects + 8 * k + 5, py0);      // where in the buffer it is read
+            atomicMax(rects + 8 * k + 6, px1); atomicMax(rects + 8 * k + 7, py1);
         }
     }
 }

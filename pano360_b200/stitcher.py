@@ -37,10 +37,11 @@ from .geometry import CylProj, SphProj  # noqa: F401  (module globals, looked up
 
 MAX_RESOLUTION = 1400
 
-# Row windows of the streamed end-to-end pipeline (Compositor.composite_streamed); 0 = off.
-# B200, cfg4 (36 x 4000x3000 -> 8819 x 31654): 46.9 ms without, 40.2 ms with 3 windows (4 and 6: the
-# same — the tail is the part of the mosaic that needs the last images, profiles/r02_e2e_probe.log).
-STREAM_WINDOWS = int(os.environ.get("P360_STREAM_WINDOWS", "3"))
+# Column windows of the streamed end-to-end pipeline (Compositor.composite_streamed); 0 = off.
+# B200, cfg4 (36 x 4000x3000 -> 8819 x 31654): 46.9 ms without; 40.2 ms with 3 ROW windows (the tail
+# was the third of the mosaic that needs the bottom row of images, profiles/r02_e2e_probe.log);
+# column windows depend on a few images each, so the tail is one narrow window.
+STREAM_WINDOWS = int(os.environ.get("P360_STREAM_WINDOWS", "12"))
 STREAM_MIN_PIXELS = 1 << 24
 
 _compositors = {}

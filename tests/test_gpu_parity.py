@@ -658,6 +658,83 @@ def test_column_windows_equal_full_mosaic(comp):
         comp.direct = saved
 
 
+def _scrambled_outside(regs, rects, seed=3):
+    """Copies of the images with everything outside their rectangle replaced by noise."""
+    from pano360_b200.camera import Image
+    rng = np.random.default_rng(seed)
+    out = []
+    for i, reg in enumerate(regs):
+        img = rng.integers(0, 256, reg.img.shape, dtype=np.uint8)
+        if i in rects:
+            r0, r1, c0, c1 = rects[i]
+            img[r0:r1, c0:c1] = reg.img[r0:r1, c0:c1]
+        out.append(Image(img, reg.rot, reg.intr))
+    return out
+
+
+def test_source_rectangles_cover_every_tap(comp):
+    """K0s (p360_source_rects): the seam plan names, per image, the rectangle that holds every
+    source pixel the tile warp can load — an image is read only where it is a tile's single
+    candidate or takes part in a seam.  Scrambling everything outside the rectangles must not
+    change a byte (of the whole mosaic with the whole plan's rectangles — also for windows of it
+    planned on their own — and of a row window with that window's rectangles), and uploading just
+    the rectangles (``upload(rects_of=...)``, the rest of the device image uninitialised) gives
+    the same bytes.  Small rig here (the tile-granular reach of the seam zone covers most of a
+    500-pixel image: the saving is in the rows of a window); the benchmark rig at full size on
+    the GPU, where a fifth of every image is never read."""
+    from dataclasses import replace
+    wl = replace(synth.workload("cfg1"), width=1600, height=500, focal=1800.0, yaws=(-0.55, 0.0, 0.55),
+                 pitches=(0.0, 0.02, -0.02))
+    regs = synth.make_views(wl, noise=5.0)
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    hh, ww = plan.shape
+    tiles = -(-ww // 64)
+    total = sum(r.img.nbytes for r in regs)
+    for levels in (2, 5):
+        full = comp.composite(regs, comp.upload(regs), plan, "multiband", levels)[0].cpu().numpy()
+        for rows in (None, (288, 352)):
+            rects = comp.source_rects(regs, plan, "multiband", levels, rows=rows)
+            assert rects is not None and set(rects) == set(range(len(regs)))
+            assert all(0 <= r0 < r1 <= 500 and 0 <= c0 < c1 <= 1600 for r0, r1, c0, c1 in rects.values())
+            scrambled = _scrambled_outside(regs, rects)
+            src = comp.upload(scrambled)
+            ya, yb = rows or (0, hh)
+            got = comp.composite(scrambled, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+            assert np.array_equal(got, full[ya:yb]), (levels, rows)
+            if rows is None:        # windows planned on their own read subsets of the whole plan's rectangles
+                for win_rows, cols in [(None, (0, 64 * (tiles // 4))), ((hh // 3, hh // 2), None),
+                                       ((hh // 5, 4 * hh // 5), (64 * (tiles // 2), ww))]:
+                    part = comp.composite(scrambled, src, plan, "multiband", levels, rows=win_rows, cols=cols)[0].cpu().numpy()
+                    wa, wb = win_rows or (0, hh)
+                    xa, xb = cols or (0, ww)
+                    assert np.array_equal(part, full[wa:wb, xa:xb]), (levels, win_rows, cols)
+            else:
+                assert sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in rects.values()) < 0.6 * total / 3
+            src = comp.upload(regs, rects_of=rects, need=set(rects))
+            assert src.bytes_up <= total and (rows is None or src.bytes_up < 0.6 * total)
+            got = comp.composite(regs, src, plan, "multiband", levels, rows=rows)[0].cpu().numpy()
+            assert np.array_equal(got, full[ya:yb]), (levels, rows)
+    # other blenders read whole boxes: no rectangles
+    assert comp.source_rects(regs, geo.plan_mosaic(regs, False, 1e9), "linear") is None
+    if comp.device.type != "cuda":
+        return
+    wl = synth.workload("cfg4")
+    regs = synth.make_views(wl)
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    rects = comp.source_rects(regs, plan, "multiband", wl.n_levels)
+    share = sum((r1 - r0) * (c1 - c0) * 3 for r0, r1, c0, c1 in rects.values()) / sum(r.img.nbytes for r in regs)
+    assert share < 0.85, share
+    full = comp.composite(regs, comp.upload(regs), plan, "multiband", wl.n_levels)[0].clone()
+    comp.release()
+    import torch
+    got = comp.composite(regs, comp.upload(_scrambled_outside(regs, rects)), plan, "multiband", wl.n_levels)[0]
+    assert bool(torch.equal(got, full))
+    comp.release()
+    got = comp.composite(regs, comp.upload(regs, rects_of=rects, need=set(rects)), plan, "multiband", wl.n_levels)[0]
+    assert bool(torch.equal(got, full))
+    comp.release(everything=True)
+
+
 def test_partial_row_uploads_are_sufficient(comp):
     """A row window reads only some rows of the images it meets (geometry.source_rows_needed,
     interval arithmetic): uploading and packing just those must not change a byte — every other

@@ -53,6 +53,7 @@ test_cropped_stitch_matches_oracle = gpu.test_cropped_stitch_matches_oracle
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_column_windows_equal_full_mosaic = gpu.test_column_windows_equal_full_mosaic
+test_source_rectangles_cover_every_tap = gpu.test_source_rectangles_cover_every_tap
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
 test_partial_row_uploads_are_sufficient = gpu.test_partial_row_uploads_are_sufficient
@@ -67,10 +68,11 @@ test_batched_blur_paths = gpu.test_batched_blur_paths
 
 
 def test_streamed_windows_pipeline(st, monkeypatch, restore_globals):
-    """(Host build only until the stream / event choreography has run on a B200; then it moves to
-    test_gpu_parity.py.)  The opt-in end-to-end pipeline that overlaps the two PCIe directions (uploads ordered top
-    edge first, row windows composited and downloaded as their images arrive) returns the bytes
-    of the plain stitch, for every blender and window count."""
+    """The end-to-end pipeline that overlaps the two PCIe directions (uploads ordered left edge
+    first, only the rectangle of each image the seam plan reads; column windows composited and
+    downloaded as their images arrive) returns the bytes of the plain stitch, for every blender
+    and window count.  (The gpu tier runs it at full size: test_full_size_cfg3_windows_and_properties /
+    the bench's checksum.)"""
     import torch
     regs = gpu.synth.make_views(gpu.synth.workload("cfg3", scale=8.0), noise=10.0)
     st.MAX_RESOLUTION = 10 ** 9
@@ -85,9 +87,14 @@ def test_streamed_windows_pipeline(st, monkeypatch, restore_globals):
             got = st.stitch(regs, blender=st.BLENDERS[kind], out=out)
             assert got is out and gpu.np.array_equal(got, want), (kind, windows)
     comp = st._compositor()
-    order, wins = comp.streamed_windows(gpu.geo.plan_mosaic(regs, True, 1e9), "multiband", 5, 3)
-    assert sorted(order) == list(range(len(regs))) and wins[0][0] == 0 and wins[-1][2] == len(regs)
-    assert all(a[1] == b[0] and a[2] <= b[2] for a, b in zip(wins, wins[1:])) and len(wins) >= 2
+    plan = gpu.geo.plan_mosaic(regs, True, 1e9)
+    for used in (None, comp.used_boxes(regs, plan, "multiband", 5)):
+        order, wins = comp.streamed_windows(plan, "multiband", 5, 3, used=used)
+        assert sorted(order) == list(range(len(regs))) and wins[-1][2] == len(regs) and len(wins) >= 2
+        assert all(a[2] <= b[2] for a, b in zip(wins, wins[1:]))          # in the order their images arrive
+        cover = sorted(w[:2] for w in wins)                                # ... they tile the mosaic's columns
+        assert cover[0][0] == 0 and cover[-1][1] == plan.shape[1] and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        assert all(a % 64 == 0 for a, _ in cover)
 
 
 def test_pageable_buffers_are_staged(st, comp, monkeypatch, restore_globals):
