@@ -997,9 +997,9 @@ class Compositor:
             dev_table.copy_(prep["pristine"])                     # (K0 grows the `own` boxes in it)
             self._traced("K0_seam_plan", 216 * n, "p360_seam_plan_build", _lib.ptr(dev_wjobs), n, _lib.ptr(dev_table),
                          h, w, row_origin, seam["mosaic_h"], maps.ctypes.data, self.stream)
-            if src.ready is not None:          # a tile reads whichever images meet it: all uploads first
+            if src.ready is not None:          # a tile reads whichever images meet it: their uploads first
                 main = torch.cuda.current_stream(self.device)
-                for i in sorted({c[0] for c in crops}):
+                for i in sorted({c[0] for c in crops} if seam.get("reads") is None else seam["reads"]):
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
             xa, xb = (0, w) if cols is None else cols
@@ -1247,6 +1247,20 @@ class Compositor:
             local_cols = (xa - left, xb - left)
         return crops, tables, top, left, (wb - top, right - left), (ya - top, yb - top), local_cols
 
+    def _images_read(self, regions, plan, kind, n_levels, proj, crops, top, left, shape):
+        """The images a window's tile warp can sample, if the whole mosaic's seam plan is known
+        (``source_rects`` ran for this plan): those the plan reads somewhere inside the window's
+        buffer.  A patch the whole plan reads nowhere in the buffer is `present` in none of its
+        tiles, so it takes no part in the window's plan either — its job stays in the table, its
+        pixels are never loaded, and the window need not wait for its upload.  None: unknown,
+        every image of the crops counts."""
+        used = plan._crops.get(("used", len(regions), proj, None, None, kind, n_levels)) if plan._crops is not None else None
+        if used is None:
+            return None
+        x0, y0, x1, y1 = left, top, left + shape[1], top + shape[0]
+        return sorted({c[0] for c in crops
+                       if any(b[0] < x1 and b[2] > x0 and b[1] < y1 and b[3] > y0 for b in used.get(c[0], ()))})
+
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
                   on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None):
         """warp + blend for the whole mosaic or for a window of it: rows [ya, yb) and / or columns
@@ -1306,7 +1320,8 @@ class Compositor:
             patches = prep["patches"]
             self._keep["warp"] = prep["keep"][:3] + (prep["jobs"],)
             seam = {"prepared": prep, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": prep["keep"][3],
-                    "want_covered": want_covered}
+                    "want_covered": want_covered,
+                    "reads": self._images_read(regions, plan, kind, n_levels, proj, crops, top, left, shape)}
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels, out_host=out_host,
                                      seam=seam, **window)
             return result(strip), patches
