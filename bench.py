@@ -377,8 +377,9 @@ class Bench:
                 for k in range(4):                        # (one warm run, then the best of three)
                     torch.cuda.synchronize()
                     ev[0].record(torch.cuda.current_stream())
-                    if parts[rank][1] > parts[rank][0]:
-                        comp.composite(self.regions, comp.pack_sources(self.raw), plan, kind, levels, rows=parts[rank])
+                    if not strips.is_empty(parts[rank]):
+                        rows, cols = strips.window_of(parts[rank], plan.shape)
+                        comp.composite(self.regions, comp.pack_sources(self.raw), plan, kind, levels, rows=rows, cols=cols)
                     ev[1].record(torch.cuda.current_stream())
                     torch.cuda.synchronize()
                     if k:
@@ -397,8 +398,9 @@ class Bench:
         PKL user hands to stitch()), and make the rows the strip reads resident in HBM as uploaded."""
         torch, comp, wl, plan, rank = self.torch, self.comp, self.wl, self.plan, self.rank
         self.parts = parts
-        rows = parts[rank]
-        need = set(self.strips.images_for_rows(plan, rows, self.halo)) if rows[1] > rows[0] else set()
+        part = parts[rank]
+        rows, cols = self.strips.window_of(part, plan.shape)
+        need = set(self.strips.images_for_part(plan, part, wl.blend, wl.n_levels))
         if wl.equalize:
             need = set(range(wl.n_views))
         missing = need - self.rendered
@@ -412,12 +414,16 @@ class Bench:
             self.rendered |= missing
         self.need = need
         self.rows_of = None
-        if self.world > 1 and not wl.equalize and rows[1] > rows[0]:
-            self.rows_of = comp.source_rows(self.regions, plan, wl.blend, wl.n_levels, rows=rows)
+        if not wl.equalize and not self.strips.is_empty(part):
+            # the part of every image this rank's strip reads (the seam plan's rectangles, else rows) —
+            # what stitch() / stitch_strips() upload
+            self.rows_of = comp.source_rects(self.regions, plan, wl.blend, wl.n_levels, rows=rows, cols=cols)
+            if self.rows_of is None and self.world > 1:
+                self.rows_of = comp.source_rows(self.regions, plan, wl.blend, wl.n_levels, rows=rows, cols=cols)
+            if self.rows_of is not None:
+                need &= set(self.rows_of)
         self.raw = comp.upload(self.regions, need=need, pack=False, rows_of=self.rows_of)   # u8 x 3 as uploaded, resident in HBM
-        width3 = {i: int(np.prod(self.regions[i].img.shape[1:])) for i in need}
-        self.h2d_bytes = sum((self.rows_of[i][1] - self.rows_of[i][0] if self.rows_of and i in self.rows_of
-                              else self.regions[i].img.shape[0]) * width3[i] for i in need)
+        self.h2d_bytes = self.raw.bytes_up
 
     def barrier(self):
         if self.world > 1:
@@ -588,9 +594,12 @@ class Bench:
                        "n_levels": wl.n_levels if wl.blend == "multiband" else None, "equalize": wl.equalize,
                        "mosaic": list(plan.shape), "mosaic_mpix": mpix, "patch_mpix_reference_boxes": p_px / 1e6,
                        "patch_mpix_after_seam_split": crop_px / 1e6,
-                       "strips": [list(p) for p in self.parts], "strip_cuts": self.tuned or "model", "halo_rows": self.halo,
-                       "timed_region": "sources resident in HBM as uploaded (u8 x 3); RGBX packing, gains, warp, blend and "
-                                       "the gather of the strips are all inside",
+                       "strips": [list(p) for p in self.parts], "strip_axis": "cols" if len(self.parts[0]) == 4 else "rows",
+                       "strip_cuts": self.tuned or "model", "halo_rows": self.halo,
+                       "halo_cols": self.strips.col_halo(wl.blend, wl.n_levels),
+                       "timed_region": "sources resident in HBM as uploaded (u8 x 3; of each image the rectangle the seam plan "
+                                       "reads, as stitch() uploads it); RGBX packing, gains, seam plan, warp, blend and the "
+                                       "gather of the strips are all inside",
                        "l2": "no flush: each step streams >> 126 MB (model bytes %.1f GB) so nothing survives in L2 between steps"
                              % (total_bytes / 1e9)},
             "clocks": clock_summary,
@@ -622,16 +631,12 @@ class Bench:
     def crop_pixels(self):
         """Patch pixels this rank's composite covers (after the seam split; its row window only)."""
         comp, wl = self.comp, self.wl
-        rows = self.parts[self.rank]
-        if rows[1] <= rows[0]:
+        part = self.parts[self.rank]
+        if self.strips.is_empty(part):
             return 0
-        reach = comp.blur_reach(wl.blend, wl.n_levels)
-        if self.world == 1:
-            crops, _ = comp.plan_crops(self.regions, self.plan, split_dilate=2 * reach)
-        else:
-            wa, wb = comp.window_rows(rows, wl.blend, wl.n_levels, self.plan.shape[0])
-            crops, _ = comp.plan_crops(self.regions, self.plan, rows=(wa, wb), row_align=4 if reach else 1,
-                                       split_dilate=2 * reach)
+        rows, cols = (None, None) if self.world == 1 else self.strips.window_of(part, self.plan.shape)
+        from pano360_b200 import geometry as geo
+        crops = comp._window_geometry(self.regions, self.plan, wl.blend, wl.n_levels, geo.SphProj, rows, cols)[0]
         return int(sum((c[3] - c[1]) * (c[4] - c[2]) for c in crops))
 
     def block_stats(self):

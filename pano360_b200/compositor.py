@@ -514,20 +514,16 @@ class Compositor:
             plan._crops[key] = crops
         return crops, plan.rays(proj)
 
-    def source_rows(self, regions, plan, kind, n_levels=5, proj=geo.SphProj, rows=None):
-        """{image: (r0, r1)}: the source rows ``composite(..., rows=rows)`` can touch — for
-        ``upload(rows_of=...)``.  Images the composite does not meet are absent."""
-        reach = self.blur_reach(kind, n_levels)
-        if rows is None:
-            crops, _ = self.plan_crops(regions, plan, proj, split_dilate=2 * reach)
-        else:
-            wa, wb = self.window_rows(rows, kind, n_levels, plan.shape[0])
-            crops, _ = self.plan_crops(regions, plan, proj, rows=(wa, wb), row_align=4 if reach else 1,
-                                       split_dilate=2 * reach)
-        key = ("rows", len(regions), proj, rows, kind, n_levels)
+    def source_rows(self, regions, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, cols=None):
+        """{image: (r0, r1)}: the source rows ``composite(..., rows=rows, cols=cols)`` can touch — for
+        ``upload(rows_of=...)``.  Images the composite does not meet are absent.  (Interval
+        arithmetic over the cropped boxes on the host: works for every blender; ``source_rects``
+        is tighter where the seam plan applies.)"""
+        key = ("rows", len(regions), proj, rows, cols, kind, n_levels)
         cached = plan._crops.get(key) if plan._crops is not None else None
         if cached is not None:
             return cached
+        crops = self._window_geometry(regions, plan, kind, n_levels, proj, rows, cols)[0]
         needed = {}
         for c in crops:
             r0, r1 = geo.source_rows_needed(regions[c[0]], c[1:5], plan, proj)

@@ -1,18 +1,24 @@
-"""Multi-GPU compositing by horizontal output strips.
+"""Multi-GPU compositing by strips of the output.
 
 One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The
-mosaic rows are split into contiguous ranges of equal estimated cost; every
-rank warps and blends only the images that overlap its rows (plus a halo of
-the largest blur radius, re-warped locally — the warp is pointwise, so no halo
-exchange is needed) and the uint8 strips are pushed band by band into rank 0's
-mosaic over NVLink (peer-mapped destination) while the rest of the strip is
-still being computed.  There is no other data-path collective.
+mosaic is split into contiguous strips of equal estimated cost — column strips
+on 64-column tile edges for mosaics wider than tall (a 360-degree panorama: the
+horizontal seams between pitch rows, where most of the blending work sits, are
+then shared by all ranks), row strips otherwise (``P360_STRIPS=rows|cols``
+forces one); every rank warps and blends only the images that overlap its strip
+(plus a halo of the largest blur radius, re-warped locally — the warp is
+pointwise, so no halo exchange is needed) and the uint8 strips are pushed band
+by band into rank 0's mosaic over NVLink (peer-mapped destination) while the
+rest of the strip is still being computed.  There is no other data-path
+collective.  A strip is a pair ``(a, b)`` of rows or a 4-tuple ``(ya, yb, xa, xb)``.
 
 The reference has no distributed code; this module is the B200-side answer to
 its single-process ``stitch()`` (stitcher.py:274-327) for mosaics too large or
 too slow for one device.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -97,15 +103,115 @@ def partition_rows(plan, n_parts, kind="multiband", n_levels=5):
     return best
 
 
+def col_halo(kind, n_levels):
+    """Columns of context a column strip needs on each side (= ``Compositor.col_margin``)."""
+    if kind != "multiband" or n_levels < 2:
+        return 0
+    pad = geo.coarse_band_plan(n_levels)[0]
+    return max(pad + 4 + 64, 64 * -(-pad // 64) + 63) + 64 + 3
+
+
+def strip_axis(plan):
+    """"cols" or "rows": which way the mosaic is cut."""
+    forced = os.environ.get("P360_STRIPS", "")
+    if forced in ("rows", "cols"):
+        return forced
+    return "cols" if plan.shape[1] >= plan.shape[0] else "rows"
+
+
+def window_of(part, shape):
+    """(rows, cols) arguments of ``Compositor.composite`` for a strip; None = the whole axis."""
+    if len(part) == 2:
+        return tuple(part), None
+    ya, yb, xa, xb = part
+    rows = None if (ya, yb) == (0, shape[0]) else (ya, yb)
+    cols = None if (xa, xb) == (0, shape[1]) else (xa, xb)
+    return rows, cols
+
+
+def part_box(part, shape):
+    """(ya, yb, xa, xb) of a strip in either form."""
+    return (part[0], part[1], 0, shape[1]) if len(part) == 2 else tuple(part)
+
+
+def is_empty(part):
+    return part[1] <= part[0] or (len(part) == 4 and part[3] <= part[2])
+
+
+def col_costs(plan, kind="multiband", n_levels=5):
+    """Estimated work per mosaic column: patch pixels touching it."""
+    height, width = plan.shape
+    cost = np.zeros(width + 1, dtype=np.float64)
+    reach = geo.coarse_band_plan(n_levels)[0] + 4 if kind == "multiband" and n_levels > 1 else 0
+    for i, (x0, y0, x1, y1) in enumerate(plan.boxes):
+        if x1 <= x0 or y1 <= y0:
+            continue
+        for a, b in geo.active_column_runs(i, (x0, y0, x1, y1), plan, dilate=2 * reach):
+            cost[max(a, 0)] += y1 - y0
+            cost[min(b, width)] -= y1 - y0
+    return np.cumsum(cost[:-1]) + height * 0.25
+
+
+def partition_cols(plan, n_parts, kind="multiband", n_levels=5):
+    """Split [0, W) into ``n_parts`` contiguous column ranges on 64-column tile edges of ~equal
+    cost, counting the halo columns each strip has to recompute.  Returns 4-tuples."""
+    height, width = plan.shape
+    if n_parts <= 1:
+        return [(0, height, 0, width)]
+    prefix = np.concatenate([[0.0], np.cumsum(col_costs(plan, kind, n_levels))])
+    halo = col_halo(kind, n_levels)
+    tiles = -(-width // 64)
+    if tiles < n_parts:
+        raise ValueError(f"a {width}-column mosaic cannot be cut into {n_parts} column strips of whole tiles")
+
+    def cost(ta, tb):
+        lo, hi = max(0, 64 * ta - halo), min(width, 64 * tb + halo)
+        return prefix[hi] - prefix[lo]
+
+    lo_c, hi_c = 0.0, cost(0, tiles)
+    best = None
+    for _ in range(40):
+        mid = 0.5 * (lo_c + hi_c)
+        cuts, a, ok = [], 0, True
+        for k in range(n_parts):
+            left = n_parts - k - 1                       # strips still to come: each needs a tile
+            lo_b, hi_b = a + 1, tiles - left
+            if lo_b > hi_b or cost(a, lo_b) > mid:
+                ok = False
+                break
+            while lo_b < hi_b:
+                m = (lo_b + hi_b + 1) // 2
+                if cost(a, m) <= mid:
+                    lo_b = m
+                else:
+                    hi_b = m - 1
+            cuts.append((a, lo_b))
+            a = lo_b
+        if ok and a >= tiles:
+            best, hi_c = cuts, mid
+        else:
+            lo_c = mid
+    if best is None:
+        edges = np.linspace(0, tiles, n_parts + 1).astype(int)
+        best = [(int(edges[i]), int(edges[i + 1])) for i in range(n_parts)]
+    return [(0, height, 64 * a, min(64 * b, width)) for a, b in best]
+
+
 def rebalance(parts, times, height, align=32, damping=0.75):
-    """New row cuts from the measured device time of every strip (same cuts -> same bytes, so the
-    partition is free to follow the measurement): the cost per row is taken as constant within
-    each old strip, the new cuts sit at equal shares of the total, moved ``damping`` of the way
-    and rounded to whole 32-row tiles (a cut inside a tile makes two ranks plan and warp it)."""
+    """New cuts from the measured device time of every strip (same cuts -> same bytes, so the
+    partition is free to follow the measurement): the cost per row (column) is taken as constant
+    within each old strip, the new cuts sit at equal shares of the total, moved ``damping`` of the
+    way and rounded to whole tiles (32 rows; 64 columns for column strips, where ``height`` is
+    ignored: 4-tuples carry their own extent).  A cut inside a tile makes two ranks plan and warp it."""
     n = len(parts)
     if n < 2 or min(times) <= 0:
         return list(parts)
-    edges = [p[0] for p in parts] + [parts[-1][1]]
+    by_cols = len(parts[0]) == 4
+    if by_cols:
+        align, height, rows = 64, parts[-1][3], parts[0][:2]
+        edges = [p[2] for p in parts] + [parts[-1][3]]
+    else:
+        edges = [p[0] for p in parts] + [parts[-1][1]]
     cum = np.concatenate([[0.0], np.cumsum(times)])
     new = [0]
     for k in range(1, n):
@@ -117,7 +223,16 @@ def rebalance(parts, times, height, align=32, damping=0.75):
         y = int(round(y / align)) * align
         new.append(min(max(y, new[-1] + align), height - align * (n - k)))
     new.append(height)
+    if by_cols:
+        return [(rows[0], rows[1], new[i], new[i + 1]) for i in range(n)]
     return [(new[i], new[i + 1]) for i in range(n)]
+
+
+def partition(plan, n_parts, kind="multiband", n_levels=5):
+    """The model's cuts along ``strip_axis(plan)``."""
+    if strip_axis(plan) == "cols" and -(-plan.shape[1] // 64) >= n_parts:
+        return partition_cols(plan, n_parts, kind, n_levels)
+    return partition_rows(plan, n_parts, kind, n_levels)
 
 
 def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds=4, log=None):
@@ -128,7 +243,7 @@ def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds
     where ``stitch_strips`` / ``strip_cuts`` find it.  Returns the cuts."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    parts = partition_rows(plan, world, kind, n_levels)
+    parts = partition(plan, world, kind, n_levels)
     best = None
     if world > 1:
         damping = 0.6
@@ -156,12 +271,12 @@ def tune_partition(comp, regions, plan, kind, n_levels, step, group=None, rounds
 
 
 def strip_cuts(plan, world, kind, n_levels):
-    """The row cuts in force for this plan: tuned ones if ``tune_partition`` ran, else the model's."""
+    """The cuts in force for this plan: tuned ones if ``tune_partition`` ran, else the model's."""
     if getattr(plan, "_parts", None) is None:
         plan._parts = {}
     key = (world, kind, n_levels)
     if key not in plan._parts:
-        plan._parts[key] = partition_rows(plan, world, kind, n_levels)
+        plan._parts[key] = partition(plan, world, kind, n_levels)
     return plan._parts[key]
 
 
@@ -169,6 +284,24 @@ def images_for_rows(plan, rows, halo):
     """Indices of images whose box intersects rows [ya - halo, yb + halo)."""
     ya, yb = rows[0] - halo, rows[1] + halo
     return [i for i, (x0, y0, x1, y1) in enumerate(plan.boxes) if y0 < yb and y1 > ya and x1 > x0]
+
+
+def images_for_part(plan, part, kind, n_levels):
+    """Indices of the images a strip (either form) can depend on: box rows within the row halo,
+    a column run within the column halo."""
+    ya, yb, xa, xb = part_box(part, plan.shape)
+    if yb <= ya or xb <= xa:
+        return []
+    hr, hc = blur_halo(kind, n_levels), col_halo(kind, n_levels)
+    reach = geo.coarse_band_plan(n_levels)[0] + 4 if kind == "multiband" and n_levels > 1 else 0
+    out = []
+    for i, (x0, y0, x1, y1) in enumerate(plan.boxes):
+        if x1 <= x0 or not (y0 < yb + hr and y1 > ya - hr):
+            continue
+        if len(part) == 2 or any(a < xb + hc and b > xa - hc
+                                 for a, b in geo.active_column_runs(i, (x0, y0, x1, y1), plan, dilate=2 * reach)):
+            out.append(i)
+    return out
 
 
 def gather_strips(strip, parts, shape, dst=0, group=None):
@@ -258,7 +391,8 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
     if world == 1:
         return comp.composite(regions, src, plan, kind, n_levels, proj)[0]
     h, w = plan.shape
-    rows = parts[rank]
+    part = parts[rank]
+    rows, cols = window_of(part, plan.shape)
     peer = None
     if _peer_ok and comp.device.type == "cuda":
         try:
@@ -268,21 +402,27 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
             import logging
             logging.getLogger(__name__).warning("peer-mapped gather unavailable (%s); using NCCL send/recv", exc)
             _peer_ok, peer = False, None
+
+    def place(dst, piece, y0, y1):
+        """strip rows [y0, y1) (mosaic coordinates) into their place in a whole-mosaic tensor"""
+        target = dst[y0:y1] if cols is None else dst[y0:y1, cols[0]:cols[1]]
+        target.copy_(piece, non_blocking=True)
     if peer is not None:
         main, side = torch.cuda.current_stream(comp.device), comp.copy_stream()
         dst = peer.rows_of_rank0(h, w)                # (the buffer the previous step did not write)
-        if rows[1] > rows[0]:
+        if not is_empty(part):
             if rank == 0:
-                strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
-                dst[rows[0]:rows[1]].copy_(strip)
+                strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols)
+                ya = part_box(part, plan.shape)[0]
+                place(dst, strip, ya, ya + strip.shape[0])
             else:
-                def push_band(part, y0, y1):
+                def push_band(piece, y0, y1):
                     done = torch.cuda.Event()
                     done.record(main)
                     side.wait_event(done)
                     with torch.cuda.stream(side):
-                        dst[y0:y1].copy_(part, non_blocking=True)
-                comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, on_band=push_band,
+                        place(dst, piece, y0, y1)
+                comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, on_band=push_band,
                                bands=bands)
                 main.wait_stream(side)
         peer.barrier()                                # every strip has landed
@@ -290,31 +430,39 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
     if rank != 0:
         works = []
 
-        def send_band(part, y0, y1):
-            works.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, part, 0, group)]))
-        if rows[1] > rows[0]:
-            comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, on_band=send_band, bands=bands)
+        def send_band(piece, y0, y1):
+            works.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, piece.contiguous(), 0, group)]))
+        if not is_empty(part):
+            comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, on_band=send_band, bands=bands)
         for work in works:
             work.wait()
         return None
     mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=comp.device)
-    if rows[1] > rows[0]:
-        strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows)
-        mosaic[rows[0]:rows[1]].copy_(strip)
-    works = []
+    if not is_empty(part):
+        strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols)
+        ya = part_box(part, plan.shape)[0]
+        (mosaic[ya:ya + strip.shape[0]] if cols is None else mosaic[ya:ya + strip.shape[0], cols[0]:cols[1]]).copy_(strip)
+    works, landing = [], []
     for k in range(bands):
         ops = []
         for r in range(1, world):
-            a, b = parts[r]
-            if b <= a:
+            if is_empty(parts[r]):
                 continue
+            a, b, xa, xb = part_box(parts[r], plan.shape)
             y0, y1 = band_edges(a, b, bands)[k]
             if y1 > y0:
-                ops.append(dist.P2POp(dist.irecv, mosaic[y0:y1], r, group))
+                if len(parts[r]) == 2 or (xa, xb) == (0, w):
+                    ops.append(dist.P2POp(dist.irecv, mosaic[y0:y1], r, group))
+                else:                                 # a column strip arrives contiguous and is copied into place
+                    tmp = torch.empty((y1 - y0, xb - xa, 3), dtype=torch.uint8, device=comp.device)
+                    landing.append((tmp, y0, y1, xa, xb))
+                    ops.append(dist.P2POp(dist.irecv, tmp, r, group))
         if ops:
             works.extend(dist.batch_isend_irecv(ops))
     for work in works:
         work.wait()
+    for tmp, y0, y1, xa, xb in landing:
+        mosaic[y0:y1, xa:xb].copy_(tmp)
     return mosaic
 
 
@@ -421,15 +569,21 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
             phases.append((label, time.perf_counter()))
     plan = geo.plan_mosaic_cached(regions, kind == "multiband", max_resolution, proj)
     parts = strip_cuts(plan, world, kind, n_levels)
-    halo = blur_halo(kind, n_levels)
-    rows = parts[rank]
-    need = set(images_for_rows(plan, rows, halo)) if rows[1] > rows[0] else set()
+    part = parts[rank]
+    rows, cols = window_of(part, plan.shape)
+    need = set(images_for_part(plan, part, kind, n_levels))
     if equalize:
         need = set(range(len(regions)))          # pair statistics touch every image
-    # a strip reads only some rows of every image it meets: upload (and pack) just those
-    rows_of = None if equalize or rows[1] <= rows[0] else comp.source_rows(regions, plan, kind, n_levels, proj, rows)
+    # a strip reads only part of every image it meets: upload (and pack) just that
+    exact = kind == "multiband" and n_levels > 1 and comp.needs_exact(regions)
+    parts_of = None
+    if not equalize and not is_empty(part):
+        parts_of = None if exact else comp.source_rects(regions, plan, kind, n_levels, proj, rows=rows, cols=cols)
+        if parts_of is None:
+            parts_of = comp.source_rows(regions, plan, kind, n_levels, proj, rows=rows, cols=cols)
+        need &= set(parts_of)
     phase("planned")
-    src = comp.upload(regions, need=need, overlap=not equalize, rows_of=rows_of, reuse=True)
+    src = comp.upload(regions, need=need, overlap=not equalize, rows_of=parts_of, reuse=True)
     phase("uploads queued")
     if equalize:
         overlaps, sizes = all_pair_statistics(comp, regions, src, group)
@@ -448,11 +602,12 @@ def stitch_strips(comp, regions, kind, n_levels=5, equalize=False, max_resolutio
     shared = SharedHostMosaic.get(group)
     shared.ensure(h * w * 3)                     # collective on first use / growth
     host = shared.rows(h, w)
-    if rows[1] > rows[0]:
+    if not is_empty(part):
         if comp.device.type == "cuda":
-            shared.register(rows[0] * w * 3, rows[1] * w * 3)
-        comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, out_host=host, bands=4,
-                       exact=kind == "multiband" and n_levels > 1 and comp.needs_exact(regions))
+            ya, yb = part_box(part, plan.shape)[:2]
+            shared.register(ya * w * 3, yb * w * 3)      # (a column strip spans every row: the whole mapping)
+        comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, out_host=host, bands=4,
+                       exact=exact)
         phase("kernels queued")
         comp.finish_download()
         phase("strip landed")

@@ -148,9 +148,10 @@ def test_barrier_misuse_is_detected():
 
 
 # ---- the multi-rank path end to end: strips over gloo, kernels on the host -------------------
-def _strip_worker(rank, world, port, golden, kind, equalize, out_path):
+def _strip_worker(rank, world, port, golden, kind, equalize, out_path, axis="cols"):
     import os
     os.environ["P360_SEAM_MAPS"] = "1" if rank % 2 else "0"      # ranks may differ: the bytes do not
+    os.environ["P360_STRIPS"] = axis
 
     import numpy as np
     import torch.distributed as dist
@@ -173,11 +174,13 @@ def _strip_worker(rank, world, port, golden, kind, equalize, out_path):
         patcher.undo()
 
 
-@pytest.mark.parametrize("golden,kind,equalize,world", [("tiny4", "multiband", False, 2), ("tiny4", "linear", True, 2),
-                                                        ("ring12", "multiband", True, 3), ("tiny4", "none", False, 2)])
-def test_strips_over_gloo_equal_single_rank(st, tmp_path, golden, kind, equalize, world):
-    """stitch_strips on 2-3 ranks (row strips with halo, banded sends to rank 0, pair statistics
-    all-reduced) gives the bytes of the single-rank stitch — SURVEY.md §8(e)."""
+@pytest.mark.parametrize("golden,kind,equalize,world,axis", [
+    ("tiny4", "multiband", False, 2, "cols"), ("tiny4", "linear", True, 2, "cols"), ("ring12", "multiband", True, 3, "cols"),
+    ("ring12", "multiband", False, 3, "rows"), ("tiny4", "none", False, 2, "rows")])
+def test_strips_over_gloo_equal_single_rank(st, tmp_path, golden, kind, equalize, world, axis):
+    """stitch_strips on 2-3 ranks (column or row strips with halo, each rank downloading its strip
+    into the host buffer the ranks share, pair statistics all-reduced) gives the bytes of the
+    single-rank stitch — SURVEY.md §8(e)."""
     import numpy as np
     import torch.multiprocessing as mp
 
@@ -186,7 +189,7 @@ def test_strips_over_gloo_equal_single_rank(st, tmp_path, golden, kind, equalize
     regs = regions_from_golden(load_golden(golden))
     want = st.stitch(regs, blender=st.BLENDERS[kind], equalize=equalize)
     out = str(tmp_path / "mosaic.npy")
-    mp.spawn(_strip_worker, args=(world, _free_port(), golden, kind, equalize, out), nprocs=world, join=True)
+    mp.spawn(_strip_worker, args=(world, _free_port(), golden, kind, equalize, out, axis), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
 
 

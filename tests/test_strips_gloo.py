@@ -68,6 +68,23 @@ def test_partition_covers_mosaic_and_balances(name, n):
             x0, y0, x1, y1 = plan.boxes[i]
             assert y0 < rows[1] + halo and y1 > rows[0] - halo
     assert seen == set(range(wl.n_views))
+    # column strips: whole 64-column tiles, covering the mosaic, balanced, every image somewhere
+    if -(-plan.shape[1] // 64) >= n:
+        cols = strips.partition_cols(plan, n, wl.blend, wl.n_levels)
+        assert len(cols) == n and cols[0][2] == 0 and cols[-1][3] == plan.shape[1]
+        assert all(a[3] == b[2] and a[2] % 64 == 0 and a[3] > a[2] for a, b in zip(cols, cols[1:] + [cols[-1]]) if a is not b)
+        assert all(c[:2] == (0, plan.shape[0]) for c in cols)
+        per_col = strips.col_costs(plan, wl.blend, wl.n_levels)
+        halo = strips.col_halo(wl.blend, wl.n_levels)
+        costs = [per_col[max(0, c[2] - halo):c[3] + halo].sum() for c in cols]
+        assert max(costs) <= 1.15 * (sum(costs) / len(costs)) + per_col.max() * 128
+        seen = set()
+        for c in cols:
+            seen.update(strips.images_for_part(plan, c, wl.blend, wl.n_levels))
+        assert seen == set(range(wl.n_views))
+        moved = strips.rebalance(cols, [1.0 + 0.3 * (k % 2) for k in range(n)], plan.shape[0])
+        assert len(moved) == n and moved[0][2] == 0 and moved[-1][3] == plan.shape[1]
+        assert all(a[3] == b[2] and a[3] % 64 == 0 for a, b in zip(moved, moved[1:]))
 
 
 def test_single_rank_is_identity():
