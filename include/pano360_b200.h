@@ -334,6 +334,17 @@ int p360_exact_collapse(const float *acc_rgbw, int n_levels, const uint8_t *cove
 int64_t p360_crop_scratch_bytes(int H, int W);
 int p360_crop_rect(const uint8_t *covered, int H, int W, void *scratch, int32_t *rect_dev, void *stream);
 
+/* ---- ingest: cv2.resize(img, None, fx=1/S, fy=1/S) on uint8 (stitcher.py:418-421, `-s`) ------
+ * Bit-exact with OpenCV's 8-bit path (resize.cpp).  src: h x w x c, dst: dh x dw x c (c = 1, 3, 4).
+ * area2 != 0: the exact 2x shrink, which OpenCV reroutes from INTER_LINEAR to INTER_AREA's 2 x 2
+ * integer mean (tables unused).  Else INTER_LINEAR in 11-bit fixed point from DEVICE tables built as
+ * resize.cpp builds them (pano360_b200/geometry.py: resize_tables): xofs[dw] / yofs[dh] = first
+ * source index, xw[2 dw] / yw[2 dh] = the two int16 weights (sum 2048).  Column indices are already
+ * clamped (fraction 0 at the edges), row indices are clipped by the kernel. */
+int p360_resize_u8(const uint8_t *src, int h, int w, int c, uint8_t *dst, int dh, int dw,
+                   const int32_t *xofs, const int16_t *xw, const int32_t *yofs, const int16_t *yw,
+                   int area2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

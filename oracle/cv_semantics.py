@@ -174,3 +174,74 @@ def warp_perspective_transparent(src, hom, width, height):
     val = bilinear_taps(src, np.where(written, ix, 0), np.where(written, iy, 0),
                         fx, fy, lambda p, n: np.clip(p, 0, n - 1))
     return np.where(written[..., None], val, np.float32(0)), written
+
+
+# ---- cv2.resize(img, None, fx=1/S, fy=1/S) on uint8 (stitcher.py:418-421, the `-s` flag) --------
+# OpenCV's published algorithm (modules/imgproc/src/resize.cpp): the destination size is
+# cvRound(size * f) (round-half-even); INTER_LINEAR on 8-bit images runs in 11-bit fixed point
+# (HResizeLinear / VResizeLinear with FixedPtCast<22>), except that an exact 2x shrink is rerouted
+# to INTER_AREA's integer 2x2 mean (resizeAreaFast_).
+RESIZE_COEF_BITS = 11
+RESIZE_COEF_SCALE = 1 << RESIZE_COEF_BITS
+
+
+def resize_dsize(h, w, f):
+    """Size of cv2.resize(..., dsize=None, fx=f, fy=f): saturate_cast<int>(size * f) = cvRound."""
+    return int(np.rint(h * f)), int(np.rint(w * f))
+
+
+def resize_linear_tables(n_src, n_dst, f, clamp_fraction=True):
+    """Per destination index: the first source index and the two fixed-point weights
+    (int16) of the linear resampling along one axis — resize.cpp's xofs / ialpha (columns: an
+    index clamped at an image edge gets the fraction 0) and yofs / ibeta (rows: the fraction is
+    kept, the two row indices are clipped into the image by the row loop)."""
+    scale = 1.0 / f
+    d = np.arange(n_dst, dtype=np.float64)
+    fx = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    sx = np.floor(fx).astype(np.int64)
+    fx = (fx - sx.astype(np.float32)).astype(np.float32)
+    if clamp_fraction:
+        low = sx < 0
+        fx[low], sx[low] = 0.0, 0
+        high = sx >= n_src - 1
+        fx[high], sx[high] = 0.0, n_src - 1
+
+    def to_short(v):
+        return np.clip(np.rint(v.astype(np.float32) * np.float32(RESIZE_COEF_SCALE)), -32768, 32767).astype(np.int64)
+    return sx, to_short(np.float32(1.0) - fx), to_short(fx)
+
+
+def resize_u8(img, f):
+    """cv2.resize(img, None, fx=f, fy=f) (default INTER_LINEAR) for uint8 HxWxC, f <= 1."""
+    h, w = img.shape[:2]
+    dh, dw = resize_dsize(h, w, f)
+    if (dh, dw) == (h, w):                         # "source and destination are of same size: simple copy"
+        return img.copy()
+    scale = 1.0 / f
+    s = img.astype(np.int64)
+    if abs(scale - 2.0) < np.finfo(np.float64).eps:
+        # INTER_AREA (resizeAreaFast_): 2 x 2 integer mean with rounding; a block that sticks out of
+        # an odd-sized image averages the pixels it has (float division, round-half-even)
+        fh, fw = min(dh, h // 2), min(dw, w // 2)
+        out = np.zeros((dh, dw) + img.shape[2:], np.uint8)
+        out[:fh, :fw] = ((s[0:2 * fh:2, 0:2 * fw:2] + s[0:2 * fh:2, 1:2 * fw:2] + s[1:2 * fh:2, 0:2 * fw:2]
+                          + s[1:2 * fh:2, 1:2 * fw:2] + 2) >> 2).astype(np.uint8)
+        for dy in range(dh):
+            for dx in range(dw):
+                if dy < fh and dx < fw:
+                    continue
+                block = s[2 * dy:min(2 * dy + 2, h), 2 * dx:min(2 * dx + 2, w)]
+                count = block.shape[0] * block.shape[1]
+                mean = block.reshape(count, -1).sum(0).astype(np.float32) / np.float32(count)
+                out[dy, dx] = np.clip(np.rint(mean), 0, 255).astype(np.uint8).reshape(img.shape[2:])
+        return out
+    sx, a0, a1 = resize_linear_tables(w, dw, f)
+    sy, b0, b1 = resize_linear_tables(h, dh, f, clamp_fraction=False)
+    x1 = np.minimum(sx + 1, w - 1)
+    y0, y1 = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+    shape = (1, dw) + (1,) * (img.ndim - 2)
+    rows = s[:, sx] * a0.reshape(shape) + s[:, x1] * a1.reshape(shape)          # horizontal pass: int, 11 fractional bits
+    top, bot = rows[y0], rows[y1]
+    shape = (dh, 1) + (1,) * (img.ndim - 2)
+    out = (((b0.reshape(shape) * (top >> 4)) >> 16) + ((b1.reshape(shape) * (bot >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)

@@ -51,6 +51,7 @@ SIGNATURES = {
     "p360_exact_collapse": [_vp, _i, _vp, _vp, _i, _i, _vp],
     "p360_crop_scratch_bytes": [_i, _i],
     "p360_crop_rect": [_vp, _i, _i, _vp, _vp, _vp],
+    "p360_resize_u8": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
 }
 MAX_LEVELS = 8
 
@@ -88,7 +89,8 @@ _LAUNCHES = {"p360_pack_rgbx": 1, "p360_pack_rgbx_rect": 1, "p360_source_rects":
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,
              "p360_multiband_collapse": 1, "p360_linear_collapse": 1, "p360_paste_collapse": 1,
              "p360_pair_overlap_stats": 2, "p360_cover_update": 1, "p360_crop_rect": 3,
-             "p360_owner_to_alpha": 1, "p360_band_accumulate": 1, "p360_exact_collapse": 1}
+             "p360_owner_to_alpha": 1, "p360_band_accumulate": 1, "p360_exact_collapse": 1,
+             "p360_resize_u8": 1}
 
 
 def load():

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpano360_b200.so")
-SOURCES = ["p360_api.cu", "p360_warp.cu", "p360_blend.cu", "p360_blur.cu", "p360_gain.cu", "p360_pyramid.cu", "p360_crop.cu", "p360_exact.cu"]
+SOURCES = ["p360_api.cu", "p360_warp.cu", "p360_blend.cu", "p360_blur.cu", "p360_gain.cu", "p360_pyramid.cu", "p360_crop.cu", "p360_exact.cu", "p360_resize.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "shared"]
 

@@ -375,3 +375,26 @@ def invert3x3(m):
         [c00 * d, (m[0, 2] * m[2, 1] - m[0, 1] * m[2, 2]) * d, (m[0, 1] * m[1, 2] - m[0, 2] * m[1, 1]) * d],
         [-c01 * d, (m[0, 0] * m[2, 2] - m[0, 2] * m[2, 0]) * d, (m[0, 2] * m[1, 0] - m[0, 0] * m[1, 2]) * d],
         [c02 * d, (m[0, 1] * m[2, 0] - m[0, 0] * m[2, 1]) * d, (m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]) * d]])
+
+
+# ---- ingest: cv2.resize(img, None, fx=1/S, fy=1/S) tables (stitcher.py:418-421) ---------------
+def resize_dsize(h, w, f):
+    """Size cv2.resize gives for fx = fy = f: saturate_cast<int>(size * f), i.e. round-half-even."""
+    return int(np.rint(h * f)), int(np.rint(w * f))
+
+
+def resize_tables(n_src, n_dst, f, clamp_fraction):
+    """First source index and the two 11-bit fixed-point weights per destination index along one
+    axis, as OpenCV's resize.cpp builds xofs / ialpha (``clamp_fraction``: an index clamped at an
+    image edge gets the fraction 0) and yofs / ibeta (fraction kept, the row loop clips the
+    indices).  -> (int32 [n_dst], int16 [n_dst, 2])."""
+    d = np.arange(n_dst, dtype=np.float64)
+    pos = ((d + 0.5) * (1.0 / f) - 0.5).astype(np.float32)
+    first = np.floor(pos).astype(np.int32)
+    frac = (pos - first.astype(np.float32)).astype(np.float32)
+    if clamp_fraction:
+        low, high = first < 0, first >= n_src - 1
+        frac[low | high] = 0.0
+        first[low], first[high] = 0, n_src - 1
+    weights = np.stack([np.float32(1.0) - frac, frac], axis=1).astype(np.float32) * np.float32(2048.0)
+    return first, np.clip(np.rint(weights), -32768, 32767).astype(np.int16)

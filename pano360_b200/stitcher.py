@@ -303,13 +303,10 @@ def main(argv=None):
                         help="(extra) do not open a window with the result.")
     args = parser.parse_args(argv)
 
-    exts = [".jpg", ".png", ".bmp"]
-    exts += [ex.upper() for ex in exts]
+    from .ingest import read_images
     name = f"{os.path.basename(os.path.normpath(args.path))}_s{args.shrink}"
-    files = [f for f in os.listdir(args.path) if any(f.endswith(ext) for ext in exts)]
-    imgs = [cv2.imread(os.path.join(args.path, f)) for f in files]
-    if args.shrink > 1:
-        imgs = [cv2.resize(im, None, fx=1 / args.shrink, fy=1 / args.shrink) for im in imgs]
+    # threaded decode; the `-s` shrink (cv2.resize at stitcher.py:420-421) runs on the device, bit-exact
+    imgs = read_images(args.path, args.shrink)
 
     try:
         regions = load_regions(f"ba_{name}.pkl")

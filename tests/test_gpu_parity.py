@@ -403,6 +403,30 @@ def test_edge_cases(st, restore_globals):
     assert np.array_equal(cropped, rs.stitch(regs, "linear", crop=True))
 
 
+def test_device_resize_is_cv2_resize(comp):
+    """Ingest (stitcher.py:418-421): p360_resize_u8 against the installed cv2.resize — the call the
+    reference makes for `-s` — bit for bit: the exact 2x shrink (OpenCV reroutes it to the 2 x 2 area
+    mean, odd sizes included), fractional and integer factors in 11-bit fixed point, 1 / 3 / 4
+    channels, and a factor that leaves the size unchanged (a copy)."""
+    import cv2
+    from pano360_b200 import ingest
+    rng = np.random.default_rng(2)
+    big = comp.device.type == "cuda"
+    shapes = [(480, 640, 3), (375, 501, 3), (97, 131, 4), (64, 64), (31, 50, 3)] + ([(3000, 4000, 3)] if big else [])
+    for shape in shapes:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        for shrink in (2, 1.5, 3, 4, 2.5, 1.7, 1.01, 6.3):
+            want = cv2.resize(img, None, fx=1 / shrink, fy=1 / shrink)
+            got = ingest.resize_on_device(comp, [img], shrink)[0]
+            assert got.shape == want.shape and got.dtype == np.uint8, (shape, shrink, got.shape, want.shape)
+            assert np.array_equal(got, want), (shape, shrink, int(np.abs(got.astype(int) - want.astype(int)).max()))
+    batch = [rng.integers(0, 256, (120, 160, 3), dtype=np.uint8) for _ in range(5)]
+    for got, img in zip(ingest.resize_on_device(comp, batch, 2), batch):
+        assert np.array_equal(got, cv2.resize(img, None, fx=0.5, fy=0.5))
+    with pytest.raises(TypeError):
+        ingest.resize_on_device(comp, [batch[0].astype(np.float32)], 2)
+
+
 def test_crop_rectangle_matches_the_reference_scan(st, comp):
     """K9 (p360_crop_rect) against the oracle's statement-by-statement restatement of the
     reference's scan (stitcher.py:346-367; pinned against the live crop_mosaic in

@@ -49,6 +49,7 @@ test_two_row_six_band_layout = gpu.test_two_row_six_band_layout
 test_many_small_views = gpu.test_many_small_views
 test_edge_cases = gpu.test_edge_cases
 test_crop_rectangle_matches_the_reference_scan = gpu.test_crop_rectangle_matches_the_reference_scan
+test_device_resize_is_cv2_resize = gpu.test_device_resize_is_cv2_resize
 test_cropped_stitch_matches_oracle = gpu.test_cropped_stitch_matches_oracle
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere

@@ -46,3 +46,20 @@ def test_warp_perspective_transparent():
     assert np.array_equal(written, (want != 0).any(-1))
     assert np.abs(got - want).max() < 1e-6
     assert np.array_equal(cv2.invert(hom)[1], cs.invert3x3(hom))
+
+
+def test_resize_restatement_is_cv2_resize():
+    """cv_semantics.resize_u8 (the published resize.cpp arithmetic) against the installed cv2 — the
+    pin of the ingest oracle (stitcher.py:418-421)."""
+    import cv2
+    from oracle import cv_semantics as cs
+    rng = np.random.default_rng(1)
+    for shape in [(480, 640, 3), (375, 500, 3), (97, 131, 4), (301, 403), (64, 64, 3), (31, 50, 3), (5, 3, 3)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        for shrink in (2, 1.5, 3, 4, 2.5, 1.7, 1.01, 2.0000001, 1.25, 5, 6.3):
+            dh, dw = cs.resize_dsize(shape[0], shape[1], 1 / shrink)
+            if dh < 1 or dw < 1:
+                continue
+            want = cv2.resize(img, None, fx=1 / shrink, fy=1 / shrink)
+            got = cs.resize_u8(img, 1 / shrink)
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, shrink)
