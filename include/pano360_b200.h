@@ -94,6 +94,15 @@ typedef struct p360_warp_job {
 int p360_pack_rgbx(const uint8_t *src_rgb, int h, int w, uint8_t *dst_rgbx, void *stream);
 int p360_pack_rgbx_rect(const uint8_t *src_rgb, int h, int w, int r0, int r1, int c0, int c1,
                         uint8_t *dst_rgbx, void *stream);
+/* One launch for all the images of a composite.  jobs_dev: DEVICE array; every job converts pixels
+ * [c0, c1) of rows [r0, r1) of an h x w image (c0 % 4 == 0; w % 4 == 0 for the vector path, any w
+ * is correct); max_rows / max_cols: the largest r1 - r0 / c1 - c0 among the jobs. */
+typedef struct p360_pack_job {
+    const uint8_t *src;
+    uint8_t *dst;
+    int32_t h, w, r0, r1, c0, c1;
+} p360_pack_job;
+int p360_pack_rgbx_batch(const p360_pack_job *jobs_dev, int n_jobs, int max_rows, int max_cols, void *stream);
 /* Rectangle copy (cudaMemcpy2DAsync, direction inferred): `rows` runs of width_bytes bytes, pitches
  * in bytes; device, peer-device and page-locked host addresses alike.  Uploads of image
  * sub-rectangles, downloads / NVLink pushes of mosaic column windows. */

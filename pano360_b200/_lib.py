@@ -26,6 +26,7 @@ SIGNATURES = {
     "p360_device_info": [_i, C.POINTER(C.c_int32)],
     "p360_pack_rgbx": [_vp, _i, _i, _vp, _vp],
     "p360_pack_rgbx_rect": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_pack_rgbx_batch": [_vp, _i, _i, _i, _vp],
     "p360_copy_rect": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
     "p360_source_rects": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "p360_warp_batch": [_vp, _vp, _i, _vp, _vp, _i, _vp],
@@ -73,6 +74,8 @@ TILE_MAPS = np.dtype([("present", "u8"), ("cand", "u8"), ("need", "u8"), ("multi
                       ("work_count", "u8"), ("wneed", "u8"), ("tiles_x", "i4"), ("tiles_y", "i4"), ("words", "i4"), ("row0", "i4"),
                       ("reach_x", "i4"), ("reach_y", "i4"), ("work_cap", "i4"), ("h_rows", "i4")])
 PAIR_JOB = np.dtype([("src_i", "u8"), ("src_j", "u8"), ("inv", "f8", (9,))])
+PACK_JOB = np.dtype([("src", "u8"), ("dst", "u8"), ("h", "i4"), ("w", "i4"), ("r0", "i4"), ("r1", "i4"), ("c0", "i4"), ("c1", "i4")])
+assert PACK_JOB.itemsize == 40
 assert PAIR_JOB.itemsize == 88
 assert WARP_JOB.itemsize == 224 and BLUR_JOB.itemsize == 56 and BAND_PATCH.itemsize == 136
 assert TILE_MAPS.itemsize == 88
@@ -83,7 +86,7 @@ _VALUE_RETURN = {"p360_version", "p360_pair_stats_blocks", "p360_crop_scratch_by
 
 _lib = None
 launch_count = 0      # kernels launched through this binding (bench.py: gpu_launches)
-_LAUNCHES = {"p360_pack_rgbx": 1, "p360_pack_rgbx_rect": 1, "p360_source_rects": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
+_LAUNCHES = {"p360_pack_rgbx": 1, "p360_pack_rgbx_rect": 1, "p360_pack_rgbx_batch": 1, "p360_source_rects": 1, "p360_warp_batch": 1, "p360_owner_update": 1, "p360_owner_decode": 1,
              "p360_gauss_blur": 2, "p360_gauss_blur_batch": 2, "p360_pyramid_reduce_batch": 1,
              "p360_owned_boxes": 1,            # (+1 scan kernel per pass with maps, counted by the caller)
              "p360_tile_maps_build": 3, "p360_seam_plan_build": 3, "p360_warp_tiles": 1,

@@ -143,6 +143,7 @@ class DeviceSources:
     ready: list = None                 # per image CUDA event (uploads issued on the copy stream)
     rows: list = None                  # per image (r0, r1) or (r0, r1, c0, c1): only that part is resident / packed (None: all)
     bytes_up: int = 0                  # image bytes that crossed PCIe for this set
+    issue: object = None               # upload(lazy=True): issue(count) copies the first `count` images of the order
 
 
 class Compositor:
@@ -284,25 +285,39 @@ class Compositor:
     def pack_sources(self, raw):
         """A ``DeviceSources`` whose images are in the warp's RGBX layout, from one holding the
         images as uploaded (``upload(pack=False)``): the device-side part of ``_add_weights``
-        (stitcher.py:257-263) that is executed once per image and stitch."""
+        (stitcher.py:257-263) that is executed once per image and stitch — ONE launch for all
+        the images (p360_pack_rgbx_batch), each converting only the part that was uploaded."""
         rows = raw.rows or [None] * len(raw.pixels)
         # the packed copies of one set of resident images always land in the same buffers: stable
         # addresses let ``composite`` reuse everything it prepared for them
-        key = tuple(0 if p is None else p.data_ptr() for p in raw.pixels)
-        outs = self._packed.get(key)
-        if outs is None:
+        key = tuple(0 if p is None else p.data_ptr() for p in raw.pixels) + (tuple(rows),)
+        entry = self._packed.get(key)
+        if entry is None:
             if len(self._packed) >= 8:
                 self._packed.pop(next(iter(self._packed)))
-            outs = self._packed[key] = [None] * len(raw.pixels)
-        pixels = []
-        for i, (p, r) in enumerate(zip(raw.pixels, rows)):
-            if p is not None and p.shape[2] != 4 and (outs[i] is None or outs[i].shape[:2] != p.shape[:2]):
-                outs[i] = torch.empty(p.shape[:2] + (4,), dtype=torch.uint8, device=self.device)
-            pixels.append(None if p is None else self.pack_pixels(p, r, out=outs[i]))
-        return DeviceSources(pixels, raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
+            outs, jobs = [None] * len(raw.pixels), []
+            for i, (p, r) in enumerate(zip(raw.pixels, rows)):
+                if p is None or p.shape[2] == 4:
+                    outs[i] = p
+                    continue
+                h, w = p.shape[:2]
+                outs[i] = torch.empty((h, w, 4), dtype=torch.uint8, device=self.device)
+                r0, r1 = (0, h) if r is None else r[:2]
+                c0, c1 = (0, w) if r is None or len(r) < 4 else r[2:]
+                jobs.append((p.data_ptr(), outs[i].data_ptr(), h, w, r0, r1, c0 // 4 * 4, c1))
+            table = np.array(jobs, dtype=_lib.PACK_JOB) if jobs else np.zeros(0, dtype=_lib.PACK_JOB)
+            entry = self._packed[key] = {
+                "outs": outs, "n": len(jobs), "jobs": self._to_device(table.view(np.uint8).reshape(-1)) if jobs else None,
+                "rows": int((table["r1"] - table["r0"]).max()) if jobs else 0,
+                "cols": int((table["c1"] - table["c0"]).max()) if jobs else 0,
+                "bytes": int(7 * ((table["r1"] - table["r0"]).astype(np.int64) * (table["c1"] - table["c0"])).sum()) if jobs else 0}
+        if entry["n"]:
+            self._traced("K1p_pack_rgbx", entry["bytes"], "p360_pack_rgbx_batch", _lib.ptr(entry["jobs"]), entry["n"],
+                         entry["rows"], entry["cols"], self.stream)
+        return DeviceSources(list(entry["outs"]), raw.luts, raw.hats, raw.shapes, raw.ready, raw.rows)
 
     def upload(self, regions, gains=None, need=None, overlap=False, pack=True, order=None, rows_of=None, reuse=False,
-               rects_of=None):
+               rects_of=None, lazy=False):
         """H2D copy of the u8 images (+ LUT / hat tables).  Images backed by
         pinned memory are copied asynchronously.  ``need`` (a set of indices)
         restricts the copy to the images a rank's strip touches.  With
@@ -315,7 +330,10 @@ class Compositor:
         of the result counts what crossed PCIe.
         ``reuse``: the images go to device buffers kept from the previous such call (same slot,
         same shape) — for callers that drop the result before they upload again (``stitch``):
-        stable addresses let ``composite`` reuse what it prepared."""
+        stable addresses let ``composite`` reuse what it prepared.
+        ``lazy``: only the device buffers are set up (their addresses are final); the copies are
+        issued by ``src.issue(count)`` — the first ``count`` images of ``order`` — so that a caller
+        can interleave the staging of pageable images with the work that consumes the earlier ones."""
         n = len(regions)
         src = DeviceSources([None] * n, [None] * n)
         if rects_of is not None:
@@ -331,77 +349,101 @@ class Compositor:
         if overlap:
             src.ready = [None] * n
             side.wait_stream(main)
-        for i in (range(n) if order is None else order):
-            reg = regions[i]
-            img = reg.img
-            h, w = img.shape[:2]
-            if need is None or i in need:
-                if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
-                    raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
-                host = torch.from_numpy(np.ascontiguousarray(img))
-                part = None if rows_of is None else rows_of.get(i)
-                rect = False
-                if part is not None and len(part) == 4 and (part[2] > 0 or part[3] < w):
-                    part = (part[0], part[1], part[2] // 4 * 4, part[3])     # (the packing converts 4 pixels per thread)
-                    rect = True
-                    whole = host
-                    host = host[part[0]:part[1], part[2]:part[3]]          # a strided view
-                elif part is not None:
-                    part = (part[0] // 4 * 4, part[1])        # (4-row granularity: aligned addresses for the packing)
-                    host = host[part[0]:part[1]]
-                src.bytes_up += host.numel()
-                if (h, w) not in src.hats:
-                    fresh = ("hat", h) not in self._consts or ("hat", w) not in self._consts
-                    src.hats[(h, w)] = (self._constant(("hat", h), lambda: geo.hat(h)),
-                                        self._constant(("hat", w), lambda: geo.hat(w)))
-                    if overlap and fresh:
-                        side.wait_stream(main)               # hat tables were copied on the main stream
-                pinned = (whole if rect else host).is_pinned()
-                if not pinned and (host.numel() >= self.stage_min_bytes or rect):
-                    host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
-                with torch.cuda.stream(side):
-                    if reuse or rect:
-                        slot = (n, i, tuple(img.shape))
-                        dev_img = self._images.get(slot) if reuse else None
-                        if dev_img is None:
-                            dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
-                            if reuse:
-                                self._images[slot] = dev_img
-                        if rect:           # the rectangle lands at its place in the full-size device image
-                            r0, r1, c0, c1 = part
-                            ch = img.shape[2]
-                            _lib.call("p360_copy_rect", dev_img.data_ptr() + ch * (r0 * w + c0), ch * w, host.data_ptr(),
-                                      host.stride(0), ch * (c1 - c0), r1 - r0, side.cuda_stream)
-                        else:
-                            target = dev_img if part is None else dev_img[part[0]:part[1]]
-                            target.copy_(host, non_blocking=host.is_pinned())
-                    elif part is None:
-                        dev_img = host.to(self.device, non_blocking=host.is_pinned())
-                    else:                                    # rows outside `part` stay unwritten: nobody reads them
-                        dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
-                        dev_img[part[0]:part[1]].copy_(host, non_blocking=host.is_pinned())
-                    if getattr(host, "_p360_slot", None) is not None:
-                        busy = torch.cuda.Event()
-                        busy.record(side)
-                        host._p360_slot[1] = busy
-                    # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
-                    out = None
-                    if pack and reuse and img.shape[2] != 4:
-                        slot = (n, i, tuple(img.shape), "rgbx")
-                        out = self._images.get(slot)
-                        if out is None:
-                            out = self._images[slot] = torch.empty(img.shape[:2] + (4,), dtype=torch.uint8, device=self.device)
-                    src.pixels[i] = self.pack_pixels(dev_img, part, out=out) if pack else dev_img
-                    if overlap:
-                        src.ready[i] = torch.cuda.Event()
-                        src.ready[i].record(side)
-                    self._mark(f"image {i} uploaded + packed", side)
+        sequence = [i for i in (range(n) if order is None else order) if need is None or i in need]
+        todo = {}
+        for i in range(n):
             if gains is None:
                 lut0 = self._constant("lut0", lambda: geo.sample_lut(None)) if lut0 is None else lut0
                 src.luts[i] = lut0
             else:
                 src.luts[i] = self._to_device(geo.sample_lut(gains[i]))
-        self.last_upload_bytes = src.bytes_up
+        # ---- phase 1: where every image goes (device buffers, the part of it that is copied)
+        for i in sequence:
+            img = regions[i].img
+            h, w = img.shape[:2]
+            if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+                raise TypeError("region images must be uint8 HxWx3 (what the reference accepts)")
+            host = torch.from_numpy(np.ascontiguousarray(img))
+            part = None if rows_of is None else rows_of.get(i)
+            rect, whole = False, host
+            if part is not None and len(part) == 4 and (part[2] > 0 or part[3] < w):
+                part = (part[0], part[1], part[2] // 4 * 4, part[3])     # (the packing converts 4 pixels per thread)
+                rect = True
+                host = host[part[0]:part[1], part[2]:part[3]]          # a strided view
+            elif part is not None:
+                part = (part[0] // 4 * 4, part[1])        # (4-row granularity: aligned addresses for the packing)
+                host = host[part[0]:part[1]]
+            if (h, w) not in src.hats:
+                fresh = ("hat", h) not in self._consts or ("hat", w) not in self._consts
+                src.hats[(h, w)] = (self._constant(("hat", h), lambda: geo.hat(h)),
+                                    self._constant(("hat", w), lambda: geo.hat(w)))
+                if overlap and fresh:
+                    side.wait_stream(main)               # hat tables were copied on the main stream
+            dev_img = None
+            if reuse or rect or part is not None or lazy:
+                slot = (n, i, tuple(img.shape))
+                dev_img = self._images.get(slot) if reuse else None
+                if dev_img is None:                      # parts outside `part` stay unwritten: nobody reads them
+                    dev_img = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+                    if reuse:
+                        self._images[slot] = dev_img
+            out = None
+            if pack and img.shape[2] != 4 and (reuse or lazy):
+                slot = (n, i, tuple(img.shape), "rgbx")
+                out = self._images.get(slot) if reuse else None
+                if out is None:
+                    out = torch.empty(img.shape[:2] + (4,), dtype=torch.uint8, device=self.device)
+                    if reuse:
+                        self._images[slot] = out
+            if lazy:                                     # final addresses before any byte has moved
+                src.pixels[i] = dev_img if (not pack or img.shape[2] == 4) else out
+            todo[i] = (host, whole, part, rect, dev_img, out)
+
+        # ---- phase 2: the copies (+ RGBX packing) of one image
+        def put(i):
+            host, whole, part, rect, dev_img, out = todo.pop(i)
+            img = regions[i].img
+            w = img.shape[1]
+            src.bytes_up += host.numel()
+            pinned = (whole if rect else host).is_pinned()
+            if not pinned and (host.numel() >= self.stage_min_bytes or rect):
+                host = self._stage_pageable(host, side)      # -> a pinned slot of the ring (async copy below)
+            with torch.cuda.stream(side):
+                if rect:           # the rectangle lands at its place in the full-size device image
+                    r0, r1, c0, c1 = part
+                    ch = img.shape[2]
+                    _lib.call("p360_copy_rect", dev_img.data_ptr() + ch * (r0 * w + c0), ch * w, host.data_ptr(),
+                              host.stride(0), ch * (c1 - c0), r1 - r0, side.cuda_stream)
+                elif dev_img is not None:
+                    target = dev_img if part is None else dev_img[part[0]:part[1]]
+                    target.copy_(host, non_blocking=host.is_pinned())
+                else:
+                    dev_img = host.to(self.device, non_blocking=host.is_pinned())
+                if getattr(host, "_p360_slot", None) is not None:
+                    busy = torch.cuda.Event()
+                    busy.record(side)
+                    host._p360_slot[1] = busy
+                # pack=False keeps the uploaded u8 x 3 layout (three byte loads per tap)
+                src.pixels[i] = self.pack_pixels(dev_img, part, out=out) if pack else dev_img
+                if overlap:
+                    src.ready[i] = torch.cuda.Event()
+                    src.ready[i].record(side)
+                self._mark(f"image {i} uploaded + packed", side)
+
+        state = {"at": 0}
+        positions = list(range(n) if order is None else order)
+
+        def issue(count=None):
+            """copy the images at the first ``count`` positions of ``order`` (all: None) that are still due"""
+            upto = n if count is None else min(count, n)
+            while state["at"] < upto:
+                if positions[state["at"]] in todo:
+                    put(positions[state["at"]])
+                state["at"] += 1
+            self.last_upload_bytes = src.bytes_up
+        src.issue = issue
+        if not lazy:
+            issue()
         return src
 
     def _constant(self, key, make):
@@ -932,6 +974,18 @@ class Compositor:
         for key in ("warp", "warp_jobs", "bands", "collapse", "streamed", "seam", "exact"):
             self._keep.pop(key, None)
 
+    def drain_landed(self, copy_to, staged):
+        """Copy the bands of a banded download that have already landed from the pinned staging
+        buffer into the caller's (pageable) array, without waiting for the others."""
+        rest = []
+        for band in self._bands_down:
+            y0, y1, landed, x0, x1 = band
+            if landed.query():
+                parallel_copy(copy_to[y0:y1, x0:x1], staged[y0:y1, x0:x1])
+            else:
+                rest.append(band)
+        self._bands_down = rest
+
     def finish_download(self, copy_to=None, staged=None):
         """Block until a banded download started by ``_collapse`` has landed.  ``copy_to`` (a
         pageable host array) receives the rows from the pinned staging buffer ``staged`` band by
@@ -1378,24 +1432,32 @@ class Compositor:
         wins.sort(key=lambda w: (w[2], w[0]))
         return order, wins
 
-    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=8, bands=2, exact=False):
+    def composite_streamed(self, regions, plan, kind, n_levels, proj, out_host, windows=8, bands=2, exact=False,
+                           copy_to=None):
         """Upload + composite + download with both PCIe directions busy: the images are uploaded
         left edge first — of each only the rectangle the seam plan can sample (``source_rects``) —
         and as soon as the images a column window of the mosaic depends on have arrived that
         window is composited (exactly the bytes of the whole composite, see ``composite``) and
         downloaded, while the uploads for the windows to its right continue on their own stream.
-        ``out_host``: pinned uint8 H x W x 3.  Call ``finish_download`` afterwards."""
+        ``out_host``: pinned uint8 H x W x 3; ``copy_to``: the pageable array the pixels finally go
+        to (bands that have landed are copied on between windows).  Call ``finish_download`` afterwards."""
         rects = None if exact else self.source_rects(regions, plan, kind, n_levels, proj)
         order, wins = self.streamed_windows(plan, kind, n_levels, windows,
                                             used=None if rects is None else self.used_boxes(regions, plan, kind, n_levels, proj))
         self.prepared_max = max(self.prepared_max, len(wins) + 2)
+        # the copies are issued window by window: staging a pageable image (a threaded memcpy into a
+        # pinned slot) then overlaps the kernels and transfers of the windows before it
         src = self.upload(regions, overlap=True, order=order, reuse=True, rects_of=rects,
-                          need=None if rects is None else set(rects))
+                          need=None if rects is None else set(rects), lazy=True)
         strips = []
-        for xa, xb, _ in wins:
+        for xa, xb, count in wins:
+            src.issue(count)
             strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, cols=(xa, xb), out_host=out_host,
                                       bands=bands, exact=exact)
             strips.append(strip)          # the download stream still reads it: keep it allocated
+            if copy_to is not None:       # bands that have landed meanwhile go on to the caller's array
+                self.drain_landed(copy_to, out_host)
+        src.issue()
         self._keep["streamed"] = (strips, src)
         return src
 

@@ -636,6 +636,38 @@ pack_rgbx_rect_kernel(const uint8_t *__restrict__ src, int w, int r0, int c0, in
     }
 }
 
+// All images of a composite in one launch: grid.z = job, every job a rectangle of one image.
+struct PackJob {                        // == p360_pack_job
+    const uint8_t *src;
+    uint32_t *dst;
+    int h, w, r0, r1, c0, c1;
+};
+static_assert(sizeof(PackJob) == sizeof(p360_pack_job), "ABI struct mismatch");
+
+__global__ void __launch_bounds__(256)
+pack_rgbx_batch_kernel(const PackJob *__restrict__ jobs) {
+    const PackJob j = jobs[blockIdx.z];
+    const int row = j.r0 + (int)blockIdx.y;
+    const int first = j.c0 + 4 * ((int)blockIdx.x * 256 + (int)threadIdx.x);
+    if (row >= j.r1 || first >= j.c1) return;
+    const size_t px = (size_t)row * j.w + first;
+    if (first + 4 <= j.c1 && (px & 3) == 0) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(j.src + 3 * px);
+        const uint32_t a = __ldg(in), b = __ldg(in + 1), c = __ldg(in + 2);
+        uint4 o;
+        o.x = a & 0xffffffu;
+        o.y = (a >> 24) | ((b & 0xffffu) << 8);
+        o.z = (b >> 16) | ((c & 0xffu) << 16);
+        o.w = c >> 8;
+        *reinterpret_cast<uint4 *>(j.dst + px) = o;
+        return;
+    }
+    for (int i = first; i < min(first + 4, j.c1); ++i) {
+        const uint8_t *q = j.src + 3 * ((size_t)row * j.w + i);
+        j.dst[(size_t)row * j.w + i] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+    }
+}
+
 // ---- K0s: which source pixels does the plan read? ---------------------------------------------
 // For every patch, the box (source pixels) around everything its tiles can sample: the tiles
 // where it is warped to float (`wneed`) and the solo tiles it writes directly, each pushed through
@@ -741,6 +773,16 @@ extern "C" int p360_pack_rgbx_rect(const uint8_t *src_rgb, int h, int w, int r0,
     if (r1 == r0 || c1 == c0) return 0;
     dim3 grid(cdiv((c1 - c0 + 3) / 4, 256), r1 - r0);
     pack_rgbx_rect_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_rgb, w, r0, c0, c1, reinterpret_cast<uint32_t *>(dst_rgbx));
+    return check_launch(where);
+}
+
+extern "C" int p360_pack_rgbx_batch(const p360_pack_job *jobs_dev, int n_jobs, int max_rows, int max_cols, void *stream) {
+    using namespace p360;
+    const char *where = "p360_pack_rgbx_batch";
+    P360_REQUIRE(jobs_dev && n_jobs >= 0 && n_jobs <= 65535 && max_rows >= 0 && max_rows <= 65535 && max_cols >= 0, where);
+    if (n_jobs == 0 || max_rows == 0 || max_cols == 0) return 0;
+    dim3 grid(cdiv((max_cols + 3) / 4, 256), max_rows, n_jobs);
+    pack_rgbx_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackJob *>(jobs_dev));
     return check_launch(where);
 }
 

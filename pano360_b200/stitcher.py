@@ -222,7 +222,8 @@ def stitch(regions, blender=no_blend, equalize=False, crop=False, n_levels=None,
         # both PCIe directions at once: row windows are composited and downloaded while the
         # images of the windows below are still being uploaded
         stage, result = landing()
-        comp.composite_streamed(regions, plan, kind, levels, proj, stage, windows=STREAM_WINDOWS, exact=exact)
+        comp.composite_streamed(regions, plan, kind, levels, proj, stage, windows=STREAM_WINDOWS, exact=exact,
+                                copy_to=result)
         comp.finish_download(result, stage)
         comp.release()
         return out if direct_out else result

@@ -404,9 +404,17 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
             _peer_ok, peer = False, None
 
     def place(dst, piece, y0, y1):
-        """strip rows [y0, y1) (mosaic coordinates) into their place in a whole-mosaic tensor"""
-        target = dst[y0:y1] if cols is None else dst[y0:y1, cols[0]:cols[1]]
-        target.copy_(piece, non_blocking=True)
+        """strip rows [y0, y1) (mosaic coordinates) into their place in a whole-mosaic tensor: a DMA
+        (rows: one contiguous copy; a column strip: a rectangle copy — an elementwise copy kernel
+        would write the peer's memory byte by byte)"""
+        if cols is None:
+            dst[y0:y1].copy_(piece, non_blocking=True)
+        elif comp.device.type != "cuda":
+            dst[y0:y1, cols[0]:cols[1]].copy_(piece)
+        else:
+            from . import _lib
+            _lib.call("p360_copy_rect", dst.data_ptr() + 3 * (y0 * w + cols[0]), 3 * w, piece.data_ptr(), piece.stride(0),
+                      3 * (cols[1] - cols[0]), y1 - y0, torch.cuda.current_stream(comp.device).cuda_stream)
     if peer is not None:
         main, side = torch.cuda.current_stream(comp.device), comp.copy_stream()
         dst = peer.rows_of_rank0(h, w)                # (the buffer the previous step did not write)

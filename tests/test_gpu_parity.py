@@ -803,6 +803,24 @@ def test_unpacked_source_layout_is_equivalent(comp, tiny4):
             assert torch_equal(a.rgba, b.rgba) and torch_equal(a.invalid, b.invalid)
 
 
+def test_batched_packing_equals_per_image(comp, tiny4):
+    """pack_sources (one p360_pack_rgbx_batch launch over all resident images — what the bench's
+    device-timed leg runs) produces the RGBX copies the per-image packing of ``upload`` produces:
+    whole images, row ranges and rectangles (only the named part is defined)."""
+    _, regs = tiny4
+    h, w = regs[0].img.shape[:2]
+    parts = [None, {i: (8, h - 5) for i in range(len(regs))}, {i: (3 + i, h - 9, 12, w - 7 - i) for i in range(len(regs))}]
+    for part in parts:
+        one = comp.upload(regs, rows_of=part)
+        many = comp.pack_sources(comp.upload(regs, pack=False, rows_of=part))
+        for i, (a, b) in enumerate(zip(one.pixels, many.pixels)):
+            r0, r1, c0, c1 = (0, h, 0, w) if part is None else (part[i] + (0, w))[:4]
+            c0 = c0 // 4 * 4
+            assert a.shape == b.shape == (h, w, 4)
+            assert torch_equal(a[r0:r1, c0:c1, :3], b[r0:r1, c0:c1, :3]), (part, i)
+            assert bool((b[r0:r1, c0:c1, :3].cpu() == __import__("torch").from_numpy(regs[i].img[r0:r1, c0:c1])).all())
+
+
 def torch_equal(a, b):
     import torch
     return bool(torch.equal(a, b))

@@ -57,6 +57,7 @@ test_column_windows_equal_full_mosaic = gpu.test_column_windows_equal_full_mosai
 test_source_rectangles_cover_every_tap = gpu.test_source_rectangles_cover_every_tap
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
+test_batched_packing_equals_per_image = gpu.test_batched_packing_equals_per_image
 test_partial_row_uploads_are_sufficient = gpu.test_partial_row_uploads_are_sufficient
 test_seam_split_is_exact = gpu.test_seam_split_is_exact
 test_full_resolution_path_is_the_reference_to_rounding = gpu.test_full_resolution_path_is_the_reference_to_rounding
