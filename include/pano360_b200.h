@@ -146,7 +146,12 @@ int p360_warp_batch(const p360_warp_job *jobs_host, const p360_warp_job *jobs_de
  * p360_multiband_collapse with the same record writes only the multi tiles.
  * Mosaic bytes are produced for rows [y_begin, y_end) x columns [x_begin, x_end) of the buffer
  * (x_begin % 64 == 0; x_end % 64 == 0 or x_end == W): a window of the mosaic, computed in a buffer
- * that also holds the halo the blurs need.  The buffer's column 0 must sit on a multiple of 64 of
+ * that also holds the halo the blurs need.  out_u8 is addressed as out_u8[(y * out_pitch + x) * 3]
+ * for buffer pixel (x, y) — out_pitch in pixels, 0 = W — so that a window can be written straight
+ * into its place in a larger image: the whole mosaic, or rank 0's mosaic mapped into this rank's
+ * address space over NVLink (the strip gather of the multi-GPU path then costs no extra pass: the
+ * tile warp and the collapse store their bytes in the peer's memory as they produce them; pass
+ * out_u8 = that image's address of buffer pixel (0, 0)).  The buffer's column 0 must sit on a multiple of 64 of
  * the whole mosaic and its width must be a multiple of 64 unless it ends at the mosaic's right
  * edge, so that its tiles are tiles of the whole mosaic.
  *
@@ -162,7 +167,7 @@ int p360_seam_plan_build(const p360_warp_job *jobs_dev, int n_jobs, struct p360_
                          int H, int W, int abs_row0, int mosaic_h,
                          const struct p360_tile_maps *maps_host, void *stream);
 int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
-                    uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                    uint8_t *covered, uint8_t *out_u8, int out_pitch, int y_begin, int y_end, int x_begin, int x_end,
                     int H, int W, int want_covered, const struct p360_tile_maps *maps_host, void *stream);
 int p360_source_rects(const p360_warp_job *jobs_dev, int n_jobs, int H, int W, int abs_row0, int mosaic_h,
                       const struct p360_tile_maps *maps_host, int32_t *rects_dev, void *stream);
@@ -289,11 +294,11 @@ int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_patches, int
                               const p360_tile_maps *maps_host, void *stream);
 int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                             const uint64_t *owner_keys, const uint8_t *covered,
-                            uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                            uint8_t *out_u8, int out_pitch, int y_begin, int y_end, int x_begin, int x_end,
                             int row_origin, int W, const p360_tile_maps *maps_host, void *stream);
-int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8, int out_pitch,
                          int y_begin, int y_end, int row_origin, int W, void *stream);
-int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8, int out_pitch,
                         int y_begin, int y_end, int row_origin, int W, void *stream);
 
 /* ---- K8: pair overlap statistics for exposure gains (stitcher.py:48-63) ---

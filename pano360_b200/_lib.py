@@ -31,7 +31,7 @@ SIGNATURES = {
     "p360_source_rects": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "p360_warp_batch": [_vp, _vp, _i, _vp, _vp, _i, _vp],
     "p360_seam_plan_build": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
-    "p360_warp_tiles": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_warp_tiles": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "p360_owner_update": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "p360_owner_decode": [_vp, _vp, _i64, _vp],
     "p360_gauss_blur": [_vp, _vp, _vp, _i, _i, C.POINTER(C.c_float), _i, _vp],
@@ -41,9 +41,9 @@ SIGNATURES = {
     "p360_tile_maps_build": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "p360_pyramid_dims": [_i, _i, _i, C.POINTER(C.c_int32)],
     "p360_pyramid_reduce_batch": [_vp, _i, _i, _i, _vp, _i, _vp, _vp],
-    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
-    "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "p360_multiband_collapse": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "p360_linear_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "p360_paste_collapse": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "p360_pair_stats_blocks": [_i, _i],
     "p360_pair_overlap_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "p360_cover_update": [_vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -902,21 +902,24 @@ class Compositor:
         self._taps_key = n_levels
 
     def _collapse(self, name, nbytes, fn, head, mosaic, out_host=None, rows=None, on_band=None, bands=8,
-                  row_origin=0, tail=(), cols=None, col_origin=0):
+                  row_origin=0, tail=(), cols=None, col_origin=0, out=None):
         """Launch a collapse kernel over rows ``rows`` (default: all) of the
         mosaic buffer.  With ``out_host`` (pinned host array) or ``on_band``
         (callback(y0, y1), e.g. an NVLink send) the rows are produced band by
         band so that the transfer of each finished band overlaps the
         computation of the next.  ``cols = (xa, xb)`` (buffer columns, xa a multiple of 64): only
         those columns are wanted — the multiband collapse produces just them, and just they are
-        downloaded (buffer column x is mosaic column x + ``col_origin``)."""
+        downloaded (buffer column x is mosaic column x + ``col_origin``).  ``out = (address, pitch)``:
+        the kernel stores its bytes there instead of in ``mosaic`` — buffer pixel (x, y) at
+        address + 3 (y pitch + x): the window's place in a larger image (``composite(out_dev=...)``)."""
         h, w = mosaic.shape[:2]
         ya, yb = (0, h) if rows is None else rows
         xa, xb = (0, w) if cols is None else cols
         xargs = (xa, xb) if fn == "p360_multiband_collapse" else ()
+        optr, opitch = (_lib.ptr(mosaic), 0) if out is None else out
         if out_host is None and on_band is None:
             if fn is not None:
-                self._traced(name, nbytes, fn, *head, _lib.ptr(mosaic), ya, yb, *xargs, row_origin, w, *tail, self.stream)
+                self._traced(name, nbytes, fn, *head, optr, opitch, ya, yb, *xargs, row_origin, w, *tail, self.stream)
             return
         host = None if out_host is None else torch.from_numpy(out_host)
         whole_rows = host is not None and xa == 0 and xb == w and col_origin == 0 and host.shape[1] == w
@@ -925,7 +928,7 @@ class Compositor:
             if y1 <= y0:
                 continue
             if fn is not None:             # (None: the rows are already final, e.g. a blank window)
-                self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, _lib.ptr(mosaic), y0, y1, *xargs,
+                self._traced(name, nbytes * (y1 - y0) // max(yb - ya, 1), fn, *head, optr, opitch, y0, y1, *xargs,
                              row_origin, w, *tail, self.stream)
             if on_band is not None:
                 on_band(y0, y1)
@@ -950,7 +953,7 @@ class Compositor:
             self._download = torch.cuda.Event()
             self._download.record(side)
 
-    def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin, cols=None, col_origin=0):
+    def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin, cols=None, col_origin=0, out=None):
         """A mosaic (or window) no image touches: zeros — through the same banded path as a
         collapse, so that ``out_host`` receives its rows and ``on_band`` fires for every band
         (a strip that falls into a gap between images must still send its bands)."""
@@ -1001,7 +1004,7 @@ class Compositor:
 
     def blend_multiband(self, patches, shape, n_levels=5, stages=None, owner_state=None, out_host=None,
                         rows=None, on_band=None, mosaic=None, bands=8, row_origin=0, use_maps=None, seam=None,
-                        cols=None, col_origin=0):
+                        cols=None, col_origin=0, out=None):
         """stitcher.py:186-241.  The wide blurs are evaluated on coarse grids
         and every mosaic pixel gathers its bands from the patches covering it,
         in list order, so no mosaic-sized accumulator ever touches HBM.
@@ -1053,8 +1056,9 @@ class Compositor:
                     main.wait_event(src.ready[i])
             ya, yb = (0, h) if rows is None else rows
             xa, xb = (0, w) if cols is None else cols
+            optr, opitch = (_lib.ptr(mosaic), 0) if out is None else out
             self._traced("K1t_warp_tiles", 30 * seam["pixels"], "p360_warp_tiles", jobs.ctypes.data, _lib.ptr(dev_wjobs), n,
-                         _lib.ptr(keys), _lib.ptr(covered), _lib.ptr(mosaic), ya, yb, xa, xb, h, w,
+                         _lib.ptr(keys), _lib.ptr(covered), optr, opitch, ya, yb, xa, xb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
             self._keep["seam"] = (prep,)
         else:
@@ -1095,7 +1099,7 @@ class Compositor:
         self._collapse("K4_multiband_collapse", 16 * pix + 12 * h * w, "p360_multiband_collapse",
                        (_lib.ptr(dev_table), n, n_levels, _lib.ptr(keys), _lib.ptr(covered)), mosaic, out_host,
                        rows, on_band, bands, row_origin, tail=(None if maps is None else maps.ctypes.data,),
-                       cols=cols, col_origin=col_origin)
+                       cols=cols, col_origin=col_origin, out=out)
         self._keep["collapse"] = (dev_table, keys, covered)
         self.last_covered = covered
         if stages is not None:
@@ -1143,7 +1147,7 @@ class Compositor:
         return mosaic
 
     def _pointwise(self, fn, name, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None,
-                   bands=8, row_origin=0, cols=None, col_origin=0):
+                   bands=8, row_origin=0, cols=None, col_origin=0, out=None):
         h, w = shape
         if mosaic is None:
             mosaic = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
@@ -1153,21 +1157,21 @@ class Compositor:
         dev_table = self._table(table, "band_table")
         pix = int((table["pw"].astype(np.int64) * table["ph"]).sum())
         self._collapse(name, 17 * pix + 3 * h * w, fn, (_lib.ptr(dev_table), len(patches)), mosaic, out_host,
-                       rows, on_band, bands, row_origin, cols=cols, col_origin=col_origin)
+                       rows, on_band, bands, row_origin, cols=cols, col_origin=col_origin, out=out)
         self._keep["collapse"] = (dev_table,)
         return mosaic
 
     def blend_none(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
-                   row_origin=0, cols=None, col_origin=0):
+                   row_origin=0, cols=None, col_origin=0, out=None):
         """stitcher.py:160-168 (last valid writer wins), gather form."""
         return self._pointwise("p360_paste_collapse", "K7_paste_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands, row_origin, cols, col_origin)
+                               on_band, mosaic, bands, row_origin, cols, col_origin, out)
 
     def blend_linear(self, patches, shape, out_host=None, rows=None, on_band=None, mosaic=None, bands=8,
-                     row_origin=0, cols=None, col_origin=0):
+                     row_origin=0, cols=None, col_origin=0, out=None):
         """stitcher.py:171-183, gather form."""
         return self._pointwise("p360_linear_collapse", "K6_linear_collapse", patches, shape, out_host, rows,
-                               on_band, mosaic, bands, row_origin, cols, col_origin)
+                               on_band, mosaic, bands, row_origin, cols, col_origin, out)
 
     def covered_mask(self, patches, shape):
         """Area of validity for the crop stage (stitcher.py:266-271)."""
@@ -1312,7 +1316,7 @@ class Compositor:
                        if any(b[0] < x1 and b[2] > x0 and b[1] < y1 and b[3] > y0 for b in used.get(c[0], ()))})
 
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None):
+                  on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None, out_dev=None):
         """warp + blend for the whole mosaic or for a window of it: rows [ya, yb) and / or columns
         [xa, xb) (xa a multiple of 64; xb too unless it is the mosaic width).  The returned strip
         has exactly (yb - ya) x (xb - xa) pixels and is bit-identical to that part of the full
@@ -1323,7 +1327,9 @@ class Compositor:
         is called after the collapse of mosaic rows [y0, y1) has been launched
         (``strip_part`` = that part of the device result, columns [xa, xb) only).  ``want_covered``:
         keep the union of valid pixels of the rows produced in ``last_covered`` (crop stage,
-        stitcher.py:266-271)."""
+        stitcher.py:266-271).  ``out_dev = (address, width)`` of a device image of the WHOLE mosaic —
+        this GPU's, or a peer's mapped over NVLink: the kernels store the window's bytes straight
+        into their place there (no local result: the returned strip is None)."""
         self._mark(f"composite {rows} {cols} begins")
         if cols is not None and want_covered:
             raise ValueError("want_covered needs every column of the mosaic")
@@ -1340,6 +1346,15 @@ class Compositor:
             strip = strip[local[0]:local[1]]
             return strip if local_cols is None else strip[:, local_cols[0]:local_cols[1]]
         window = dict(rows=local, on_band=band_cb, bands=bands, row_origin=top, cols=local_cols, col_origin=left)
+        if out_dev is not None:
+            if exact or on_band is not None or out_host is not None:
+                raise ValueError("out_dev excludes exact / on_band / out_host")
+            window["out"] = (out_dev[0] + 3 * (top * out_dev[1] + left), out_dev[1])
+            if not crops:             # nothing lands here: zeros in place
+                view = out_dev[2][top + local[0]:top + local[1]]
+                (view if local_cols is None else view[:, left + local_cols[0]:left + local_cols[1]]).zero_()
+                return None, []
+            result = lambda strip: None
         if exact and kind == "multiband" and n_levels > 1:      # (stitch() asks for it when needs_exact())
             # full-resolution loop nest on the whole window, then hand the rows on like a collapse
             state = self.new_owner_state(shape)

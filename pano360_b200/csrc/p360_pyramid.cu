@@ -372,7 +372,7 @@ template <int L>
 __global__ void __launch_bounds__(256, (L <= 5) ? 4 : 3)
 multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                           const unsigned long long *__restrict__ keys,
-                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int first_tile_row,
+                          const uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int OW, int first_tile_row,
                           int y_begin, int H, int first_tile_col, int x_end, int W, TileMaps maps) {
     // Tiles are anchored at absolute mosaic rows (first_tile_row may be < y_begin, even < 0):
     // whether a tile takes the single-contributor shortcut must not depend on how the
@@ -431,7 +431,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
                 if ((unsigned)px < (unsigned)bp.pw && (unsigned)py < (unsigned)bp.ph &&
                     (pure || key_is_owner(key, bp.index))) {
                     const float4 pix = ld_stream(bp.rgba + (size_t)py * bp.pw + px);
-                    uint8_t *o = out + mi * 3;
+                    uint8_t *o = out + ((size_t)Y * OW + X) * 3;
                     o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.x, 0.f), 1.f)));
                     o[1] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.y, 0.f), 1.f)));
                     o[2] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(pix.z, 0.f), 1.f)));
@@ -485,7 +485,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
             m1 = fmaf(lo[l].y, inv, m1);
             m2 = fmaf(hi[l].x, inv, m2);
         }
-        uint8_t *o = out + mi * 3;                            // stitcher.py:240-241
+        uint8_t *o = out + ((size_t)Y * OW + X) * 3;          // stitcher.py:240-241
         o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(m0, 0.f), 1.f)));
         o[1] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(m1, 0.f), 1.f)));
         o[2] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, fminf(fmaxf(m2, 0.f), 1.f)));
@@ -498,7 +498,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
 template <int MODE>
 __global__ void __launch_bounds__(256)
 pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
-                          uint8_t *__restrict__ out, int first_tile_row, int y_begin, int H, int W) {
+                          uint8_t *__restrict__ out, int OW, int first_tile_row, int y_begin, int H, int W) {
     __shared__ int16_t list[MAX_TILE_PATCHES];
     const int tx0 = blockIdx.x * CT_X, ty0 = first_tile_row + blockIdx.y * CT_Y;
     const int n_hit = build_tile_list<false>(patches, n_patches, tx0, ty0, list);
@@ -533,7 +533,7 @@ pointwise_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
             a0 = __fdiv_rn(a0, w); a1 = __fdiv_rn(a1, w); a2 = __fdiv_rn(a2, w);
         }
         // (255 * v).astype(uint8): truncation, no clip in either reference blender
-        uint8_t *o = out + mi * 3;
+        uint8_t *o = out + ((size_t)Y * OW + X) * 3;
         o[0] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a0));
         o[1] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a1));
         o[2] = (uint8_t)__float2int_rz(__fmul_rn(255.0f, a2));
@@ -548,11 +548,11 @@ inline int first_tile(int y_begin, int row_origin) {     // absolute-row-aligned
 
 template <int L>
 int launch_collapse(const BandPatch *patches, int n_patches, const unsigned long long *keys,
-                    const uint8_t *covered, uint8_t *out, int y0, int y1, int x0, int x1, int row_origin, int W,
+                    const uint8_t *covered, uint8_t *out, int OW, int y0, int y1, int x0, int x1, int row_origin, int W,
                     const TileMaps &maps, cudaStream_t s) {
     const int first = first_tile(y0, row_origin);
     dim3 grid(cdiv(x1 - x0, CT_X), cdiv(y1 - first, CT_Y)), block(CT_X, 4);
-    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, first, y0, y1,
+    multiband_collapse_kernel<L><<<grid, block, 0, s>>>(patches, n_patches, keys, covered, out, OW, first, y0, y1,
                                                         x0 / CT_X, x1, W, maps);
     return check_launch("p360_multiband_collapse");
 }
@@ -645,9 +645,10 @@ extern "C" int p360_pyramid_reduce_batch(const p360_band_patch *patches, int n_p
 
 extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_patches, int n_levels,
                                        const uint64_t *owner_keys, const uint8_t *covered,
-                                       uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
+                                       uint8_t *out_u8, int out_pitch, int y_begin, int y_end, int x_begin, int x_end,
                                        int row_origin, int W, const p360_tile_maps *maps_host, void *stream) {
     const char *where = "p360_multiband_collapse";
+    const int OW = out_pitch ? out_pitch : W;
     P360_REQUIRE(maps_ok(maps_host), where);
     const TileMaps maps = device_maps(maps_host);
     if (maps_host != nullptr) {         // the maps' tile grid must be the collapse's
@@ -660,47 +661,48 @@ extern "C" int p360_multiband_collapse(const p360_band_patch *patches, int n_pat
     P360_REQUIRE(n_patches >= 0 && n_patches <= MAX_TILE_PATCHES, where);
     P360_REQUIRE(n_levels >= 1 && n_levels <= P360_MAX_LEVELS && W > 0, where);
     P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
-    P360_REQUIRE(x_begin >= 0 && x_begin <= x_end && x_end <= W && x_begin % CT_X == 0, where);
+    P360_REQUIRE(x_begin >= 0 && x_begin <= x_end && x_end <= W && x_begin % CT_X == 0 && OW >= x_end, where);
     if (y_end == y_begin || x_end == x_begin) return 0;
     const int H = y_end;
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     auto keys = reinterpret_cast<const unsigned long long *>(owner_keys);
     cudaStream_t s = (cudaStream_t)stream;
     switch (n_levels) {
-        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
-        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 1: return launch_collapse<1>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 2: return launch_collapse<2>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 3: return launch_collapse<3>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 4: return launch_collapse<4>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 5: return launch_collapse<5>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 6: return launch_collapse<6>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        case 7: return launch_collapse<7>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
+        default: return launch_collapse<8>(bp, n_patches, keys, covered, out_u8, OW, y_begin, H, x_begin, x_end, row_origin, W, maps, s);
     }
 }
 
 static int pointwise_collapse(const char *where, int mode, const p360_band_patch *patches, int n_patches,
-                              uint8_t *out_u8, int y_begin, int y_end, int row_origin, int W, void *stream) {
-    P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && W > 0, where);
+                              uint8_t *out_u8, int out_pitch, int y_begin, int y_end, int row_origin, int W, void *stream) {
+    const int OW = out_pitch ? out_pitch : W;
+    P360_REQUIRE(patches && out_u8 && n_patches >= 0 && n_patches <= MAX_TILE_PATCHES && W > 0 && OW >= W, where);
     P360_REQUIRE(y_begin >= 0 && y_end >= y_begin, where);
     if (y_end == y_begin) return 0;
     const int first = first_tile(y_begin, row_origin);
     dim3 grid(cdiv(W, CT_X), cdiv(y_end - first, CT_Y)), block(CT_X, 4);
     auto bp = reinterpret_cast<const BandPatch *>(patches);
     if (mode == 0)
-        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, first, y_begin, y_end, W);
+        pointwise_collapse_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, OW, first, y_begin, y_end, W);
     else
-        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, first, y_begin, y_end, W);
+        pointwise_collapse_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(bp, n_patches, out_u8, OW, first, y_begin, y_end, W);
     return check_launch(where);
 }
 
-extern "C" int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+extern "C" int p360_linear_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8, int out_pitch,
                                     int y_begin, int y_end, int row_origin, int W, void *stream) {
-    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, y_begin, y_end,
+    return pointwise_collapse("p360_linear_collapse", 0, patches, n_patches, out_u8, out_pitch, y_begin, y_end,
                               row_origin, W, stream);
 }
 
-extern "C" int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8,
+extern "C" int p360_paste_collapse(const p360_band_patch *patches, int n_patches, uint8_t *out_u8, int out_pitch,
                                    int y_begin, int y_end, int row_origin, int W, void *stream) {
-    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, y_begin, y_end,
+    return pointwise_collapse("p360_paste_collapse", 1, patches, n_patches, out_u8, out_pitch, y_begin, y_end,
                               row_origin, W, stream);
 }

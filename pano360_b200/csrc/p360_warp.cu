@@ -499,7 +499,7 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
 template <bool RGBX>
 __global__ void __launch_bounds__(256, P360_TILE_BLOCKS)
 warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
-                  uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int y_begin, int y_end,
+                  uint8_t *__restrict__ covered, uint8_t *__restrict__ out, int OW, int y_begin, int y_end,
                   int x_begin, int x_end, int H, int W, int want_covered, TileMaps m) {
     __align__(16) __shared__ uint8_t rows[TILE_Y][DT_PITCH];
     __shared__ float lut[256];
@@ -555,10 +555,10 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
                 __syncthreads();
             }
             if (as_float)
-                warp_tile_patch<RGBX, true>(job, lut, tx0, ty0, bytes && id == solo, rows, out, W, y_begin, y_end,
+                warp_tile_patch<RGBX, true>(job, lut, tx0, ty0, bytes && id == solo, rows, out, OW, y_begin, y_end,
                                             best_a, best_p, valid_bits);
             else
-                warp_tile_patch<RGBX, false>(job, lut, tx0, ty0, true, rows, out, W, y_begin, y_end,
+                warp_tile_patch<RGBX, false>(job, lut, tx0, ty0, true, rows, out, OW, y_begin, y_end,
                                              best_a, best_p, valid_bits);
             solo_done |= id == solo;
         }
@@ -582,7 +582,7 @@ warp_tiles_kernel(int n_jobs, unsigned long long *__restrict__ keys,
     // 8 threads per row: aligned 128-bit stores of the staged bytes
     const int ry = tid >> 3, Y = ty0 + ry;
     if (Y >= y_begin && Y < y_end)
-        store_row_bytes(out + ((size_t)Y * W + tx0) * 3, rows[ry], 3 * min(TILE_X, W - tx0), tid & 7, 8);
+        store_row_bytes(out + ((size_t)Y * OW + tx0) * 3, rows[ry], 3 * min(TILE_X, W - tx0), tid & 7, 8);
 }
 
 // u8 x 3 -> u8 x 4 (RGBX): one aligned 32-bit word per source pixel, so that a bilinear tap of the
@@ -832,14 +832,16 @@ extern "C" int p360_source_rects(const p360_warp_job *jobs_dev, int n_jobs, int 
 }
 
 extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_job *jobs_dev, int n_jobs, uint64_t *owner_keys,
-                               uint8_t *covered, uint8_t *out_u8, int y_begin, int y_end, int x_begin, int x_end,
-                               int H, int W, int want_covered, const p360_tile_maps *maps_host, void *stream) {
+                               uint8_t *covered, uint8_t *out_u8, int out_pitch, int y_begin, int y_end, int x_begin,
+                               int x_end, int H, int W, int want_covered, const p360_tile_maps *maps_host, void *stream) {
     using namespace p360;
     const char *where = "p360_warp_tiles";
     P360_REQUIRE(jobs_host && maps_host && owner_keys && covered && out_u8, where);
     P360_REQUIRE(n_jobs > 0 && n_jobs <= TILE_JOBS_MAX && H > 0 && W > 0 && y_begin >= 0 && y_end <= H, where);
     P360_REQUIRE(x_begin >= 0 && x_begin <= x_end && x_end <= W && x_begin % TILE_X == 0 &&
                  (x_end % TILE_X == 0 || x_end == W), where);
+    P360_REQUIRE(out_pitch == 0 || out_pitch >= x_end, where);
+    const int OW = out_pitch ? out_pitch : W;
     TileMaps m;
     memcpy(&m, maps_host, sizeof(m));
     if (int e = seam_maps_ok(m, n_jobs, H, W, where)) return e;
@@ -864,10 +866,10 @@ extern "C" int p360_warp_tiles(const p360_warp_job *jobs_host, const p360_warp_j
     }
     auto keys = reinterpret_cast<unsigned long long *>(owner_keys);
     if (rgbx)
-        warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, y_begin, y_end, x_begin, x_end,
+        warp_tiles_kernel<true><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, OW, y_begin, y_end, x_begin, x_end,
                                                        H, W, want_covered, m);
     else
-        warp_tiles_kernel<false><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, y_begin, y_end, x_begin, x_end,
+        warp_tiles_kernel<false><<<grid, block, 0, s>>>(n_jobs, keys, covered, out_u8, OW, y_begin, y_end, x_begin, x_end,
                                                         H, W, want_covered, m);
     return check_launch(where);
 }

@@ -374,6 +374,9 @@ class PeerMosaic:
 
 
 _peer_ok = True
+# Strips written into rank 0's mosaic by the kernels that produce them (P360_FUSED_GATHER=0: strips
+# composited locally and pushed band by band with the copy engines while the next band is computed).
+FUSED_GATHER = os.environ.get("P360_FUSED_GATHER", "1") == "1"
 
 
 def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,
@@ -418,9 +421,16 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
     if peer is not None:
         main, side = torch.cuda.current_stream(comp.device), comp.copy_stream()
         dst = peer.rows_of_rank0(h, w)                # (the buffer the previous step did not write)
+        exact = kind == "multiband" and n_levels > 1 and comp.needs_exact(regions)
         if not is_empty(part):
-            if rank == 0:
-                strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols)
+            if FUSED_GATHER and not exact:
+                # compute + gather in one: the tile warp and the collapse store the strip's bytes
+                # straight into their place in rank 0's mosaic (peer stores over NVLink / NVSwitch,
+                # tile by tile as they are produced) — no strip buffer, no copy pass
+                comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols,
+                               out_dev=(dst.data_ptr(), w, dst))
+            elif rank == 0:
+                strip, _ = comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, exact=exact)
                 ya = part_box(part, plan.shape)[0]
                 place(dst, strip, ya, ya + strip.shape[0])
             else:
@@ -431,7 +441,7 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
                     with torch.cuda.stream(side):
                         place(dst, piece, y0, y1)
                 comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, on_band=push_band,
-                               bands=bands)
+                               bands=bands, exact=exact)
                 main.wait_stream(side)
         peer.barrier()                                # every strip has landed
         return dst if rank == 0 else None

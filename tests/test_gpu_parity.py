@@ -682,6 +682,33 @@ def test_column_windows_equal_full_mosaic(comp):
         comp.direct = saved
 
 
+def test_windows_written_in_place(comp):
+    """``composite(out_dev=...)``: the tile warp and the collapse store a window's bytes straight
+    into their place in a whole-mosaic image (the fused strip gather of the multi-GPU path points
+    this at rank 0's mosaic over NVLink): column and row windows written one after the other give
+    the whole composite, and nothing outside a window is touched."""
+    import torch
+    regs = synth.make_views(synth.workload("cfg4", scale=8.0), noise=5.0)
+    for kind in ("multiband", "linear", "none"):
+        plan = geo.plan_mosaic(regs, kind == "multiband", 1e9)
+        src = comp.upload(regs)
+        full = comp.composite(regs, src, plan, kind, 5)[0].cpu().numpy()
+        h, w = plan.shape
+        tiles = -(-w // 64)
+        for axis, cuts in (("cols", [0, 64 * (tiles // 3), 64 * (2 * tiles // 3), w]), ("rows", [0, h // 3 + 5, 2 * h // 3 + 1, h])):
+            whole = torch.full((h, w, 3), 9, dtype=torch.uint8, device=comp.device)
+            for k, (a, b) in enumerate(zip(cuts, cuts[1:])):
+                window = dict(cols=(a, b)) if axis == "cols" else dict(rows=(a, b))
+                strip, _ = comp.composite(regs, src, plan, kind, 5, out_dev=(whole.data_ptr(), w, whole), **window)
+                assert strip is None
+                got = whole.cpu().numpy()
+                done = slice(0, b)
+                if axis == "cols":
+                    assert np.array_equal(got[:, done], full[:, done]) and bool((got[:, b:] == 9).all()), (kind, axis, k)
+                else:
+                    assert np.array_equal(got[done], full[done]) and bool((got[b:] == 9).all()), (kind, axis, k)
+
+
 def _scrambled_outside(regs, rects, seed=3):
     """Copies of the images with everything outside their rectangle replaced by noise."""
     from pano360_b200.camera import Image

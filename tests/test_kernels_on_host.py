@@ -54,6 +54,7 @@ test_cropped_stitch_matches_oracle = gpu.test_cropped_stitch_matches_oracle
 test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_column_windows_equal_full_mosaic = gpu.test_column_windows_equal_full_mosaic
+test_windows_written_in_place = gpu.test_windows_written_in_place
 test_source_rectangles_cover_every_tap = gpu.test_source_rectangles_cover_every_tap
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent

@@ -23,6 +23,15 @@ for name, scale, noise in (("cfg1", 1.0, 20.0), ("cfg2", 2.0, 0.0), ("cfg4", 8.0
         d = np.abs(got.astype(int) - want.astype(int)).max() if got.shape == want.shape else -1
         print(f"{name} x{world} ranks: mosaic {got.shape} identical={same} max|d|={d}", flush=True)
         ok &= bool(same) or (wl.equalize and d <= 1)
+    # the device-resident result (strips stored into rank 0's mosaic by the kernels / pushed by DMA)
+    for fused in (True, False):
+        strips.FUSED_GATHER = fused
+        dev = strips.stitch_strips(comp, regs, wl.blend, wl.n_levels, wl.equalize, wl.max_resolution, to_host=False)
+        if rank == 0:
+            same = np.array_equal(dev.cpu().numpy(), got)
+            print(f"{name} x{world} ranks, device gather fused={fused}: identical={same}", flush=True)
+            ok &= bool(same)
+    strips.FUSED_GATHER = True
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
