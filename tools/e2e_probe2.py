@@ -45,9 +45,10 @@ def timed(fn, n=5):
     return (time.perf_counter() - t0) / n * 1e3
 
 
-for rects in (True, False):
+short = os.environ.get("P360_PROBE_SHORT") == "1"
+for rects in ((True,) if short else (True, False)):
     comp.partial_uploads = rects
-    for windows in (0, 6, 12, 16, 24):
+    for windows in ((0, 12) if short else (0, 6, 12, 16, 24)):
         stitcher.STREAM_WINDOWS = windows
         ms = timed(e2e)
         ok = zlib.crc32(out.numpy().tobytes()) == crc0

@@ -17,7 +17,7 @@ TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 TRACE_NAMES = {"warp_tiles": "K1t_warp_tiles", "blur_h_list": "K3_gauss_blur", "blur_v_list": "K3_gauss_blur",
                "multiband_collapse": "K4_multiband_collapse", "pyramid_reduce_list": "K3a_pyramid_reduce",
-               "pack_rgbx": "K1p_pack_rgbx", "seam_candidates": "K0_seam_plan"}
+               "pack_rgbx": "K1p_pack_rgbx", "pack_rgbx_batch": "K1p_pack_rgbx", "seam_candidates": "K0_seam_plan"}
 WANT = {
     "gpu__time_duration.sum": "time",
     "dram__bytes_read.sum": "dram_read",
