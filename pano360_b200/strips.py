@@ -374,9 +374,12 @@ class PeerMosaic:
 
 
 _peer_ok = True
-# Strips written into rank 0's mosaic by the kernels that produce them (P360_FUSED_GATHER=0: strips
-# composited locally and pushed band by band with the copy engines while the next band is computed).
-FUSED_GATHER = os.environ.get("P360_FUSED_GATHER", "1") == "1"
+# P360_FUSED_GATHER=1: strips are stored into rank 0's mosaic by the kernels that produce them (peer
+# stores over NVLink, no copy pass).  Measured on 8 x B200, cfg4 (profiles/r02o_*): byte-identical, but
+# 3.24 ms per step against 2.05 ms for the default — strips composited locally and pushed band by band
+# with the copy engines (rectangle DMA): a tile row is a 192-byte segment and the collapse stores
+# single bytes, which NVLink carries at a third of the rate of the DMA's long bursts.
+FUSED_GATHER = os.environ.get("P360_FUSED_GATHER", "0") == "1"
 
 
 def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,

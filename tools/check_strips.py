@@ -31,7 +31,7 @@ for name, scale, noise in (("cfg1", 1.0, 20.0), ("cfg2", 2.0, 0.0), ("cfg4", 8.0
             same = np.array_equal(dev.cpu().numpy(), got)
             print(f"{name} x{world} ranks, device gather fused={fused}: identical={same}", flush=True)
             ok &= bool(same)
-    strips.FUSED_GATHER = True
+    strips.FUSED_GATHER = False
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

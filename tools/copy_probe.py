@@ -71,3 +71,32 @@ for c0, c1 in ((0, 4000), (336, 3664), (1000, 3000)):
 ms = timed(lambda: (h2d_full(), d2h_full())); print(f"both contiguous at once: {ms:.2f} ms")
 ms = timed(lambda: (h2d_rect(336, 3664)(), d2h_rect(2688)())); print(f"both as rectangles at once: {ms:.2f} ms")
 ms = timed(lambda: (h2d_rect(336, 3664)(), d2h_full())); print(f"H2D rectangles + D2H contiguous: {ms:.2f} ms")
+
+# the multi-GPU path downloads into a /dev/shm mapping registered with cudaHostRegister: same rate?
+import numpy as np  # noqa: E402
+name = f"/dev/shm/p360_probe_{os.getpid()}"
+with open(name, "wb") as fid:
+    fid.truncate(H * W * 3)
+shm = np.memmap(name, dtype=np.uint8, mode="r+", shape=(H * W * 3,))
+os.unlink(name)
+shm[:] = 0                                             # touch every page
+rt = torch.cuda.cudart()
+t0 = time.perf_counter(); err = rt.cudaHostRegister(shm.ctypes.data, shm.nbytes, 0)
+print(f"cudaHostRegister of a {shm.nbytes / 1e6:.0f} MB /dev/shm mapping: {(time.perf_counter() - t0) * 1e3:.0f} ms ({err})")
+shm_t = torch.from_numpy(shm).view(H, W, 3)
+
+
+def d2h_shm():
+    with torch.cuda.stream(down):
+        _lib.call("p360_copy_rect", shm_t.data_ptr(), 3 * W, dev.data_ptr(), 3 * W, 3 * W, H, down.cuda_stream)
+
+
+def d2h_shm_cols(cols=3968):
+    for xa in range(0, W, cols):
+        xb = min(xa + cols, W)
+        _lib.call("p360_copy_rect", shm_t.data_ptr() + 3 * xa, 3 * W, dev.data_ptr() + 3 * xa, 3 * W, 3 * (xb - xa), H, down.cuda_stream)
+
+
+ms = timed(d2h_shm); print(f"D2H mosaic into the registered /dev/shm mapping: {ms:.2f} ms = {mb_m / ms:.1f} GB/s")
+ms = timed(d2h_shm_cols); print(f"... in 8 column strips: {ms:.2f} ms = {mb_m / ms:.1f} GB/s")
+rt.cudaHostUnregister(shm.ctypes.data)

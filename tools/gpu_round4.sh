@@ -7,6 +7,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/${TAG}_pytest.log 2>&1
 echo "== pytest -m gpu: $(tail -n 2 gpurun_out/${TAG}_pytest.log | tr '\n' ' ')"; grep "cfg4 whole" gpurun_out/${TAG}_pytest.log
+timeout 300 python tools/copy_probe.py > gpurun_out/${TAG}_copy_probe.log 2>&1; grep -i "shm" gpurun_out/${TAG}_copy_probe.log
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "== bench rc=$? $(python tools/show_bench.py gpurun_out/${TAG}_bench.json 2>/dev/null | head -3 | cut -c1-300)"
 P360_PROBE_SHORT=1 timeout 300 python tools/e2e_probe2.py cfg4 > gpurun_out/${TAG}_e2e_probe.log 2>&1
