@@ -196,6 +196,7 @@ class Compositor:
         self.partial_uploads = os.environ.get("P360_SOURCE_RECTS", "1") == "1"
         self.last_covered = None
         self.last_upload_bytes = 0     # image bytes the last ``upload`` sent over PCIe
+        self.used_after_warp = False   # did the last composite call its ``after_warp`` hook
 
     # -- plumbing -----------------------------------------------------------
     @property
@@ -1061,6 +1062,14 @@ class Compositor:
                          _lib.ptr(keys), _lib.ptr(covered), optr, opitch, ya, yb, xa, xb, h, w,
                          int(bool(seam.get("want_covered"))), maps.ctypes.data, self.stream)
             self._keep["seam"] = (prep,)
+            if seam.get("after_warp") is not None:
+                # the caller wants to move the tiles that are final after the tile warp (all but the
+                # multi tiles) while reduce / blur / collapse still run: hand it the plan's multi map
+                # (a function of the geometry alone: fetched once per prepared window)
+                if "multi_host" not in prep:
+                    torch.cuda.current_stream(self.device).synchronize()
+                    prep["multi_host"] = maps_keep[1].cpu().numpy().reshape(int(maps["tiles_y"][0]), int(maps["tiles_x"][0])) != 0
+                seam["after_warp"](mosaic, prep["multi_host"], int(maps["row0"][0]))
         else:
             keys, covered = owner_state if owner_state is not None else self.owner_state_for(patches, shape)
             table = self._band_table(patches, pad, coarse=True)
@@ -1316,7 +1325,8 @@ class Compositor:
                        if any(b[0] < x1 and b[2] > x0 and b[1] < y1 and b[3] > y0 for b in used.get(c[0], ()))})
 
     def composite(self, regions, src, plan, kind, n_levels=5, proj=geo.SphProj, rows=None, out_host=None,
-                  on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None, out_dev=None):
+                  on_band=None, bands=8, direct=None, want_covered=False, exact=False, cols=None, out_dev=None,
+                  after_warp=None):
         """warp + blend for the whole mosaic or for a window of it: rows [ya, yb) and / or columns
         [xa, xb) (xa a multiple of 64; xb too unless it is the mosaic width).  The returned strip
         has exactly (yb - ya) x (xb - xa) pixels and is bit-identical to that part of the full
@@ -1329,8 +1339,14 @@ class Compositor:
         keep the union of valid pixels of the rows produced in ``last_covered`` (crop stage,
         stitcher.py:266-271).  ``out_dev = (address, width)`` of a device image of the WHOLE mosaic —
         this GPU's, or a peer's mapped over NVLink: the kernels store the window's bytes straight
-        into their place there (no local result: the returned strip is None)."""
+        into their place there (no local result: the returned strip is None).
+        ``after_warp(buffer, multi, geometry)``: called (seam-plan path only) once the tile warp has
+        been launched — every tile that is not ``multi`` (bool [tiles_y, tiles_x] over the 64 x 32
+        tiles of the window's buffer) is final from then on; ``geometry`` = dict(top, left, row0,
+        rows, cols): where the buffer sits in the mosaic, where its tile rows start, and the
+        window in buffer coordinates.  Returns with ``used_after_warp`` telling whether it fired."""
         self._mark(f"composite {rows} {cols} begins")
+        self.used_after_warp = False
         if cols is not None and want_covered:
             raise ValueError("want_covered needs every column of the mosaic")
         crops, tables, top, left, shape, local, local_cols = self._window_geometry(regions, plan, kind, n_levels, proj,
@@ -1387,6 +1403,12 @@ class Compositor:
             seam = {"prepared": prep, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": prep["keep"][3],
                     "want_covered": want_covered,
                     "reads": self._images_read(regions, plan, kind, n_levels, proj, crops, top, left, shape)}
+            if after_warp is not None:
+                def fire(buffer, multi, row0):
+                    self.used_after_warp = True
+                    after_warp(buffer, multi, dict(top=top, left=left, row0=row0, rows=local,
+                                                   cols=local_cols if local_cols is not None else (0, shape[1])))
+                seam["after_warp"] = fire
             strip = self._blend_into(holder, self.blend_multiband, patches, shape, n_levels, out_host=out_host,
                                      seam=seam, **window)
             return result(strip), patches

@@ -334,6 +334,40 @@ def gather_strips(strip, parts, shape, dst=0, group=None):
     return None
 
 
+def final_after_warp(multi, geometry, seam_share=0.5):
+    """Cut a window into rectangles that are final once the tile warp has run (no multi tile
+    inside: ``early``) and the rest (``late``: final after the collapse).  ``multi``: bool
+    [tiles_y, tiles_x] over the 64 x 32 tiles of the window's buffer, ``geometry`` as handed to
+    ``Compositor.composite(after_warp=...)``.  Tile rows in which more than ``seam_share`` of the
+    tiles are multi (a horizontal seam band) go late whole; between them, runs of tile columns
+    without a multi tile go early.  Rectangles are (y0, y1, x0, x1) in BUFFER pixels, disjoint,
+    and cover the window exactly."""
+    (ya, yb), (xa, xb), row0 = geometry["rows"], geometry["cols"], geometry["row0"]
+    ty0, ty1 = (ya - row0) // 32, (yb - 1 - row0) // 32 + 1
+    tx0, tx1 = xa // 64, (xb - 1) // 64 + 1
+    sub = multi[ty0:ty1, tx0:tx1]
+    early, late = [], []
+    if sub.size == 0:
+        return early, late
+    heavy = sub.mean(axis=1) > seam_share
+    a = 0
+    for t in range(1, len(heavy) + 1):
+        if t == len(heavy) or heavy[t] != heavy[a]:
+            y0, y1 = max(ya, row0 + 32 * (ty0 + a)), min(yb, row0 + 32 * (ty0 + t))
+            if heavy[a]:
+                late.append((y0, y1, xa, xb))
+            else:
+                busy = sub[a:t].any(axis=0)
+                c = 0
+                for u in range(1, len(busy) + 1):
+                    if u == len(busy) or busy[u] != busy[c]:
+                        x0, x1 = max(xa, 64 * (tx0 + c)), min(xb, 64 * (tx0 + u))
+                        (late if busy[c] else early).append((y0, y1, x0, x1))
+                        c = u
+            a = t
+    return early, late
+
+
 class PeerMosaic:
     """Rank 0's mosaic buffer mapped into every rank's address space over
     NVLink / NVSwitch (torch symmetric memory): strips are written by DMA
@@ -380,6 +414,10 @@ _peer_ok = True
 # with the copy engines (rectangle DMA): a tile row is a 192-byte segment and the collapse stores
 # single bytes, which NVLink carries at a third of the rate of the DMA's long bursts.
 FUSED_GATHER = os.environ.get("P360_FUSED_GATHER", "0") == "1"
+# Push everything outside the seam zone right after the tile warp (final from then on), so that the
+# transfer overlaps reduce / blur / collapse and only the seam zone's rectangles are left for the end.
+EARLY_PUSH = os.environ.get("P360_EARLY_PUSH", "1") == "1"
+_early_cache = {}
 
 
 def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,
@@ -437,14 +475,44 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
                 ya = part_box(part, plan.shape)[0]
                 place(dst, strip, ya, ya + strip.shape[0])
             else:
+                state = {}
+
+                def push_rects(buffer, rects, geometry):
+                    """DMA rectangles of the window's buffer into their place in rank 0's mosaic"""
+                    from . import _lib
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    side.wait_event(done)
+                    top, left, pitch = geometry["top"], geometry["left"], buffer.shape[1]
+                    for y0, y1, x0, x1 in rects:
+                        _lib.call("p360_copy_rect", dst.data_ptr() + 3 * ((y0 + top) * w + x0 + left), 3 * w,
+                                  buffer.data_ptr() + 3 * (y0 * pitch + x0), 3 * pitch, 3 * (x1 - x0), y1 - y0, side.cuda_stream)
+
+                def after_warp(buffer, multi, geometry):
+                    # everything but the seam zone is final now: it travels while reduce / blur /
+                    # collapse run, and only the seam zone's rectangles are left for the end
+                    key = (id(multi), geometry["top"], geometry["left"], geometry["rows"], geometry["cols"])
+                    cuts = _early_cache.get(key)
+                    if cuts is None:
+                        if len(_early_cache) > 64:
+                            _early_cache.clear()
+                        cuts = _early_cache[key] = final_after_warp(multi, geometry)
+                    state.update(buffer=buffer, geometry=geometry, late=cuts[1])
+                    push_rects(buffer, cuts[0], geometry)
+
                 def push_band(piece, y0, y1):
+                    if state:                         # (the early pushes fired: the rest goes at the end)
+                        return
                     done = torch.cuda.Event()
                     done.record(main)
                     side.wait_event(done)
                     with torch.cuda.stream(side):
                         place(dst, piece, y0, y1)
+                early_ok = EARLY_PUSH and comp.device.type == "cuda" and not exact
                 comp.composite(regions, src, plan, kind, n_levels, proj, rows=rows, cols=cols, on_band=push_band,
-                               bands=bands, exact=exact)
+                               bands=bands, exact=exact, after_warp=after_warp if early_ok else None)
+                if state:
+                    push_rects(state["buffer"], state["late"], state["geometry"])
                 main.wait_stream(side)
         peer.barrier()                                # every strip has landed
         return dst if rank == 0 else None

@@ -717,6 +717,51 @@ def test_windows_written_in_place(comp):
                     assert np.array_equal(got[done], full[done]) and bool((got[b:] == 9).all()), (kind, axis, k)
 
 
+def test_tiles_final_after_the_tile_warp(comp):
+    """The early push of the multi-GPU gather (strips.final_after_warp): once the tile warp has been
+    launched every tile outside the seam zone holds its final bytes — rectangles without a multi
+    tile are copied out at that moment (before reduce / blur / collapse have run), the rest after
+    the collapse; together they are the window of the whole composite, byte for byte."""
+    import torch
+    from dataclasses import replace
+    from pano360_b200 import strips
+    wl = replace(synth.workload("cfg1"), width=1600, height=500, focal=1800.0, yaws=(-0.55, 0.0, 0.55, 0.3),
+                 pitches=(0.0, 0.02, -0.02, 0.2))
+    regs = synth.make_views(wl, noise=5.0)
+    plan = geo.plan_mosaic(regs, True, 1e9)
+    src = comp.upload(regs)
+    levels = 3
+    full = comp.composite(regs, src, plan, "multiband", levels)[0].cpu().numpy()
+    h, w = plan.shape
+    tiles = -(-w // 64)
+    for rows, cols in [(None, (64 * (tiles // 4), 64 * (3 * tiles // 4))), ((h // 4, 3 * h // 4 + 3), None), (None, None)]:
+        remote = torch.full((h, w, 3), 9, dtype=torch.uint8, device=comp.device)
+        state = {}
+
+        def move(buffer, rects, g):
+            for y0, y1, x0, x1 in rects:
+                remote[y0 + g["top"]:y1 + g["top"], x0 + g["left"]:x1 + g["left"]] = buffer[y0:y1, x0:x1]
+
+        def after_warp(buffer, multi, g):
+            early, late = strips.final_after_warp(multi, g)
+            state.update(buffer=buffer, g=g, late=late, early=early)
+            move(buffer, early, g)                     # NOW: the collapse has not been launched yet
+            if comp.device.type == "cuda":
+                torch.cuda.synchronize()
+        comp.composite(regs, src, plan, "multiband", levels, rows=rows, cols=cols, after_warp=after_warp)
+        assert comp.used_after_warp and state["early"] and state["late"]
+        move(state["buffer"], state["late"], state["g"])
+        ya, yb = rows or (0, h)
+        xa, xb = cols or (0, w)
+        got = remote.cpu().numpy()
+        assert np.array_equal(got[ya:yb, xa:xb], full[ya:yb, xa:xb]), (rows, cols)
+        outside = np.ones((h, w), bool)
+        outside[ya:yb, xa:xb] = False
+        assert bool((got[outside] == 9).all())
+        share = sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in state["early"]) / ((yb - ya) * (xb - xa))
+        assert share > 0.15, share
+
+
 def _scrambled_outside(regs, rects, seed=3):
     """Copies of the images with everything outside their rectangle replaced by noise."""
     from pano360_b200.camera import Image

@@ -55,6 +55,7 @@ test_row_window_equals_full_mosaic = gpu.test_row_window_equals_full_mosaic
 test_row_windows_cut_anywhere = gpu.test_row_windows_cut_anywhere
 test_column_windows_equal_full_mosaic = gpu.test_column_windows_equal_full_mosaic
 test_windows_written_in_place = gpu.test_windows_written_in_place
+test_tiles_final_after_the_tile_warp = gpu.test_tiles_final_after_the_tile_warp
 test_source_rectangles_cover_every_tap = gpu.test_source_rectangles_cover_every_tap
 test_view_over_the_pole = gpu.test_view_over_the_pole
 test_unpacked_source_layout_is_equivalent = gpu.test_unpacked_source_layout_is_equivalent
