@@ -171,7 +171,8 @@ class Compositor:
         self._copy = None      # side streams for uploads / downloads that overlap the kernels
         self._down = None
         self._download = None
-        self._bands_down = []  # (y0, y1, event) of the banded download in flight
+        self._bands_down = []  # (y0, y1, event, x0, x1) of the banded download in flight
+        self._drain = None     # (queue, thread, errors) while a copy-out thread moves landed bands to the caller's array
         self._ring = []        # pinned staging slots for pageable inputs: [tensor, busy event]
         self._ring_at = 0
         self._out_stage = None  # pinned staging for a pageable output
@@ -947,7 +948,11 @@ class Compositor:
                                   side.cuda_stream)
                 landed = torch.cuda.Event()
                 landed.record(side)
-                self._bands_down.append((y0 + row_origin, y1 + row_origin, landed, xa + col_origin, xb + col_origin))
+                band = (y0 + row_origin, y1 + row_origin, landed, xa + col_origin, xb + col_origin)
+                if self._drain is not None:
+                    self._drain[0].put(band)           # (a copy-out thread is running: composite_streamed)
+                else:
+                    self._bands_down.append(band)
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} collapsed")
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} downloaded", side)
         if host is not None:
@@ -978,17 +983,36 @@ class Compositor:
         for key in ("warp", "warp_jobs", "bands", "collapse", "streamed", "seam", "exact"):
             self._keep.pop(key, None)
 
-    def drain_landed(self, copy_to, staged):
-        """Copy the bands of a banded download that have already landed from the pinned staging
-        buffer into the caller's (pageable) array, without waiting for the others."""
-        rest = []
-        for band in self._bands_down:
-            y0, y1, landed, x0, x1 = band
-            if landed.query():
-                parallel_copy(copy_to[y0:y1, x0:x1], staged[y0:y1, x0:x1])
-            else:
-                rest.append(band)
-        self._bands_down = rest
+    def _start_copy_out(self, copy_to, staged):
+        """A thread that moves every band of the banded download from the pinned staging buffer to
+        the caller's (pageable) array as soon as it has landed — while the main thread goes on
+        staging images and queueing windows (the copies release the GIL)."""
+        import queue
+        import threading
+        bands, errors = queue.Queue(), []
+
+        def run():
+            try:
+                while True:
+                    band = bands.get()
+                    if band is None:
+                        return
+                    y0, y1, landed, x0, x1 = band
+                    landed.synchronize()
+                    parallel_copy(copy_to[y0:y1, x0:x1], staged[y0:y1, x0:x1])
+            except BaseException as exc:          # handed to the caller by _join_copy_out
+                errors.append(exc)
+        thread = threading.Thread(target=run, name="p360-copy-out", daemon=True)
+        self._drain = (bands, thread, errors)
+        thread.start()
+
+    def _join_copy_out(self):
+        bands, thread, errors = self._drain
+        self._drain = None
+        bands.put(None)
+        thread.join()
+        if errors:
+            raise errors[0]
 
     def finish_download(self, copy_to=None, staged=None):
         """Block until a banded download started by ``_collapse`` has landed.  ``copy_to`` (a
@@ -1477,7 +1501,8 @@ class Compositor:
         window is composited (exactly the bytes of the whole composite, see ``composite``) and
         downloaded, while the uploads for the windows to its right continue on their own stream.
         ``out_host``: pinned uint8 H x W x 3; ``copy_to``: the pageable array the pixels finally go
-        to (bands that have landed are copied on between windows).  Call ``finish_download`` afterwards."""
+        to (a thread copies every band on as soon as it has landed; the call then returns when the
+        last one is there).  Call ``finish_download`` afterwards."""
         rects = None if exact else self.source_rects(regions, plan, kind, n_levels, proj)
         order, wins = self.streamed_windows(plan, kind, n_levels, windows,
                                             used=None if rects is None else self.used_boxes(regions, plan, kind, n_levels, proj))
@@ -1487,13 +1512,17 @@ class Compositor:
         src = self.upload(regions, overlap=True, order=order, reuse=True, rects_of=rects,
                           need=None if rects is None else set(rects), lazy=True)
         strips = []
-        for xa, xb, count in wins:
-            src.issue(count)
-            strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, cols=(xa, xb), out_host=out_host,
-                                      bands=bands, exact=exact)
-            strips.append(strip)          # the download stream still reads it: keep it allocated
-            if copy_to is not None:       # bands that have landed meanwhile go on to the caller's array
-                self.drain_landed(copy_to, out_host)
+        if copy_to is not None:
+            self._start_copy_out(copy_to, out_host)
+        try:
+            for xa, xb, count in wins:
+                src.issue(count)
+                strip, _ = self.composite(regions, src, plan, kind, n_levels, proj, cols=(xa, xb), out_host=out_host,
+                                          bands=bands, exact=exact)
+                strips.append(strip)          # the download stream still reads it: keep it allocated
+        finally:
+            if copy_to is not None:
+                self._join_copy_out()
         src.issue()
         self._keep["streamed"] = (strips, src)
         return src
