@@ -308,15 +308,17 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8, 
             regs, plan, _, out = scenes[pano % n_scenes]
             stitcher.stitch(regs, blender=stitcher.multiband_blend, n_levels=wl.n_levels, out=out.numpy())
 
-    def timed(fn, steps):
+    def timed(fn, steps, trace=False):
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0, t0 = _lib.launch_count, time.perf_counter()
+        comp.trace = [] if trace else None
         start.record(torch.cuda.current_stream())
         for _ in range(steps):
             fn()
         end.record(torch.cuda.current_stream())
         barrier()
+        traced["events"], comp.trace = comp.trace, None
         host_ms, dev_ms, launched = (time.perf_counter() - t0) * 1e3, start.elapsed_time(end), _lib.launch_count - n0
         if world > 1:
             t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device=comp.device)
@@ -328,10 +330,41 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8, 
         return dev_ms / steps, host_ms / steps, launched
 
     steps = args.steps if steps is None else steps
+    traced = {}
     for _ in range(args.warmup):
         device_step()
     with ClockSampler(comp.device.index or 0) as clocks:
-        ms, _, launches = timed(device_step, steps)
+        ms, host_ms, launches = timed(device_step, steps, trace=True)
+    # per-kernel times of the batch and the roofline of its dominant kernel (this rank's panoramas;
+    # SURVEY 8(d) bytes on the patch pixels after the seam split)
+    per_kernel = {}
+    for name, _, ev0, ev1 in traced.get("events") or []:
+        agg = per_kernel.setdefault(name, [0.0, 0])
+        agg[0] += ev0.elapsed_time(ev1)
+        agg[1] += 1
+    roofline = None
+    if per_kernel:
+        reach = comp.blur_reach(wl.blend, wl.n_levels)
+        crop_px = src_b = m_px = 0
+        for pano in mine:
+            regs, plan, _, _ = scenes[pano % n_scenes]
+            crops, _ = comp.plan_crops(regs, plan, split_dilate=2 * reach)
+            crop_px += sum((c[3] - c[1]) * (c[4] - c[2]) for c in crops)
+            src_b += sum(int(np.prod(r.img.shape)) for r in regs)
+            m_px += plan.shape[0] * plan.shape[1]
+        top = max(per_kernel, key=lambda k: per_kernel[k][0])
+        nbytes = algorithmic_bytes(top, wl, crop_px, src_b, m_px) or 0
+        peak = 6650.0
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak))
+        except OSError:
+            pass
+        t_ms = max(per_kernel[top][0] / steps, 1e-9)
+        roofline = {"kernel": top, "bound": "hbm", "achieved": nbytes / t_ms / 1e6, "peak": peak, "unit": "GB/s",
+                    "frac": nbytes / t_ms / 1e6 / peak, "traffic": None, "launch_ms": t_ms / (per_kernel[top][1] / steps),
+                    "algorithmic_bytes_per_launch": nbytes / (per_kernel[top][1] / steps),
+                    "share_of_step": t_ms / max(ms, 1e-9),
+                    "bytes_model": "SURVEY 8(d) bytes of the stage the kernel stands for, summed over this rank's panoramas"}
     e2e_step()
     _, e2e_ms, _ = timed(e2e_step, steps)
     mpix = sum(np.prod(scenes[p % n_scenes][1].shape) for p in range(n_panos)) / 1e6
@@ -349,7 +382,9 @@ def run_batch_of_panoramas(args, wl, comp, world, rank, n_panos=64, n_scenes=8, 
             "clocks": clocks.summary(),
             "e2e": {"value": mpix / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": src_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms, "api": "pano360_b200.stitcher.stitch"},
-            "gpu_launches": launches, "roofline": None}
+            "gpu_launches": launches, "roofline": roofline,
+            "kernels": {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in sorted(per_kernel.items())},
+            "host_ms_per_step": host_ms}
     return None
 
 
@@ -697,7 +732,8 @@ def run_gpu_arm(args):
             torch.cuda.empty_cache()
         sub = run_batch_of_panoramas(args, synth.workload("cfg5"), comp, world, rank, steps=max(2, min(args.steps, 3)))
         if sub is not None:
-            others["cfg5"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "n_gpus")}
+            others["cfg5"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "n_gpus", "roofline",
+                                                  "kernels", "host_ms_per_step")}
             others["cfg5"]["config"] = sub["config"]["workload"] + "; replicas: pano_id % n_gpus"
     if rank == 0 and line is not None:
         if others:
