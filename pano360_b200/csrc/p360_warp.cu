@@ -67,8 +67,7 @@ __device__ __forceinline__ ColumnTerms column_terms(const WarpJob &s, int c) {
 }
 
 template <bool ALPHA>
-__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, const ColumnTerms &col, int r, TapAlpha &alpha) {
-    const double ry = __ldg(s.ray_y + s.row0 + r);
+__device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, const ColumnTerms &col, double ry, TapAlpha &alpha) {
     const float px = (float)fma(s.kr[2], col.rz, fma(s.kr[1], ry, col.x0));     // then cast to float32 (stitcher.py:306)
     const float py = (float)fma(s.kr[5], col.rz, fma(s.kr[4], ry, col.x1));
     const float pz = (float)fma(s.kr[8], col.rz, fma(s.kr[7], ry, col.x2));
@@ -78,10 +77,12 @@ __device__ __forceinline__ TapPlan plan_taps(const WarpJob &s, const ColumnTerms
     const float y = __fadd_rn(__fdiv_rn(py, pz), s.half_h);
     t.bad |= (x < 0.0f) | (x > s.max_x) | (y < 0.0f) | (y > s.max_y);   // :311-312
     const int sx = to_fixed5(x), sy = to_fixed5(y);
-    const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);
-    int x0 = ix, x1 = ix + 1, y0 = iy, y1 = iy + 1;
-    if ((unsigned)ix >= (unsigned)(s.w - 1) || (unsigned)iy >= (unsigned)(s.h - 1)) {
+    // integer parts; inside the image (w, h <= 32767) the int16 saturation of OpenCV's map is the identity
+    int x0 = sx >> 5, y0 = sy >> 5;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    if ((unsigned)x0 >= (unsigned)(s.w - 1) || (unsigned)y0 >= (unsigned)(s.h - 1)) {
         // a tap falls outside the image: BORDER_REFLECT (cv2.remap at stitcher.py:315-316)
+        const int ix = sat16(x0), iy = sat16(y0);
         x0 = reflect_fast(ix, s.w, s.inv_2w); x1 = reflect_fast(ix + 1, s.w, s.inv_2w);
         y0 = reflect_fast(iy, s.h, s.inv_2h); y1 = reflect_fast(iy + 1, s.h, s.inv_2h);
     }
@@ -200,7 +201,8 @@ __device__ __forceinline__ void warp_block(const WarpJob &job, float *lut, unsig
     const ColumnTerms col = column_terms(job, c);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k)
-        plan[k] = plan_taps<true>(job, col, min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1), alpha[k]);
+        plan[k] = plan_taps<true>(job, col, __ldg(job.ray_y + job.row0 + min(r0 + (int)threadIdx.y + k * WARP_BY, job.ph - 1)),
+                                  alpha[k]);
 #pragma unroll
     for (int k = 0; k < WARP_ROWS; ++k) {
         load_row_taps<RGBX>(job, plan[k].off00, plan[k].off01, taps[k][0], taps[k][1]);
@@ -447,6 +449,10 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
     const int X = tx0 + threadIdx.x, c = X - job.x0;
     if ((unsigned)c >= (unsigned)job.pw) return;
     const ColumnTerms col = column_terms(job, c);
+    const double *ray_rows = job.ray_y + job.row0;            // y component of the ray per patch row
+    // byte phase of a staged row at its destination: (out + 3 (Y W + tx0)) & 15, in 32-bit arithmetic
+    const unsigned phase0 = (unsigned)(reinterpret_cast<uintptr_t>(out) + 3u * (unsigned)tx0) & 15u;
+    const unsigned phase_step = (3u * (unsigned)W) & 15u;
     constexpr int RP = FLOAT ? 2 : 4;       // rows per pass (the float path carries alpha and more addresses)
 #pragma unroll 1
     for (int half = 0; half < TW_ROWS / RP; ++half) {
@@ -458,7 +464,7 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
 #pragma unroll
         for (int k = 0; k < RP; ++k) {
             const int r = ty0 + (int)threadIdx.y + 4 * (RP * half + k) - job.y0;
-            plan[k] = plan_taps<FLOAT>(job, col, min(max(r, 0), job.ph - 1), alpha[k]);
+            plan[k] = plan_taps<FLOAT>(job, col, __ldg(ray_rows + min(max(r, 0), job.ph - 1)), alpha[k]);
         }
 #pragma unroll
         for (int k = 0; k < RP; ++k) {
@@ -485,8 +491,7 @@ __device__ __forceinline__ void warp_tile_patch(const WarpJob &job, const float 
             }
             if (!bad) valid_bits |= 1u << slot;
             if (to_bytes && !bad && Y >= y_lo && Y < y_hi) {
-                const uint8_t *dst = out + ((size_t)Y * W + tx0) * 3;
-                uint8_t *stage = rows[ry] + (reinterpret_cast<uintptr_t>(dst) & 15) + 3 * threadIdx.x;
+                uint8_t *stage = rows[ry] + ((phase0 + (unsigned)Y * phase_step) & 15u) + 3 * threadIdx.x;
                 stage[0] = to_u8_unit(rgb.x); stage[1] = to_u8_unit(rgb.y); stage[2] = to_u8_unit(rgb.z);
             }
         }
