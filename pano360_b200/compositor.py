@@ -1450,7 +1450,7 @@ class Compositor:
 
     def streamed_windows(self, plan, kind, n_levels, windows=8, used=None):
         """Plan of ``composite_streamed``: the order in which to upload the images (left edge
-        first; an image that straddles the +-pi seam counts with its left column run) and column
+        first; images that straddle the +-pi seam last) and column
         windows [xa, xb) of the mosaic, on 64-column tile edges, with the number of uploads each
         one has to wait for — a window needs nothing beyond the first ``count`` images — sorted by
         that number: the order in which they can be composited."""
@@ -1462,7 +1462,11 @@ class Compositor:
                 for i, box in enumerate(plan.boxes) if box[2] > box[0] and box[3] > box[1]}
         if used is not None:        # (``used_boxes``) where the seam plan reads each image: tighter than its box
             runs = {i: sorted((b[0], b[2]) for b in boxes) for i, boxes in used.items() if boxes}
-        order = sorted(range(n), key=lambda i: (runs[i][0][0] if i in runs else 0, plan.boxes[i][1], i))
+        # left edge first — but an image with two column runs (it straddles the +-pi seam: both ends of
+        # the mosaic wait for it) goes last: the first window then needs one column of images, not two
+        late = os.environ.get("P360_STRADDLERS_LAST", "1") == "1"
+        order = sorted(range(n), key=lambda i: (late and len(runs.get(i, ())) > 1, runs[i][0][0] if i in runs else 0,
+                                                plan.boxes[i][1], i))
         rank = {i: r for r, i in enumerate(order)}
         last = np.zeros(width, dtype=np.int64)            # per mosaic column: rank of the last upload it needs
         for i, parts in runs.items():
