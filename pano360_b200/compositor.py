@@ -239,10 +239,14 @@ class Compositor:
 
     def download_stream(self):
         """Side stream of the banded mosaic downloads: its own stream, so that device -> host
-        copies are not queued behind uploads still in flight (PCIe is full duplex)."""
+        copies are not queued behind uploads still in flight (PCIe is full duplex).  With
+        P360_DOWN_STREAMS=2 consecutive calls alternate between two streams (two copy engines
+        share the device -> host direction)."""
         if self._down is None:
-            self._down = torch.cuda.Stream(self.device)
-        return self._down
+            self._down = [torch.cuda.Stream(self.device) for _ in range(max(1, int(os.environ.get("P360_DOWN_STREAMS", "1"))))]
+            self._down_at = 0
+        self._down_at = (self._down_at + 1) % len(self._down)
+        return self._down[self._down_at]
 
     def _table(self, records, key):
         """Structured job table -> device bytes."""
@@ -925,7 +929,7 @@ class Compositor:
             return
         host = None if out_host is None else torch.from_numpy(out_host)
         whole_rows = host is not None and xa == 0 and xb == w and col_origin == 0 and host.shape[1] == w
-        main, side = torch.cuda.current_stream(self.device), self.download_stream()
+        main = torch.cuda.current_stream(self.device)
         for y0, y1 in band_edges(ya, yb, bands):
             if y1 <= y0:
                 continue
@@ -935,6 +939,7 @@ class Compositor:
             if on_band is not None:
                 on_band(y0, y1)
             if host is not None:
+                side = self.download_stream()
                 done = torch.cuda.Event()
                 done.record(main)
                 side.wait_event(done)
@@ -955,9 +960,12 @@ class Compositor:
                     self._bands_down.append(band)
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} collapsed")
                 self._mark(f"rows {y0 + row_origin}-{y1 + row_origin} downloaded", side)
-        if host is not None:
+        if host is not None and self._down is not None:
+            tail = self._down[0]
+            for other in self._down[1:]:
+                tail.wait_stream(other)
             self._download = torch.cuda.Event()
-            self._download.record(side)
+            self._download.record(tail)
 
     def _blank(self, mosaic, out_host, rows, on_band, bands, row_origin, cols=None, col_origin=0, out=None):
         """A mosaic (or window) no image touches: zeros — through the same banded path as a
