@@ -301,11 +301,6 @@ __device__ __forceinline__ bool alpha_range(const WarpJob &j, Interval rx, Inter
 __global__ void __launch_bounds__(128)
 seam_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, BandPatch *patches, int H, int W,
                        int abs_row0, int mosaic_h, TileMaps m) {
-    // the true boxes of all jobs, staged once per block: the per-tile loops below reject most jobs on
-    // these four numbers alone
-    __shared__ int4 boxes[1024];                                             // {tx0, tx1, ty0, ty1}
-    for (int k = threadIdx.x; k < n_jobs; k += 128) boxes[k] = make_int4(jobs[k].tx0, jobs[k].tx1, jobs[k].ty0, jobs[k].ty1);
-    __syncthreads();
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= m.tiles_x * m.tiles_y) return;
     const int tx = t % m.tiles_x, ty = t / m.tiles_x;
@@ -319,45 +314,30 @@ seam_candidates_kernel(const WarpJob *__restrict__ jobs, int n_jobs, BandPatch *
     const int dc = j0.col0 - j0.x0, dr = j0.row0 - j0.y0;
     const Interval rx = table_range(j0.ray_x, xa + dc, xb + dc), rz = table_range(j0.ray_z, xa + dc, xb + dc);
     const Interval ry = table_range(j0.ray_y, ya + dr, yb + dr);
-    // one pass over the jobs that meet the tile: alpha bounds of each (remembered for up to HITS of
-    // them), and the best lower bound among those that cover the tile completely — a patch only
-    // dominates a tile it covers completely: beyond its box it has no pixels, however large alpha
-    // would be there (boxes end where the reference's ranges end)
-    constexpr int HITS = 8;
-    int hit_k[HITS];
-    double hit_max[HITS];
-    int n_hit = 0;
     double best_min = 0.0;
     for (int k = 0; k < n_jobs; ++k) {
-        const int4 b = boxes[k];
-        if (b.x >= xb || b.y <= xa || b.z >= yb || b.w <= ya) continue;
-        double a_min, a_max;
-        if (!alpha_range(jobs[k], rx, ry, rz, a_min, a_max)) continue;
-        if (b.x <= xa && b.y >= xb && b.z <= ya && b.w >= yb) best_min = fmax(best_min, a_min);
-        if (n_hit < HITS) { hit_k[n_hit] = k; hit_max[n_hit] = a_max; }
-        ++n_hit;
-    }
-    auto mark = [&](int k) {
         const WarpJob &j = jobs[k];
-        m.present[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
-        if (patches != nullptr) {
-            BandPatch &bp = patches[j.patch];
-            atomicMin(&bp.own[0], max(xa - bp.x0, 0));
-            atomicMin(&bp.own[1], max(max(ta, 0) - bp.y0, 0));
-            atomicMax(&bp.own[2], min(xa + TILE_X - bp.x0, bp.pw));
-            atomicMax(&bp.own[3], min(ta + TILE_Y - bp.y0, bp.ph));
-        }
-    };
-    if (n_hit <= HITS) {
-        for (int i = 0; i < n_hit; ++i)
-            if (hit_max[i] >= best_min) mark(hit_k[i]);
-        return;
-    }
-    for (int k = 0; k < n_jobs; ++k) {                   // (more patches over one tile than remembered: again)
-        const int4 b = boxes[k];
-        if (b.x >= xb || b.y <= xa || b.z >= yb || b.w <= ya) continue;
+        if (j.tx0 >= xb || j.tx1 <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
+        // a patch only dominates a tile it covers completely: beyond its box it has no pixels,
+        // however large alpha would be there (boxes end where the reference's ranges end)
+        if (j.tx0 > xa || j.tx1 < xb || j.ty0 > ya || j.ty1 < yb) continue;
         double a_min, a_max;
-        if (alpha_range(jobs[k], rx, ry, rz, a_min, a_max) && a_max >= best_min) mark(k);
+        if (alpha_range(j, rx, ry, rz, a_min, a_max)) best_min = fmax(best_min, a_min);
+    }
+    for (int k = 0; k < n_jobs; ++k) {
+        const WarpJob &j = jobs[k];
+        if (j.tx0 >= xb || j.tx1 <= xa || j.ty0 >= yb || j.ty1 <= ya) continue;
+        double a_min, a_max;
+        if (alpha_range(j, rx, ry, rz, a_min, a_max) && a_max >= best_min) {
+            m.present[(size_t)t * m.words + (j.patch >> 5)] |= 1u << (j.patch & 31);
+            if (patches != nullptr) {
+                BandPatch &bp = patches[j.patch];
+                atomicMin(&bp.own[0], max(xa - bp.x0, 0));
+                atomicMin(&bp.own[1], max(max(ta, 0) - bp.y0, 0));
+                atomicMax(&bp.own[2], min(xa + TILE_X - bp.x0, bp.pw));
+                atomicMax(&bp.own[3], min(ta + TILE_Y - bp.y0, bp.ph));
+            }
+        }
     }
 }
 

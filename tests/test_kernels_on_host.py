@@ -101,6 +101,26 @@ def test_streamed_windows_pipeline(st, monkeypatch, restore_globals):
         assert all(a % 64 == 0 for a, _ in cover)
 
 
+def test_streamed_window_plan_of_the_benchmark_ring(comp):
+    """The window plan of the streamed pipeline on the benchmark rig (cameras only, full size): the
+    six images that straddle the +-pi seam are uploaded last, the windows tile the mosaic's columns
+    on tile edges in the order their images arrive, the first one waits for a single column of
+    images, and the seam plan's rectangles save a sixth of the upload."""
+    wl = gpu.synth.workload("cfg4")
+    regs = gpu.synth.make_views(wl, only=set())
+    plan = gpu.geo.plan_mosaic(regs, True, 1e9)
+    rects = comp.source_rects(regs, plan, "multiband", wl.n_levels)
+    used = comp.used_boxes(regs, plan, "multiband", wl.n_levels)
+    order, wins = comp.streamed_windows(plan, "multiband", wl.n_levels, 12, used=used)
+    straddlers = {i for i, boxes in used.items() if len(boxes) > 1}
+    assert len(straddlers) == 6 and set(order[-6:]) == straddlers
+    assert wins[0][2] <= 3 and wins[-1][2] == len(regs) and all(a[2] <= b[2] for a, b in zip(wins, wins[1:]))
+    cover = sorted(w[:2] for w in wins)
+    assert cover[0][0] == 0 and cover[-1][1] == plan.shape[1] and all(a[1] == b[0] and a[0] % 64 == 0 for a, b in zip(cover, cover[1:]))
+    share = sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in rects.values()) / (len(regs) * wl.width * wl.height)
+    assert 0.7 < share < 0.86, share
+
+
 def test_pageable_buffers_are_staged(st, comp, monkeypatch, restore_globals):
     """Pageable inputs go through the ring of pinned slots (threaded memcpy + asynchronous DMA),
     a pageable / absent ``out`` through the pinned staging buffer, band by band — streamed and
