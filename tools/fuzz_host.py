@@ -132,22 +132,52 @@ def run_blender_api(st, case):
 
 
 def run_windows(comp, case, whole, rng):
-    """Random row windows of the same composite against the whole mosaic (no gains: the window
-    API takes the sources as uploaded)."""
+    """Random windows of the same composite against the whole mosaic (no gains: the window API
+    takes the sources as uploaded): row windows, rows x tile-aligned columns, the same written in
+    place into a whole-mosaic image, and — where the seam plan applies — the composite from sources
+    scrambled outside the plan's source rectangles."""
     if case["equalize"]:
         return
+    import torch
     regs, blend, levels = case["regs"], case["blend"], case["levels"]
     proj = geo.CylProj if case["cylindrical"] else geo.SphProj
     plan = geo.plan_mosaic(regs, blend == "multiband", case["cap"], proj)
     src = comp.upload(regs)
-    h = plan.shape[0]
-    for _ in range(2):
+    h, w = plan.shape
+    exact = comp.needs_exact(regs)
+    tiles = -(-w // 64)
+    for k in range(3):
         if h < 2:
             break
         ya, yb = sorted(int(v) for v in rng.choice(h + 1, 2, replace=False))
-        strip = comp.composite(regs, src, plan, blend, levels, proj, rows=(ya, yb),
-                               exact=comp.needs_exact(regs))[0].numpy()           # (the path stitch() took)
-        assert np.array_equal(strip, whole[ya:yb]), ("window", ya, yb)
+        cols = None
+        if k and tiles > 1:
+            ta, tb = sorted(int(v) for v in rng.choice(tiles + 1, 2, replace=False))
+            cols = (64 * ta, min(64 * tb, w))
+        rows = (ya, yb) if k < 2 else None
+        y0, y1 = rows or (0, h)
+        x0, x1 = cols or (0, w)
+        strip = comp.composite(regs, src, plan, blend, levels, proj, rows=rows, cols=cols,
+                               exact=exact)[0].numpy()           # (the path stitch() took)
+        assert np.array_equal(strip, whole[y0:y1, x0:x1]), ("window", rows, cols)
+        if not exact:
+            target = torch.full((h, w, 3), 9, dtype=torch.uint8)
+            comp.composite(regs, src, plan, blend, levels, proj, rows=rows, cols=cols, out_dev=(target.data_ptr(), w, target))
+            got = target.numpy()
+            assert np.array_equal(got[y0:y1, x0:x1], whole[y0:y1, x0:x1]), ("in place", rows, cols)
+            got[y0:y1, x0:x1] = 9
+            assert (got == 9).all(), ("in place: outside touched", rows, cols)
+    rects = comp.source_rects(regs, plan, blend, levels, proj)
+    if rects is not None and comp.direct:
+        noisy = []
+        for i, reg in enumerate(regs):
+            img = rng.integers(0, 256, reg.img.shape, dtype=np.uint8)
+            if i in rects:
+                r0, r1, c0, c1 = rects[i]
+                img[r0:r1, c0:c1] = reg.img[r0:r1, c0:c1]
+            noisy.append(Image(img, reg.rot, reg.intr))
+        again = comp.composite(noisy, comp.upload(noisy), plan, blend, levels, proj)[0].numpy()
+        assert np.array_equal(again, whole), "source rectangles"
 
 
 def main():
