@@ -422,12 +422,13 @@ _early_cache = {}
 
 def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.SphProj, group=None,
                      bands=4):
-    """Strip composite + gather, overlapped: every rank collapses its strip in
-    ``bands`` row bands and pushes each band into rank 0's mosaic over NVLink as
-    soon as it is done, while the next band is being computed.  Preferred
-    transport: peer-mapped destination (``PeerMosaic``, copy-engine DMA); if
-    symmetric memory cannot be set up, grouped NCCL send/recv.  Returns the
-    device mosaic on rank 0 (valid until the call after the next), None elsewhere."""
+    """Strip composite + gather, overlapped.  Preferred transport: rank 0's mosaic mapped into
+    every rank (``PeerMosaic``) and copy-engine DMA into it — everything outside the seam zone
+    right after the tile warp, when those tiles are final (``final_after_warp``), the seam zone's
+    rectangles after the collapse; without the seam plan, row bands as they are collapsed.
+    ``P360_FUSED_GATHER=1``: the kernels store into the peer mosaic themselves.  If symmetric
+    memory cannot be set up: grouped NCCL send/recv of row bands.  Returns the device mosaic on
+    rank 0 (valid until the call after the next), None elsewhere."""
     global _peer_ok
     from .compositor import band_edges
     world = dist.get_world_size(group) if dist.is_initialized() else 1
