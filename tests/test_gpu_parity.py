@@ -285,6 +285,25 @@ def test_cli_with_reference_style_caches(st, tmp_path, monkeypatch, restore_glob
         if "-c" in extra:
             want = rs.stitch(regs, blend, False, 5, 1400, crop=True)
         assert_mosaic_close(mosaic, want, what=blend)
+    # `-s 2`: the ingest shrinks the images on the device exactly as the reference's cv2.resize does
+    # (stitcher.py:418-421); with the `ba_room_s2.0.pkl` cache present the run goes on to the mosaic
+    import os
+    from pano360_b200 import ingest
+    files = ingest.list_images(str(img_dir))
+    assert sorted(files) == sorted(os.listdir(img_dir))
+    small = ingest.read_images(str(img_dir), 2.0)
+    for name, got in zip(files, small):
+        assert np.array_equal(got, cv2.resize(cv2.imread(str(img_dir / name)), None, fx=0.5, fy=0.5)), name
+    half = synth.make_views(synth.workload("cfg1", scale=8.0), noise=10.0)
+    objs = []
+    for reg in half:
+        o = fake.Image()
+        o.img, o.rot, o.intr, o.range = reg.img, reg.rot, reg.intr, reg.range
+        objs.append(o)
+    with open("ba_room_s2.0.pkl", "wb") as fid:
+        pickle.dump(objs, fid, protocol=pickle.HIGHEST_PROTOCOL)
+    mosaic = st.main([str(img_dir), "-s", "2", "-b", "linear", "-o", str(out), "--no-show"])
+    assert np.array_equal(mosaic, rs.stitch(half, "linear", False, 5, 1400))
 
 
 def test_many_small_views(st, restore_globals):
