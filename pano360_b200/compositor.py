@@ -2,29 +2,34 @@
 for allocation, streams and copies only) and sequences the sm_100a kernels of
 ``libpano360_b200.so`` through the C ABI.
 
-A whole multiband composite is six launches, whatever the number of images:
-one warp over every patch (K1, grid.z = patch, owner competition fused), one
-owned-box pass over the owner keys, one reduce, one horizontal and one vertical
-coarse blur over every (patch, level) job, one output-stationary collapse.
-Per-patch parameters travel in small job tables.
+A whole multiband composite is seven calls, whatever the number of images: one
+packing launch over the uploaded parts of all images (K1p), the seam plan from the
+geometry (K0), one tile warp (K1t: single-owner tiles straight to uint8, float
+patches + owner keys only in the seam zone), one reduce, one horizontal and one
+vertical coarse blur over every (patch, level) job, one output-stationary collapse
+of the seam-zone tiles.  Per-patch parameters travel in small job tables.  Any
+rows x columns window of the mosaic (columns on 64-pixel tile edges) can be
+composited on its own, byte-identical to that part of the whole: the strips of the
+multi-GPU path and the windows of the streamed end-to-end pipeline.
 
 Data layout in HBM
 ------------------
-* source image      {u32 RGBX, f32 alpha} [h][w]   packed on device from the u8x3 upload
+* source image      u8 RGBX [h][w][4]        packed on device from the u8x3 upload (only the part the plan reads)
 * sample LUT        f32 [256] per image      u8 -> float value (gain folded in)
 * hat tables        f64 [h], [w]             shared by images of equal size
 * ray tables        f64 [W], [W], [H]        proj2hom per mosaic column (x, z) / row (y); K*R per patch
 * patch pool        f32 [ph][pw][4] RGBA + u8 [ph][pw] invalid, all patches back to back
-* owner keys        u64 [H][W]               float_bits(alpha) << 32 | ~patch (atomicMax)
+* owner keys        u64 [H][W]               float_bits(alpha) << 32 | ~patch (seam zone only; atomicMax on the dense path)
 * covered           u8  [H][W]               union of valid pixels
 * coarse levels     f32 [h/f][w/f][4]        reduced (d2, d4), H-pass scratch and blurred
                                              f=2 (level 0) / f=4 (levels >= 1) images per patch
 * mosaic            u8  [H][W][3]            the only mosaic-sized output
 
-A *row window* ``(ya, yb)`` restricts all work to mosaic rows [ya, yb) plus a
-halo of the reach of the widest coarse blur (strip sharding, SURVEY.md §8e);
-patches are cropped in rows but keep their true columns, so reflections happen
-at true patch edges wherever they influence rows inside the window.
+A *window* (rows ``(ya, yb)`` and / or columns ``(xa, xb)``) restricts all work to
+that part of the mosaic plus a halo of the reach of the widest coarse blur and one
+tile (strip sharding; streamed pipeline); patches are cropped to
+the window + halo, far enough from it that neither the dropped pixels nor the
+reflections at the artificial edges reach a pixel with non-zero weight.
 """
 from __future__ import annotations
 
@@ -190,7 +195,7 @@ class Compositor:
         self.blur_h_rows = 1 if os.environ.get("P360_BLUR_H_ROWS", "4") == "1" else 4
         # seam plan (p360_seam_plan_build): ownership is geometric, so before anything is sampled the
         # mosaic tiles are split into solo tiles — written straight from the sources as uint8
-        # (p360_warp_direct) — and the seam zone, the only place where float patches, owner keys and
+        # (p360_warp_tiles) — and the seam zone, the only place where float patches, owner keys and
         # coarse levels exist.  P360_DIRECT=0: every patch warped to float, maps from the owner keys.
         self.direct = os.environ.get("P360_DIRECT", "1") == "1"
         # upload only the rectangle of every image the seam plan can sample (``source_rects``); P360_SOURCE_RECTS=0: whole images

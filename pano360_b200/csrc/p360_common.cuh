@@ -119,7 +119,7 @@ struct TileMaps {                       // == p360_tile_maps
     uint2 *work;                        // compacted list of the blocks a pass has to run
     int *work_count;
     uint32_t *wneed;                    // seam plan only (p360_seam_plan_build): where float pixels are wanted;
-                                        // non-null also says: solo tiles were written by p360_warp_direct
+                                        // non-null also says: solo tiles were written by p360_warp_tiles
     int tiles_x, tiles_y, words;
     int row0;                           // window row of tile row 0 (<= 0; tiles sit on absolute mosaic rows)
     int reach_x, reach_y;               // blur reach in tiles

@@ -387,7 +387,7 @@ multiband_collapse_kernel(const BandPatch *__restrict__ patches, int n_patches,
         // coarse level is read and none was computed here — nothing to cull either
         const size_t tile = (size_t)((ty0 - maps.row0) >> 5) * maps.tiles_x + tile_col;
         const bool blended = __ldg(maps.multi + tile) != 0;
-        if (maps.wneed != nullptr && !blended) return;   // seam plan: p360_warp_direct wrote this tile (block-uniform)
+        if (maps.wneed != nullptr && !blended) return;   // seam plan: p360_warp_tiles wrote this tile (block-uniform)
         n_hit = tile_list_from_maps(patches, n_patches, maps, tile, tx0, ty0, list);
         if (n_hit > 1 || blended) n_hit = cull_tile_list<L>(patches, n_hit, tx0, ty0, list);
         pure = L > 1 && n_hit == 1 && !blended;

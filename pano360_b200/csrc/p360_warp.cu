@@ -236,7 +236,7 @@ warp_batch_kernel(unsigned long long *__restrict__ keys, uint8_t *__restrict__ c
 //   present  candidates for owning a pixel of the tile
 //   cand     candidates within the blur reach whose box meets the tile: the only patches that can
 //            carry weight there.  One bit set ("solo"): the multiband sum telescopes to that
-//            patch's warped pixel on the whole tile -> p360_warp_direct writes uint8 straight into
+//            patch's warped pixel on the whole tile -> p360_warp_tiles writes uint8 straight into
 //            the mosaic and nothing else ever touches the tile.  More ("multi"): full blend.
 //   need     candidates of the multi tiles within reach: where coarse levels are consumed
 //   wneed    where float pixels / owner keys are consumed: candidates of the multi tiles within
