@@ -493,13 +493,13 @@ def composite_gather(comp, regions, src, plan, kind, n_levels, parts, proj=geo.S
                     # everything but the seam zone is final now: it travels while reduce / blur /
                     # collapse run, and only the seam zone's rectangles are left for the end
                     key = (id(multi), geometry["top"], geometry["left"], geometry["rows"], geometry["cols"])
-                    cuts = _early_cache.get(key)
-                    if cuts is None:
+                    entry = _early_cache.get(key)
+                    if entry is None or entry[0] is not multi:       # (an id can be reused: the map itself is kept and compared)
                         if len(_early_cache) > 64:
                             _early_cache.clear()
-                        cuts = _early_cache[key] = final_after_warp(multi, geometry)
-                    state.update(buffer=buffer, geometry=geometry, late=cuts[1])
-                    push_rects(buffer, cuts[0], geometry)
+                        entry = _early_cache[key] = (multi,) + final_after_warp(multi, geometry)
+                    state.update(buffer=buffer, geometry=geometry, late=entry[2])
+                    push_rects(buffer, entry[1], geometry)
 
                 def push_band(piece, y0, y1):
                     if state:                         # (the early pushes fired: the rest goes at the end)
