@@ -301,7 +301,7 @@ class Compositor:
         rows = raw.rows or [None] * len(raw.pixels)
         # the packed copies of one set of resident images always land in the same buffers: stable
         # addresses let ``composite`` reuse everything it prepared for them
-        key = tuple(0 if p is None else p.data_ptr() for p in raw.pixels) + (tuple(rows),)
+        key = tuple(0 if p is None else (p.data_ptr(), tuple(p.shape)) for p in raw.pixels) + (tuple(rows),)
         entry = self._packed.get(key)
         if entry is None:
             if len(self._packed) >= 8:
