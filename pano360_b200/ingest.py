@@ -27,21 +27,31 @@ def resize_on_device(comp, images, shrink):
     """[cv2.resize(im, None, fx=1/shrink, fy=1/shrink) for im in images] computed on ``comp``'s GPU;
     uint8 HxW, HxWx3 or HxWx4 arrays in, arrays of the same kind out."""
     import torch
+    from .compositor import parallel_copy
     f = 1.0 / shrink
     side, main = comp.copy_stream(), torch.cuda.current_stream(comp.device)
-    tables, out, pending = {}, [], []
+    area2 = abs(shrink - 2.0) < np.finfo(np.float64).eps
+    # one pinned landing buffer for all the shrunk images (kept by the compositor, grow-only)
+    sizes = []
     for img in images:
         if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] not in (1, 3, 4)):
             raise TypeError("resize_on_device takes uint8 HxW, HxWx3 or HxWx4 images")
+        dh, dw = geo.resize_dsize(img.shape[0], img.shape[1], f)
+        if dh < 1 or dw < 1:
+            raise ValueError(f"a {img.shape[0]} x {img.shape[1]} image cannot be shrunk by {shrink}")
+        sizes.append(dh * dw * (1 if img.ndim == 2 else img.shape[2]))
+    total = int(sum(sizes))
+    stage = getattr(comp, "_ingest_stage", None)
+    if stage is None or stage.numel() < total:
+        stage = comp._ingest_stage = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=comp.device.type == "cuda")
+    tables, out, pending, at = {}, [], [], 0
+    for img, size in zip(images, sizes):
         h, w = img.shape[:2]
         c = 1 if img.ndim == 2 else img.shape[2]
         dh, dw = geo.resize_dsize(h, w, f)
-        if dh < 1 or dw < 1:
-            raise ValueError(f"a {h} x {w} image cannot be shrunk by {shrink}")
         if (dh, dw) == (h, w):                           # cv2.resize copies when nothing changes
             out.append(img.copy())
             continue
-        area2 = abs(shrink - 2.0) < np.finfo(np.float64).eps
         if (h, w) not in tables and not area2:
             xo, xw = geo.resize_tables(w, dw, f, True)
             yo, yw = geo.resize_tables(h, dh, f, False)
@@ -59,14 +69,17 @@ def resize_on_device(comp, images, shrink):
             t = tables.get((h, w), (None,) * 4)
             _lib.call("p360_resize_u8", dev.data_ptr(), h, w, c, small.data_ptr(), dh, dw, _lib.ptr(t[0]), _lib.ptr(t[1]),
                       _lib.ptr(t[2]), _lib.ptr(t[3]), int(area2), side.cuda_stream)
-            landing = torch.empty(small.shape, dtype=torch.uint8, pin_memory=comp.device.type == "cuda")
+            landing = stage[at:at + size].view(small.shape)
             landing.copy_(small, non_blocking=True)
+            at += size
         pending.append((len(out), landing, dev, small))
         out.append(None)
     side.synchronize()
     main.wait_stream(side)
-    for k, landing, _, _ in pending:
-        out[k] = landing.numpy().copy()                  # plain (pageable) arrays, like cv2's
+    for k, landing, _, _ in pending:                     # plain (pageable) arrays, like cv2's
+        fresh = np.empty(tuple(landing.shape), np.uint8)
+        parallel_copy(fresh, landing.numpy())
+        out[k] = fresh
     return out
 
 
