@@ -29,7 +29,7 @@ for shrink in (2.0, 1.5):
     t0 = time.perf_counter()
     want = [cv2.resize(p, None, fx=f, fy=f) for p in pinned]
     host_ms = (time.perf_counter() - t0) * 1e3
-    ingest.resize_on_device(comp, pinned[:2], shrink)
+    ingest.resize_on_device(comp, pinned, shrink)          # (warm: the pinned landing buffer is allocated once)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     got = ingest.resize_on_device(comp, pinned, shrink)
