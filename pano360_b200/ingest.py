@@ -4,6 +4,13 @@ factor **on the device** (p360_resize_u8: bit-exact with ``cv2.resize(im, None, 
 including OpenCV's reroute of the exact 2x shrink to the 2 x 2 area mean), through pinned staging.
 The registration code of the reference (features.py / bundle_adj.py) wants host arrays, so the
 resized images come back to the host; uploads, kernels and downloads of consecutive images overlap.
+
+Measured on a B200 box (tools/ingest_probe.py, 36 images of 4000 x 3000, profiles/r02z_ingest_probe.log):
+the kernel takes 41 us per image (S = 2; 1.1 TB/s on the 45 MB it reads and writes) where the host's
+cv2.resize takes 1.05 ms on 16 threads — but end to end the device path is PCIe-bound (36 MB up for
+9 MB of result): 1.66 ms per image against 1.05 ms (S = 1.5: 2.04 against 1.73 ms).  It pays once the
+full-resolution image is on the device anyway (a device decoder); until then it is the bit-exact
+device form of this stage, and P360_DEVICE_RESIZE=0 keeps the host call.
 """
 from __future__ import annotations
 
@@ -90,6 +97,8 @@ def read_images(path, shrink=1.0, comp=None, workers=8):
     files = list_images(path)
     with ThreadPoolExecutor(max(1, min(workers, len(files) or 1))) as pool:
         imgs = list(pool.map(lambda name: cv2.imread(os.path.join(path, name)), files))
+    if shrink > 1 and os.environ.get("P360_DEVICE_RESIZE", "1") != "1":
+        return [cv2.resize(im, None, fx=1 / shrink, fy=1 / shrink) for im in imgs]     # the reference's call, on the host
     if shrink > 1:
         if comp is None:
             from .stitcher import _compositor
