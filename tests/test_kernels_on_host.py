@@ -191,7 +191,23 @@ def _strip_worker(rank, world, port, golden, kind, equalize, out_path, axis="col
         mosaic = strips.stitch_strips(comp, regs, kind, n_levels=5, equalize=equalize)
         assert (mosaic is not None) == (rank == 0)
         if rank == 0:
+            mosaic = np.array(mosaic)           # (a view of the buffer the ranks share: the next call overwrites it)
+        # the device-resident result: strips gathered on rank 0 by send / recv of row bands (what a
+        # system without peer-mapped memory runs; a column strip arrives contiguous and is copied in)
+        gathered = strips.stitch_strips(comp, regs, kind, n_levels=5, equalize=equalize, to_host=False)
+        assert (gathered is not None) == (rank == 0)
+        if rank == 0:
+            assert np.array_equal(gathered.numpy(), mosaic)
             np.save(out_path, mosaic)
+        # measured-feedback cuts: same cuts on every rank, still a partition of the mosaic
+        from pano360_b200 import geometry as geo
+        plan = geo.plan_mosaic_cached(regs, kind == "multiband", 1400)
+        parts = strips.tune_partition(comp, regs, plan, kind, 5, lambda p: 1.0 + 0.5 * rank, rounds=2)
+        box = [strips.part_box(p, plan.shape) for p in parts]
+        assert len(parts) == world and box[0][0] == 0 and box[0][2] == 0 and box[-1][1] == plan.shape[0] and box[-1][3] == plan.shape[1]
+        again = strips.stitch_strips(comp, regs, kind, n_levels=5, equalize=equalize)      # (with the tuned cuts)
+        if rank == 0:
+            assert np.array_equal(again, mosaic)
         dist.barrier()
     finally:
         dist.destroy_process_group()
