@@ -181,6 +181,7 @@ class Compositor:
         self._ring = []        # pinned staging slots for pageable inputs: [tensor, busy event]
         self._ring_at = 0
         self._out_stage = None  # pinned staging for a pageable output
+        self._ingest_stage = None  # pinned landing buffer of ingest.resize_on_device
         self.stage_min_bytes = 1 << 20   # pageable images from this size on go through the pinned ring
         self.trace = None      # list of (kernel, algorithmic_bytes, start_event, end_event) when enabled
         self.phases = None     # host-side phase times of stitch_strips calls when enabled (bench.py)
@@ -989,6 +990,7 @@ class Compositor:
         ``everything``."""
         self.last_covered = None
         if everything:
+            self._ingest_stage = None
             self._prepared.clear()
             self._pools.clear()
             self._images.clear()
