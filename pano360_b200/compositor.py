@@ -1134,11 +1134,17 @@ class Compositor:
             else:
                 jobs = self._blur_jobs(table, layout, dev_table, pad)
                 dev_jobs = self._table(jobs, "blur_jobs")
+            if seam is not None and "w4h4" in seam["prepared"]:        # (prepared composite: computed once)
+                max_w4, max_h4 = seam["prepared"]["w4h4"]
+            else:
+                max_w4, max_h4 = int(table["w4"].max()), int(table["h4"].max())
+                if seam is not None:
+                    seam["prepared"]["w4h4"] = (max_w4, max_h4)
             self._traced("K3a_pyramid_reduce", 25 * pix, "p360_pyramid_reduce_batch", _lib.ptr(dev_table), n,
-                         int(table["w4"].max()), int(table["h4"].max()), _lib.ptr(keys), w, maps_ptr, self.stream)
+                         max_w4, max_h4, _lib.ptr(keys), w, maps_ptr, self.stream)
             coarse_px = int((4 + len(plan) - 1) * layout["cells"])
             self._traced("K3_gauss_blur", 32 * coarse_px, "p360_gauss_blur_batch", _lib.ptr(dev_jobs),
-                         len(jobs), int(2 * table["w4"].max()), int(2 * table["h4"].max()), maps_ptr, self.stream)
+                         len(jobs), 2 * max_w4, 2 * max_h4, maps_ptr, self.stream)
             if maps is not None:
                 _lib.launch_count += 3          # the scan kernels that compact the block lists
             self._keep["bands"] = (layout["pool2"], layout["pool4"], dev_jobs, maps, maps_keep)
@@ -1440,8 +1446,12 @@ class Compositor:
             patches = prep["patches"]
             self._keep["warp"] = prep["keep"][:3] + (prep["jobs"],)
             seam = {"prepared": prep, "crops": crops, "src": src, "mosaic_h": plan.shape[0], "pixels": prep["keep"][3],
-                    "want_covered": want_covered,
-                    "reads": self._images_read(regions, plan, kind, n_levels, proj, crops, top, left, shape)}
+                    "want_covered": want_covered}
+            used_known = plan._crops is not None and ("used", len(regions), proj, None, None, kind, n_levels) in plan._crops
+            if prep.get("reads_known") != used_known:               # (per prepared window; redone once the plan's rectangles exist)
+                prep["reads"] = self._images_read(regions, plan, kind, n_levels, proj, crops, top, left, shape)
+                prep["reads_known"] = used_known
+            seam["reads"] = prep["reads"]
             if after_warp is not None:
                 def fire(buffer, multi, row0):
                     self.used_after_warp = True
